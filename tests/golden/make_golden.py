@@ -1,0 +1,97 @@
+"""Generate golden fixtures by running the REFERENCE's own importable code.
+
+Run once in the build container (`python tests/golden/make_golden.py`); the
+reference tree (/root/reference) does not exist on the GPU box, so the outputs
+are committed as `tests/golden/*.npz` next to this script.
+
+What is importable from the reference without JAX:
+  * MipNeRF360/internal/geopoly.py        (pure NumPy)   -> IPE basis, column order
+  * nerfacto/utils/ray_utils.py           (torch)        -> sample / sample_intervals /
+                                                            density_to_weight (torch twins of
+                                                            stepfun.sample*, render.compute_alpha_weights)
+  * nerfacto/utils/loss_utils.py          (torch)        -> lossfun_outer / lossfun_distortion
+  * nerfacto/models/custom_functions.py   (torch)        -> contraction, pos_enc
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = '/root/reference'
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def load(path, name):
+  spec = importlib.util.spec_from_file_location(name, path)
+  mod = importlib.util.module_from_spec(spec)
+  spec.loader.exec_module(mod)
+  return mod
+
+
+def main():
+  torch.manual_seed(0)
+  rng = np.random.default_rng(0)
+
+  geopoly = load(f'{REF}/MipNeRF360/internal/geopoly.py', 'ref_geopoly')
+  np.savez(f'{OUT}/geopoly_basis.npz',
+           icosahedron_2=geopoly.generate_basis('icosahedron', 2),
+           octahedron_1=geopoly.generate_basis('octahedron', 1),
+           octahedron_4=geopoly.generate_basis('octahedron', 4),
+           icosahedron_1=geopoly.generate_basis('icosahedron', 1))
+
+  ray_utils = load(f'{REF}/nerfacto/utils/ray_utils.py', 'ref_ray_utils')
+  loss_utils = load(f'{REF}/nerfacto/utils/loss_utils.py', 'ref_loss_utils')
+  cf = load(f'{REF}/nerfacto/models/custom_functions.py', 'ref_custom_functions')
+
+  # --- sample_intervals (deterministic branch == stepfun.sample_intervals(rng=None)) ---
+  cases = {}
+  for name, (n_rays, n_bins, n_samples) in {
+      'small': (7, 5, 10), 'prop': (64, 64, 64), 'nerf': (64, 190, 128), 'odd': (33, 17, 31)}.items():
+    t = np.sort(rng.uniform(0, 1, (n_rays, n_bins + 1)).astype(np.float32), -1)
+    t[:, 0], t[:, -1] = 0.0, 1.0
+    if name == 'odd':           # zero-width bins (weight forced to -inf by the reference)
+      t[:, 5] = t[:, 4]
+    w = rng.uniform(0, 1, (n_rays, n_bins)).astype(np.float32) ** 4
+    w /= w.sum(-1, keepdims=True)
+    for anneal in (1.0, 0.3):
+      out = ray_utils.sample_intervals(torch.tensor(t), torch.tensor(w), anneal, 0.0, n_samples,
+                                       perturb=False, single_jitter=True, domain=(0.0, 1.0))
+      cases[f'{name}_a{anneal}_t'] = t
+      cases[f'{name}_a{anneal}_w'] = w
+      cases[f'{name}_a{anneal}_out'] = out.numpy()
+  # the reference's own known-answer case (stepfun_test.py:579-586)
+  t = torch.tensor([[1., 2, 3, 4, 5, 6]])
+  w = torch.softmax(torch.tensor([[0., 0, 100, 0, 0]]), -1)
+  cases['single_out'] = ray_utils.sample_intervals(t, w, 1.0, 0.0, 10, False, True,
+                                                   (-float('inf'), float('inf'))).numpy()
+  np.savez(f'{OUT}/sample_intervals.npz', **cases)
+
+  # --- lossfun_distortion / lossfun_outer ---
+  n_rays = 32
+  t = np.sort(rng.uniform(0, 1, (n_rays, 129)).astype(np.float32), -1)
+  w = rng.uniform(0, 1, (n_rays, 128)).astype(np.float32); w /= (1.3 * w.sum(-1, keepdims=True))
+  te = np.sort(rng.uniform(0, 1, (n_rays, 65)).astype(np.float32), -1)
+  te[:, 0], te[:, -1] = 0.0, 1.0
+  t[:, 0] = np.maximum(t[:, 0], 0.0)
+  we = rng.uniform(0, 1, (n_rays, 64)).astype(np.float32); we /= (1.1 * we.sum(-1, keepdims=True))
+  np.savez(f'{OUT}/losses.npz', t=t, w=w, t_env=te, w_env=we,
+           distortion=loss_utils.lossfun_distortion(torch.tensor(t), torch.tensor(w)).numpy(),
+           outer=loss_utils.outer(torch.tensor(t[:, :-1]), torch.tensor(t[:, 1:]),
+                                  torch.tensor(te[:, :-1]), torch.tensor(te[:, 1:]),
+                                  torch.tensor(we)).numpy())
+
+  # --- contraction + pos_enc ---
+  x = (rng.normal(size=(256, 3)) * np.array([0.3, 2.0, 30.0])).astype(np.float32)
+  v = rng.normal(size=(64, 3)).astype(np.float32)
+  v /= np.linalg.norm(v, axis=-1, keepdims=True)
+  np.savez(f'{OUT}/coord.npz', x=x, contract=cf.spatial_distortion_norm2(torch.tensor(x)).numpy(),
+           v=v, pos_enc_0_4=cf.pos_enc(torch.tensor(v), 0, 4, True).numpy())
+
+  print('wrote fixtures to', OUT)
+
+
+if __name__ == '__main__':
+  main()
