@@ -1,0 +1,194 @@
+/* hugs_b200.h — C ABI of the B200-native NeRF-HuGS volume-rendering path.
+ *
+ * The reference (cnhaox/NeRF-HuGS) has no FFI: its boundary is the Python call surface
+ * MipNeRF360/internal/{train_utils,models}.py exposes to MipNeRF360/{train,eval,render}.py.
+ * Each entry point below names the reference function(s) it replaces (paths relative to
+ * /root/reference).  The Python host (nerf_hugs_b200/) binds these with ctypes and re-creates
+ * the reference call surface on top.
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative hugs_status otherwise; the message is
+ *    available (thread-local) from hugs_last_error().  Nothing throws or aborts across the ABI.
+ *  - all tensor arguments are caller-owned DEVICE pointers (fp32 unless noted) with explicit
+ *    element counts; `stream` is a cudaStream_t passed as void*; calls are asynchronous on it.
+ *  - a handle is bound to the device that was current at hugs_create and is not thread-safe.
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with
+ *    HUGS_ERR_CUDA.
+ */
+#ifndef HUGS_B200_H_
+#define HUGS_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HUGS_ABI_VERSION 1
+
+typedef enum {
+  HUGS_OK = 0,
+  HUGS_ERR_INVALID = -1,   /* bad argument / unsupported configuration */
+  HUGS_ERR_CUDA = -2,      /* CUDA runtime / driver error (message has the cudaError string) */
+  HUGS_ERR_NOMEM = -3,
+  HUGS_ERR_UNSUPPORTED = -4
+} hugs_status;
+
+typedef enum { HUGS_RAYDIST_NONE = 0, HUGS_RAYDIST_RECIPROCAL = 1, HUGS_RAYDIST_LOG = 2,
+               HUGS_RAYDIST_PIECEWISE = 3 } hugs_raydist_fn;   /* coord.py:63-99 */
+typedef enum { HUGS_RAY_CONE = 0, HUGS_RAY_CYLINDER = 1 } hugs_ray_shape; /* render.py:103-127 */
+typedef enum { HUGS_PRECISION_FP32 = 0,   /* CUDA-core fp32 MLP: parity mode (1e-4 vs oracle) */
+               HUGS_PRECISION_BF16_TC = 1 /* tcgen05 bf16 x bf16 -> fp32: throughput mode     */
+} hugs_precision;
+typedef enum { HUGS_LOSS_CHARB = 0, HUGS_LOSS_MSE = 1 } hugs_data_loss;  /* train_utils.py:96-103 */
+
+/* Model description == the gin-bound fields of models.Model / NerfMLP / PropMLP
+ * (MipNeRF360/internal/models.py:47-71, :360-391) the hot path reads. */
+typedef struct {
+  int32_t num_levels;          /* Model.num_levels            */
+  int32_t num_prop_samples;    /* Model.num_prop_samples      */
+  int32_t num_nerf_samples;    /* Model.num_nerf_samples      */
+  int32_t nerf_depth;          /* NerfMLP.net_depth           */
+  int32_t nerf_width;          /* NerfMLP.net_width           */
+  int32_t prop_depth;          /* PropMLP.net_depth           */
+  int32_t prop_width;          /* PropMLP.net_width           */
+  int32_t bottleneck_width;    /* MLP.bottleneck_width        */
+  int32_t view_width;          /* MLP.net_width_viewdirs (depth 1) */
+  int32_t skip_layer;          /* MLP.skip_layer              */
+  int32_t min_deg_point, max_deg_point, deg_view;
+  int32_t num_basis;           /* columns of pos_basis_t (21 for icosahedron/2) */
+  float   basis[3 * 32];       /* pos_basis_t, row-major [3][num_basis] (geopoly.py:78) */
+  int32_t raydist_fn;          /* hugs_raydist_fn: Model.raydist_fn */
+  int32_t ray_shape;           /* hugs_ray_shape                    */
+  int32_t nerf_contract;       /* NerfMLP.warp_fn == @coord.contract */
+  int32_t prop_contract;       /* PropMLP.warp_fn == @coord.contract */
+  int32_t opaque_background;
+  float   bg_intensity;        /* Model.bg_intensity_range (min==max) */
+  float   anneal_slope, dilation_multiplier, dilation_bias, resample_padding;
+  float   near_anneal_rate;    /* <= 0: disabled (None) */
+  float   near_anneal_init;
+  int32_t num_glo_features, num_embeddings;
+  float   density_bias, rgb_premultiplier, rgb_bias, rgb_padding;
+  int32_t precision;           /* hugs_precision */
+  int32_t max_rays;            /* workspace is sized for this many rays per call */
+} hugs_model_desc;
+
+/* utils.Rays (MipNeRF360/internal/utils.py:44-57) as struct-of-arrays device pointers,
+ * each [n_rays, C] contiguous.  pix_coords / cam_idx are not read by this path. */
+typedef struct {
+  const float* origins;      /* [n,3] */
+  const float* directions;   /* [n,3] */
+  const float* viewdirs;     /* [n,3] */
+  const float* radii;        /* [n,1] */
+  const float* near;         /* [n,1] */
+  const float* far;          /* [n,1] */
+  const float* lossmult;     /* [n,1] (train only; may be NULL => 1) */
+  const float* static_mask;  /* [n,1] HuGS mask gathered per pixel (datasets.py:473); NULL => 1 */
+  const int32_t* embed_idx;  /* [n,1] (GLO; may be NULL when num_glo_features == 0) */
+} hugs_rays;
+
+/* Loss / optimiser fields of configs.Config (configs.py:84-107,131-132). */
+typedef struct {
+  int32_t data_loss_type;          /* hugs_data_loss */
+  float   charb_padding, data_loss_mult, data_coarse_loss_mult;
+  float   interlevel_loss_mult, distortion_loss_mult;
+  int32_t use_static_mask;         /* transient_type == 'withmask' (train_utils.py:80-82, quirk B1) */
+  float   withmask_transient_weight;
+  int32_t disable_multiscale_loss;
+} hugs_loss_cfg;
+
+typedef struct {
+  float lr;                        /* math.learning_rate_decay(step) evaluated by the host */
+  float beta1, beta2, eps;         /* optax.adam (train_utils.py:489-510) */
+  float grad_max_norm, grad_max_val; /* clip_gradients (train_utils.py:351-369) */
+  int32_t step;                    /* optax count before this update (0-based) */
+} hugs_adam_cfg;
+
+/* One named view into the flat fp32 parameter buffer (flax names, e.g. "NerfMLP_0/Dense_3/kernel"). */
+typedef struct {
+  char    name[64];
+  int64_t offset;                  /* in floats */
+  int32_t rows, cols;              /* kernel: [in,out]; bias: [1,out]; embedding: [num,feat] */
+  int32_t module;                  /* 0 NerfMLP_0, 1 PropMLP_0, 2 GloEmbed_0 (clip groups) */
+} hugs_tensor_desc;
+
+/* Per-level rendering outputs (render.volumetric_rendering, render.py:185-244). NULL = skip. */
+typedef struct {
+  float* rgb;            /* [n,3] */
+  float* acc;            /* [n]   */
+  float* distance_mean, *distance_median, *distance_p5, *distance_p95; /* [n] (compute_extras) */
+  float* sdist;          /* [n, S+1] ray_history['sdist']   */
+  float* weights;        /* [n, S]   ray_history['weights'] */
+  float* density;        /* [n, S]   */
+  float* rgbs;           /* [n, S, 3] (NeRF level only) */
+} hugs_level_out;
+
+typedef struct hugs_handle hugs_handle;
+
+const char* hugs_last_error(void);
+int hugs_abi_version(void);
+
+/* models.construct_model + train_utils.setup_model (models.py:333-357, train_utils.py:579-596) */
+int hugs_create(const hugs_model_desc* desc, hugs_handle** out);
+int hugs_destroy(hugs_handle* h);
+int64_t hugs_param_count(const hugs_handle* h);
+int hugs_param_layout(const hugs_handle* h, hugs_tensor_desc* out, int32_t capacity, int32_t* count);
+/* Re-derive the packed bf16 operand copies after the caller wrote the fp32 parameters. */
+int hugs_params_changed(hugs_handle* h, const float* params, void* stream);
+
+/* ---- operator-level entry points (parity tests bind these one-to-one) ---- */
+
+/* stepfun.sample_intervals (stepfun.py:214-263) incl. softmax/integrate_weights/sorted_interp
+ * (stepfun.py:131-161, math.py:108-127).  u = u_base[j] + jitter[ray]*max_jitter (jitter may be NULL).
+ * idx_out (optional) receives the selected CDF interval of every sample centre. */
+int hugs_sample_intervals(const float* t, const float* w_logits, const float* u_base,
+                          const float* jitter, float max_jitter, int32_t n_rays, int32_t n_bins,
+                          int32_t n_samples, float dom_lo, float dom_hi,
+                          float* t_out, int32_t* idx_out, void* stream);
+/* math.sorted_interp on a caller-provided CDF: bit-exact index + value contract. */
+int hugs_invert_cdf(const float* t, const float* cw, const float* u, int32_t n_rays, int32_t n_bins,
+                    int32_t n_samples, float* centers_out, int32_t* idx_out, void* stream);
+/* stepfun.max_dilate_weights(renormalize=True) + the [1:-1] trim of models.py:171-179.
+ * t_out [n, 3*n_bins-1], w_out [n, 3*n_bins-2]. */
+int hugs_max_dilate_weights(const float* t, const float* w, int32_t n_rays, int32_t n_bins,
+                            float dilation, float dom_lo, float dom_hi,
+                            float* t_out, float* w_out, void* stream);
+/* render.compute_alpha_weights + render.volumetric_rendering (render.py:130-151,185-244).
+ * raw_density [n,S] is pre-activation (softplus(raw + density_bias) applied inside);
+ * raw_rgb [n,S,3] pre-sigmoid or NULL (proposal levels: rgb = 0). */
+int hugs_alpha_composite(const hugs_handle* h, const float* raw_density, const float* raw_rgb,
+                         const float* tdist, const float* sdist, const float* directions,
+                         const float* far, int32_t n_rays, int32_t n_samples, int32_t compute_extras,
+                         const hugs_level_out* out, void* stream);
+/* coord.track_linearize(contract) + lift_and_diagonalize + integrated_pos_enc on cast_rays
+ * Gaussians (render.py:103-127, coord.py:39-60,102-133): features [n*S, 2*num_basis*degs],
+ * reference column order.  exact != 0 uses the reference's safe_sin arithmetic. */
+int hugs_ipe_features(const hugs_handle* h, const hugs_rays* rays, const float* tdist,
+                      int32_t n_rays, int32_t n_samples, int32_t contract, float* features,
+                      void* stream);
+
+/* ---- model-level entry points ---- */
+
+/* Model.__call__ with rng=None or caller-provided jitter (models.py:74-330);
+ * render_eval_pfn's payload (train_utils.py:558-575).  jitter: [num_levels, n_rays] or NULL.
+ * out: array of num_levels hugs_level_out. */
+int hugs_forward(hugs_handle* h, const float* params, const hugs_rays* rays, int32_t n_rays,
+                 float train_frac, const float* jitter, int32_t compute_extras, int32_t zero_glo,
+                 const hugs_level_out* out, void* stream);
+
+/* loss_fn + value_and_grad of train_utils.train_step (train_utils.py:407-455) on this rank's
+ * rays.  grad_out: flat fp32 [param_count] (overwritten).  stats_out: fp32[16]:
+ * [0] loss, [1] data, [2] interlevel, [3] distortion, [4..4+L) mse per level. */
+int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* rays,
+                       const float* rgb_gt, int32_t n_rays, float train_frac, const float* jitter,
+                       const hugs_loss_cfg* loss, float* grad_out, float* stats_out, void* stream);
+
+/* clip_gradients + nan_to_num + optax.adam apply (train_utils.py:351-369,464-468) on the
+ * (already all-reduced) flat gradient.  norms_out (optional) fp32[9]: {grad norm, abs-max, clip multiplier} per module. */
+int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
+                   const hugs_adam_cfg* cfg, float* norms_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* HUGS_B200_H_ */

@@ -1,0 +1,97 @@
+"""ctypes binding of libhugs_b200.so (include/hugs_b200.h).  No torch types cross this boundary:
+device pointers are passed as integers (tensor.data_ptr()), the stream as cudaStream_t.
+
+There is no CPU fallback: if the shared library is missing this module raises at import.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libhugs_b200.so')
+
+
+class HugsError(RuntimeError):
+  def __init__(self, code, msg):
+    super().__init__(f'hugs_b200 error {code}: {msg}')
+    self.code = code
+
+
+class ModelDesc(C.Structure):
+  _fields_ = [
+      ('num_levels', C.c_int32), ('num_prop_samples', C.c_int32), ('num_nerf_samples', C.c_int32),
+      ('nerf_depth', C.c_int32), ('nerf_width', C.c_int32), ('prop_depth', C.c_int32), ('prop_width', C.c_int32),
+      ('bottleneck_width', C.c_int32), ('view_width', C.c_int32), ('skip_layer', C.c_int32),
+      ('min_deg_point', C.c_int32), ('max_deg_point', C.c_int32), ('deg_view', C.c_int32),
+      ('num_basis', C.c_int32), ('basis', C.c_float * 96),
+      ('raydist_fn', C.c_int32), ('ray_shape', C.c_int32), ('nerf_contract', C.c_int32), ('prop_contract', C.c_int32),
+      ('opaque_background', C.c_int32), ('bg_intensity', C.c_float),
+      ('anneal_slope', C.c_float), ('dilation_multiplier', C.c_float), ('dilation_bias', C.c_float),
+      ('resample_padding', C.c_float), ('near_anneal_rate', C.c_float), ('near_anneal_init', C.c_float),
+      ('num_glo_features', C.c_int32), ('num_embeddings', C.c_int32),
+      ('density_bias', C.c_float), ('rgb_premultiplier', C.c_float), ('rgb_bias', C.c_float), ('rgb_padding', C.c_float),
+      ('precision', C.c_int32), ('max_rays', C.c_int32),
+  ]
+
+
+class Rays(C.Structure):
+  _fields_ = [(n, C.c_void_p) for n in ('origins', 'directions', 'viewdirs', 'radii', 'near', 'far', 'lossmult',
+                                        'static_mask', 'embed_idx')]
+
+
+class LossCfg(C.Structure):
+  _fields_ = [('data_loss_type', C.c_int32), ('charb_padding', C.c_float), ('data_loss_mult', C.c_float),
+              ('data_coarse_loss_mult', C.c_float), ('interlevel_loss_mult', C.c_float),
+              ('distortion_loss_mult', C.c_float), ('use_static_mask', C.c_int32),
+              ('withmask_transient_weight', C.c_float), ('disable_multiscale_loss', C.c_int32)]
+
+
+class AdamCfg(C.Structure):
+  _fields_ = [('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
+              ('grad_max_norm', C.c_float), ('grad_max_val', C.c_float), ('step', C.c_int32)]
+
+
+class TensorDesc(C.Structure):
+  _fields_ = [('name', C.c_char * 64), ('offset', C.c_int64), ('rows', C.c_int32), ('cols', C.c_int32),
+              ('module', C.c_int32)]
+
+
+class LevelOut(C.Structure):
+  _fields_ = [(n, C.c_void_p) for n in ('rgb', 'acc', 'distance_mean', 'distance_median', 'distance_p5',
+                                        'distance_p95', 'sdist', 'weights', 'density', 'rgbs')]
+
+
+# every symbol include/hugs_b200.h declares: (name, restype, argtypes)
+_P, _I, _F = C.c_void_p, C.c_int32, C.c_float
+SYMBOLS = {
+    'hugs_last_error': (C.c_char_p, []),
+    'hugs_abi_version': (C.c_int, []),
+    'hugs_create': (C.c_int, [C.POINTER(ModelDesc), C.POINTER(_P)]),
+    'hugs_destroy': (C.c_int, [_P]),
+    'hugs_param_count': (C.c_int64, [_P]),
+    'hugs_param_layout': (C.c_int, [_P, C.POINTER(TensorDesc), _I, C.POINTER(_I)]),
+    'hugs_params_changed': (C.c_int, [_P, _P, _P]),
+    'hugs_sample_intervals': (C.c_int, [_P, _P, _P, _P, _F, _I, _I, _I, _F, _F, _P, _P, _P]),
+    'hugs_invert_cdf': (C.c_int, [_P, _P, _P, _I, _I, _I, _P, _P, _P]),
+    'hugs_max_dilate_weights': (C.c_int, [_P, _P, _I, _I, _F, _F, _F, _P, _P, _P]),
+    'hugs_alpha_composite': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(LevelOut), _P]),
+    'hugs_ipe_features': (C.c_int, [_P, C.POINTER(Rays), _P, _I, _I, _I, _P, _P]),
+    'hugs_forward': (C.c_int, [_P, _P, C.POINTER(Rays), _I, _F, _P, _I, _I, C.POINTER(LevelOut), _P]),
+    'hugs_loss_and_grad': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _F, _P, C.POINTER(LossCfg), _P, _P, _P]),
+    'hugs_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P]),
+}
+
+if not os.path.exists(LIB_PATH):
+  raise ImportError(
+      f'{LIB_PATH} is missing: build it with `python -m nerf_hugs_b200.build` (nvcc, sm_100a). '
+      'nerf_hugs_b200 has no CPU or PyTorch fallback path.')
+
+lib = C.CDLL(LIB_PATH)
+for _name, (_res, _args) in SYMBOLS.items():
+  _fn = getattr(lib, _name)
+  _fn.restype = _res
+  _fn.argtypes = _args
+
+
+def check(rc):
+  if rc != 0:
+    raise HugsError(rc, lib.hugs_last_error().decode('utf-8', 'replace'))

@@ -1,0 +1,487 @@
+// C ABI of libhugs_b200.so (see include/hugs_b200.h).  Host-side orchestration only: every
+// numeric step is a kernel in sampling.cu / composite.cu / mlp_simt.cu / mlp_tc.cu / optim.cu.
+#include <stdarg.h>
+#include <math.h>
+
+#include <algorithm>
+#include <new>
+
+#include "handle.h"
+#include "tc.h"
+
+namespace hugs {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  set_error("CUDA error %s (%s) at %s:%d in `%s`", cudaGetErrorName(e), cudaGetErrorString(e), file, line, what);
+  return HUGS_ERR_CUDA;
+}
+
+namespace {
+
+template <class T>
+int dev_alloc(hugs_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return HUGS_ERR_NOMEM;
+  }
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return HUGS_OK;
+}
+
+void add_tensor(hugs_handle* h, const std::string& name, int rows, int cols, int module, int64_t* off) {
+  hugs_tensor_desc t{};
+  snprintf(t.name, sizeof(t.name), "%s", name.c_str());
+  t.offset = *off; t.rows = rows; t.cols = cols; t.module = module;
+  h->tensors.push_back(t);
+  *off += (int64_t)rows * cols;
+}
+
+// Dense shapes in flax creation order (models.py:449-515).
+void build_mlp(hugs_handle* h, MlpViews* m, const char* mod, int module, int depth, int width, bool rgb,
+               int glo, int64_t* off) {
+  const hugs_model_desc& d = h->d;
+  m->depth = depth; m->width = width; m->has_rgb = rgb; m->module = module;
+  auto add = [&](int in, int out) {
+    DenseView v{};
+    v.in = in; v.out = out;
+    std::string base = std::string(mod) + "/Dense_" + std::to_string(m->dense.size());
+    v.kernel_off = *off; add_tensor(h, base + "/kernel", in, out, module, off);
+    v.bias_off = *off;   add_tensor(h, base + "/bias", 1, out, module, off);
+    m->dense.push_back(v);
+  };
+  int in = h->feat_dim;
+  for (int i = 0; i < depth; ++i) {
+    add(in, width);
+    in = width;
+    if (i % d.skip_layer == 0 && i > 0) in = width + h->feat_dim;
+  }
+  add(in, 1);
+  if (rgb) {
+    add(in, d.bottleneck_width);
+    add(d.bottleneck_width + 3 + 6 * d.deg_view + glo, d.view_width);
+    add(d.view_width, 3);
+  }
+}
+
+int validate(const hugs_model_desc& d) {
+  HUGS_REQUIRE(d.num_levels >= 1 && d.num_levels <= 4, "num_levels must be in [1,4], got %d", d.num_levels);
+  HUGS_REQUIRE(d.num_nerf_samples >= 2 && d.num_nerf_samples <= 256, "num_nerf_samples must be in [2,256]");
+  HUGS_REQUIRE(d.num_levels == 1 || (d.num_prop_samples >= 2 && d.num_prop_samples <= 256),
+               "num_prop_samples must be in [2,256]");
+  HUGS_REQUIRE(d.num_basis >= 1 && d.num_basis <= 32, "num_basis must be in [1,32]");
+  HUGS_REQUIRE(d.max_deg_point > d.min_deg_point && d.max_deg_point - d.min_deg_point <= 16, "bad IPE degrees");
+  HUGS_REQUIRE(d.nerf_depth >= 1 && d.prop_depth >= 1 && d.nerf_width >= 1 && d.prop_width >= 1, "bad MLP shape");
+  HUGS_REQUIRE(d.skip_layer >= 1, "skip_layer must be >= 1");
+  HUGS_REQUIRE(d.deg_view >= 0 && d.deg_view <= 8, "deg_view must be in [0,8]");
+  HUGS_REQUIRE(d.bottleneck_width >= 1 && d.view_width >= 1, "bottleneck/view widths must be >= 1");
+  HUGS_REQUIRE(d.num_glo_features >= 0 && d.num_glo_features <= 64, "num_glo_features must be in [0,64]");
+  HUGS_REQUIRE(d.num_glo_features == 0 || d.num_embeddings > 0, "num_embeddings must be > 0 with GLO");
+  HUGS_REQUIRE(d.max_rays >= 1, "max_rays must be >= 1");
+  HUGS_REQUIRE(d.raydist_fn >= 0 && d.raydist_fn <= 3, "unknown raydist_fn %d", d.raydist_fn);
+  HUGS_REQUIRE(d.ray_shape == HUGS_RAY_CONE || d.ray_shape == HUGS_RAY_CYLINDER, "unknown ray_shape");
+  HUGS_REQUIRE(d.precision == HUGS_PRECISION_FP32 || d.precision == HUGS_PRECISION_BF16_TC, "unknown precision");
+  return HUGS_OK;
+}
+
+// The `u` grids of stepfun.sample (stepfun.py:188-209): numpy-style float64 linspace
+// (i * step + start, last point exact) rounded once to fp32 — identical to oracle.sample_u.
+void linspace_f32(double lo, double hi, int n, std::vector<float>* u) {
+  u->resize(n);
+  const double step = n > 1 ? (hi - lo) / (n - 1) : 0.0;
+  for (int i = 0; i < n; ++i) (*u)[i] = (float)(i * step + lo);
+  if (n > 1) (*u)[n - 1] = (float)hi;
+}
+
+void make_u(int ns, bool train, std::vector<float>* u, float* max_jitter) {
+  const double eps = (double)kF32Eps;
+  if (!train) {
+    const double pad = 1.0 / (2.0 * ns);
+    linspace_f32(pad, 1.0 - pad - eps, ns, u);
+    *max_jitter = 0.f;
+  } else {
+    const double u_max = eps + (1.0 - eps) / ns;
+    *max_jitter = (float)((1.0 - u_max) / (ns - 1) - eps);
+    linspace_f32(0.0, 1.0 - u_max, ns, u);
+  }
+}
+
+}  // namespace
+}  // namespace hugs
+
+using namespace hugs;
+
+HUGS_API const char* hugs_last_error(void) { return g_err; }
+HUGS_API int hugs_abi_version(void) { return HUGS_ABI_VERSION; }
+
+HUGS_API int hugs_create(const hugs_model_desc* desc, hugs_handle** out) {
+  HUGS_REQUIRE(desc && out, "hugs_create: null argument");
+  *out = nullptr;
+  int rc = validate(*desc);
+  if (rc) return rc;
+  int ndev = 0;
+  HUGS_CUDA(cudaGetDeviceCount(&ndev));
+  HUGS_REQUIRE(ndev > 0, "no CUDA device: this library has no CPU path");
+  hugs_handle* h = new (std::nothrow) hugs_handle();
+  if (!h) { set_error("out of host memory"); return HUGS_ERR_NOMEM; }
+  h->d = *desc;
+  const hugs_model_desc& d = h->d;
+  rc = HUGS_OK;
+  auto fail = [&](int code) { hugs_destroy(h); return code; };
+  if (cudaGetDevice(&h->device) != cudaSuccess) return fail(HUGS_ERR_CUDA);
+  h->feat_dim = 2 * d.num_basis * (d.max_deg_point - d.min_deg_point);
+  h->view_in_dim = 3 + 6 * d.deg_view + d.num_glo_features;
+
+  int64_t off = 0;
+  h->module_begin[0] = off;
+  build_mlp(h, &h->nerf, "NerfMLP_0", 0, d.nerf_depth, d.nerf_width, true, d.num_glo_features, &off);
+  h->module_end[0] = off;
+  h->module_begin[1] = off;
+  if (d.num_levels > 1) build_mlp(h, &h->prop, "PropMLP_0", 1, d.prop_depth, d.prop_width, false, 0, &off);
+  h->module_end[1] = off;
+  h->module_begin[2] = off;
+  if (d.num_glo_features > 0) {
+    h->glo_off = off;
+    add_tensor(h, "GloEmbed_0/embedding", d.num_embeddings, d.num_glo_features, 2, &off);
+  }
+  h->module_end[2] = off;
+  h->n_params = off;
+
+  const int L = d.num_levels;
+  const size_t n = (size_t)d.max_rays;
+  if ((rc = dev_alloc(h, &h->basis, 3 * 32))) return fail(rc);
+  if (cudaMemcpy(h->basis, d.basis, sizeof(float) * 3 * d.num_basis, cudaMemcpyHostToDevice) != cudaSuccess)
+    return fail(cuda_fail(cudaGetLastError(), "basis upload", __FILE__, __LINE__));
+  h->u_det.resize(L); h->u_train.resize(L); h->max_jitter.resize(L);
+  h->sdist.resize(L); h->tdist.resize(L); h->weights.resize(L); h->raw.resize(L); h->d_raw.resize(L);
+  int smax = 0;
+  for (int l = 0; l < L; ++l) {
+    const int S = h->samples(l);
+    smax = std::max(smax, S);
+    std::vector<float> u;
+    float mj;
+    if ((rc = dev_alloc(h, &h->u_det[l], S)) || (rc = dev_alloc(h, &h->u_train[l], S))) return fail(rc);
+    make_u(S, false, &u, &mj);
+    cudaMemcpy(h->u_det[l], u.data(), sizeof(float) * S, cudaMemcpyHostToDevice);
+    make_u(S, true, &u, &mj);
+    cudaMemcpy(h->u_train[l], u.data(), sizeof(float) * S, cudaMemcpyHostToDevice);
+    h->max_jitter[l] = mj;
+    const int c = (l == L - 1) ? 4 : 1;
+    if ((rc = dev_alloc(h, &h->sdist[l], n * (S + 1))) || (rc = dev_alloc(h, &h->tdist[l], n * (S + 1))) ||
+        (rc = dev_alloc(h, &h->weights[l], n * S)) || (rc = dev_alloc(h, &h->raw[l], n * S * c)) ||
+        (rc = dev_alloc(h, &h->d_raw[l], n * S * c)))
+      return fail(rc);
+  }
+  if ((rc = dev_alloc(h, &h->view_in, n * h->view_in_dim))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->ray_stats, n * 8))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->scalars, 2048))) return fail(rc);
+  if (d.precision == HUGS_PRECISION_FP32) {
+    const int wmax = std::max({d.nerf_width, d.prop_width, d.bottleneck_width, d.view_width});
+    if ((rc = dev_alloc(h, &h->feat, n * smax * h->feat_dim))) return fail(rc);
+    for (int i = 0; i < 3; ++i)
+      if ((rc = dev_alloc(h, &h->act[i], n * smax * wmax))) return fail(rc);
+  } else {
+    if ((rc = tc_create(h))) return fail(rc);
+  }
+  if (cudaDeviceSynchronize() != cudaSuccess)
+    return fail(cuda_fail(cudaGetLastError(), "hugs_create sync", __FILE__, __LINE__));
+  *out = h;
+  return HUGS_OK;
+}
+
+HUGS_API int hugs_destroy(hugs_handle* h) {
+  if (!h) return HUGS_OK;
+  tc_destroy(h);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+  return HUGS_OK;
+}
+
+HUGS_API int64_t hugs_param_count(const hugs_handle* h) { return h ? h->n_params : -1; }
+
+HUGS_API int hugs_param_layout(const hugs_handle* h, hugs_tensor_desc* out, int32_t capacity, int32_t* count) {
+  HUGS_REQUIRE(h && count, "hugs_param_layout: null argument");
+  *count = (int32_t)h->tensors.size();
+  if (!out) return HUGS_OK;
+  HUGS_REQUIRE(capacity >= *count, "hugs_param_layout: capacity %d < %d tensors", capacity, *count);
+  memcpy(out, h->tensors.data(), sizeof(hugs_tensor_desc) * h->tensors.size());
+  return HUGS_OK;
+}
+
+HUGS_API int hugs_params_changed(hugs_handle* h, const float* params, void* stream) {
+  HUGS_REQUIRE(h && params, "hugs_params_changed: null argument");
+  if (h->d.precision == HUGS_PRECISION_BF16_TC) return tc_pack_params(h, params, (cudaStream_t)stream);
+  return HUGS_OK;
+}
+
+// ------------------------------------------------------------------ operator-level entry points
+
+HUGS_API int hugs_sample_intervals(const float* t, const float* w_logits, const float* u_base,
+                                   const float* jitter, float max_jitter, int32_t n_rays, int32_t n_bins,
+                                   int32_t n_samples, float dom_lo, float dom_hi, float* t_out,
+                                   int32_t* idx_out, void* stream) {
+  HUGS_REQUIRE(t && w_logits && u_base && t_out, "hugs_sample_intervals: null argument");
+  HUGS_REQUIRE(n_samples > 1, "num_samples must be > 1, is %d.", n_samples);   // stepfun.py:240-241
+  HUGS_REQUIRE(n_bins >= 1 && n_rays >= 0, "hugs_sample_intervals: bad sizes");
+  ResampleArgs a;
+  a.t_in = t; a.w_in = w_logits; a.w_is_logits = 1; a.n_rays = n_rays; a.np = n_bins; a.ns = n_samples;
+  a.dom_lo = dom_lo; a.dom_hi = dom_hi; a.u_base = u_base; a.jitter = jitter; a.max_jitter = max_jitter;
+  a.s_out = t_out; a.idx_out = idx_out;
+  return launch_resample(a, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_invert_cdf(const float* t, const float* cw, const float* u, int32_t n_rays, int32_t n_bins,
+                             int32_t n_samples, float* centers_out, int32_t* idx_out, void* stream) {
+  HUGS_REQUIRE(t && cw && u && centers_out, "hugs_invert_cdf: null argument");
+  HUGS_REQUIRE(n_bins >= 1 && n_samples >= 1 && n_rays >= 0, "hugs_invert_cdf: bad sizes");
+  ResampleArgs a;
+  a.t_in = t; a.w_in = t; a.cw_in = cw; a.u_in = u; a.n_rays = n_rays; a.np = n_bins; a.ns = n_samples;
+  a.centers_out = centers_out; a.idx_out = idx_out;
+  return launch_resample(a, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_max_dilate_weights(const float* t, const float* w, int32_t n_rays, int32_t n_bins,
+                                     float dilation, float dom_lo, float dom_hi, float* t_out, float* w_out,
+                                     void* stream) {
+  HUGS_REQUIRE(t && w && t_out && w_out, "hugs_max_dilate_weights: null argument");
+  HUGS_REQUIRE(n_bins >= 1 && n_rays >= 0, "hugs_max_dilate_weights: bad sizes");
+  ResampleArgs a;
+  a.t_in = t; a.w_in = w; a.n_rays = n_rays; a.np = n_bins; a.ns = 0; a.dilate = 1; a.dilation = dilation;
+  a.dom_lo = dom_lo; a.dom_hi = dom_hi; a.td_out = t_out; a.wd_out = w_out;
+  return launch_resample(a, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_alpha_composite(const hugs_handle* h, const float* raw_density, const float* raw_rgb,
+                                  const float* tdist, const float* sdist, const float* directions,
+                                  const float* far, int32_t n_rays, int32_t n_samples, int32_t compute_extras,
+                                  const hugs_level_out* out, void* stream) {
+  (void)sdist;
+  HUGS_REQUIRE(h && raw_density && tdist && directions && out, "hugs_alpha_composite: null argument");
+  HUGS_REQUIRE(!compute_extras || far, "hugs_alpha_composite: far is required with compute_extras");
+  CompositeArgs a;
+  a.raw_density = raw_density; a.raw_rgb = raw_rgb; a.raw_stride = 1; a.rgb_stride = 3;
+  a.tdist = tdist; a.directions = directions; a.far = far; a.n_rays = n_rays; a.S = n_samples;
+  a.opaque_background = h->d.opaque_background; a.compute_extras = compute_extras; a.bg = h->d.bg_intensity;
+  a.density_bias = h->d.density_bias; a.rgb_premult = h->d.rgb_premultiplier; a.rgb_bias = h->d.rgb_bias;
+  a.rgb_padding = h->d.rgb_padding; a.out = *out;
+  return launch_composite(a, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_ipe_features(const hugs_handle* h, const hugs_rays* rays, const float* tdist, int32_t n_rays,
+                               int32_t n_samples, int32_t contract, float* features, void* stream) {
+  HUGS_REQUIRE(h && rays && tdist && features, "hugs_ipe_features: null argument");
+  IpeArgs a{rays->origins, rays->directions, rays->radii, tdist, h->basis, n_rays, n_samples,
+            h->d.num_basis, h->d.min_deg_point, h->d.max_deg_point, h->d.ray_shape, contract, features};
+  return launch_ipe_features(a, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ model-level entry points
+namespace hugs {
+namespace {
+
+int run_level_sampling(hugs_handle* h, int l, const hugs_rays* rays, int n, float train_frac,
+                       const float* jitter, float s_near, float* prod_samples, cudaStream_t st) {
+  const hugs_model_desc& d = h->d;
+  const int S = h->samples(l);
+  ResampleArgs a;
+  a.n_rays = n; a.ns = S; a.dom_lo = s_near; a.dom_hi = 1.f;
+  const float dilation = d.dilation_bias + d.dilation_multiplier * (1.f - s_near) / *prod_samples;
+  *prod_samples *= (float)S;
+  if (l > 0) {
+    a.t_in = h->sdist[l - 1]; a.w_in = h->weights[l - 1]; a.np = h->samples(l - 1);
+    a.dilate = (d.dilation_bias > 0 || d.dilation_multiplier > 0) ? 1 : 0;
+    a.dilation = dilation;
+  } else {
+    a.np = 1;
+  }
+  a.anneal = d.anneal_slope > 0 ? (d.anneal_slope * train_frac) / ((d.anneal_slope - 1.f) * train_frac + 1.f) : 1.f;
+  a.padding = d.resample_padding;
+  if (jitter) { a.u_base = h->u_train[l]; a.jitter = jitter + (size_t)l * n; a.max_jitter = h->max_jitter[l]; }
+  else        { a.u_base = h->u_det[l]; }
+  a.s_out = h->sdist[l]; a.t_out = h->tdist[l];
+  a.raydist_fn = d.raydist_fn; a.near = rays->near; a.far = rays->far;
+  return launch_resample(a, st);
+}
+
+// fp32 CUDA-core MLP for level l: fills h->raw[l].
+int run_level_mlp_fp32(hugs_handle* h, int l, const float* params, const hugs_rays* rays, int n, cudaStream_t st) {
+  const hugs_model_desc& d = h->d;
+  const bool is_prop = l < d.num_levels - 1;
+  const MlpViews& m = is_prop ? h->prop : h->nerf;
+  const int S = h->samples(l);
+  const int M = n * S;
+  IpeArgs ia{rays->origins, rays->directions, rays->radii, h->tdist[l], h->basis, n, S, d.num_basis,
+             d.min_deg_point, d.max_deg_point, d.ray_shape, is_prop ? d.prop_contract : d.nerf_contract, h->feat};
+  int rc = launch_ipe_features(ia, st);
+  if (rc) return rc;
+  const float* x = h->feat;
+  int xk = h->feat_dim;
+  bool cat = false;
+  int li = 0, buf = 0;
+  auto dense = [&](const DenseView& v, bool relu, float* y, int ldy) {
+    DenseArgs a{};
+    a.nseg = 0;
+    a.seg[a.nseg++] = DenseSeg{x, xk, xk, 1};
+    if (cat) a.seg[a.nseg++] = DenseSeg{h->feat, h->feat_dim, h->feat_dim, 1};
+    a.W = params + v.kernel_off; a.bias = params + v.bias_off; a.M = M; a.N = v.out; a.relu = relu;
+    a.y = y; a.ldy = ldy;
+    return launch_dense_simt(a, st);
+  };
+  for (int i = 0; i < m.depth; ++i) {
+    float* y = h->act[buf];
+    if ((rc = dense(m.dense[li++], true, y, m.width))) return rc;
+    x = y; xk = m.width; buf ^= 1;
+    cat = (i % d.skip_layer == 0 && i > 0);
+  }
+  const int c = is_prop ? 1 : 4;
+  if ((rc = dense(m.dense[li++], false, h->raw[l], c))) return rc;       // density head
+  if (!is_prop) {
+    float* bott = h->act[buf];
+    if ((rc = dense(m.dense[li++], false, bott, d.bottleneck_width))) return rc;
+    DenseArgs a{};
+    const DenseView& vv = m.dense[li++];
+    a.nseg = 2;
+    a.seg[0] = DenseSeg{bott, d.bottleneck_width, d.bottleneck_width, 1};
+    a.seg[1] = DenseSeg{h->view_in, h->view_in_dim, h->view_in_dim, S};
+    a.W = params + vv.kernel_off; a.bias = params + vv.bias_off; a.M = M; a.N = vv.out; a.relu = 1;
+    a.y = h->act[2]; a.ldy = d.view_width;
+    if ((rc = launch_dense_simt(a, st))) return rc;
+    x = h->act[2]; xk = d.view_width; cat = false;
+    if ((rc = dense(m.dense[li++], false, h->raw[l] + 1, 4))) return rc;  // rgb head
+  }
+  return HUGS_OK;
+}
+
+int check_rays(const hugs_handle* h, const hugs_rays* rays, int n) {
+  HUGS_REQUIRE(rays && rays->origins && rays->directions && rays->viewdirs && rays->radii && rays->near && rays->far,
+               "rays: origins/directions/viewdirs/radii/near/far are required");
+  HUGS_REQUIRE(n >= 0 && n <= h->d.max_rays, "n_rays %d exceeds max_rays %d of this handle", n, h->d.max_rays);
+  HUGS_REQUIRE(h->d.num_glo_features == 0 || rays->embed_idx, "rays: embed_idx is required with GLO features");
+  return HUGS_OK;
+}
+
+float s_near_of(const hugs_model_desc& d, float train_frac) {
+  if (!(d.near_anneal_rate > 0.f)) return 0.f;
+  return fminf(fmaxf(1.f - train_frac / d.near_anneal_rate, 0.f), d.near_anneal_init);
+}
+
+// Levels 0..L-1 forward: sampling -> MLP -> (composite: weights for the next level + outputs).
+int forward_levels(hugs_handle* h, const float* params, const hugs_rays* rays, int n, float train_frac,
+                   const float* jitter, int compute_extras, int zero_glo, const hugs_level_out* out,
+                   bool training, cudaStream_t st) {
+  const hugs_model_desc& d = h->d;
+  int rc;
+  const float s_near = s_near_of(d, train_frac);
+  float prod = 1.f;
+  h->cur_params = params;
+  if ((rc = launch_view_inputs(rays->viewdirs, rays->embed_idx, h->glo_off >= 0 ? params + h->glo_off : nullptr,
+                               n, d.deg_view, d.num_glo_features, zero_glo, h->view_in, st)))
+    return rc;
+  for (int l = 0; l < d.num_levels; ++l) {
+    const bool is_prop = l < d.num_levels - 1;
+    const int S = h->samples(l);
+    if ((rc = run_level_sampling(h, l, rays, n, train_frac, jitter, s_near, &prod, st))) return rc;
+    if (d.precision == HUGS_PRECISION_FP32) rc = run_level_mlp_fp32(h, l, params, rays, n, st);
+    else rc = tc_mlp_forward(h, l, rays, n, training, st);
+    if (rc) return rc;
+    // the final level's compositing is folded into the loss kernel when training
+    if (training && !is_prop) break;
+    CompositeArgs a;
+    a.raw_density = h->raw[l]; a.raw_stride = is_prop ? 1 : 4;
+    a.raw_rgb = is_prop ? nullptr : h->raw[l] + 1; a.rgb_stride = 4;
+    a.tdist = h->tdist[l]; a.directions = rays->directions; a.far = rays->far; a.n_rays = n; a.S = S;
+    a.opaque_background = d.opaque_background; a.compute_extras = compute_extras; a.bg = d.bg_intensity;
+    a.density_bias = d.density_bias; a.rgb_premult = d.rgb_premultiplier; a.rgb_bias = d.rgb_bias;
+    a.rgb_padding = d.rgb_padding;
+    if (out) a.out = out[l];
+    float* user_w = a.out.weights;
+    a.out.weights = h->weights[l];
+    if ((rc = launch_composite(a, st))) return rc;
+    if (out) {
+      if (user_w) HUGS_CUDA(cudaMemcpyAsync(user_w, h->weights[l], sizeof(float) * n * S, cudaMemcpyDeviceToDevice, st));
+      if (out[l].sdist) HUGS_CUDA(cudaMemcpyAsync(out[l].sdist, h->sdist[l], sizeof(float) * n * (S + 1), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+  return HUGS_OK;
+}
+
+}  // namespace
+}  // namespace hugs
+
+HUGS_API int hugs_forward(hugs_handle* h, const float* params, const hugs_rays* rays, int32_t n_rays,
+                          float train_frac, const float* jitter, int32_t compute_extras, int32_t zero_glo,
+                          const hugs_level_out* out, void* stream) {
+  HUGS_REQUIRE(h && params && out, "hugs_forward: null argument");
+  int rc = check_rays(h, rays, n_rays);
+  if (rc) return rc;
+  if (n_rays == 0) return HUGS_OK;
+  return forward_levels(h, params, rays, n_rays, train_frac, jitter, compute_extras, zero_glo, out, false,
+                        (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* rays, const float* rgb_gt,
+                                int32_t n_rays, float train_frac, const float* jitter, const hugs_loss_cfg* loss,
+                                float* grad_out, float* stats_out, void* stream) {
+  HUGS_REQUIRE(h && params && rgb_gt && loss && grad_out && stats_out, "hugs_loss_and_grad: null argument");
+  int rc = check_rays(h, rays, n_rays);
+  if (rc) return rc;
+  HUGS_REQUIRE(n_rays > 0, "hugs_loss_and_grad: empty batch");
+  const hugs_model_desc& d = h->d;
+  if (d.precision != HUGS_PRECISION_BF16_TC) {
+    set_error("hugs_loss_and_grad needs HUGS_PRECISION_BF16_TC (the fp32 CUDA-core path is render-only)");
+    return HUGS_ERR_UNSUPPORTED;
+  }
+  if (loss->data_coarse_loss_mult != 0.f) {
+    set_error("data_coarse_loss_mult != 0 is not supported (shipped configs use 0, configs.py:88)");
+    return HUGS_ERR_UNSUPPORTED;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = d.num_levels, n = n_rays;
+  if ((rc = forward_levels(h, params, rays, n, train_frac, jitter, 0, 0, nullptr, true, st))) return rc;
+
+  float* denom = h->scalars;          // [0] loss normaliser
+  float* sums = h->scalars + 8;       // [8..] column sums of ray_stats
+  if ((rc = launch_lossmult_sum(rays->lossmult, rays->static_mask, loss->use_static_mask,
+                                loss->withmask_transient_weight, loss->disable_multiscale_loss, n, denom, st)))
+    return rc;
+  {
+    LossBwdArgs a;
+    const int S = h->samples(L - 1);
+    a.raw = h->raw[L - 1]; a.tdist = h->tdist[L - 1]; a.sdist = h->sdist[L - 1]; a.directions = rays->directions;
+    a.rgb_gt = rgb_gt; a.lossmult = rays->lossmult; a.static_mask = rays->static_mask; a.denom = denom;
+    a.n_rays = n; a.S = S; a.opaque_background = d.opaque_background; a.bg = d.bg_intensity;
+    a.density_bias = d.density_bias; a.rgb_premult = d.rgb_premultiplier; a.rgb_bias = d.rgb_bias;
+    a.rgb_padding = d.rgb_padding; a.loss = *loss; a.d_raw = h->d_raw[L - 1]; a.weights = h->weights[L - 1];
+    a.ray_stats = h->ray_stats;
+    if ((rc = launch_final_loss_bwd(a, st))) return rc;
+  }
+  for (int l = 0; l < L - 1; ++l) {
+    PropLossBwdArgs a;
+    a.raw_density = h->raw[l]; a.tdist = h->tdist[l]; a.sdist = h->sdist[l]; a.directions = rays->directions;
+    a.sdist_final = h->sdist[L - 1]; a.w_final = h->weights[L - 1]; a.n_rays = n; a.Sp = h->samples(l);
+    a.S = h->samples(L - 1); a.opaque_background = d.opaque_background; a.density_bias = d.density_bias;
+    a.scale = loss->interlevel_loss_mult / ((float)n * (float)a.S);
+    a.d_raw = h->d_raw[l]; a.ray_stats = h->ray_stats + (size_t)n * (4 + l);
+    if ((rc = launch_prop_loss_bwd(a, st))) return rc;
+  }
+  if ((rc = launch_column_sums(h->ray_stats, n, 4, 3, sums, st))) return rc;
+  for (int l = 0; l < L - 1; ++l)
+    if ((rc = launch_column_sums(h->ray_stats + (size_t)n * (4 + l), n, 1, 1, sums + 4 + l, st))) return rc;
+  if ((rc = launch_finalize_stats(h, *loss, n, denom, sums, stats_out, st))) return rc;
+
+  HUGS_CUDA(cudaMemsetAsync(grad_out, 0, sizeof(float) * h->n_params, st));
+  for (int l = L - 1; l >= 0; --l)
+    if ((rc = tc_mlp_backward(h, l, rays, n, grad_out, st))) return rc;
+  return HUGS_OK;
+}

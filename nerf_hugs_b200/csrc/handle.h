@@ -1,0 +1,56 @@
+// The opaque handle behind the C ABI: model description, parameter layout, device workspace.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "mlp.h"
+
+namespace hugs {
+
+struct DenseView {
+  int64_t kernel_off, bias_off;   // float offsets into the flat parameter buffer
+  int in, out;
+};
+
+struct MlpViews {
+  std::vector<DenseView> dense;   // flax creation order: trunk..., density, [bottleneck, view, rgb]
+  int depth = 0, width = 0;
+  bool has_rgb = false;
+  int module = 0;
+};
+
+struct TcState;                   // tensor-core path state (mlp_tc.cu)
+
+}  // namespace hugs
+
+struct hugs_handle {
+  hugs_model_desc d{};
+  int device = 0;
+  int feat_dim = 0;               // 2 * num_basis * (max_deg - min_deg)
+  int view_in_dim = 0;            // 3 + 6*deg_view + glo
+  int64_t n_params = 0;
+  int64_t glo_off = -1;
+  std::vector<hugs_tensor_desc> tensors;
+  hugs::MlpViews nerf, prop;
+  int64_t module_begin[3] = {0, 0, 0}, module_end[3] = {0, 0, 0};
+
+  // ---- device workspace (sized for d.max_rays) ----
+  float* basis = nullptr;                     // [3][num_basis]
+  std::vector<float*> u_det, u_train;         // per level [S]
+  std::vector<float> max_jitter;              // per level
+  std::vector<float*> sdist, tdist, weights;  // per level [n,S+1], [n,S+1], [n,S]
+  std::vector<float*> raw;                    // per level: prop [n,S]; nerf [n,S,4]
+  std::vector<float*> d_raw;                  // same shapes (training)
+  float* view_in = nullptr;                   // [n, view_in_dim]
+  float* feat = nullptr;                      // fp32 path: [n*Smax, feat_dim]
+  float* act[3] = {nullptr, nullptr, nullptr};// fp32 path: [n*Smax, max width]
+  float* ray_stats = nullptr;                 // [n, 4 + L]
+  float* scalars = nullptr;                   // [64] device scalars (denominators, norms, ...)
+  std::vector<void*> allocs;
+  hugs::TcState* tc = nullptr;
+  const float* cur_params = nullptr;          // parameters of the call in flight
+
+  int samples(int level) const { return level < d.num_levels - 1 ? d.num_prop_samples : d.num_nerf_samples; }
+};

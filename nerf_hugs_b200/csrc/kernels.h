@@ -1,0 +1,94 @@
+// Internal launch interfaces between the translation units of libhugs_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/hugs_b200.h"
+
+namespace hugs {
+
+// ---------------------------------------------------------------- sampling.cu
+struct ResampleArgs {
+  const float* t_in = nullptr;    // [n, np+1]; nullptr => single interval [dom_lo, dom_hi], weight 1
+  const float* w_in = nullptr;    // [n, np] weights (or logits when w_is_logits)
+  const float* cw_in = nullptr;   // optional caller-provided CDF [n, nb+1] (skips softmax/cumsum)
+  const float* u_in = nullptr;    // optional per-ray u [n, ns] (overrides u_base/jitter)
+  int n_rays = 0, np = 1, ns = 0; // ns == 0: dilation only
+  int dilate = 0;
+  float dilation = 0.f, dom_lo = 0.f, dom_hi = 1.f;
+  int w_is_logits = 0;
+  float anneal = 1.f, padding = 0.f;
+  const float* u_base = nullptr;  // [ns]
+  const float* jitter = nullptr;  // [n] uniform draws in [0,1) or nullptr
+  float max_jitter = 0.f;
+  float* s_out = nullptr;         // [n, ns+1]
+  float* t_out = nullptr;         // [n, ns+1] metric distances (optional)
+  float* centers_out = nullptr;   // [n, ns] (optional)
+  int32_t* idx_out = nullptr;     // [n, ns] (optional)
+  int raydist_fn = 0;
+  const float* near = nullptr;
+  const float* far = nullptr;
+  float* td_out = nullptr;        // dilated + trimmed t [n, 3np-1] (optional)
+  float* wd_out = nullptr;        // dilated + trimmed w [n, 3np-2] (optional)
+};
+int launch_resample(const ResampleArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------- composite.cu
+struct CompositeArgs {
+  const float* raw_density = nullptr;  // [n, S]
+  const float* raw_rgb = nullptr;      // [n, S, 3] or nullptr
+  int raw_stride = 1;                  // floats between consecutive samples of raw_density
+  int rgb_stride = 3;                  // floats between consecutive samples of raw_rgb
+  const float* tdist = nullptr;        // [n, S+1]
+  const float* directions = nullptr;   // [n, 3]
+  const float* far = nullptr;          // [n]
+  int n_rays = 0, S = 0;
+  int opaque_background = 0, compute_extras = 0;
+  float bg = 1.f, density_bias = -1.f, rgb_premult = 1.f, rgb_bias = 0.f, rgb_padding = 0.001f;
+  hugs_level_out out{};
+};
+int launch_composite(const CompositeArgs& a, cudaStream_t stream);
+
+struct LossBwdArgs {
+  // final (NeRF) level
+  const float* raw = nullptr;          // [n, S, 4] (raw_density, raw_r, raw_g, raw_b)
+  const float* tdist = nullptr;        // [n, S+1]
+  const float* sdist = nullptr;        // [n, S+1]
+  const float* directions = nullptr;   // [n, 3]
+  const float* rgb_gt = nullptr;       // [n, 3]
+  const float* lossmult = nullptr;     // [n] or nullptr
+  const float* static_mask = nullptr;  // [n] or nullptr
+  const float* denom = nullptr;        // device scalar: sum of loss multipliers (pre-clamp)
+  int n_rays = 0, S = 0;
+  int opaque_background = 0;
+  float bg = 1.f, density_bias = -1.f, rgb_premult = 1.f, rgb_bias = 0.f, rgb_padding = 0.001f;
+  hugs_loss_cfg loss{};
+  float* d_raw = nullptr;              // [n, S, 4] out
+  float* weights = nullptr;            // [n, S] out (final-level weights, reused by interlevel)
+  float* ray_stats = nullptr;          // [n, 4] out: data-loss numerator, sq-err numerator, distortion, unused
+};
+int launch_final_loss_bwd(const LossBwdArgs& a, cudaStream_t stream);
+
+struct PropLossBwdArgs {
+  const float* raw_density = nullptr;  // [n, Sp]
+  const float* tdist = nullptr;        // [n, Sp+1]
+  const float* sdist = nullptr;        // [n, Sp+1]
+  const float* directions = nullptr;
+  const float* sdist_final = nullptr;  // [n, S+1]
+  const float* w_final = nullptr;      // [n, S]
+  int n_rays = 0, Sp = 0, S = 0;
+  int opaque_background = 0;
+  float density_bias = -1.f;
+  float scale = 0.f;                   // interlevel_loss_mult / (n_rays * S)
+  float* d_raw = nullptr;              // [n, Sp] out
+  float* ray_stats = nullptr;          // [n] out: per-ray sum of lossfun_outer
+};
+int launch_prop_loss_bwd(const PropLossBwdArgs& a, cudaStream_t stream);
+
+// sums `n` floats (optionally thresholded at 0.5 like the static mask) into out[0]
+int launch_lossmult_sum(const float* lossmult, const float* static_mask, int use_mask, float transient_w,
+                        int disable_multiscale, int n, float* out, cudaStream_t stream);
+// out[k] = scale_k * sum_r in[r*stride + k]  (deterministic single-block reduction)
+int launch_column_sums(const float* in, int n_rows, int stride, int n_cols, float* out, cudaStream_t stream);
+
+}  // namespace hugs

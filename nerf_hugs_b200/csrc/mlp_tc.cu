@@ -1,0 +1,916 @@
+// Tensor-core MLP path (HUGS_PRECISION_BF16_TC): bf16 x bf16 -> fp32 on tcgen05, sm_100a only.
+//
+// One persistent CTA per SM walks 128-sample tiles.  For every tile the whole MLP of
+// models.py:437-519 runs as a *chain* of GEMMs without leaving the SM:
+//
+//   TMA (weights K-panels, streamed feature panels) -> 6-stage shared-memory ring
+//   tcgen05.mma (M=128, N=128|16, K=16, fp32 accumulators in TMEM, one issuing thread)
+//   epilogue warps: tcgen05.ld -> bias/ReLU -> bf16 -> 128B-swizzled shared-memory panels that are
+//   directly the next layer's A operand (activations never touch HBM in inference;
+//   in training each panel is additionally TMA-stored for the weight-gradient pass).
+//
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-9 = two epilogue groups of 128 threads (group g owns output columns [128g, 128g+128)).
+// TMEM: 512 columns = two 256-column accumulators, ping-ponged by layer so that the epilogue of
+// layer l overlaps the MMAs of layer l+1 (n-half-major issue order: columns [0,128) complete first).
+//
+// Layer schedule, packing and the feature-column permutation are documented in DESIGN.md.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <vector>
+
+#include "encode.cuh"
+#include "ptx.cuh"
+#include "tc.h"
+
+namespace hugs {
+
+// ------------------------------------------------------------------------------------------
+// constants / schedule description
+// ------------------------------------------------------------------------------------------
+constexpr int kTileM = 128;             // samples per tile (= TMEM lanes)
+constexpr int kPanelBytes = 16384;      // 128 rows x 64 bf16, SWIZZLE_128B
+constexpr int kNumPanels = 8;           // two activation buffers of 4 K-panels (256 columns) each
+constexpr int kStages = 6;              // TMA ring depth
+constexpr int kW = 256;                 // trunk / bottleneck width of this path
+constexpr int kFeatPad = 512;           // IPE features padded to 8 K-panels
+constexpr int kKP = kW + kFeatPad;      // K extent of the packed forward weights
+constexpr int kThreads = 320;
+constexpr int kSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + 512;
+
+enum Epi : int {
+  EPI_RELU = 0,      // bias + ReLU -> bf16 panels            (trunk)
+  EPI_LINEAR = 1,    // bias         -> bf16 panels            (bottleneck)
+  EPI_DENSITY = 2,   // column 0 + bias -> raw density         (group 0)
+  EPI_VIEW = 3,      // per-ray view bias + ReLU -> panels 0,1 (N = 128)
+  EPI_RGB = 4,       // columns 0..2 + bias -> raw rgb         (group 0)
+  // backward chain
+  EPI_BWD_START = 5, // no MMA: d_raw -> dZ_view panels (+ rgb head dgrad on CUDA cores)
+  EPI_BWD_LINEAR = 6,// dA -> bf16 panels                      (through the linear bottleneck)
+  EPI_BWD_RELU = 7,  // dA * [A > 0] -> bf16 panels
+  EPI_BWD_RELU_D = 8,// (dA + d_density * w_density) * [A > 0] -> bf16 panels
+  EPI_BWD_START_PROP = 9,  // no MMA: d_raw_density * w_density * [A > 0] -> panels
+};
+
+struct TcLayer {
+  int a_res, a_str, a_buf, wait_panels;
+  int n_halves, n_mma, acc_col, acc_bar;
+  int w_row, w_map;
+  int epi, dst_buf, bias_off;
+  int save_row;      // base row in the save tensor (activations fwd / dZ bwd), -1 = do not save
+  int mask_row;      // bwd: base row of the saved forward activation whose sign gates this epilogue
+};
+
+constexpr int kMaxLayers = 14;
+
+struct alignas(64) TcParams {
+  CUtensorMap map_w128, map_w16, map_feat, map_save;
+  TcLayer layers[kMaxLayers];
+  int n_layers;
+  int n_tiles, n_samples, S;
+  int feat_row0;
+  const float* bias;                 // packed fp32 biases (+ head weights, see TcMlp)
+  const float* viewbias;             // [n_rays, 128]
+  float* raw_out; int raw_c;         // [n_samples, raw_c]
+  const float* d_raw;                // bwd: [n_samples, raw_c]
+  const __nv_bfloat16* act;          // bwd: saved forward activations [rows, 256]
+  __nv_bfloat16* drgb_out;           // bwd: [n_samples, 16] bf16 (d raw rgb, padded) for the rgb-head wgrad
+  int w_dens_off, w_rgb_off;         // float offsets of head weights inside `bias`
+};
+
+struct TcMlp {
+  bool present = false, has_rgb = false;
+  int depth = 0;
+  __nv_bfloat16* wt = nullptr; int rows_f = 0;   // forward pack  [rows_f, kKP]   (K-major rows = outputs)
+  __nv_bfloat16* wn = nullptr; int rows_b = 0;   // backward pack [rows_b, kW]    (rows = inputs, cols = outputs)
+  float* bias = nullptr; int bias_floats = 0;
+  int w_dens_off = 0, w_rgb_off = 0, view_bias_off = 0, view_w_row = 0;
+  std::vector<TcLayer> fwd, bwd;
+  CUtensorMap map_wt128, map_wt16, map_wn128;
+  // packing tables
+  struct PackLayer { int row0, rows_pad, out, in, x_in, feat_in; long long koff, boff; int bias_off, brow0, b_out_pad; };
+  std::vector<PackLayer> pack;
+};
+
+struct TcState {
+  TcMlp nerf, prop;
+  __nv_bfloat16* feat = nullptr;     // per level region [cap_l, 512]
+  __nv_bfloat16* act = nullptr;      // saved forward activations
+  __nv_bfloat16* dz = nullptr;       // saved backward dZ
+  __nv_bfloat16* drgb = nullptr;     // [cap, 16]
+  float* viewbias = nullptr;
+  CUtensorMap map_feat, map_act, map_dz;
+  std::vector<int> cap, feat_row0, save_row0;   // per level
+  int total_feat_rows = 0, total_save_rows = 0;
+  int num_sms = 148;
+  void* pack_tables = nullptr;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t swz_chunk(uint32_t row, uint32_t chunk) { return chunk ^ (row & 7u); }
+
+// reference feature column of my column f' = (b*ndeg + k)*2 + s   ->   s*(nb*ndeg) + k*nb + b
+__host__ __device__ inline int ref_feature_col(int fp, int nb, int ndeg) {
+  int s = fp & 1, bk = fp >> 1, b = bk / ndeg, k = bk % ndeg;
+  return s * (nb * ndeg) + k * nb + b;
+}
+
+// ------------------------------------------------------------------------------------------
+// bf16 feature encoder (throughput mode): one thread = (sample, half of the basis directions)
+// ------------------------------------------------------------------------------------------
+struct EncArgs {
+  const float* origins; const float* directions; const float* radii; const float* tdist;
+  const float* basis;     // [3][nb]
+  int n_samples, S, nb, min_deg, ndeg, ray_shape, contract;
+  __nv_bfloat16* feat;    // [rows, 512] (already offset to the level's first row)
+};
+
+constexpr int kEncRows = 32;
+__global__ void __launch_bounds__(2 * kEncRows) encode_bf16_kernel(EncArgs a) {
+  __shared__ __align__(16) uint4 tile[kEncRows * 64];   // rows x 64 chunks of 16 B, chunk index swizzled
+  const int tid = threadIdx.x, rl = tid % kEncRows, half = tid / kEncRows;
+  const int s = blockIdx.x * kEncRows + rl;
+  const int nb0 = (a.nb + 1) >> 1;
+  const int b_beg = half ? nb0 : 0, b_end = half ? a.nb : nb0;
+  const int cpb = a.ndeg >> 2;                    // 16-byte chunks per basis direction
+  if (s < a.n_samples) {
+    const int ray = s / a.S, i = s % a.S;
+    float o[3], d[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { o[c] = a.origins[ray * 3 + c]; d[c] = a.directions[ray * 3 + c]; }
+    const float t0 = a.tdist[(size_t)ray * (a.S + 1) + i], t1 = a.tdist[(size_t)ray * (a.S + 1) + i + 1];
+    SampleGauss g;
+    frustum_gaussian(o, d, a.radii[ray], t0, t1, a.ray_shape, a.contract, g);
+    const float sc0 = exp2f((float)a.min_deg);
+    for (int b = b_beg; b < b_end; ++b) {
+      float p[3] = {a.basis[b], a.basis[a.nb + b], a.basis[2 * a.nb + b]};
+      float mu, var;
+      lift_basis(g, d, p, mu, var);
+      // phase in turns, split hi/lo so that 2^k * phase (mod 1) stays accurate at degree 11
+      const float kInv2PiHi = 0.15915494309189535f, kInv2PiLo = -1.2154201256553420e-10f;   // 1/(2 pi)
+      const float r_hi = mu * kInv2PiHi;
+      const float r_lo = fmaf(mu, kInv2PiHi, -r_hi) + mu * kInv2PiLo;
+      const float av = -0.5f * 1.4426950408889634f * var;                                  // exp(x)=2^(x log2e)
+      float sc = sc0;
+      uint32_t w[16];
+#pragma unroll 2
+      for (int k = 0; k < a.ndeg; k += 2) {
+        float t = r_hi * sc;
+        float f = (t - rintf(t)) + r_lo * sc;
+        float x = f * 6.283185307179586f;
+        float sn = __sinf(x), cs = __cosf(x);
+        float e = exp2f(av * sc * sc);
+        w[k] = ptx::pack_bf16x2(e * sn, e * cs);
+        float sn2 = 2.f * sn * cs, cs2 = 1.f - 2.f * sn * sn;
+        float e2 = e * e; e2 = e2 * e2;
+        w[k + 1] = ptx::pack_bf16x2(e2 * sn2, e2 * cs2);
+        sc *= 4.f;
+      }
+      for (int c = 0; c < cpb; ++c) {
+        uint4 v = make_uint4(w[c * 4], w[c * 4 + 1], w[c * 4 + 2], w[c * 4 + 3]);
+        tile[rl * 64 + swz_chunk(rl, b * cpb + c)] = v;
+      }
+    }
+    if (half) {
+      for (int c = a.nb * cpb; c < 64; ++c) tile[rl * 64 + swz_chunk(rl, c)] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  __syncthreads();
+  // coalesced copy-out of the block's consecutive rows
+  const int rows = min(kEncRows, a.n_samples - blockIdx.x * kEncRows);
+  uint4* dst = reinterpret_cast<uint4*>(a.feat) + (size_t)blockIdx.x * kEncRows * 64;
+  for (int e = tid; e < rows * 64; e += 2 * kEncRows) {
+    int r = e >> 6, c = e & 63;
+    dst[e] = tile[r * 64 + swz_chunk(r, c)];
+  }
+}
+
+// viewbias[ray][c] = sum_j bf16(view_in[ray][j]) * bf16(W_view[256 + j][c]) + b_view[c]
+__global__ void viewbias_kernel(const float* view_in, int view_in_dim, const float* params, long long koff,
+                                long long boff, int bott_w, int out, int n_rays, float* vb) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_rays * out) return;
+  const int ray = idx / out, c = idx % out;
+  float acc = 0.f;
+  for (int j = 0; j < view_in_dim; ++j) {
+    float x = __bfloat162float(__float2bfloat16(view_in[(size_t)ray * view_in_dim + j]));
+    float w = __bfloat162float(__float2bfloat16(params[koff + (long long)(bott_w + j) * out + c]));
+    acc = fmaf(x, w, acc);
+  }
+  vb[idx] = acc + params[boff + c];
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter packing: flat fp32 (flax layout) -> bf16 operand tensors
+// ------------------------------------------------------------------------------------------
+struct PackArgs {
+  TcMlp::PackLayer layers[16];
+  int n_layers, rows_f, rows_b, nb, ndeg, feat_dim, bias_floats;
+  const float* params;
+  __nv_bfloat16* wt; __nv_bfloat16* wn; float* bias;
+  int w_dens_off, w_rgb_off; long long dens_koff, rgb_koff; int dens_in, rgb_in;
+};
+
+__global__ void pack_params_kernel(PackArgs a) {
+  const long long nf = (long long)a.rows_f * kKP, nbk = (long long)a.rows_b * kW;
+  const long long total = nf + nbk + a.bias_floats;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    if (e < nf) {
+      const int r = (int)(e / kKP), k = (int)(e % kKP);
+      float v = 0.f;
+      for (int l = 0; l < a.n_layers; ++l) {
+        const auto& L = a.layers[l];
+        if (r < L.row0 || r >= L.row0 + L.rows_pad) continue;
+        const int n = r - L.row0;
+        if (n >= L.out) break;
+        int i = -1;
+        if (k < L.x_in) i = k;
+        else if (L.feat_in > 0 && k < L.x_in + kFeatPad) {
+          int fp = k - L.x_in;
+          if (fp < a.feat_dim) i = L.x_in + ref_feature_col(fp, a.nb, a.ndeg);
+        }
+        if (i >= 0 && i < L.in) v = a.params[L.koff + (long long)i * L.out + n];
+        break;
+      }
+      a.wt[e] = __float2bfloat16(v);
+    } else if (e < nf + nbk) {
+      const long long q = e - nf;
+      const int r = (int)(q / kW), c = (int)(q % kW);
+      float v = 0.f;
+      for (int l = 0; l < a.n_layers; ++l) {
+        const auto& L = a.layers[l];
+        if (L.brow0 < 0 || r < L.brow0 || r >= L.brow0 + kW) continue;
+        const int i = r - L.brow0;
+        if (c < L.out && i < L.x_in) v = a.params[L.koff + (long long)i * L.out + c];
+        break;
+      }
+      a.wn[q] = __float2bfloat16(v);
+    } else {
+      const int q = (int)(e - nf - nbk);
+      float v = 0.f;
+      for (int l = 0; l < a.n_layers; ++l) {
+        const auto& L = a.layers[l];
+        if (q >= L.bias_off && q < L.bias_off + L.out) { v = a.params[L.boff + (q - L.bias_off)]; break; }
+      }
+      if (q >= a.w_dens_off && q < a.w_dens_off + a.dens_in)     // density kernel [in,1], bf16-rounded
+        v = __bfloat162float(__float2bfloat16(a.params[a.dens_koff + (q - a.w_dens_off)]));
+      if (a.w_rgb_off >= 0 && q >= a.w_rgb_off && q < a.w_rgb_off + a.rgb_in * 3)  // rgb kernel [in,3]
+        v = __bfloat162float(__float2bfloat16(a.params[a.rgb_koff + (q - a.w_rgb_off)]));
+      a.bias[q] = v;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// the fused MLP chain kernel
+// ------------------------------------------------------------------------------------------
+struct Smem {
+  uint8_t* panels;          // [kNumPanels][kPanelBytes]
+  uint8_t* ring;            // [kStages][kPanelBytes]
+  uint64_t* full;           // [kStages]
+  uint64_t* empty;          // [kStages]
+  uint64_t* panel_ready;    // [kNumPanels]
+  uint64_t* acc_full;       // [8]
+  uint32_t* tmem_ptr;
+};
+
+__device__ __forceinline__ Smem carve(uint8_t* raw) {
+  Smem s;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  s.panels = base;
+  s.ring = base + kNumPanels * kPanelBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.ring + kStages * kPanelBytes);
+  s.full = bars; s.empty = bars + kStages; s.panel_ready = bars + 2 * kStages;
+  s.acc_full = s.panel_ready + kNumPanels;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.acc_full + 8);
+  return s;
+}
+
+__device__ __forceinline__ bool layer_has_mma(const TcLayer& L) {
+  return L.epi != EPI_BWD_START && L.epi != EPI_BWD_START_PROP;
+}
+
+// write 64 fp32 values of one row as bf16 into a swizzled panel row (8 x 16-byte chunks)
+__device__ __forceinline__ void store_row_chunk64(uint8_t* panel, int row, const float (&v)[64]) {
+  uint4* prow = reinterpret_cast<uint4*>(panel + row * 128);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 q;
+    q.x = ptx::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]);
+    q.y = ptx::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+    q.z = ptx::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
+    q.w = ptx::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    prow[swz_chunk(row, c)] = q;
+  }
+}
+
+__device__ __forceinline__ void load_acc64(uint32_t taddr, float (&v)[64]) {
+  uint32_t r0[32], r1[32];
+  ptx::tmem_ld32(taddr, r0);
+  ptx::tmem_ld32(taddr + 32, r1);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
+}
+
+// relu gate from a saved bf16 activation row: 64 columns starting at `col`
+__device__ __forceinline__ void apply_relu_mask64(const __nv_bfloat16* act_row, int col, float (&v)[64]) {
+  const uint4* src = reinterpret_cast<const uint4*>(act_row + col);
+#pragma unroll
+  for (int c = 0; c < 8; ++c) {
+    uint4 q = __ldg(src + c);
+    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      // activations are post-ReLU (>= 0): zero <=> inactive unit (bf16 +0 is 0x0000)
+      if ((w[j] & 0xFFFFu) == 0u) v[c * 8 + j * 2] = 0.f;
+      if ((w[j] >> 16) == 0u) v[c * 8 + j * 2 + 1] = 0.f;
+    }
+  }
+}
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  Smem sm = carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.map_w128); ptx::prefetch_tmap(&p.map_w16);
+    ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
+    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&sm.full[i], 1); ptx::mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < kNumPanels; ++i) ptx::mbar_init(&sm.panel_ready[i], 128);
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&sm.acc_full[i], 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(sm.tmem_ptr, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < p.n_layers; ++l) {
+          const TcLayer& L = p.layers[l];
+          if (!layer_has_mma(L)) continue;
+          const int kps = L.a_res + L.a_str;
+          for (int h = 0; h < L.n_halves; ++h) {
+            for (int kp = 0; kp < kps; ++kp) {
+              if (kp >= L.a_res) {
+                ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
+                ptx::mbar_expect_tx(&sm.full[stage], kPanelBytes);
+                ptx::tma_load_2d(sm.ring + stage * kPanelBytes, &p.map_feat, &sm.full[stage],
+                                 (kp - L.a_res) * 64, p.feat_row0 + tile * kTileM);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
+              ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
+              ptx::mbar_expect_tx(&sm.full[stage], L.n_mma * 128);
+              ptx::tma_load_2d(sm.ring + stage * kPanelBytes, L.w_map ? &p.map_w16 : &p.map_w128,
+                               &sm.full[stage], kp * 64, L.w_row + h * 128);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t panel_phase = 0;   // bit i: parity to wait for on panel_ready[i]
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        for (int l = 0; l < p.n_layers; ++l) {
+          const TcLayer& L = p.layers[l];
+          if (!layer_has_mma(L)) continue;
+          const int kps = L.a_res + L.a_str;
+          const uint32_t idesc = ptx::make_idesc_bf16(128, L.n_mma, 0, 0);
+          for (int h = 0; h < L.n_halves; ++h) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(L.acc_col + h * 128);
+            for (int kp = 0; kp < kps; ++kp) {
+              uint32_t a_addr;
+              int a_stage = -1;
+              if (kp < L.a_res) {
+                const int pi = L.a_buf * 4 + kp;
+                if (h == 0 && L.wait_panels) {
+                  ptx::mbar_wait(&sm.panel_ready[pi], (panel_phase >> pi) & 1u);
+                  panel_phase ^= 1u << pi;
+                }
+                a_addr = ptx::smem_u32(sm.panels + pi * kPanelBytes);
+              } else {
+                ptx::mbar_wait(&sm.full[stage], phase);
+                a_stage = stage;
+                a_addr = ptx::smem_u32(sm.ring + stage * kPanelBytes);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
+              ptx::mbar_wait(&sm.full[stage], phase);
+              const uint32_t b_addr = ptx::smem_u32(sm.ring + stage * kPanelBytes);
+              ptx::tc_fence_after();
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16) {
+                const uint64_t da = ptx::make_desc_sw128(a_addr + k16 * 32, 0, 1024);
+                const uint64_t db = ptx::make_desc_sw128(b_addr + k16 * 32, 0, 1024);
+                ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kp > 0 || k16 > 0) ? 1u : 0u);
+              }
+              ptx::mma_commit(&sm.empty[stage]);
+              if (a_stage >= 0) ptx::mma_commit(&sm.empty[a_stage]);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
+            ptx::mma_commit(&sm.acc_full[L.acc_bar + h]);
+          }
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue groups ===============================
+    const int ew = warp - 2;               // 0..7
+    const int g = ew >> 2;                 // group: output columns [128g, 128g+128)
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;   // tile row == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool group_leader = (ew & 3) == 0 && lane == 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int s = tile * kTileM + row;   // global sample index
+      const bool valid = s < p.n_samples;
+      float raw_d = 0.f;
+      for (int l = 0; l < p.n_layers; ++l) {
+        const TcLayer& L = p.layers[l];
+        float v[64];
+        switch (L.epi) {
+          case EPI_RELU: case EPI_LINEAR: case EPI_BWD_LINEAR: case EPI_BWD_RELU: case EPI_BWD_RELU_D: {
+            const int bar = L.acc_bar + g;
+            ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
+            acc_phase ^= 1u << bar;
+            ptx::tc_fence_after();
+            float dd = 0.f;
+            if (L.epi == EPI_BWD_RELU_D) dd = valid ? p.d_raw[(size_t)s * p.raw_c] : 0.f;
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+              const int col = g * 128 + j * 64;
+              load_acc64(lane_addr + (uint32_t)(L.acc_col + col), v);
+              if (L.epi == EPI_RELU || L.epi == EPI_LINEAR) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + L.bias_off + col);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                  float4 b = __ldg(b4 + c);
+                  v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                }
+                if (L.epi == EPI_RELU) {
+#pragma unroll
+                  for (int c = 0; c < 64; ++c) v[c] = fmaxf(v[c], 0.f);
+                }
+              } else {
+                if (L.epi == EPI_BWD_RELU_D) {
+                  const float4* w4 = reinterpret_cast<const float4*>(p.bias + p.w_dens_off + col);
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) {
+                    float4 w = __ldg(w4 + c);
+                    v[c * 4 + 0] = fmaf(dd, w.x, v[c * 4 + 0]); v[c * 4 + 1] = fmaf(dd, w.y, v[c * 4 + 1]);
+                    v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
+                  }
+                }
+                if (L.epi != EPI_BWD_LINEAR) {
+                  if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
+                  else {
+#pragma unroll
+                    for (int c = 0; c < 64; ++c) v[c] = 0.f;
+                  }
+                }
+              }
+              const int pi = L.dst_buf * 4 + g * 2 + j;
+              uint8_t* panel = sm.panels + pi * kPanelBytes;
+              store_row_chunk64(panel, row, v);
+              ptx::fence_proxy_async();
+              if (kTrain && L.save_row >= 0) {
+                if (group_leader) ptx::tma_wait_group_read<2>();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                if (group_leader) {
+                  ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
+                  ptx::tma_commit_group();
+                }
+              }
+              ptx::tc_fence_before();
+              ptx::mbar_arrive(&sm.panel_ready[pi]);
+            }
+            break;
+          }
+          case EPI_VIEW: {
+            const int bar = L.acc_bar;
+            ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
+            acc_phase ^= 1u << bar;
+            ptx::tc_fence_after();
+            const int col = g * 64;
+            load_acc64(lane_addr + (uint32_t)(L.acc_col + col), v);
+            if (valid) {
+              const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(s / p.S) * 128 + col);
+#pragma unroll
+              for (int c = 0; c < 16; ++c) {
+                float4 b = __ldg(b4 + c);
+                v[c * 4 + 0] = fmaxf(v[c * 4 + 0] + b.x, 0.f); v[c * 4 + 1] = fmaxf(v[c * 4 + 1] + b.y, 0.f);
+                v[c * 4 + 2] = fmaxf(v[c * 4 + 2] + b.z, 0.f); v[c * 4 + 3] = fmaxf(v[c * 4 + 3] + b.w, 0.f);
+              }
+            }
+            const int pi = L.dst_buf * 4 + g;
+            uint8_t* panel = sm.panels + pi * kPanelBytes;
+            store_row_chunk64(panel, row, v);
+            ptx::fence_proxy_async();
+            if (kTrain && L.save_row >= 0) {
+              if (group_leader) ptx::tma_wait_group_read<2>();
+              asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+              if (group_leader) {
+                ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
+                ptx::tma_commit_group();
+              }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(&sm.panel_ready[pi]);
+            break;
+          }
+          case EPI_DENSITY: case EPI_RGB: {
+            if (g != 0) break;
+            const int bar = L.acc_bar;
+            ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
+            acc_phase ^= 1u << bar;
+            ptx::tc_fence_after();
+            uint32_t r4[4];
+            ptx::tmem_ld4(lane_addr + (uint32_t)L.acc_col, r4);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            if (L.epi == EPI_DENSITY) {
+              raw_d = __uint_as_float(r4[0]) + __ldg(p.bias + L.bias_off);
+              if (p.raw_c == 1 && valid) p.raw_out[s] = raw_d;
+            } else if (valid) {
+              float4 o;
+              o.x = raw_d;
+              o.y = __uint_as_float(r4[0]) + __ldg(p.bias + L.bias_off + 0);
+              o.z = __uint_as_float(r4[1]) + __ldg(p.bias + L.bias_off + 1);
+              o.w = __uint_as_float(r4[2]) + __ldg(p.bias + L.bias_off + 2);
+              reinterpret_cast<float4*>(p.raw_out)[s] = o;
+            }
+            break;
+          }
+          case EPI_BWD_START: {
+            // dV = W_rgb^T d_rgb (CUDA cores), gated by the saved view activation; 128 columns:
+            // group g produces columns [64g, 64g+64) -> panel g.
+            float4 dr = valid ? reinterpret_cast<const float4*>(p.d_raw)[s] : make_float4(0, 0, 0, 0);
+            // bf16-round the head gradient once so that dgrad (here) and wgrad (tensor cores) agree
+            const float d0 = __bfloat162float(__float2bfloat16(dr.y)), d1 = __bfloat162float(__float2bfloat16(dr.z)),
+                        d2 = __bfloat162float(__float2bfloat16(dr.w));
+            const int col = g * 64;
+            const float* wr = p.bias + p.w_rgb_off + col * 3;
+#pragma unroll
+            for (int c = 0; c < 64; ++c)
+              v[c] = d0 * __ldg(wr + c * 3) + d1 * __ldg(wr + c * 3 + 1) + d2 * __ldg(wr + c * 3 + 2);
+            if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
+            if (g == 0 && valid) {
+              uint4 q0 = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, 0.f), 0u, 0u);
+              uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * 16);
+              dst[0] = q0; dst[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            const int pi = L.dst_buf * 4 + g;
+            uint8_t* panel = sm.panels + pi * kPanelBytes;
+            store_row_chunk64(panel, row, v);
+            ptx::fence_proxy_async();
+            if (L.save_row >= 0) {
+              if (group_leader) ptx::tma_wait_group_read<2>();
+              asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+              if (group_leader) {
+                ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
+                ptx::tma_commit_group();
+              }
+            }
+            ptx::mbar_arrive(&sm.panel_ready[pi]);
+            break;
+          }
+          case EPI_BWD_START_PROP: {
+            // dZ_last = d_raw_density * w_density gated by the last trunk activation; 256 columns
+            const float dd0 = valid ? p.d_raw[s] : 0.f;
+            const float dd = __bfloat162float(__float2bfloat16(dd0));
+#pragma unroll 1
+            for (int j = 0; j < 2; ++j) {
+              const int col = g * 128 + j * 64;
+              const float* wd = p.bias + p.w_dens_off + col;
+#pragma unroll
+              for (int c = 0; c < 64; ++c) v[c] = dd * __ldg(wd + c);
+              if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
+              const int pi = L.dst_buf * 4 + g * 2 + j;
+              uint8_t* panel = sm.panels + pi * kPanelBytes;
+              store_row_chunk64(panel, row, v);
+              ptx::fence_proxy_async();
+              if (L.save_row >= 0) {
+                if (group_leader) ptx::tma_wait_group_read<2>();
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+                if (group_leader) {
+                  ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
+                  ptx::tma_commit_group();
+                }
+              }
+              ptx::mbar_arrive(&sm.panel_ready[pi]);
+            }
+            break;
+          }
+          default: break;
+        }
+      }
+    }
+    if (group_leader) ptx::tma_wait_group<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+  }
+  return fn;
+}
+
+// row-major bf16 [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle
+int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+  auto fn = get_encode_fn();
+  if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return HUGS_ERR_CUDA; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {64, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return HUGS_ERR_CUDA; }
+  return HUGS_OK;
+}
+
+template <class T>
+int tc_alloc(hugs_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    return HUGS_ERR_NOMEM;
+  }
+  h->allocs.push_back(q);
+  *p = static_cast<T*>(q);
+  return HUGS_OK;
+}
+
+// Build packing tables and the forward/backward layer schedules of one MLP.
+int build_mlp_schedule(hugs_handle* h, const MlpViews& mv, TcMlp* m, int save_layers_base) {
+  (void)save_layers_base;
+  const hugs_model_desc& d = h->d;
+  m->present = true; m->has_rgb = mv.has_rgb; m->depth = mv.depth;
+  int row_f = 0, row_b = 0, boff = 0;
+  std::vector<int> layer_w_row(mv.dense.size()), layer_b_row(mv.dense.size(), -1), layer_bias(mv.dense.size());
+  // ---- packing ----
+  for (size_t li = 0; li < mv.dense.size(); ++li) {
+    const DenseView& v = mv.dense[li];
+    TcMlp::PackLayer P{};
+    const bool trunk = (int)li < mv.depth;
+    const bool is_density = (int)li == mv.depth;
+    const bool is_view = mv.has_rgb && (int)li == mv.depth + 2;
+    P.out = v.out; P.in = v.in; P.koff = v.kernel_off; P.boff = v.bias_off;
+    if (is_view) { P.x_in = d.bottleneck_width; P.feat_in = 0; }
+    else if (v.in == h->feat_dim) { P.x_in = 0; P.feat_in = h->feat_dim; }
+    else if (v.in == kW + h->feat_dim) { P.x_in = kW; P.feat_in = h->feat_dim; }
+    else { P.x_in = v.in; P.feat_in = 0; }
+    P.rows_pad = v.out >= 128 ? ((v.out + 127) / 128) * 128 : 16;
+    P.row0 = row_f; row_f += P.rows_pad;
+    P.bias_off = boff; boff += ((v.out + 3) / 4) * 4;
+    // natural-layout copy for dgrad: every layer whose *input* carries a gradient
+    const bool needs_dgrad = (trunk && li > 0) || (mv.has_rgb && ((int)li == mv.depth + 1 || is_view));
+    P.brow0 = -1;
+    if (needs_dgrad) { P.brow0 = row_b; row_b += kW; }
+    (void)is_density;
+    layer_w_row[li] = P.row0; layer_b_row[li] = P.brow0; layer_bias[li] = P.bias_off;
+    m->pack.push_back(P);
+  }
+  m->rows_f = row_f; m->rows_b = std::max(row_b, kW);
+  // head weights for the CUDA-core parts of the backward chain
+  const DenseView& dens = mv.dense[mv.depth];
+  m->w_dens_off = boff; boff += ((dens.in + 3) / 4) * 4;
+  m->w_rgb_off = -1;
+  if (mv.has_rgb) { m->w_rgb_off = boff; boff += mv.dense[mv.depth + 3].in * 3 + 4; }
+  m->bias_floats = boff;
+
+  // ---- forward schedule ----
+  auto trunk_layer = [&](int i, bool first, bool cat) {
+    TcLayer L{};
+    L.a_res = first ? 0 : 4; L.a_str = (first || cat) ? kFeatPad / 64 : 0;
+    L.a_buf = i % 2; L.wait_panels = 1; L.n_halves = 2; L.n_mma = 128;
+    L.acc_col = (i % 2) * 256; L.acc_bar = (i % 2) * 2;
+    L.w_row = layer_w_row[i]; L.w_map = 0; L.epi = EPI_RELU; L.dst_buf = (i + 1) % 2; L.bias_off = layer_bias[i];
+    L.save_row = -1; L.mask_row = -1;
+    return L;
+  };
+  bool cat = false;
+  for (int i = 0; i < mv.depth; ++i) {
+    m->fwd.push_back(trunk_layer(i, i == 0, cat));
+    cat = (i % d.skip_layer == 0 && i > 0);
+  }
+  HUGS_REQUIRE(!cat, "tensor-core path: a skip connection into the heads is not supported (depth %d, skip %d)",
+               mv.depth, d.skip_layer);
+  const int D = mv.depth;
+  const int head_buf = D % 2;             // buffer holding the last trunk activation
+  if (!mv.has_rgb) {
+    TcLayer L{};
+    L.a_res = 4; L.a_buf = head_buf; L.wait_panels = 1; L.n_halves = 1; L.n_mma = 16;
+    L.acc_col = (D % 2) * 256; L.acc_bar = 4; L.w_row = layer_w_row[D]; L.w_map = 1; L.epi = EPI_DENSITY;
+    L.bias_off = layer_bias[D]; L.save_row = -1; L.mask_row = -1;
+    m->fwd.push_back(L);
+  } else {
+    const int other = (D + 1) % 2;        // accumulator / buffer parity not used by the bottleneck
+    TcLayer B{};                          // bottleneck (linear)
+    B.a_res = 4; B.a_buf = head_buf; B.wait_panels = 1; B.n_halves = 2; B.n_mma = 128;
+    B.acc_col = (D % 2) * 256; B.acc_bar = (D % 2) * 2; B.w_row = layer_w_row[D + 1]; B.w_map = 0;
+    B.epi = EPI_LINEAR; B.dst_buf = other; B.bias_off = layer_bias[D + 1]; B.save_row = -1; B.mask_row = -1;
+    m->fwd.push_back(B);
+    TcLayer Dn{};                         // density head reads the same activation (already waited for)
+    Dn.a_res = 4; Dn.a_buf = head_buf; Dn.wait_panels = 0; Dn.n_halves = 1; Dn.n_mma = 16;
+    Dn.acc_col = other * 256; Dn.acc_bar = 4; Dn.w_row = layer_w_row[D]; Dn.w_map = 1; Dn.epi = EPI_DENSITY;
+    Dn.bias_off = layer_bias[D]; Dn.save_row = -1; Dn.mask_row = -1;
+    m->fwd.push_back(Dn);
+    TcLayer V{};                          // view layer: K = bottleneck (dir/GLO terms live in viewbias)
+    V.a_res = 4; V.a_buf = other; V.wait_panels = 1; V.n_halves = 1; V.n_mma = 128;
+    V.acc_col = other * 256 + 128; V.acc_bar = 5; V.w_row = layer_w_row[D + 2]; V.w_map = 0; V.epi = EPI_VIEW;
+    V.dst_buf = head_buf; V.bias_off = 0; V.save_row = -1; V.mask_row = -1;
+    m->fwd.push_back(V);
+    TcLayer R{};                          // rgb head, K = 128 (2 panels)
+    R.a_res = 2; R.a_buf = head_buf; R.wait_panels = 1; R.n_halves = 1; R.n_mma = 16;
+    R.acc_col = other * 256 + 16; R.acc_bar = 6; R.w_row = layer_w_row[D + 3]; R.w_map = 1; R.epi = EPI_RGB;
+    R.bias_off = layer_bias[D + 3]; R.save_row = -1; R.mask_row = -1;
+    m->fwd.push_back(R);
+    m->view_w_row = layer_w_row[D + 2];
+  }
+  HUGS_REQUIRE((int)m->fwd.size() <= kMaxLayers, "tensor-core path: too many layers (%zu)", m->fwd.size());
+  return HUGS_OK;
+}
+
+int fill_pack_args(hugs_handle* h, const MlpViews& mv, const TcMlp& m, const float* params, PackArgs* a) {
+  memset(a, 0, sizeof(*a));
+  HUGS_REQUIRE(m.pack.size() <= 16, "too many layers to pack");
+  for (size_t i = 0; i < m.pack.size(); ++i) a->layers[i] = m.pack[i];
+  a->n_layers = (int)m.pack.size(); a->rows_f = m.rows_f; a->rows_b = m.rows_b;
+  a->nb = h->d.num_basis; a->ndeg = h->d.max_deg_point - h->d.min_deg_point; a->feat_dim = h->feat_dim;
+  a->bias_floats = m.bias_floats; a->params = params; a->wt = m.wt; a->wn = m.wn; a->bias = m.bias;
+  a->w_dens_off = m.w_dens_off; a->w_rgb_off = m.w_rgb_off;
+  a->dens_koff = mv.dense[mv.depth].kernel_off; a->dens_in = mv.dense[mv.depth].in;
+  if (mv.has_rgb) { a->rgb_koff = mv.dense[mv.depth + 3].kernel_off; a->rgb_in = mv.dense[mv.depth + 3].in; }
+  return HUGS_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+int tc_create(hugs_handle* h) {
+  const hugs_model_desc& d = h->d;
+  const int ndeg = d.max_deg_point - d.min_deg_point;
+  if (d.nerf_width != kW || (d.num_levels > 1 && d.prop_width != kW) || d.bottleneck_width != kW ||
+      d.view_width != 128 || h->feat_dim > kFeatPad || (ndeg % 4) != 0 || ndeg > 16) {
+    set_error("tensor-core path supports net_width 256, bottleneck 256, view width 128 and <= 512 IPE features "
+              "with a degree count divisible by 4 (got widths %d/%d/%d/%d, %d features); use HUGS_PRECISION_FP32",
+              d.nerf_width, d.prop_width, d.bottleneck_width, d.view_width, h->feat_dim);
+    return HUGS_ERR_UNSUPPORTED;
+  }
+  cudaDeviceProp prop;
+  HUGS_CUDA(cudaGetDeviceProperties(&prop, h->device));
+  if (prop.major != 10) {
+    set_error("tensor-core path needs an sm_100 device (found sm_%d%d)", prop.major, prop.minor);
+    return HUGS_ERR_UNSUPPORTED;
+  }
+  TcState* tc = new TcState();
+  h->tc = tc;
+  tc->num_sms = prop.multiProcessorCount;
+  int rc;
+  if ((rc = build_mlp_schedule(h, h->nerf, &tc->nerf, 0))) return rc;
+  if (d.num_levels > 1 && (rc = build_mlp_schedule(h, h->prop, &tc->prop, 0))) return rc;
+  for (TcMlp* m : {&tc->nerf, &tc->prop}) {
+    if (!m->present) continue;
+    if ((rc = tc_alloc(h, &m->wt, (size_t)m->rows_f * kKP)) || (rc = tc_alloc(h, &m->wn, (size_t)m->rows_b * kW)) ||
+        (rc = tc_alloc(h, &m->bias, (size_t)m->bias_floats)))
+      return rc;
+    if ((rc = make_map(&m->map_wt128, m->wt, m->rows_f, kKP, 128)) ||
+        (rc = make_map(&m->map_wt16, m->wt, m->rows_f, kKP, 16)) ||
+        (rc = make_map(&m->map_wn128, m->wn, m->rows_b, kW, 128)))
+      return rc;
+  }
+  // per-level feature / saved-activation regions
+  const int L = d.num_levels;
+  tc->cap.resize(L); tc->feat_row0.resize(L); tc->save_row0.resize(L);
+  int frow = 0, srow = 0;
+  for (int l = 0; l < L; ++l) {
+    const int S = h->samples(l);
+    tc->cap[l] = (int)((((long long)d.max_rays * S + kTileM - 1) / kTileM) * kTileM);
+    tc->feat_row0[l] = frow; frow += tc->cap[l];
+    const int n_saved = (l == L - 1) ? d.nerf_depth + 2 : d.prop_depth;
+    tc->save_row0[l] = srow; srow += n_saved * tc->cap[l];
+  }
+  tc->total_feat_rows = frow; tc->total_save_rows = srow;
+  if ((rc = tc_alloc(h, &tc->feat, (size_t)frow * kFeatPad))) return rc;
+  if ((rc = tc_alloc(h, &tc->act, (size_t)srow * kW)) || (rc = tc_alloc(h, &tc->dz, (size_t)srow * kW))) return rc;
+  if ((rc = tc_alloc(h, &tc->drgb, (size_t)tc->cap[L - 1] * 16))) return rc;
+  if ((rc = tc_alloc(h, &tc->viewbias, (size_t)d.max_rays * 128))) return rc;
+  if ((rc = make_map(&tc->map_feat, tc->feat, frow, kFeatPad, 128)) ||
+      (rc = make_map(&tc->map_act, tc->act, srow, kW, 128)) || (rc = make_map(&tc->map_dz, tc->dz, srow, kW, 128)))
+    return rc;
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  return HUGS_OK;
+}
+
+void tc_destroy(hugs_handle* h) {
+  if (h->tc) { delete h->tc; h->tc = nullptr; }
+}
+
+int tc_pack_params(hugs_handle* h, const float* params, cudaStream_t st) {
+  TcState* tc = h->tc;
+  HUGS_REQUIRE(tc, "tensor-core state missing");
+  PackArgs a;
+  int rc;
+  if ((rc = fill_pack_args(h, h->nerf, tc->nerf, params, &a))) return rc;
+  pack_params_kernel<<<512, 256, 0, st>>>(a);
+  HUGS_LAUNCH_CHECK();
+  if (tc->prop.present) {
+    if ((rc = fill_pack_args(h, h->prop, tc->prop, params, &a))) return rc;
+    pack_params_kernel<<<512, 256, 0, st>>>(a);
+    HUGS_LAUNCH_CHECK();
+  }
+  return HUGS_OK;
+}
+
+int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, bool training, cudaStream_t st) {
+  TcState* tc = h->tc;
+  const hugs_model_desc& d = h->d;
+  const bool is_prop = level < d.num_levels - 1;
+  const TcMlp& m = is_prop ? tc->prop : tc->nerf;
+  const MlpViews& mv = is_prop ? h->prop : h->nerf;
+  const int S = h->samples(level);
+  const int n_samples = n_rays * S;
+  const int n_tiles = (n_samples + kTileM - 1) / kTileM;
+  // 1. bf16 IPE features (own column order) -> feat[level]
+  EncArgs ea{rays->origins, rays->directions, rays->radii, h->tdist[level], h->basis, n_samples, S, d.num_basis,
+             d.min_deg_point, d.max_deg_point - d.min_deg_point, d.ray_shape,
+             is_prop ? d.prop_contract : d.nerf_contract, tc->feat + (size_t)tc->feat_row0[level] * kFeatPad};
+  encode_bf16_kernel<<<(n_samples + kEncRows - 1) / kEncRows, 2 * kEncRows, 0, st>>>(ea);
+  HUGS_LAUNCH_CHECK();
+  // 2. per-ray view bias (direction encoding + GLO folded through the view layer)
+  if (!is_prop) {
+    const DenseView& vv = mv.dense[mv.depth + 2];
+    viewbias_kernel<<<(n_rays * 128 + 255) / 256, 256, 0, st>>>(h->view_in, h->view_in_dim, h->cur_params,
+                                                               vv.kernel_off, vv.bias_off, d.bottleneck_width,
+                                                               128, n_rays, tc->viewbias);
+    HUGS_LAUNCH_CHECK();
+  }
+  // 3. fused chain
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.map_w128 = m.map_wt128; p.map_w16 = m.map_wt16; p.map_feat = tc->map_feat; p.map_save = tc->map_act;
+  p.n_layers = (int)m.fwd.size();
+  for (int i = 0; i < p.n_layers; ++i) {
+    p.layers[i] = m.fwd[i];
+    if (training) {
+      // save every panel-producing layer's output: slot i of this level's region
+      const int e = p.layers[i].epi;
+      if (e == EPI_RELU || e == EPI_LINEAR || e == EPI_VIEW) {
+        int slot = i;
+        if (e == EPI_VIEW) slot = mv.depth + 1;       // after trunk (0..D-1) and bottleneck (D)
+        if (e == EPI_LINEAR) slot = mv.depth;
+        p.layers[i].save_row = tc->save_row0[level] + slot * tc->cap[level];
+      }
+    }
+  }
+  p.n_tiles = n_tiles; p.n_samples = n_samples; p.S = S; p.feat_row0 = tc->feat_row0[level];
+  p.bias = m.bias; p.viewbias = tc->viewbias; p.raw_out = h->raw[level]; p.raw_c = is_prop ? 1 : 4;
+  p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
+  const int grid = std::min(n_tiles, tc->num_sms);
+  if (training) mlp_chain_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
+  else mlp_chain_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(p);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, float* grad, cudaStream_t st) {
+  (void)h; (void)level; (void)rays; (void)n_rays; (void)grad; (void)st;
+  set_error("tensor-core backward is not built yet");
+  return HUGS_ERR_UNSUPPORTED;
+}
+
+}  // namespace hugs

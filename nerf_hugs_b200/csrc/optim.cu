@@ -1,0 +1,129 @@
+// Per-module gradient clipping + nan_to_num + Adam (one fused elementwise pass over the flat
+// parameter buffer), and the small reductions that feed it.
+//
+// Reference semantics (paths under /root/reference/MipNeRF360/internal):
+//   train_utils.py:351-369  clip_gradients: per top-level module, value clip then norm clip
+//   train_utils.py:464-468  nan_to_num, state.apply_gradients (optax.adam, b1/b2/eps from configs.py:99-107)
+//   train_utils.py:461-462  stats['grad_norms'], stats['grad_maxes']
+#include "handle.h"
+#include "tc.h"
+
+namespace hugs {
+namespace {
+
+constexpr int kRedBlocks = 128;
+
+__device__ __forceinline__ float clipv(float g, float max_val) {
+  return max_val > 0.f ? fminf(fmaxf(g, -max_val), max_val) : g;
+}
+
+// partial[m][b] = {sum g^2 (raw), max |g| (raw), sum clip(g)^2}
+__global__ void __launch_bounds__(256) grad_norm_partial_kernel(const float* grad, int64_t b0, int64_t e0, int64_t b1,
+                                                                int64_t e1, int64_t b2, int64_t e2, float max_val,
+                                                                float* partial) {
+  __shared__ float red[3][8];
+  const int m = blockIdx.y;
+  const int64_t beg = m == 0 ? b0 : (m == 1 ? b1 : b2), end = m == 0 ? e0 : (m == 1 ? e1 : e2);
+  float s = 0.f, mx = 0.f, sc = 0.f;
+  for (int64_t i = beg + (int64_t)blockIdx.x * 256 + threadIdx.x; i < end; i += (int64_t)kRedBlocks * 256) {
+    float g = grad[i];
+    s += g * g;
+    mx = fmaxf(mx, fabsf(g));
+    float c = clipv(g, max_val);
+    sc += c * c;
+  }
+  s = warp_sum(s); sc = warp_sum(sc); mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = mx; red[2][threadIdx.x >> 5] = sc; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f, c = 0.f;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; b = fmaxf(b, red[1][w]); c += red[2][w]; }
+    float* p = partial + ((size_t)m * kRedBlocks + blockIdx.x) * 3;
+    p[0] = a; p[1] = b; p[2] = c;
+  }
+}
+
+// out[m] = {norm_raw, max_raw, clip multiplier}
+__global__ void grad_norm_final_kernel(const float* partial, float max_norm, float* out) {
+  const int m = threadIdx.x;
+  if (m >= 3) return;
+  float a = 0.f, b = 0.f, c = 0.f;
+  for (int i = 0; i < kRedBlocks; ++i) {
+    const float* p = partial + ((size_t)m * kRedBlocks + i) * 3;
+    a += p[0]; b = fmaxf(b, p[1]); c += p[2];
+  }
+  out[m * 3 + 0] = sqrtf(a);
+  out[m * 3 + 1] = b;
+  out[m * 3 + 2] = max_norm > 0.f ? fminf(1.f, max_norm / (kF32Eps + sqrtf(c))) : 1.f;
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* params, const float* grad, float* mu, float* nu,
+                                                   int64_t n, int64_t e0, int64_t e1, const float* norms,
+                                                   hugs_adam_cfg cfg, float bc1, float bc2) {
+  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n) return;
+  const int m = i < e0 ? 0 : (i < e1 ? 1 : 2);
+  float g = clipv(grad[i], cfg.grad_max_val) * norms[m * 3 + 2];
+  if (g != g) g = 0.f;                                  // jnp.nan_to_num
+  else if (isinf(g)) g = g > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+  float m1 = cfg.beta1 * mu[i] + (1.f - cfg.beta1) * g;
+  float m2 = cfg.beta2 * nu[i] + (1.f - cfg.beta2) * g * g;
+  mu[i] = m1; nu[i] = m2;
+  float mhat = m1 / bc1, vhat = m2 / bc2;
+  params[i] = params[i] - cfg.lr * mhat / (sqrtf(vhat) + cfg.eps);
+}
+
+__global__ void finalize_stats_kernel(hugs_loss_cfg loss, int n, int L, int S_final, const float* denom,
+                                      const float* sums, float* stats) {
+  if (threadIdx.x != 0) return;
+  const float dn = fmaxf(denom[0], kF32Eps);
+  const float data = loss.data_loss_mult * sums[0] / dn;
+  const float mse = sums[1] / dn;
+  const float dist = loss.distortion_loss_mult > 0.f ? loss.distortion_loss_mult * sums[2] / (float)n : 0.f;
+  float inter = 0.f;
+  if (loss.interlevel_loss_mult > 0.f)
+    for (int l = 0; l < L - 1; ++l) inter += sums[4 + l] / ((float)n * (float)S_final);
+  inter *= loss.interlevel_loss_mult;
+  for (int i = 0; i < 16; ++i) stats[i] = 0.f;
+  stats[0] = data + inter + dist; stats[1] = data; stats[2] = inter; stats[3] = dist;
+  stats[4 + L - 1] = mse;
+}
+
+}  // namespace
+
+int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, const float* denom, const float* sums,
+                          float* stats_out, cudaStream_t st) {
+  finalize_stats_kernel<<<1, 32, 0, st>>>(loss, n, h->d.num_levels, h->samples(h->d.num_levels - 1), denom, sums,
+                                          stats_out);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+}  // namespace hugs
+
+using namespace hugs;
+
+HUGS_API int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
+                            const hugs_adam_cfg* cfg, float* norms_out, void* stream) {
+  HUGS_REQUIRE(h && params && grad && mu && nu && cfg, "hugs_adam_step: null argument");
+  HUGS_REQUIRE(cfg->step >= 0, "hugs_adam_step: step must be >= 0");
+  cudaStream_t st = (cudaStream_t)stream;
+  float* partial = h->scalars + 64;   // see hugs_create: scalars has room for 64 + 3*kRedBlocks*3
+  float* norms = h->scalars + 32;
+  dim3 grid(kRedBlocks, 3);
+  grad_norm_partial_kernel<<<grid, 256, 0, st>>>(grad, h->module_begin[0], h->module_end[0], h->module_begin[1],
+                                                 h->module_end[1], h->module_begin[2], h->module_end[2],
+                                                 cfg->grad_max_val, partial);
+  HUGS_LAUNCH_CHECK();
+  grad_norm_final_kernel<<<1, 32, 0, st>>>(partial, cfg->grad_max_norm, norms);
+  HUGS_LAUNCH_CHECK();
+  const double t = (double)cfg->step + 1.0;
+  const float bc1 = (float)(1.0 - pow((double)cfg->beta1, t)), bc2 = (float)(1.0 - pow((double)cfg->beta2, t));
+  const int64_t n = h->n_params;
+  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
+                                                           h->module_end[1], norms, *cfg, bc1, bc2);
+  HUGS_LAUNCH_CHECK();
+  if (norms_out) HUGS_CUDA(cudaMemcpyAsync(norms_out, norms, sizeof(float) * 9, cudaMemcpyDeviceToDevice, st));
+  if (h->d.precision == HUGS_PRECISION_BF16_TC) return tc_pack_params(h, params, st);
+  return HUGS_OK;
+}

@@ -1,0 +1,19 @@
+// Tensor-core (tcgen05) MLP path: host interface used by api.cu / optim.cu.
+#pragma once
+#include "handle.h"
+
+namespace hugs {
+
+int tc_create(hugs_handle* h);
+void tc_destroy(hugs_handle* h);
+// fp32 flat params -> packed bf16 operand tensors (+ fp32 bias packs)
+int tc_pack_params(hugs_handle* h, const float* params, cudaStream_t st);
+// encode + fused MLP chain for level l; fills h->raw[l]; saves activations when `training`
+int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, bool training, cudaStream_t st);
+// dgrad chain + wgrad for level l from h->d_raw[l]; accumulates into grad (flat fp32, flax layout)
+int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, float* grad, cudaStream_t st);
+
+int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, const float* denom, const float* sums,
+                          float* stats_out, cudaStream_t st);
+
+}  // namespace hugs

@@ -1,0 +1,118 @@
+"""Model-level parity: hugs_forward (both precision modes) vs the CPU oracle on identical rays/weights.
+
+fp32 mode ("parity mode"): rendered rgb / distances within 1e-4 relative of the fp32 oracle
+(the north-star tolerance).  bf16 tensor-core mode: compared against the oracle run with bf16-rounded
+Dense operands (the arithmetic the kernel implements); its distance to the fp32 oracle is recorded.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import mipnerf360 as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+
+
+def _report(name, d):
+  try:
+    os.makedirs(REPORT, exist_ok=True)
+    path = os.path.join(REPORT, 'parity_report.json')
+    cur = json.load(open(path)) if os.path.exists(path) else {}
+    cur[name] = d
+    json.dump(cur, open(path, 'w'), indent=1, sort_keys=True)
+  except Exception:
+    pass
+
+
+def _run_pair(precision, quant, n=96, seed=0, num_levels=2, n_prop=64, n_nerf=128, glo=0, contract=True,
+              raydist='reciprocal', jitter=False, near=0.2, far=1e6):
+  from nerf_hugs_b200.engine import Engine
+  ocfg, ecfg = H.config_pair(num_levels=num_levels, n_prop=n_prop, n_nerf=n_nerf, precision=precision,
+                             max_rays=max(n, 128), glo=glo, contract=contract, raydist=raydist)
+  basis = H.basis_np()
+  params = O.init_params(ocfg, seed=seed, bias_scale=0.1)
+  rays, gt = H.make_rays(n, seed=seed + 1, near=near, far=far)
+  jit = None
+  if jitter:
+    g = torch.Generator().manual_seed(5)
+    jit = [torch.rand(n, 1, generator=g) for _ in range(num_levels)]
+  with torch.no_grad():
+    rend, hist = O.model_apply(ocfg, params, rays, 0.6, True, torch.tensor(basis), jitter=jit, quant=quant)
+  eng = Engine(ecfg, basis)
+  flat = eng.flatten_params(params)
+  eng.params_changed(flat)
+  jt = None if jit is None else torch.stack([j[:, 0] for j in jit])
+  res, eh = eng.forward(flat, rays, 0.6, jitter=jt, compute_extras=True)
+  torch.cuda.synchronize()
+  out = ([{k: v.cpu() for k, v in r.items()} for r in res], [{k: v.cpu() for k, v in r.items()} for r in eh])
+  eng.close()
+  return rend, hist, out[0], out[1]
+
+
+def _relerr(a, b):
+  return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.mark.parametrize('levels', [1, 2])
+def test_forward_fp32_parity(levels):
+  """North-star parity: rgb/depth within 1e-4 relative of the fp32 oracle; sampling near-exact."""
+  rend, hist, res, eh = _run_pair('fp32', None, num_levels=levels)
+  stats = {}
+  for l in range(levels):
+    ds = float((eh[l]['sdist'] - hist[l]['sdist']).abs().max())
+    stats[f'sdist_abs_l{l}'] = ds
+    assert ds < 5e-5, f'level {l} sdist differs by {ds}'
+  np.testing.assert_allclose(eh[-1]['density'].numpy(), hist[-1]['density'].numpy(), rtol=2e-3, atol=2e-4)
+  for k in ('rgb', 'acc', 'distance_mean', 'distance_median'):
+    e = _relerr(res[-1][k], rend[-1][k])
+    stats[k] = e
+    assert e < 1e-4, f'{k}: rel err {e}'
+  _report(f'forward_fp32_L{levels}', stats)
+
+
+def test_forward_fp32_parity_train_jitter_no_contract():
+  """Jittered (train-mode) sampling, no contraction / linear ray spacing (phototourism-style gin)."""
+  rend, hist, res, eh = _run_pair('fp32', None, contract=False, raydist=None, jitter=True, near=1.0, far=2.0)
+  assert float((eh[0]['sdist'] - hist[0]['sdist']).abs().max()) < 5e-6
+  for k in ('rgb', 'acc', 'distance_mean'):
+    assert _relerr(res[-1][k], rend[-1][k]) < 1e-4, k
+
+
+@pytest.mark.parametrize('levels', [1, 2])
+def test_forward_tc_vs_bf16_oracle(levels):
+  """tcgen05 path vs the oracle with bf16-rounded Dense operands."""
+  rend, hist, res, eh = _run_pair('bf16_tc', 'bf16', num_levels=levels)
+  rend32, hist32, _, _ = None, None, None, None
+  stats = {}
+  d_err = float((eh[-1]['density'] - hist[-1]['density']).abs().max())
+  d_scale = float(hist[-1]['density'].abs().max())
+  stats['density_abs'] = d_err; stats['density_scale'] = d_scale
+  c_err = float((eh[-1]['rgb'] - hist[-1]['rgb']).abs().max())
+  stats['sample_rgb_abs'] = c_err
+  for k in ('rgb', 'acc', 'distance_mean', 'distance_median'):
+    stats[k] = _relerr(res[-1][k], rend[-1][k])
+  _report(f'forward_tc_L{levels}', stats)
+  assert d_err < 0.05 * max(d_scale, 1.0), stats
+  assert c_err < 0.03, stats
+  assert stats['rgb'] < 2e-2 and stats['acc'] < 2e-2, stats
+
+
+def test_forward_tc_error_vs_fp32_oracle_recorded():
+  """The precision cost of bf16 operands themselves (kernel vs the *fp32* oracle) — reported, loosely bounded."""
+  rend, hist, res, eh = _run_pair('bf16_tc', None, num_levels=2)
+  stats = {k: _relerr(res[-1][k], rend[-1][k]) for k in ('rgb', 'acc', 'distance_mean', 'distance_median')}
+  _report('forward_tc_vs_fp32_oracle', stats)
+  assert stats['rgb'] < 5e-2, stats
+
+
+def test_forward_tc_ragged_and_glo():
+  """Ray count that is not a multiple of the 128-sample tile (64-sample proposal level) + GLO vectors."""
+  rend, hist, res, eh = _run_pair('bf16_tc', 'bf16', n=37, glo=4)
+  assert res[-1]['rgb'].shape == (37, 3)
+  assert _relerr(res[-1]['rgb'], rend[-1]['rgb']) < 2e-2
