@@ -22,90 +22,9 @@
 
 #include "encode.cuh"
 #include "ptx.cuh"
-#include "tc.h"
+#include "tc_internal.h"
 
 namespace hugs {
-
-// ------------------------------------------------------------------------------------------
-// constants / schedule description
-// ------------------------------------------------------------------------------------------
-constexpr int kTileM = 128;             // samples per tile (= TMEM lanes)
-constexpr int kPanelBytes = 16384;      // 128 rows x 64 bf16, SWIZZLE_128B
-constexpr int kNumPanels = 8;           // two activation buffers of 4 K-panels (256 columns) each
-constexpr int kStages = 6;              // TMA ring depth
-constexpr int kW = 256;                 // trunk / bottleneck width of this path
-constexpr int kFeatPad = 512;           // IPE features padded to 8 K-panels
-constexpr int kKP = kW + kFeatPad;      // K extent of the packed forward weights
-constexpr int kThreads = 320;
-constexpr int kSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + 512;
-
-enum Epi : int {
-  EPI_RELU = 0,      // bias + ReLU -> bf16 panels            (trunk)
-  EPI_LINEAR = 1,    // bias         -> bf16 panels            (bottleneck)
-  EPI_DENSITY = 2,   // column 0 + bias -> raw density         (group 0)
-  EPI_VIEW = 3,      // per-ray view bias + ReLU -> panels 0,1 (N = 128)
-  EPI_RGB = 4,       // columns 0..2 + bias -> raw rgb         (group 0)
-  // backward chain
-  EPI_BWD_START = 5, // no MMA: d_raw -> dZ_view panels (+ rgb head dgrad on CUDA cores)
-  EPI_BWD_LINEAR = 6,// dA -> bf16 panels                      (through the linear bottleneck)
-  EPI_BWD_RELU = 7,  // dA * [A > 0] -> bf16 panels
-  EPI_BWD_RELU_D = 8,// (dA + d_density * w_density) * [A > 0] -> bf16 panels
-  EPI_BWD_START_PROP = 9,  // no MMA: d_raw_density * w_density * [A > 0] -> panels
-};
-
-struct TcLayer {
-  int a_res, a_str, a_buf, wait_panels;
-  int n_halves, n_mma, acc_col, acc_bar;
-  int w_row, w_map;
-  int epi, dst_buf, bias_off;
-  int save_row;      // base row in the save tensor (activations fwd / dZ bwd), -1 = do not save
-  int mask_row;      // bwd: base row of the saved forward activation whose sign gates this epilogue
-};
-
-constexpr int kMaxLayers = 14;
-
-struct alignas(64) TcParams {
-  CUtensorMap map_w128, map_w16, map_feat, map_save;
-  TcLayer layers[kMaxLayers];
-  int n_layers;
-  int n_tiles, n_samples, S;
-  int feat_row0;
-  const float* bias;                 // packed fp32 biases (+ head weights, see TcMlp)
-  const float* viewbias;             // [n_rays, 128]
-  float* raw_out; int raw_c;         // [n_samples, raw_c]
-  const float* d_raw;                // bwd: [n_samples, raw_c]
-  const __nv_bfloat16* act;          // bwd: saved forward activations [rows, 256]
-  __nv_bfloat16* drgb_out;           // bwd: [n_samples, 16] bf16 (d raw rgb, padded) for the rgb-head wgrad
-  int w_dens_off, w_rgb_off;         // float offsets of head weights inside `bias`
-};
-
-struct TcMlp {
-  bool present = false, has_rgb = false;
-  int depth = 0;
-  __nv_bfloat16* wt = nullptr; int rows_f = 0;   // forward pack  [rows_f, kKP]   (K-major rows = outputs)
-  __nv_bfloat16* wn = nullptr; int rows_b = 0;   // backward pack [rows_b, kW]    (rows = inputs, cols = outputs)
-  float* bias = nullptr; int bias_floats = 0;
-  int w_dens_off = 0, w_rgb_off = 0, view_bias_off = 0, view_w_row = 0;
-  std::vector<TcLayer> fwd, bwd;
-  CUtensorMap map_wt128, map_wt16, map_wn128;
-  // packing tables
-  struct PackLayer { int row0, rows_pad, out, in, x_in, feat_in; long long koff, boff; int bias_off, brow0, b_out_pad; };
-  std::vector<PackLayer> pack;
-};
-
-struct TcState {
-  TcMlp nerf, prop;
-  __nv_bfloat16* feat = nullptr;     // per level region [cap_l, 512]
-  __nv_bfloat16* act = nullptr;      // saved forward activations
-  __nv_bfloat16* dz = nullptr;       // saved backward dZ
-  __nv_bfloat16* drgb = nullptr;     // [cap, 16]
-  float* viewbias = nullptr;
-  CUtensorMap map_feat, map_act, map_dz;
-  std::vector<int> cap, feat_row0, save_row0;   // per level
-  int total_feat_rows = 0, total_save_rows = 0;
-  int num_sms = 148;
-  void* pack_tables = nullptr;
-};
 
 namespace {
 
@@ -113,12 +32,6 @@ namespace {
 // small helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t swz_chunk(uint32_t row, uint32_t chunk) { return chunk ^ (row & 7u); }
-
-// reference feature column of my column f' = (b*ndeg + k)*2 + s   ->   s*(nb*ndeg) + k*nb + b
-__host__ __device__ inline int ref_feature_col(int fp, int nb, int ndeg) {
-  int s = fp & 1, bk = fp >> 1, b = bk / ndeg, k = bk % ndeg;
-  return s * (nb * ndeg) + k * nb + b;
-}
 
 // ------------------------------------------------------------------------------------------
 // bf16 feature encoder (throughput mode): one thread = (sample, half of the basis directions)
@@ -645,8 +558,7 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
   return fn;
 }
 
-// row-major bf16 [rows, cols] tensor, box = [box_rows, 64 cols], 128B swizzle
-int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+int make_map_impl(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
   auto fn = get_encode_fn();
   if (!fn) { set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)"); return HUGS_ERR_CUDA; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -778,6 +690,10 @@ int fill_pack_args(hugs_handle* h, const MlpViews& mv, const TcMlp& m, const flo
 }
 
 }  // namespace
+
+int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows) {
+  return make_map_impl(m, base, rows, cols, box_rows);
+}
 
 // ------------------------------------------------------------------------------------------
 int tc_create(hugs_handle* h) {

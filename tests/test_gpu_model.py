@@ -88,7 +88,6 @@ def test_forward_fp32_parity_train_jitter_no_contract():
 def test_forward_tc_vs_bf16_oracle(levels):
   """tcgen05 path vs the oracle with bf16-rounded Dense operands."""
   rend, hist, res, eh = _run_pair('bf16_tc', 'bf16', num_levels=levels)
-  rend32, hist32, _, _ = None, None, None, None
   stats = {}
   d_err = float((eh[-1]['density'] - hist[-1]['density']).abs().max())
   d_scale = float(hist[-1]['density'].abs().max())
@@ -98,9 +97,10 @@ def test_forward_tc_vs_bf16_oracle(levels):
   for k in ('rgb', 'acc', 'distance_mean', 'distance_median'):
     stats[k] = _relerr(res[-1][k], rend[-1][k])
   _report(f'forward_tc_L{levels}', stats)
-  assert d_err < 0.05 * max(d_scale, 1.0), stats
-  assert c_err < 0.03, stats
-  assert stats['rgb'] < 2e-2 and stats['acc'] < 2e-2, stats
+  if levels == 1:   # identical sample positions: per-sample outputs are comparable
+    assert d_err < 0.02 * max(d_scale, 1.0), stats
+    assert c_err < 0.02, stats
+  assert stats['rgb'] < 5e-3 and stats['acc'] < 5e-3 and stats['distance_mean'] < 1e-2, stats
 
 
 def test_forward_tc_error_vs_fp32_oracle_recorded():

@@ -63,8 +63,16 @@ def test_sample_intervals_vs_oracle(eng, nb, ns, anneal):
     u_base, mj = O.sample_u(ns, True, jitter)
     ref = O.sample_intervals(jitter, t, logits, ns, single_jitter=True, domain=(0., 1.))
     out, idx = eng.sample_intervals(t, logits, u_base, jitter, mj, ns, (0., 1.), want_idx=True)
-    np.testing.assert_allclose(out.cpu().numpy(), ref.numpy(), atol=2e-6, rtol=0)
     cw = O.integrate_weights(torch.softmax(logits, -1))
+    # Compare in CDF space: a one-ulp change of the CDF moves a sample by ulp/pdf, which is unbounded in
+    # t for near-empty bins but bounded (<= 1e-6) in cumulative mass.  Most samples also agree to 2e-6 in t.
+    o, r = out.cpu().numpy().astype(np.float64), ref.numpy().astype(np.float64)
+    close_t = np.abs(o - r) <= 2e-6
+    assert close_t.mean() > 0.995
+    for i in np.unique(np.nonzero(~close_t)[0]):
+      fo = np.interp(o[i], t[i].numpy().astype(np.float64), cw[i].numpy().astype(np.float64))
+      fr = np.interp(r[i], t[i].numpy().astype(np.float64), cw[i].numpy().astype(np.float64))
+      assert np.abs(fo - fr).max() < 1e-6, (i, np.abs(fo - fr).max())
     u = u_base.expand(n, ns) if jitter is None else u_base + jitter * mj
     ref_idx = O.sorted_interp_index(u, cw)
     bad = (idx.cpu().long() != ref_idx)
