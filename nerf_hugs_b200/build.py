@@ -19,6 +19,7 @@ SOURCES = [
     ('composite.cu', ['-fmad=false']),
     ('mlp_simt.cu', ['-fmad=false']),
     ('mlp_tc.cu', []),
+    ('wgrad_tc.cu', []),
     ('optim.cu', []),
 ]
 

@@ -385,6 +385,7 @@ int forward_levels(hugs_handle* h, const float* params, const hugs_rays* rays, i
   const float s_near = s_near_of(d, train_frac);
   float prod = 1.f;
   h->cur_params = params;
+  h->cur_embed_idx = rays->embed_idx;
   if ((rc = launch_view_inputs(rays->viewdirs, rays->embed_idx, h->glo_off >= 0 ? params + h->glo_off : nullptr,
                                n, d.deg_view, d.num_glo_features, zero_glo, h->view_in, st)))
     return rc;

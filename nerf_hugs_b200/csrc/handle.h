@@ -51,6 +51,7 @@ struct hugs_handle {
   std::vector<void*> allocs;
   hugs::TcState* tc = nullptr;
   const float* cur_params = nullptr;          // parameters of the call in flight
+  const int32_t* cur_embed_idx = nullptr;
 
   int samples(int level) const { return level < d.num_levels - 1 ? d.num_prop_samples : d.num_nerf_samples; }
 };

@@ -39,7 +39,7 @@ __device__ __forceinline__ uint32_t swz_chunk(uint32_t row, uint32_t chunk) { re
 struct EncArgs {
   const float* origins; const float* directions; const float* radii; const float* tdist;
   const float* basis;     // [3][nb]
-  int n_samples, S, nb, min_deg, ndeg, ray_shape, contract;
+  int n_samples, n_rows_pad, S, nb, min_deg, ndeg, ray_shape, contract;
   __nv_bfloat16* feat;    // [rows, 512] (already offset to the level's first row)
 };
 
@@ -92,10 +92,14 @@ __global__ void __launch_bounds__(2 * kEncRows) encode_bf16_kernel(EncArgs a) {
     if (half) {
       for (int c = a.nb * cpb; c < 64; ++c) tile[rl * 64 + swz_chunk(rl, c)] = make_uint4(0, 0, 0, 0);
     }
+  } else if (s < a.n_rows_pad) {
+    // rows between n_samples and the 128-row tile boundary: finite (zero) features so that the saved
+    // activations of padding rows can never poison the weight-gradient reduction
+    for (int c = half * 32; c < half * 32 + 32; ++c) tile[rl * 64 + swz_chunk(rl, c)] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   // coalesced copy-out of the block's consecutive rows
-  const int rows = min(kEncRows, a.n_samples - blockIdx.x * kEncRows);
+  const int rows = min(kEncRows, a.n_rows_pad - blockIdx.x * kEncRows);
   uint4* dst = reinterpret_cast<uint4*>(a.feat) + (size_t)blockIdx.x * kEncRows * 64;
   for (int e = tid; e < rows * 64; e += 2 * kEncRows) {
     int r = e >> 6, c = e & 63;
@@ -366,7 +370,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             acc_phase ^= 1u << bar;
             ptx::tc_fence_after();
             float dd = 0.f;
-            if (L.epi == EPI_BWD_RELU_D) dd = valid ? p.d_raw[(size_t)s * p.raw_c] : 0.f;
+            if (L.epi == EPI_BWD_RELU_D)
+              dd = valid ? __bfloat162float(__float2bfloat16(p.d_raw[(size_t)s * p.raw_c])) : 0.f;
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
               const int col = g * 128 + j * 64;
@@ -486,7 +491,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
               v[c] = d0 * __ldg(wr + c * 3) + d1 * __ldg(wr + c * 3 + 1) + d2 * __ldg(wr + c * 3 + 2);
             if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
             if (g == 0 && valid) {
-              uint4 q0 = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, 0.f), 0u, 0u);
+              uint4 q0 = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
               uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * 16);
               dst[0] = q0; dst[1] = make_uint4(0u, 0u, 0u, 0u);
             }
@@ -509,6 +514,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             // dZ_last = d_raw_density * w_density gated by the last trunk activation; 256 columns
             const float dd0 = valid ? p.d_raw[s] : 0.f;
             const float dd = __bfloat162float(__float2bfloat16(dd0));
+            if (g == 0 && valid) {
+              uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * 16);
+              dst[0] = make_uint4(0u, ptx::pack_bf16x2(0.f, dd0), 0u, 0u);
+              dst[1] = make_uint4(0u, 0u, 0u, 0u);
+            }
 #pragma unroll 1
             for (int j = 0; j < 2; ++j) {
               const int col = g * 128 + j * 64;
@@ -673,6 +683,31 @@ int build_mlp_schedule(hugs_handle* h, const MlpViews& mv, TcMlp* m, int save_la
     m->view_w_row = layer_w_row[D + 2];
   }
   HUGS_REQUIRE((int)m->fwd.size() <= kMaxLayers, "tensor-core path: too many layers (%zu)", m->fwd.size());
+
+  // ---- backward (dgrad) schedule; save_row / mask_row hold *slot* indices, resolved per call ----
+  // forward slots: j in [0,D) = output of trunk layer j, D = bottleneck output, D+1 = view activation.
+  // dZ slots use the same indexing (gradient w.r.t. the pre-activation of that layer).
+  auto mma_op = [&](int k, int a_res, int w_row, int epi, int save_slot, int mask_slot) {
+    TcLayer L{};
+    L.a_res = a_res; L.a_str = 0; L.a_buf = (k - 1) % 2; L.wait_panels = 1; L.n_halves = 2; L.n_mma = 128;
+    L.acc_col = ((k - 1) % 2) * 256; L.acc_bar = ((k - 1) % 2) * 2; L.w_row = w_row; L.w_map = 0; L.epi = epi;
+    L.dst_buf = k % 2; L.bias_off = 0; L.save_row = save_slot; L.mask_row = mask_slot;
+    return L;
+  };
+  int k = 0;
+  if (mv.has_rgb) {
+    TcLayer S0{};
+    S0.epi = EPI_BWD_START; S0.dst_buf = 0; S0.save_row = D + 1; S0.mask_row = D + 1;
+    m->bwd.push_back(S0); k = 1;
+    m->bwd.push_back(mma_op(k++, 2, layer_b_row[D + 2], EPI_BWD_LINEAR, D, -1));        // through the view layer
+    m->bwd.push_back(mma_op(k++, 4, layer_b_row[D + 1], EPI_BWD_RELU_D, D - 1, D - 1)); // through the bottleneck
+  } else {
+    TcLayer S0{};
+    S0.epi = EPI_BWD_START_PROP; S0.dst_buf = 0; S0.save_row = D - 1; S0.mask_row = D - 1;
+    m->bwd.push_back(S0); k = 1;
+  }
+  for (int l = D - 1; l >= 1; --l) m->bwd.push_back(mma_op(k++, 4, layer_b_row[l], EPI_BWD_RELU, l - 1, l - 1));
+  HUGS_REQUIRE((int)m->bwd.size() <= kMaxLayers, "tensor-core path: too many backward ops (%zu)", m->bwd.size());
   return HUGS_OK;
 }
 
@@ -749,11 +784,11 @@ int tc_create(hugs_handle* h) {
     return rc;
   HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-  return HUGS_OK;
+  return wgrad_create(h);
 }
 
 void tc_destroy(hugs_handle* h) {
-  if (h->tc) { delete h->tc; h->tc = nullptr; }
+  if (h->tc) { wgrad_destroy(h); delete h->tc; h->tc = nullptr; }
 }
 
 int tc_pack_params(hugs_handle* h, const float* params, cudaStream_t st) {
@@ -782,10 +817,10 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
   const int n_samples = n_rays * S;
   const int n_tiles = (n_samples + kTileM - 1) / kTileM;
   // 1. bf16 IPE features (own column order) -> feat[level]
-  EncArgs ea{rays->origins, rays->directions, rays->radii, h->tdist[level], h->basis, n_samples, S, d.num_basis,
+  EncArgs ea{rays->origins, rays->directions, rays->radii, h->tdist[level], h->basis, n_samples, n_tiles * kTileM, S, d.num_basis,
              d.min_deg_point, d.max_deg_point - d.min_deg_point, d.ray_shape,
              is_prop ? d.prop_contract : d.nerf_contract, tc->feat + (size_t)tc->feat_row0[level] * kFeatPad};
-  encode_bf16_kernel<<<(n_samples + kEncRows - 1) / kEncRows, 2 * kEncRows, 0, st>>>(ea);
+  encode_bf16_kernel<<<(n_tiles * kTileM + kEncRows - 1) / kEncRows, 2 * kEncRows, 0, st>>>(ea);
   HUGS_LAUNCH_CHECK();
   // 2. per-ray view bias (direction encoding + GLO folded through the view layer)
   if (!is_prop) {
@@ -824,9 +859,32 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
 }
 
 int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, float* grad, cudaStream_t st) {
-  (void)h; (void)level; (void)rays; (void)n_rays; (void)grad; (void)st;
-  set_error("tensor-core backward is not built yet");
-  return HUGS_ERR_UNSUPPORTED;
+  (void)rays;
+  TcState* tc = h->tc;
+  const hugs_model_desc& d = h->d;
+  const bool is_prop = level < d.num_levels - 1;
+  const TcMlp& m = is_prop ? tc->prop : tc->nerf;
+  const int S = h->samples(level);
+  const int n_samples = n_rays * S;
+  const int n_tiles = (n_samples + kTileM - 1) / kTileM;
+  const int cap = tc->cap[level], srow = tc->save_row0[level];
+  TcParams p;
+  memset(&p, 0, sizeof(p));
+  p.map_w128 = m.map_wn128; p.map_w16 = m.map_wn128; p.map_feat = tc->map_feat; p.map_save = tc->map_dz;
+  p.n_layers = (int)m.bwd.size();
+  for (int i = 0; i < p.n_layers; ++i) {
+    p.layers[i] = m.bwd[i];
+    if (p.layers[i].save_row >= 0) p.layers[i].save_row = srow + p.layers[i].save_row * cap;
+    if (p.layers[i].mask_row >= 0) p.layers[i].mask_row = srow + p.layers[i].mask_row * cap;
+  }
+  p.n_tiles = n_tiles; p.n_samples = n_samples; p.S = S; p.feat_row0 = tc->feat_row0[level];
+  p.bias = m.bias; p.viewbias = tc->viewbias; p.raw_out = nullptr; p.raw_c = is_prop ? 1 : 4;
+  p.d_raw = h->d_raw[level]; p.act = tc->act; p.drgb_out = tc->drgb;
+  p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
+  const int grid = std::min(n_tiles, tc->num_sms);
+  mlp_chain_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
+  HUGS_LAUNCH_CHECK();
+  return wgrad_run(h, level, n_rays, grad, st);
 }
 
 }  // namespace hugs

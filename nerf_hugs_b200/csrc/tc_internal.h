@@ -75,8 +75,11 @@ struct TcMlp {
   std::vector<PackLayer> pack;
 };
 
+struct WgState;
+
 struct TcState {
   TcMlp nerf, prop;
+  WgState* wg = nullptr;
   __nv_bfloat16* feat = nullptr;     // per level region [cap_l, 512]
   __nv_bfloat16* act = nullptr;      // saved forward activations
   __nv_bfloat16* dz = nullptr;       // saved backward dZ
@@ -101,6 +104,7 @@ __host__ __device__ inline int ref_feature_col(int fp, int nb, int ndeg) {
 
 // wgrad_tc.cu
 int wgrad_create(hugs_handle* h);
+void wgrad_destroy(hugs_handle* h);
 int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t st);
 
 }  // namespace hugs
