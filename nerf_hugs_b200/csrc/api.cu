@@ -231,9 +231,10 @@ HUGS_API int hugs_sample_intervals(const float* t, const float* w_logits, const 
                                    const float* jitter, float max_jitter, int32_t n_rays, int32_t n_bins,
                                    int32_t n_samples, float dom_lo, float dom_hi, float* t_out,
                                    int32_t* idx_out, void* stream) {
-  HUGS_REQUIRE(t && w_logits && u_base && t_out, "hugs_sample_intervals: null argument");
   HUGS_REQUIRE(n_samples > 1, "num_samples must be > 1, is %d.", n_samples);   // stepfun.py:240-241
   HUGS_REQUIRE(n_bins >= 1 && n_rays >= 0, "hugs_sample_intervals: bad sizes");
+  if (n_rays == 0) return HUGS_OK;                                             // empty batch: nothing to do
+  HUGS_REQUIRE(t && w_logits && u_base && t_out, "hugs_sample_intervals: null argument");
   ResampleArgs a;
   a.t_in = t; a.w_in = w_logits; a.w_is_logits = 1; a.n_rays = n_rays; a.np = n_bins; a.ns = n_samples;
   a.dom_lo = dom_lo; a.dom_hi = dom_hi; a.u_base = u_base; a.jitter = jitter; a.max_jitter = max_jitter;

@@ -345,6 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             ptx::mma_commit(&sm.acc_full[L.acc_bar + h]);
           }
         }
+        ptx::mma_commit(&sm.acc_full[7]);   // tile_done: every MMA of this tile has completed
       }
     }
   } else {
@@ -356,13 +357,39 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const bool group_leader = (ew & 3) == 0 && lane == 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    int tile_iter = 0;
+    // Write one 64-column chunk of this thread's row into panel `pi`, optionally TMA-store the panel
+    // (training: saved activations / dZ) and publish it to the MMA issuer.
+    auto finish_chunk = [&](const TcLayer& L, int pi, int col, const float (&vals)[64], int tile) {
+      uint8_t* panel = sm.panels + pi * kPanelBytes;
+      store_row_chunk64(panel, row, vals);
+      ptx::fence_proxy_async();
+      if (kTrain && L.save_row >= 0) {
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        if (group_leader) {
+          ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
+          ptx::tma_commit_group();
+        }
+      }
+      ptx::tc_fence_before();
+      if (!L.no_signal) ptx::mbar_arrive(&sm.panel_ready[pi]);
+    };
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_iter) {
       const int s = tile * kTileM + row;   // global sample index
       const bool valid = s < p.n_samples;
       float raw_d = 0.f;
       for (int l = 0; l < p.n_layers; ++l) {
         const TcLayer& L = p.layers[l];
         float v[64];
+        if (!layer_has_mma(L) && tile_iter > 0) {
+          // the start op of a backward tile overwrites panels the previous tile's last MMAs may still read
+          ptx::mbar_wait(&sm.acc_full[7], (uint32_t)((tile_iter - 1) & 1));
+        }
+        if (kTrain && L.save_row >= 0) {
+          // panels written by this layer were TMA-stored two layers ago: that read must have finished
+          if (group_leader) ptx::tma_wait_group_read<1>();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        }
         switch (L.epi) {
           case EPI_RELU: case EPI_LINEAR: case EPI_BWD_LINEAR: case EPI_BWD_RELU: case EPI_BWD_RELU_D: {
             const int bar = L.acc_bar + g;
@@ -405,20 +432,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                   }
                 }
               }
-              const int pi = L.dst_buf * 4 + g * 2 + j;
-              uint8_t* panel = sm.panels + pi * kPanelBytes;
-              store_row_chunk64(panel, row, v);
-              ptx::fence_proxy_async();
-              if (kTrain && L.save_row >= 0) {
-                if (group_leader) ptx::tma_wait_group_read<2>();
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-                if (group_leader) {
-                  ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
-                  ptx::tma_commit_group();
-                }
-              }
-              ptx::tc_fence_before();
-              ptx::mbar_arrive(&sm.panel_ready[pi]);
+              finish_chunk(L, L.dst_buf * 4 + g * 2 + j, col, v, tile);
             }
             break;
           }
@@ -438,20 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                 v[c * 4 + 2] = fmaxf(v[c * 4 + 2] + b.z, 0.f); v[c * 4 + 3] = fmaxf(v[c * 4 + 3] + b.w, 0.f);
               }
             }
-            const int pi = L.dst_buf * 4 + g;
-            uint8_t* panel = sm.panels + pi * kPanelBytes;
-            store_row_chunk64(panel, row, v);
-            ptx::fence_proxy_async();
-            if (kTrain && L.save_row >= 0) {
-              if (group_leader) ptx::tma_wait_group_read<2>();
-              asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-              if (group_leader) {
-                ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
-                ptx::tma_commit_group();
-              }
-            }
-            ptx::tc_fence_before();
-            ptx::mbar_arrive(&sm.panel_ready[pi]);
+            finish_chunk(L, L.dst_buf * 4 + g, col, v, tile);
             break;
           }
           case EPI_DENSITY: case EPI_RGB: {
@@ -495,19 +496,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
               uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * 16);
               dst[0] = q0; dst[1] = make_uint4(0u, 0u, 0u, 0u);
             }
-            const int pi = L.dst_buf * 4 + g;
-            uint8_t* panel = sm.panels + pi * kPanelBytes;
-            store_row_chunk64(panel, row, v);
-            ptx::fence_proxy_async();
-            if (L.save_row >= 0) {
-              if (group_leader) ptx::tma_wait_group_read<2>();
-              asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-              if (group_leader) {
-                ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
-                ptx::tma_commit_group();
-              }
-            }
-            ptx::mbar_arrive(&sm.panel_ready[pi]);
+            finish_chunk(L, L.dst_buf * 4 + g, col, v, tile);
             break;
           }
           case EPI_BWD_START_PROP: {
@@ -526,19 +515,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
 #pragma unroll
               for (int c = 0; c < 64; ++c) v[c] = dd * __ldg(wd + c);
               if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
-              const int pi = L.dst_buf * 4 + g * 2 + j;
-              uint8_t* panel = sm.panels + pi * kPanelBytes;
-              store_row_chunk64(panel, row, v);
-              ptx::fence_proxy_async();
-              if (L.save_row >= 0) {
-                if (group_leader) ptx::tma_wait_group_read<2>();
-                asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-                if (group_leader) {
-                  ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
-                  ptx::tma_commit_group();
-                }
-              }
-              ptx::mbar_arrive(&sm.panel_ready[pi]);
+              finish_chunk(L, L.dst_buf * 4 + g * 2 + j, col, v, tile);
             }
             break;
           }
@@ -707,6 +684,7 @@ int build_mlp_schedule(hugs_handle* h, const MlpViews& mv, TcMlp* m, int save_la
     m->bwd.push_back(S0); k = 1;
   }
   for (int l = D - 1; l >= 1; --l) m->bwd.push_back(mma_op(k++, 4, layer_b_row[l], EPI_BWD_RELU, l - 1, l - 1));
+  m->bwd.back().no_signal = 1;   // dZ of the first layer feeds only the weight-gradient pass
   HUGS_REQUIRE((int)m->bwd.size() <= kMaxLayers, "tensor-core path: too many backward ops (%zu)", m->bwd.size());
   return HUGS_OK;
 }

@@ -42,6 +42,7 @@ struct TcLayer {
   int epi, dst_buf, bias_off;
   int save_row;      // base row in the save tensor (activations fwd / dZ bwd), -1 = do not save
   int mask_row;      // bwd: base row of the saved forward activation whose sign gates this epilogue
+  int no_signal;     // 1: the produced panels feed no later MMA (last backward op): do not arrive on panel_ready
 };
 
 constexpr int kMaxLayers = 14;

@@ -64,15 +64,21 @@ def test_sample_intervals_vs_oracle(eng, nb, ns, anneal):
     ref = O.sample_intervals(jitter, t, logits, ns, single_jitter=True, domain=(0., 1.))
     out, idx = eng.sample_intervals(t, logits, u_base, jitter, mj, ns, (0., 1.), want_idx=True)
     cw = O.integrate_weights(torch.softmax(logits, -1))
-    # Compare in CDF space: a one-ulp change of the CDF moves a sample by ulp/pdf, which is unbounded in
-    # t for near-empty bins but bounded (<= 1e-6) in cumulative mass.  Most samples also agree to 2e-6 in t.
+    # A one-ulp change of the CDF (exp/log differ by ulps between CPU libm and CUDA) moves a sample centre
+    # by ~ulp / pdf of its bin, so the tolerance is per sample: e_j = 1e-6 * bin_width / bin_mass, capped at
+    # the bin width; interval fenceposts are averages / reflections of adjacent centres.
     o, r = out.cpu().numpy().astype(np.float64), ref.numpy().astype(np.float64)
-    close_t = np.abs(o - r) <= 2e-6
-    assert close_t.mean() > 0.995
-    for i in np.unique(np.nonzero(~close_t)[0]):
-      fo = np.interp(o[i], t[i].numpy().astype(np.float64), cw[i].numpy().astype(np.float64))
-      fr = np.interp(r[i], t[i].numpy().astype(np.float64), cw[i].numpy().astype(np.float64))
-      assert np.abs(fo - fr).max() < 1e-6, (i, np.abs(fo - fr).max())
+    ii = idx.cpu().long()
+    dt = torch.gather(t[:, 1:] - t[:, :-1], 1, ii).numpy().astype(np.float64)
+    dm = torch.gather(cw[:, 1:] - cw[:, :-1], 1, ii).numpy().astype(np.float64)
+    e = np.minimum(dt, 1e-6 * dt / np.maximum(dm, 1e-30))
+    tol = np.empty_like(o)
+    tol[:, 1:-1] = 0.5 * (e[:, 1:] + e[:, :-1])
+    tol[:, 0] = 1.5 * e[:, 0] + 0.5 * e[:, 1]
+    tol[:, -1] = 1.5 * e[:, -1] + 0.5 * e[:, -2]
+    err = np.abs(o - r)
+    assert (err <= tol + 1e-6).all(), float((err - tol).max())
+    assert (err <= 2e-6).mean() > 0.99
     u = u_base.expand(n, ns) if jitter is None else u_base + jitter * mj
     ref_idx = O.sorted_interp_index(u, cw)
     bad = (idx.cpu().long() != ref_idx)
