@@ -102,6 +102,8 @@ typedef struct {
   float beta1, beta2, eps;         /* optax.adam (train_utils.py:489-510) */
   float grad_max_norm, grad_max_val; /* clip_gradients (train_utils.py:351-369) */
   int32_t step;                    /* optax count before this update (0-based) */
+  float grad_scale;                /* gradient pre-multiplier: 1/world_size after an all-reduce(SUM) == pmean
+                                      (train_utils.py:457-458); use 1 on a single GPU */
 } hugs_adam_cfg;
 
 /* One named view into the flat fp32 parameter buffer (flax names, e.g. "NerfMLP_0/Dense_3/kernel"). */
@@ -187,6 +189,22 @@ int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* ray
  * (already all-reduced) flat gradient.  norms_out (optional) fp32[9]: {grad norm, abs-max, clip multiplier} per module. */
 int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
                    const hugs_adam_cfg* cfg, float* norms_out, void* stream);
+
+/* ---- measurement hooks (bench.py): no reference counterpart beyond train.py:162-168 wall-clock ---- */
+
+/* Number of kernels this library has launched in this process (every launch site counts itself). */
+int64_t hugs_launch_count(void);
+
+typedef enum {
+  HUGS_K_SAMPLE = 0, HUGS_K_ENCODE = 1, HUGS_K_CHAIN_FWD_PROP = 2, HUGS_K_CHAIN_FWD_NERF = 3,
+  HUGS_K_COMPOSITE_LOSS = 4, HUGS_K_CHAIN_BWD_NERF = 5, HUGS_K_CHAIN_BWD_PROP = 6, HUGS_K_WGRAD_NERF = 7,
+  HUGS_K_WGRAD_PROP = 8, HUGS_K_REDUCTIONS = 9, HUGS_K_ADAM_PACK = 10, HUGS_K_MLP_FP32 = 11, HUGS_K_COUNT = 12
+} hugs_kernel_class;
+/* Enable/disable CUDA-event timing of kernel classes on the launching stream. */
+int hugs_profile_enable(hugs_handle* h, int32_t enable);
+/* Synchronises, then returns accumulated milliseconds and launch-group counts per class (arrays of
+ * HUGS_K_COUNT) since the last read, and resets them. */
+int hugs_profile_read(hugs_handle* h, float* ms_out, int32_t* count_out);
 
 #ifdef __cplusplus
 }

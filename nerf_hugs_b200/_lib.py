@@ -47,7 +47,7 @@ class LossCfg(C.Structure):
 
 class AdamCfg(C.Structure):
   _fields_ = [('lr', C.c_float), ('beta1', C.c_float), ('beta2', C.c_float), ('eps', C.c_float),
-              ('grad_max_norm', C.c_float), ('grad_max_val', C.c_float), ('step', C.c_int32)]
+              ('grad_max_norm', C.c_float), ('grad_max_val', C.c_float), ('step', C.c_int32), ('grad_scale', C.c_float)]
 
 
 class TensorDesc(C.Structure):
@@ -78,6 +78,9 @@ SYMBOLS = {
     'hugs_forward': (C.c_int, [_P, _P, C.POINTER(Rays), _I, _F, _P, _I, _I, C.POINTER(LevelOut), _P]),
     'hugs_loss_and_grad': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _F, _P, C.POINTER(LossCfg), _P, _P, _P]),
     'hugs_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P]),
+    'hugs_launch_count': (C.c_int64, []),
+    'hugs_profile_enable': (C.c_int, [_P, _I]),
+    'hugs_profile_read': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),
 }
 
 if not os.path.exists(LIB_PATH):
@@ -90,6 +93,10 @@ for _name, (_res, _args) in SYMBOLS.items():
   _fn = getattr(lib, _name)
   _fn.restype = _res
   _fn.argtypes = _args
+
+
+KERNEL_CLASSES = ('sample', 'encode', 'chain_fwd_prop', 'chain_fwd_nerf', 'composite_loss', 'chain_bwd_nerf',
+                  'chain_bwd_prop', 'wgrad_nerf', 'wgrad_prop', 'reductions', 'adam_pack', 'mlp_fp32')
 
 
 def check(rc):

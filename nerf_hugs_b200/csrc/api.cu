@@ -12,6 +12,7 @@
 namespace hugs {
 
 static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -124,6 +125,28 @@ using namespace hugs;
 
 HUGS_API const char* hugs_last_error(void) { return g_err; }
 HUGS_API int hugs_abi_version(void) { return HUGS_ABI_VERSION; }
+HUGS_API int64_t hugs_launch_count(void) { return g_launch_count; }
+
+HUGS_API int hugs_profile_enable(hugs_handle* h, int32_t enable) {
+  HUGS_REQUIRE(h, "hugs_profile_enable: null handle");
+  h->prof_on = enable != 0;
+  return HUGS_OK;
+}
+
+HUGS_API int hugs_profile_read(hugs_handle* h, float* ms_out, int32_t* count_out) {
+  HUGS_REQUIRE(h && ms_out && count_out, "hugs_profile_read: null argument");
+  HUGS_CUDA(cudaDeviceSynchronize());
+  for (int i = 0; i < HUGS_K_COUNT; ++i) { ms_out[i] = 0.f; count_out[i] = 0; }
+  for (auto& r : h->prof_recs) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess && r.cls >= 0 && r.cls < HUGS_K_COUNT) {
+      ms_out[r.cls] += ms; count_out[r.cls] += 1;
+    }
+    h->prof_pool.push_back(r.a); h->prof_pool.push_back(r.b);
+  }
+  h->prof_recs.clear();
+  return HUGS_OK;
+}
 
 HUGS_API int hugs_create(const hugs_model_desc* desc, hugs_handle** out) {
   HUGS_REQUIRE(desc && out, "hugs_create: null argument");
@@ -312,6 +335,7 @@ int run_level_sampling(hugs_handle* h, int l, const hugs_rays* rays, int n, floa
   else        { a.u_base = h->u_det[l]; }
   a.s_out = h->sdist[l]; a.t_out = h->tdist[l];
   a.raydist_fn = d.raydist_fn; a.near = rays->near; a.far = rays->far;
+  ProfScope ps(h, HUGS_K_SAMPLE, st);
   return launch_resample(a, st);
 }
 
@@ -322,6 +346,7 @@ int run_level_mlp_fp32(hugs_handle* h, int l, const float* params, const hugs_ra
   const MlpViews& m = is_prop ? h->prop : h->nerf;
   const int S = h->samples(l);
   const int M = n * S;
+  ProfScope ps(h, HUGS_K_MLP_FP32, st);
   IpeArgs ia{rays->origins, rays->directions, rays->radii, h->tdist[l], h->basis, n, S, d.num_basis,
              d.min_deg_point, d.max_deg_point, d.ray_shape, is_prop ? d.prop_contract : d.nerf_contract, h->feat};
   int rc = launch_ipe_features(ia, st);
@@ -409,7 +434,10 @@ int forward_levels(hugs_handle* h, const float* params, const hugs_rays* rays, i
     if (out) a.out = out[l];
     float* user_w = a.out.weights;
     a.out.weights = h->weights[l];
-    if ((rc = launch_composite(a, st))) return rc;
+    {
+      ProfScope ps(h, HUGS_K_COMPOSITE_LOSS, st);
+      if ((rc = launch_composite(a, st))) return rc;
+    }
     if (out) {
       if (user_w) HUGS_CUDA(cudaMemcpyAsync(user_w, h->weights[l], sizeof(float) * n * S, cudaMemcpyDeviceToDevice, st));
       if (out[l].sdist) HUGS_CUDA(cudaMemcpyAsync(out[l].sdist, h->sdist[l], sizeof(float) * n * (S + 1), cudaMemcpyDeviceToDevice, st));
@@ -454,6 +482,8 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
 
   float* denom = h->scalars;          // [0] loss normaliser
   float* sums = h->scalars + 8;       // [8..] column sums of ray_stats
+  ProfScope* ps_loss = new ProfScope(h, HUGS_K_COMPOSITE_LOSS, st);
+  struct Guard { ProfScope** p; ~Guard() { delete *p; *p = nullptr; } } guard{&ps_loss};
   if ((rc = launch_lossmult_sum(rays->lossmult, rays->static_mask, loss->use_static_mask,
                                 loss->withmask_transient_weight, loss->disable_multiscale_loss, n, denom, st)))
     return rc;
@@ -481,6 +511,7 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
   for (int l = 0; l < L - 1; ++l)
     if ((rc = launch_column_sums(h->ray_stats + (size_t)n * (4 + l), n, 1, 1, sums + 4 + l, st))) return rc;
   if ((rc = launch_finalize_stats(h, *loss, n, denom, sums, stats_out, st))) return rc;
+  delete ps_loss; ps_loss = nullptr;
 
   HUGS_CUDA(cudaMemsetAsync(grad_out, 0, sizeof(float) * h->n_params, st));
   for (int l = L - 1; l >= 0; --l)

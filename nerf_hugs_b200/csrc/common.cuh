@@ -19,6 +19,7 @@ constexpr float kF32EpsSq = kF32Eps * kF32Eps;
 constexpr unsigned kFull = 0xffffffffu;
 
 void set_error(const char* fmt, ...);
+
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 
 #define HUGS_CUDA(expr)                                                        \
@@ -32,7 +33,12 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     if (!(cond)) { ::hugs::set_error(__VA_ARGS__); return HUGS_ERR_INVALID; }  \
   } while (0)
 
-#define HUGS_LAUNCH_CHECK() HUGS_CUDA(cudaGetLastError())
+extern long long g_launch_count;
+#define HUGS_LAUNCH_CHECK()                 \
+  do {                                      \
+    ++::hugs::g_launch_count;               \
+    HUGS_CUDA(cudaGetLastError());          \
+  } while (0)
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

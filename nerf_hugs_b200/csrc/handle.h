@@ -50,8 +50,31 @@ struct hugs_handle {
   float* scalars = nullptr;                   // [64] device scalars (denominators, norms, ...)
   std::vector<void*> allocs;
   hugs::TcState* tc = nullptr;
+  // ---- optional CUDA-event profiling of kernel classes (hugs_profile_enable / hugs_profile_read) ----
+  bool prof_on = false;
+  struct ProfRec { int cls; cudaEvent_t a, b; };
+  std::vector<ProfRec> prof_recs;
+  std::vector<cudaEvent_t> prof_pool;
+  cudaEvent_t prof_event() {
+    if (!prof_pool.empty()) { cudaEvent_t e = prof_pool.back(); prof_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+
   const float* cur_params = nullptr;          // parameters of the call in flight
   const int32_t* cur_embed_idx = nullptr;
 
   int samples(int level) const { return level < d.num_levels - 1 ? d.num_prop_samples : d.num_nerf_samples; }
 };
+
+namespace hugs {
+// Brackets the kernels launched in its scope with two events on `st` when profiling is enabled.
+struct ProfScope {
+  hugs_handle* h; cudaStream_t st; int cls; cudaEvent_t a{}, b{};
+  ProfScope(hugs_handle* h_, int cls_, cudaStream_t st_) : h(h_), st(st_), cls(cls_) {
+    if (h->prof_on) { a = h->prof_event(); b = h->prof_event(); cudaEventRecord(a, st); }
+  }
+  ~ProfScope() {
+    if (h->prof_on) { cudaEventRecord(b, st); h->prof_recs.push_back({cls, a, b}); }
+  }
+};
+}  // namespace hugs

@@ -798,8 +798,11 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
   EncArgs ea{rays->origins, rays->directions, rays->radii, h->tdist[level], h->basis, n_samples, n_tiles * kTileM, S, d.num_basis,
              d.min_deg_point, d.max_deg_point - d.min_deg_point, d.ray_shape,
              is_prop ? d.prop_contract : d.nerf_contract, tc->feat + (size_t)tc->feat_row0[level] * kFeatPad};
-  encode_bf16_kernel<<<(n_tiles * kTileM + kEncRows - 1) / kEncRows, 2 * kEncRows, 0, st>>>(ea);
-  HUGS_LAUNCH_CHECK();
+  {
+    ProfScope ps(h, HUGS_K_ENCODE, st);
+    encode_bf16_kernel<<<(n_tiles * kTileM + kEncRows - 1) / kEncRows, 2 * kEncRows, 0, st>>>(ea);
+    HUGS_LAUNCH_CHECK();
+  }
   // 2. per-ray view bias (direction encoding + GLO folded through the view layer)
   if (!is_prop) {
     const DenseView& vv = mv.dense[mv.depth + 2];
@@ -830,6 +833,7 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
   p.bias = m.bias; p.viewbias = tc->viewbias; p.raw_out = h->raw[level]; p.raw_c = is_prop ? 1 : 4;
   p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
   const int grid = std::min(n_tiles, tc->num_sms);
+  ProfScope ps(h, is_prop ? HUGS_K_CHAIN_FWD_PROP : HUGS_K_CHAIN_FWD_NERF, st);
   if (training) mlp_chain_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
   else mlp_chain_kernel<false><<<grid, kThreads, kSmemBytes, st>>>(p);
   HUGS_LAUNCH_CHECK();
@@ -860,8 +864,11 @@ int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays
   p.d_raw = h->d_raw[level]; p.act = tc->act; p.drgb_out = tc->drgb;
   p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
   const int grid = std::min(n_tiles, tc->num_sms);
-  mlp_chain_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
-  HUGS_LAUNCH_CHECK();
+  {
+    ProfScope ps(h, is_prop ? HUGS_K_CHAIN_BWD_PROP : HUGS_K_CHAIN_BWD_NERF, st);
+    mlp_chain_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
+    HUGS_LAUNCH_CHECK();
+  }
   return wgrad_run(h, level, n_rays, grad, st);
 }
 

@@ -20,13 +20,13 @@ __device__ __forceinline__ float clipv(float g, float max_val) {
 // partial[m][b] = {sum g^2 (raw), max |g| (raw), sum clip(g)^2}
 __global__ void __launch_bounds__(256) grad_norm_partial_kernel(const float* grad, int64_t b0, int64_t e0, int64_t b1,
                                                                 int64_t e1, int64_t b2, int64_t e2, float max_val,
-                                                                float* partial) {
+                                                                float gscale, float* partial) {
   __shared__ float red[3][8];
   const int m = blockIdx.y;
   const int64_t beg = m == 0 ? b0 : (m == 1 ? b1 : b2), end = m == 0 ? e0 : (m == 1 ? e1 : e2);
   float s = 0.f, mx = 0.f, sc = 0.f;
   for (int64_t i = beg + (int64_t)blockIdx.x * 256 + threadIdx.x; i < end; i += (int64_t)kRedBlocks * 256) {
-    float g = grad[i];
+    float g = grad[i] * gscale;
     s += g * g;
     mx = fmaxf(mx, fabsf(g));
     float c = clipv(g, max_val);
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(256) adam_kernel(float* params, const float* g
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (i >= n) return;
   const int m = i < e0 ? 0 : (i < e1 ? 1 : 2);
-  float g = clipv(grad[i], cfg.grad_max_val) * norms[m * 3 + 2];
+  float g = clipv(grad[i] * cfg.grad_scale, cfg.grad_max_val) * norms[m * 3 + 2];
   if (g != g) g = 0.f;                                  // jnp.nan_to_num
   else if (isinf(g)) g = g > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
   float m1 = cfg.beta1 * mu[i] + (1.f - cfg.beta1) * g;
@@ -107,13 +107,15 @@ HUGS_API int hugs_adam_step(hugs_handle* h, float* params, const float* grad, fl
                             const hugs_adam_cfg* cfg, float* norms_out, void* stream) {
   HUGS_REQUIRE(h && params && grad && mu && nu && cfg, "hugs_adam_step: null argument");
   HUGS_REQUIRE(cfg->step >= 0, "hugs_adam_step: step must be >= 0");
+  HUGS_REQUIRE(cfg->grad_scale > 0.f, "hugs_adam_step: grad_scale must be > 0 (1 on a single GPU)");
   cudaStream_t st = (cudaStream_t)stream;
+  ProfScope ps(h, HUGS_K_ADAM_PACK, st);
   float* partial = h->scalars + 64;   // see hugs_create: scalars has room for 64 + 3*kRedBlocks*3
   float* norms = h->scalars + 32;
   dim3 grid(kRedBlocks, 3);
   grad_norm_partial_kernel<<<grid, 256, 0, st>>>(grad, h->module_begin[0], h->module_end[0], h->module_begin[1],
                                                  h->module_end[1], h->module_begin[2], h->module_end[2],
-                                                 cfg->grad_max_val, partial);
+                                                 cfg->grad_max_val, cfg->grad_scale, partial);
   HUGS_LAUNCH_CHECK();
   grad_norm_final_kernel<<<1, 32, 0, st>>>(partial, cfg->grad_max_norm, norms);
   HUGS_LAUNCH_CHECK();

@@ -367,8 +367,12 @@ int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t s
   p.map_act64 = w->map_act64; p.map_feat64 = w->map_feat64; p.map_dz64 = w->map_dz64;
   p.items = w->dev[level]; p.n_items = (int)w->host[level].size();
   p.nb = d.num_basis; p.ndeg = d.max_deg_point - d.min_deg_point; p.feat_dim = h->feat_dim; p.grad = grad;
-  wgrad_kernel<<<std::min(p.n_items, tc->num_sms), kWgThreads, kWgSmem, st>>>(p);
-  HUGS_LAUNCH_CHECK();
+  {
+    ProfScope ps(h, is_prop ? HUGS_K_WGRAD_PROP : HUGS_K_WGRAD_NERF, st);
+    wgrad_kernel<<<std::min(p.n_items, tc->num_sms), kWgThreads, kWgSmem, st>>>(p);
+    HUGS_LAUNCH_CHECK();
+  }
+  ProfScope ps_red(h, HUGS_K_REDUCTIONS, st);
 
   // biases: column sums of the saved dZ slots
   ColsumArgs ca;

@@ -224,6 +224,20 @@ class Engine:
       check(lib.hugs_adam_step(self._h, _ptr(params), _ptr(grad), _ptr(mu), _ptr(nu), C.byref(adam_cfg),
                                _ptr(norms_out), self._stream()))
 
+  # ---- measurement hooks ----------------------------------------------------------------------
+  def profile(self, enable: bool):
+    check(lib.hugs_profile_enable(self._h, int(enable)))
+
+  def profile_read(self):
+    ms = (C.c_float * len(_lib.KERNEL_CLASSES))()
+    cnt = (C.c_int32 * len(_lib.KERNEL_CLASSES))()
+    check(lib.hugs_profile_read(self._h, ms, cnt))
+    return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(_lib.KERNEL_CLASSES)}
+
+  @staticmethod
+  def launch_count() -> int:
+    return int(lib.hugs_launch_count())
+
   # ---- operator-level calls (parity tests) ---------------------------------------------------
   def sample_intervals(self, t, w_logits, u_base, jitter, max_jitter, n_samples, domain, want_idx=False):
     dev = self.device

@@ -1,0 +1,185 @@
+"""train_utils.setup_model and the train / render step functions with the reference signatures
+(MipNeRF360/internal/train_utils.py:372-596), one process per GPU.
+
+The reference pmaps one program over the local devices and pmean's the gradient
+(train_utils.py:457-459, 479-483).  Here every rank runs this module on its own GPU, the flat fp32
+gradient is all-reduced with torch.distributed (NCCL over NVLink) and every rank applies the same
+clip + Adam update (`hugs_adam_step`), so parameters stay replicated exactly like under pmap.
+"""
+import dataclasses
+import math as _pymath
+from typing import Any, Callable, Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import _lib
+from . import math as hmath
+from . import models
+from . import utils
+
+
+@dataclasses.dataclass
+class TrainState:
+  """flax TrainState analogue: optimiser step, flat fp32 parameters and Adam moments (device tensors)."""
+  step: int
+  params: torch.Tensor
+  mu: torch.Tensor
+  nu: torch.Tensor
+
+  def tree(self, model):
+    """Parameters as the flax-named pytree {'params': {'NerfMLP_0': {'Dense_0': {'kernel','bias'}}, ...}}."""
+    return {'params': model.engine.unflatten_params(self.params)}
+
+
+def _world():
+  return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
+
+
+def loss_cfg_from(config, is_finetune: bool = False) -> '_lib.LossCfg':
+  c = _lib.LossCfg()
+  c.data_loss_type = {'charb': 0, 'mse': 1}[config.data_loss_type]
+  c.charb_padding, c.data_loss_mult = config.charb_padding, config.data_loss_mult
+  c.data_coarse_loss_mult = config.data_coarse_loss_mult
+  c.interlevel_loss_mult = 0.0 if is_finetune else config.interlevel_loss_mult
+  c.distortion_loss_mult = 0.0 if is_finetune else config.distortion_loss_mult
+  c.use_static_mask = int(config.transient_type == 'withmask' and not is_finetune)   # train_utils.py:422-425
+  c.withmask_transient_weight = float(config.withmask_transient_weight)
+  c.disable_multiscale_loss = int(config.disable_multiscale_loss)
+  return c
+
+
+def create_optimizer(config, variables, model):
+  """train_utils.create_optimizer (train_utils.py:487-512): Adam state + the lr schedule."""
+  flat = model.flat_params(variables)
+  lr_fn = lambda step: hmath.learning_rate_decay(step, config.lr_init, config.lr_final, config.max_steps,
+                                                config.lr_delay_steps, config.lr_delay_mult)
+  return TrainState(step=0, params=flat, mu=torch.zeros_like(flat), nu=torch.zeros_like(flat)), lr_fn
+
+
+def _to_device(x, device):
+  if x is None:
+    return None
+  if not torch.is_tensor(x):
+    x = torch.as_tensor(x)
+  return x.to(device, non_blocking=True)
+
+
+def create_train_step(model: models.Model, config, is_finetune: bool = False):
+  """train_utils.create_train_step (train_utils.py:372-484).
+
+  train_pstep(rng, state, batch, train_frac, inlier_thresholds) -> (state, stats, rng)
+    rng:   torch.Generator on the model's device (or None when config.randomized is False)
+    batch: utils.Batch of this rank's rays (host or device tensors; host tensors are copied here)
+  `state` is updated in place and returned (the reference donates it, train_utils.py:483).
+  """
+  eng = model.engine
+  lcfg = loss_cfg_from(config, is_finetune)
+  lr_fn = lambda step: hmath.learning_rate_decay(step, config.lr_init, config.lr_final, config.max_steps,
+                                                config.lr_delay_steps, config.lr_delay_mult)
+  dev = eng.device
+  grad = torch.empty(eng.n_params, device=dev)
+  stats_dev = torch.empty(16, device=dev)
+  norms_dev = torch.empty(9, device=dev)
+  L = model.num_levels
+
+  def train_step(rng, state: TrainState, batch: utils.Batch, train_frac, inlier_thresholds=None):
+    del inlier_thresholds   # RobustNeRF only (out of scope)
+    rank, world = _world()
+    rays = {k: _to_device(v, dev) for k, v in batch.rays.as_dict().items()}
+    rgb = _to_device(batch.rgb, dev)
+    n = rays['origins'].reshape(-1, 3).shape[0]
+    jitter = None
+    if config.randomized and rng is not None:
+      jitter = torch.rand(L, n, generator=rng, device=dev)
+    model._ensure_packed(state.params)
+    eng.loss_and_grad(state.params, rays, rgb[..., :3], float(train_frac), jitter, lcfg, grad, stats_dev)
+    if world > 1:                                   # pmean(grad), pmean(stats)  (train_utils.py:457-459)
+      dist.all_reduce(grad, op=dist.ReduceOp.SUM)
+      dist.all_reduce(stats_dev, op=dist.ReduceOp.SUM)
+    a = _lib.AdamCfg()
+    a.lr = float(lr_fn(state.step))
+    a.beta1, a.beta2, a.eps = config.adam_beta1, config.adam_beta2, config.adam_eps
+    a.grad_max_norm, a.grad_max_val = config.grad_max_norm, config.grad_max_val
+    a.step, a.grad_scale = int(state.step), 1.0 / world
+    eng.adam_step(state.params, grad, state.mu, state.nu, a, norms_dev)
+    model._packed_version = (state.params.data_ptr(), state.params._version)   # adam_step re-packs bf16 operands
+    state.step += 1
+    stats = _LazyStats(stats_dev, norms_dev, L, world, a.lr)
+    return state, stats, rng
+
+  return train_step
+
+
+class _LazyStats(dict):
+  """stats pytree of train_step (train_utils.py:442-476); device values are fetched on first access so
+  that the training loop does not synchronise every step (the reference reads them every print_every)."""
+
+  def __init__(self, stats_dev, norms_dev, L, world, lr):
+    super().__init__()
+    self._s, self._n, self._L, self._world, self._lr, self._done = stats_dev, norms_dev, L, world, lr, False
+
+  def _fetch(self):
+    if self._done:
+      return
+    s = (self._s / self._world).cpu().numpy()
+    n = self._n.cpu().numpy()
+    mses = s[4:4 + self._L]
+    psnrs = [-10.0 * _pymath.log10(max(float(m), 1e-30)) for m in mses]
+    dict.update(self, {
+        'loss': float(s[0]),
+        'losses': {'data': float(s[1]), 'interlevel': float(s[2]), 'distortion': float(s[3])},
+        'mses': mses, 'psnrs': psnrs, 'psnr': psnrs[-1], 'lr': self._lr,
+        'grad_norms': {'NerfMLP_0': float(n[0]), 'PropMLP_0': float(n[3]), 'GloEmbed_0': float(n[6])},
+        'grad_maxes': {'NerfMLP_0': float(n[1]), 'PropMLP_0': float(n[4]), 'GloEmbed_0': float(n[7])},
+    })
+    self._done = True
+
+  def __getitem__(self, k):
+    self._fetch()
+    return dict.__getitem__(self, k)
+
+  def keys(self):
+    self._fetch()
+    return dict.keys(self)
+
+  def items(self):
+    self._fetch()
+    return dict.items(self)
+
+
+def create_render_fn(model: models.Model, config):
+  """train_utils.create_render_fn (train_utils.py:555-575).
+
+  render_eval_pfn(variables, train_frac, _, rays) with rays sharded [world, n/world, C]; this rank renders
+  its shard and the shards are all-gathered so the result carries the reference's leading gathered axis.
+  """
+  def render_eval_fn(variables, train_frac, _, rays: utils.Rays):
+    rank, world = _world()
+    mine = rays.map(lambda r: r[rank] if r.shape[0] == world else r[0])
+    res, hist = model.apply(variables, None, mine, train_frac, True, zero_glo=config.enable_render_zero_glo)
+    out = []
+    for r in res:
+      d = {}
+      for k, v in r.items():
+        if world > 1:
+          parts = [torch.empty_like(v) for _ in range(world)]
+          dist.all_gather(parts, v.contiguous())
+          full = torch.stack(parts)
+        else:
+          full = v[None]
+        d[k] = full[None]            # [1(gather axis taken as v[0]), world, n/world, ...]
+      out.append(d)
+    return out, hist
+
+  return render_eval_fn
+
+
+def setup_model(config, rng, max_rays: Optional[int] = None, device=None):
+  """train_utils.setup_model (train_utils.py:579-596):
+  returns (model, state, render_eval_pfn, train_pstep, lr_fn)."""
+  model, variables = models.construct_model(rng, utils.dummy_rays(), config, max_rays=max_rays, device=device)
+  state, lr_fn = create_optimizer(config, variables, model)
+  render_eval_pfn = create_render_fn(model, config)
+  train_pstep = create_train_step(model, config, False)
+  return model, state, render_eval_pfn, train_pstep, lr_fn

@@ -21,7 +21,7 @@ jit = torch.rand(2, n, device=dev)
 mu, nu = torch.zeros_like(flat), torch.zeros_like(flat)
 lc = _loss_cfg(lcfg)
 grad = torch.empty_like(flat); stats = torch.empty(16, device=dev)
-a = _lib.AdamCfg(); a.lr, a.beta1, a.beta2, a.eps, a.grad_max_norm, a.grad_max_val, a.step = 2e-3, .9, .999, 1e-6, 1e-3, 0., 0
+a = _lib.AdamCfg(); a.lr, a.beta1, a.beta2, a.eps, a.grad_max_norm, a.grad_max_val, a.step, a.grad_scale = 2e-3, .9, .999, 1e-6, 1e-3, 0., 0, 1.0
 
 def timeit(fn, it=10, warm=3):
   for _ in range(warm): fn()

@@ -32,7 +32,7 @@ def test_struct_sizes_match_header():
   assert ctypes.sizeof(_lib.LevelOut) == 80
   assert ctypes.sizeof(_lib.Rays) == 72
   assert ctypes.sizeof(_lib.LossCfg) == 36
-  assert ctypes.sizeof(_lib.AdamCfg) == 28
+  assert ctypes.sizeof(_lib.AdamCfg) == 32
 
 
 def test_create_validates_and_fails_loudly_without_gpu():

@@ -104,7 +104,7 @@ def test_adam_step_vs_oracle():
       gflat[7] = float('nan')          # nan_to_num path (train_utils.py:466)
     a = _lib.AdamCfg()
     a.lr, a.beta1, a.beta2, a.eps = stats['lr'], lcfg.adam_beta1, lcfg.adam_beta2, lcfg.adam_eps
-    a.grad_max_norm, a.grad_max_val, a.step = lcfg.grad_max_norm, lcfg.grad_max_val, step
+    a.grad_max_norm, a.grad_max_val, a.step, a.grad_scale = lcfg.grad_max_norm, lcfg.grad_max_val, step, 1.0
     norms = torch.zeros(9, device=flat.device)
     eng.adam_step(flat, gflat, mu, nu, a, norms)
     torch.cuda.synchronize()
@@ -143,7 +143,7 @@ def test_training_reduces_loss():
     grad, st = eng.loss_and_grad(flat, rays, gt, 0.5, jt, lc)
     a = _lib.AdamCfg()
     a.lr, a.beta1, a.beta2, a.eps = 2e-3, 0.9, 0.999, 1e-6
-    a.grad_max_norm, a.grad_max_val, a.step = 0.0, 0.0, step
+    a.grad_max_norm, a.grad_max_val, a.step, a.grad_scale = 0.0, 0.0, step, 1.0
     eng.adam_step(flat, grad, mu, nu, a)
     losses.append(float(st[0]))
   assert all(np.isfinite(losses)), losses
