@@ -77,12 +77,12 @@ class ClockSampler(threading.Thread):
 
   def __init__(self, index):
     super().__init__(daemon=True)
-    self.index, self.rows, self._stop = index, [], threading.Event()
+    self.index, self.rows, self._halt = index, [], threading.Event()
 
   def run(self):
     q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
          'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
-    while not self._stop.is_set():
+    while not self._halt.is_set():
       try:
         out = subprocess.run(['nvidia-smi', f'--query-gpu={q}', '--format=csv,noheader,nounits', '-i', str(self.index)],
                              capture_output=True, text=True, timeout=5).stdout.strip()
@@ -90,10 +90,10 @@ class ClockSampler(threading.Thread):
           self.rows.append([c.strip() for c in out.split(',')])
       except Exception:
         pass
-      self._stop.wait(0.2)
+      self._halt.wait(0.2)
 
   def stop(self):
-    self._stop.set()
+    self._halt.set()
     self.join(timeout=5)
     sm = [float(r[0]) for r in self.rows if r and r[0].replace('.', '').isdigit()]
     mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace('.', '').isdigit()]

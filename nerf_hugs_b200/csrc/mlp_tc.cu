@@ -195,6 +195,7 @@ struct Smem {
   uint64_t* panel_ready;    // [kNumPanels]
   uint64_t* acc_full;       // [8]
   uint32_t* tmem_ptr;
+  float* bias;              // [kBiasTab]
 };
 
 __device__ __forceinline__ Smem carve(uint8_t* raw) {
@@ -202,7 +203,8 @@ __device__ __forceinline__ Smem carve(uint8_t* raw) {
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   s.panels = base;
   s.ring = base + kNumPanels * kPanelBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s.ring + kStages * kPanelBytes);
+  s.bias = reinterpret_cast<float*>(s.ring + kStages * kPanelBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.bias + kBiasTab);
   s.full = bars; s.empty = bars + kStages; s.panel_ready = bars + 2 * kStages;
   s.acc_full = s.panel_ready + kNumPanels;
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.acc_full + 8);
@@ -213,39 +215,40 @@ __device__ __forceinline__ bool layer_has_mma(const TcLayer& L) {
   return L.epi != EPI_BWD_START && L.epi != EPI_BWD_START_PROP;
 }
 
-// write 64 fp32 values of one row as bf16 into a swizzled panel row (8 x 16-byte chunks)
-__device__ __forceinline__ void store_row_chunk64(uint8_t* panel, int row, const float (&v)[64]) {
+// One 32-column half of a chunk: TMEM -> registers (fp32).
+__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  ptx::tmem_ld32(taddr, r);
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 values of one row -> bf16 -> four 16-byte chunks (chunk0 .. chunk0+3) of a swizzled panel row.
+template <bool kRelu>
+__device__ __forceinline__ void store_half32(uint8_t* panel, int row, int chunk0, const float (&v)[32]) {
   uint4* prow = reinterpret_cast<uint4*>(panel + row * 128);
 #pragma unroll
-  for (int c = 0; c < 8; ++c) {
+  for (int c = 0; c < 4; ++c) {
     uint4 q;
-    q.x = ptx::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]);
-    q.y = ptx::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
-    q.z = ptx::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]);
-    q.w = ptx::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-    prow[swz_chunk(row, c)] = q;
+    if (kRelu) {
+      q.x = ptx::pack_bf16x2_relu(v[c * 8 + 0], v[c * 8 + 1]); q.y = ptx::pack_bf16x2_relu(v[c * 8 + 2], v[c * 8 + 3]);
+      q.z = ptx::pack_bf16x2_relu(v[c * 8 + 4], v[c * 8 + 5]); q.w = ptx::pack_bf16x2_relu(v[c * 8 + 6], v[c * 8 + 7]);
+    } else {
+      q.x = ptx::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); q.y = ptx::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
+      q.z = ptx::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); q.w = ptx::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
+    }
+    prow[swz_chunk(row, chunk0 + c)] = q;
   }
 }
 
-__device__ __forceinline__ void load_acc64(uint32_t taddr, float (&v)[64]) {
-  uint32_t r0[32], r1[32];
-  ptx::tmem_ld32(taddr, r0);
-  ptx::tmem_ld32(taddr + 32, r1);
-  ptx::tmem_ld_wait();
+// ReLU gate from four 16-byte words of the saved (post-ReLU, hence >= 0) bf16 activation row.
+__device__ __forceinline__ void apply_mask32(const uint4 (&mk)[4], float (&v)[32]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) { v[i] = __uint_as_float(r0[i]); v[32 + i] = __uint_as_float(r1[i]); }
-}
-
-// relu gate from a saved bf16 activation row: 64 columns starting at `col`
-__device__ __forceinline__ void apply_relu_mask64(const __nv_bfloat16* act_row, int col, float (&v)[64]) {
-  const uint4* src = reinterpret_cast<const uint4*>(act_row + col);
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    uint4 q = __ldg(src + c);
-    uint32_t w[4] = {q.x, q.y, q.z, q.w};
+  for (int c = 0; c < 4; ++c) {
+    const uint32_t w[4] = {mk[c].x, mk[c].y, mk[c].z, mk[c].w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      // activations are post-ReLU (>= 0): zero <=> inactive unit (bf16 +0 is 0x0000)
       if ((w[j] & 0xFFFFu) == 0u) v[c * 8 + j * 2] = 0.f;
       if ((w[j] >> 16) == 0u) v[c * 8 + j * 2 + 1] = 0.f;
     }
@@ -262,261 +265,327 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
     ptx::prefetch_tmap(&p.map_w128); ptx::prefetch_tmap(&p.map_w16);
     ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&sm.full[i], 1); ptx::mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < kNumPanels; ++i) ptx::mbar_init(&sm.panel_ready[i], 128);
+    for (int i = 0; i < kNumPanels; ++i) ptx::mbar_init(&sm.panel_ready[i], 128);   // one epilogue group per panel
     for (int i = 0; i < 8; ++i) ptx::mbar_init(&sm.acc_full[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc(sm.tmem_ptr, 512);
+  for (int i = threadIdx.x; i < p.bias_floats; i += kThreads) sm.bias[i] = p.bias[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_ptr;
 
+  const uint32_t panels_u32 = ptx::smem_u32(sm.panels), ring_u32 = ptx::smem_u32(sm.ring);
+  const uint32_t full_u32 = ptx::smem_u32(sm.full), empty_u32 = ptx::smem_u32(sm.empty);
+  const uint32_t pready_u32 = ptx::smem_u32(sm.panel_ready), accfull_u32 = ptx::smem_u32(sm.acc_full);
+
   if (warp == 0) {
-    // =============================== TMA producer ===============================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < p.n_layers; ++l) {
-          const TcLayer& L = p.layers[l];
-          if (!layer_has_mma(L)) continue;
-          const int kps = L.a_res + L.a_str;
-          for (int h = 0; h < L.n_halves; ++h) {
-            for (int kp = 0; kp < kps; ++kp) {
-              if (kp >= L.a_res) {
-                ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
-                ptx::mbar_expect_tx(&sm.full[stage], kPanelBytes);
-                ptx::tma_load_2d(sm.ring + stage * kPanelBytes, &p.map_feat, &sm.full[stage],
-                                 (kp - L.a_res) * 64, p.feat_row0 + tile * kTileM);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+    // =============================== TMA producer (whole warp converged, one elected lane issues) =====
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int feat_row = p.feat_row0 + tile * kTileM;
+      for (int l = 0; l < p.n_layers; ++l) {
+        const TcLayer& L = p.layers[l];
+        if (!layer_has_mma(L)) continue;
+        const int a_res = L.a_res, kps = L.a_res + L.a_str, n_halves = L.n_halves;
+        const uint32_t w_bytes = (uint32_t)L.n_mma * 128u;
+        const CUtensorMap* wmap = L.w_map ? &p.map_w16 : &p.map_w128;
+        const int w_row = L.w_row;
+        for (int h = 0; h < n_halves; ++h) {
+          for (int kp = 0; kp < kps; ++kp) {
+            if (kp >= a_res) {
+              ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+              if (ptx::elect_one()) {
+                ptx::mbar_expect_tx_u32(full_u32 + stage * 8, kPanelBytes);
+                ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, &p.map_feat, full_u32 + stage * 8,
+                                     (kp - a_res) * 64, feat_row);
               }
-              ptx::mbar_wait(&sm.empty[stage], phase ^ 1);
-              ptx::mbar_expect_tx(&sm.full[stage], L.n_mma * 128);
-              ptx::tma_load_2d(sm.ring + stage * kPanelBytes, L.w_map ? &p.map_w16 : &p.map_w128,
-                               &sm.full[stage], kp * 64, L.w_row + h * 128);
+              __syncwarp();
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
+            ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+            if (ptx::elect_one()) {
+              ptx::mbar_expect_tx_u32(full_u32 + stage * 8, w_bytes);
+              ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, wmap, full_u32 + stage * 8, kp * 64,
+                                   w_row + h * 128);
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      uint32_t panel_phase = 0;   // bit i: parity to wait for on panel_ready[i]
-      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        for (int l = 0; l < p.n_layers; ++l) {
-          const TcLayer& L = p.layers[l];
-          if (!layer_has_mma(L)) continue;
-          const int kps = L.a_res + L.a_str;
-          const uint32_t idesc = ptx::make_idesc_bf16(128, L.n_mma, 0, 0);
-          for (int h = 0; h < L.n_halves; ++h) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)(L.acc_col + h * 128);
-            for (int kp = 0; kp < kps; ++kp) {
-              uint32_t a_addr;
-              int a_stage = -1;
-              if (kp < L.a_res) {
-                const int pi = L.a_buf * 4 + kp;
-                if (h == 0 && L.wait_panels) {
-                  ptx::mbar_wait(&sm.panel_ready[pi], (panel_phase >> pi) & 1u);
-                  panel_phase ^= 1u << pi;
-                }
-                a_addr = ptx::smem_u32(sm.panels + pi * kPanelBytes);
-              } else {
-                ptx::mbar_wait(&sm.full[stage], phase);
-                a_stage = stage;
-                a_addr = ptx::smem_u32(sm.ring + stage * kPanelBytes);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+    // =============================== MMA issuer (whole warp converged, one elected lane issues) ========
+    constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
+    int stage = 0; uint32_t phase = 0;
+    uint32_t panel_phase = 0;   // bit i: parity to wait for on panel_ready[i]
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      for (int l = 0; l < p.n_layers; ++l) {
+        const TcLayer& L = p.layers[l];
+        if (!layer_has_mma(L)) continue;
+        const int a_res = L.a_res, kps = L.a_res + L.a_str, n_halves = L.n_halves;
+        const int a_panel0 = L.a_buf * 4;
+        const bool wait_panels = L.wait_panels != 0;
+        const uint32_t idesc = ptx::make_idesc_bf16(128, L.n_mma, 0, 0);
+        const uint32_t acc_bar = accfull_u32 + L.acc_bar * 8;
+        const uint32_t acc_tmem = tmem_base + (uint32_t)L.acc_col;
+        for (int h = 0; h < n_halves; ++h) {
+          const uint32_t d_tmem = acc_tmem + (uint32_t)(h * 128);
+          for (int kp = 0; kp < kps; ++kp) {
+            uint32_t a_addr, a_empty = 0;
+            if (kp < a_res) {
+              const int pi = a_panel0 + kp;
+              if (h == 0 && wait_panels) {
+                ptx::mbar_wait_u32(pready_u32 + pi * 8, (panel_phase >> pi) & 1u);
+                panel_phase ^= 1u << pi;
               }
-              ptx::mbar_wait(&sm.full[stage], phase);
-              const uint32_t b_addr = ptx::smem_u32(sm.ring + stage * kPanelBytes);
-              ptx::tc_fence_after();
-#pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16) {
-                const uint64_t da = ptx::make_desc_sw128(a_addr + k16 * 32, 0, 1024);
-                const uint64_t db = ptx::make_desc_sw128(b_addr + k16 * 32, 0, 1024);
-                ptx::mma_bf16_ss(d_tmem, da, db, idesc, (kp > 0 || k16 > 0) ? 1u : 0u);
-              }
-              ptx::mma_commit(&sm.empty[stage]);
-              if (a_stage >= 0) ptx::mma_commit(&sm.empty[a_stage]);
+              a_addr = panels_u32 + pi * kPanelBytes;
+            } else {
+              ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+              a_addr = ring_u32 + stage * kPanelBytes;
+              a_empty = empty_u32 + stage * 8;
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            ptx::mma_commit(&sm.acc_full[L.acc_bar + h]);
+            ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+            const uint32_t b_addr = ring_u32 + stage * kPanelBytes;
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint64_t da = ptx::desc_from(kDescHi, a_addr), db = ptx::desc_from(kDescHi, b_addr);
+              // advancing K by 16 bf16 (32 bytes) inside the 128B swizzle atom = +2 in the address field
+              ptx::mma_bf16_ss(d_tmem, da, db, idesc, kp > 0 ? 1u : 0u);
+              ptx::mma_bf16_ss(d_tmem, da + 2, db + 2, idesc, 1u);
+              ptx::mma_bf16_ss(d_tmem, da + 4, db + 4, idesc, 1u);
+              ptx::mma_bf16_ss(d_tmem, da + 6, db + 6, idesc, 1u);
+              ptx::mma_commit_u32(empty_u32 + stage * 8);
+              if (a_empty) ptx::mma_commit_u32(a_empty);
+              if (kp == kps - 1) ptx::mma_commit_u32(acc_bar + h * 8);
+            }
+            __syncwarp();
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
-        ptx::mma_commit(&sm.acc_full[7]);   // tile_done: every MMA of this tile has completed
       }
+      if (ptx::elect_one()) ptx::mma_commit_u32(accfull_u32 + 7 * 8);   // tile_done: every MMA of this tile completed
+      __syncwarp();
     }
   } else {
     // =============================== epilogue groups ===============================
-    const int ew = warp - 2;               // 0..7
-    const int g = ew >> 2;                 // group: output columns [128g, 128g+128)
+    const int ew = warp - 2;               // 0..15
+    const int q = ew >> 2;                 // group: owns output columns [64q, 64q+64) of a 256-wide layer
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;   // tile row == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const bool group_leader = (ew & 3) == 0 && lane == 0;
+    const int bar_id = 1 + q;
     uint32_t acc_phase = 0;
     int tile_iter = 0;
-    // Write one 64-column chunk of this thread's row into panel `pi`, optionally TMA-store the panel
-    // (training: saved activations / dZ) and publish it to the MMA issuer.
-    auto finish_chunk = [&](const TcLayer& L, int pi, int col, const float (&vals)[64], int tile) {
-      uint8_t* panel = sm.panels + pi * kPanelBytes;
-      store_row_chunk64(panel, row, vals);
+    float v[32];
+
+    // Publish a finished panel: optional TMA store (saved activations / dZ), then signal the MMA issuer.
+    auto publish = [&](const TcLayer& L, int pi, int col, int tile) {
       ptx::fence_proxy_async();
       if (kTrain && L.save_row >= 0) {
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (group_leader) {
-          ptx::tma_store_2d(&p.map_save, panel, col, L.save_row + tile * kTileM);
+          ptx::tma_store_2d(&p.map_save, sm.panels + pi * kPanelBytes, col, L.save_row + tile * kTileM);
           ptx::tma_commit_group();
         }
       }
       ptx::tc_fence_before();
       if (!L.no_signal) ptx::mbar_arrive(&sm.panel_ready[pi]);
     };
+    // The panel this group is about to overwrite was TMA-stored two layers ago: that read must be done.
+    auto guard_panel = [&](const TcLayer& L) {
+      if (kTrain && L.save_row >= 0) {
+        if (group_leader) ptx::tma_wait_group_read<1>();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+      }
+    };
+    auto wait_acc = [&](int bar) {
+      ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
+      acc_phase ^= 1u << bar;
+      ptx::tc_fence_after();
+    };
+
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_iter) {
       const int s = tile * kTileM + row;   // global sample index
       const bool valid = s < p.n_samples;
       float raw_d = 0.f;
       for (int l = 0; l < p.n_layers; ++l) {
         const TcLayer& L = p.layers[l];
-        float v[64];
         if (!layer_has_mma(L) && tile_iter > 0) {
           // the start op of a backward tile overwrites panels the previous tile's last MMAs may still read
           ptx::mbar_wait(&sm.acc_full[7], (uint32_t)((tile_iter - 1) & 1));
         }
-        if (kTrain && L.save_row >= 0) {
-          // panels written by this layer were TMA-stored two layers ago: that read must have finished
-          if (group_leader) ptx::tma_wait_group_read<1>();
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory");
-        }
         switch (L.epi) {
-          case EPI_RELU: case EPI_LINEAR: case EPI_BWD_LINEAR: case EPI_BWD_RELU: case EPI_BWD_RELU_D: {
-            const int bar = L.acc_bar + g;
-            ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
-            acc_phase ^= 1u << bar;
-            ptx::tc_fence_after();
-            float dd = 0.f;
-            if (L.epi == EPI_BWD_RELU_D)
-              dd = valid ? __bfloat162float(__float2bfloat16(p.d_raw[(size_t)s * p.raw_c])) : 0.f;
+          case EPI_RELU: case EPI_LINEAR: {
+            const int col = q * 64, pi = L.dst_buf * 4 + q;
+            uint8_t* panel = sm.panels + pi * kPanelBytes;
+            guard_panel(L);
+            wait_acc(L.acc_bar + (q >> 1));
 #pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-              const int col = g * 128 + j * 64;
-              load_acc64(lane_addr + (uint32_t)(L.acc_col + col), v);
-              if (L.epi == EPI_RELU || L.epi == EPI_LINEAR) {
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + L.bias_off + col);
+            for (int hf = 0; hf < 2; ++hf) {
+              load_acc32(lane_addr + (uint32_t)(L.acc_col + col + hf * 32), v);
+              const float4* b4 = reinterpret_cast<const float4*>(sm.bias + L.bias_off + col + hf * 32);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                  float4 b = __ldg(b4 + c);
-                  v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
-                }
-                if (L.epi == EPI_RELU) {
+              for (int c = 0; c < 8; ++c) {
+                const float4 b = b4[c];
+                v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+              }
+              if (L.epi == EPI_RELU) store_half32<true>(panel, row, hf * 4, v);
+              else store_half32<false>(panel, row, hf * 4, v);
+            }
+            publish(L, pi, col, tile);
+            break;
+          }
+          case EPI_BWD_LINEAR: case EPI_BWD_RELU: case EPI_BWD_RELU_D: {
+            const int col = q * 64, pi = L.dst_buf * 4 + q;
+            uint8_t* panel = sm.panels + pi * kPanelBytes;
+            // side inputs do not depend on the accumulator: fetch them before waiting for the MMAs
+            uint4 mk[8];
+            float dd = 0.f;
+            if (L.epi != EPI_BWD_LINEAR) {
+              if (valid) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.act + ((size_t)L.mask_row + s) * kW + col);
 #pragma unroll
-                  for (int c = 0; c < 64; ++c) v[c] = fmaxf(v[c], 0.f);
-                }
+                for (int c = 0; c < 8; ++c) mk[c] = __ldg(src + c);
               } else {
-                if (L.epi == EPI_BWD_RELU_D) {
-                  const float4* w4 = reinterpret_cast<const float4*>(p.bias + p.w_dens_off + col);
 #pragma unroll
-                  for (int c = 0; c < 16; ++c) {
-                    float4 w = __ldg(w4 + c);
-                    v[c * 4 + 0] = fmaf(dd, w.x, v[c * 4 + 0]); v[c * 4 + 1] = fmaf(dd, w.y, v[c * 4 + 1]);
-                    v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
-                  }
-                }
-                if (L.epi != EPI_BWD_LINEAR) {
-                  if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
-                  else {
+                for (int c = 0; c < 8; ++c) mk[c] = make_uint4(0u, 0u, 0u, 0u);
+              }
+              if (L.epi == EPI_BWD_RELU_D)
+                dd = valid ? __bfloat162float(__float2bfloat16(p.d_raw[(size_t)s * p.raw_c])) : 0.f;
+            }
+            guard_panel(L);
+            wait_acc(L.acc_bar + (q >> 1));
 #pragma unroll
-                    for (int c = 0; c < 64; ++c) v[c] = 0.f;
-                  }
+            for (int hf = 0; hf < 2; ++hf) {
+              load_acc32(lane_addr + (uint32_t)(L.acc_col + col + hf * 32), v);
+              if (L.epi == EPI_BWD_RELU_D) {
+                const float4* w4 = reinterpret_cast<const float4*>(sm.bias + p.w_dens_off + col + hf * 32);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 w = w4[c];
+                  v[c * 4 + 0] = fmaf(dd, w.x, v[c * 4 + 0]); v[c * 4 + 1] = fmaf(dd, w.y, v[c * 4 + 1]);
+                  v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
                 }
               }
-              finish_chunk(L, L.dst_buf * 4 + g * 2 + j, col, v, tile);
+              if (L.epi != EPI_BWD_LINEAR) {
+                const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
+                apply_mask32(half, v);
+              }
+              store_half32<false>(panel, row, hf * 4, v);
             }
+            publish(L, pi, col, tile);
             break;
           }
           case EPI_VIEW: {
-            const int bar = L.acc_bar;
-            ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
-            acc_phase ^= 1u << bar;
-            ptx::tc_fence_after();
-            const int col = g * 64;
-            load_acc64(lane_addr + (uint32_t)(L.acc_col + col), v);
-            if (valid) {
-              const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(s / p.S) * 128 + col);
+            if (q >= 2) break;                      // N = 128: groups 0 and 1
+            const int col = q * 64, pi = L.dst_buf * 4 + q;
+            uint8_t* panel = sm.panels + pi * kPanelBytes;
+            guard_panel(L);
+            wait_acc(L.acc_bar);
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+              load_acc32(lane_addr + (uint32_t)(L.acc_col + col + hf * 32), v);
+              if (valid) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(s / p.S) * 128 + col + hf * 32);
 #pragma unroll
-              for (int c = 0; c < 16; ++c) {
-                float4 b = __ldg(b4 + c);
-                v[c * 4 + 0] = fmaxf(v[c * 4 + 0] + b.x, 0.f); v[c * 4 + 1] = fmaxf(v[c * 4 + 1] + b.y, 0.f);
-                v[c * 4 + 2] = fmaxf(v[c * 4 + 2] + b.z, 0.f); v[c * 4 + 3] = fmaxf(v[c * 4 + 3] + b.w, 0.f);
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b = __ldg(b4 + c);
+                  v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                }
               }
+              store_half32<true>(panel, row, hf * 4, v);
             }
-            finish_chunk(L, L.dst_buf * 4 + g, col, v, tile);
+            publish(L, pi, col, tile);
             break;
           }
           case EPI_DENSITY: case EPI_RGB: {
-            if (g != 0) break;
-            const int bar = L.acc_bar;
-            ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
-            acc_phase ^= 1u << bar;
-            ptx::tc_fence_after();
+            if (q != 0) break;
+            wait_acc(L.acc_bar);
             uint32_t r4[4];
             ptx::tmem_ld4(lane_addr + (uint32_t)L.acc_col, r4);
             ptx::tmem_ld_wait();
             ptx::tc_fence_before();
             if (L.epi == EPI_DENSITY) {
-              raw_d = __uint_as_float(r4[0]) + __ldg(p.bias + L.bias_off);
+              raw_d = __uint_as_float(r4[0]) + sm.bias[L.bias_off];
               if (p.raw_c == 1 && valid) p.raw_out[s] = raw_d;
             } else if (valid) {
               float4 o;
               o.x = raw_d;
-              o.y = __uint_as_float(r4[0]) + __ldg(p.bias + L.bias_off + 0);
-              o.z = __uint_as_float(r4[1]) + __ldg(p.bias + L.bias_off + 1);
-              o.w = __uint_as_float(r4[2]) + __ldg(p.bias + L.bias_off + 2);
+              o.y = __uint_as_float(r4[0]) + sm.bias[L.bias_off + 0];
+              o.z = __uint_as_float(r4[1]) + sm.bias[L.bias_off + 1];
+              o.w = __uint_as_float(r4[2]) + sm.bias[L.bias_off + 2];
               reinterpret_cast<float4*>(p.raw_out)[s] = o;
             }
             break;
           }
           case EPI_BWD_START: {
-            // dV = W_rgb^T d_rgb (CUDA cores), gated by the saved view activation; 128 columns:
-            // group g produces columns [64g, 64g+64) -> panel g.
-            float4 dr = valid ? reinterpret_cast<const float4*>(p.d_raw)[s] : make_float4(0, 0, 0, 0);
+            // dV = W_rgb^T d_rgb (CUDA cores), gated by the saved view activation; 128 columns: groups 0, 1
+            if (q >= 2) break;
+            const int col = q * 64, pi = L.dst_buf * 4 + q;
+            uint8_t* panel = sm.panels + pi * kPanelBytes;
+            const float4 dr = valid ? reinterpret_cast<const float4*>(p.d_raw)[s] : make_float4(0, 0, 0, 0);
             // bf16-round the head gradient once so that dgrad (here) and wgrad (tensor cores) agree
             const float d0 = __bfloat162float(__float2bfloat16(dr.y)), d1 = __bfloat162float(__float2bfloat16(dr.z)),
                         d2 = __bfloat162float(__float2bfloat16(dr.w));
-            const int col = g * 64;
-            const float* wr = p.bias + p.w_rgb_off + col * 3;
-#pragma unroll
-            for (int c = 0; c < 64; ++c)
-              v[c] = d0 * __ldg(wr + c * 3) + d1 * __ldg(wr + c * 3 + 1) + d2 * __ldg(wr + c * 3 + 2);
-            if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
-            if (g == 0 && valid) {
-              uint4 q0 = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
-              uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * 16);
-              dst[0] = q0; dst[1] = make_uint4(0u, 0u, 0u, 0u);
+            if (q == 0) {   // padding rows of the tile get zeros (dr == 0)
+              uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * kHeadCols);
+              dst[0] = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
             }
-            finish_chunk(L, L.dst_buf * 4 + g, col, v, tile);
+            guard_panel(L);
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+              const float* wr = sm.bias + p.w_rgb_off + (col + hf * 32) * 3;
+#pragma unroll
+              for (int c = 0; c < 32; ++c) v[c] = d0 * wr[c * 3] + d1 * wr[c * 3 + 1] + d2 * wr[c * 3 + 2];
+              uint4 mk[4];
+              if (valid) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.act + ((size_t)L.mask_row + s) * kW + col + hf * 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mk[c] = __ldg(src + c);
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mk[c] = make_uint4(0u, 0u, 0u, 0u);
+              }
+              apply_mask32(mk, v);
+              store_half32<false>(panel, row, hf * 4, v);
+            }
+            publish(L, pi, col, tile);
             break;
           }
           case EPI_BWD_START_PROP: {
-            // dZ_last = d_raw_density * w_density gated by the last trunk activation; 256 columns
+            // dZ_last = d_raw_density * w_density gated by the last trunk activation; 256 columns: all groups
+            const int col = q * 64, pi = L.dst_buf * 4 + q;
+            uint8_t* panel = sm.panels + pi * kPanelBytes;
             const float dd0 = valid ? p.d_raw[s] : 0.f;
             const float dd = __bfloat162float(__float2bfloat16(dd0));
-            if (g == 0 && valid) {
-              uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * 16);
+            if (q == 0) {
+              uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * kHeadCols);
               dst[0] = make_uint4(0u, ptx::pack_bf16x2(0.f, dd0), 0u, 0u);
-              dst[1] = make_uint4(0u, 0u, 0u, 0u);
             }
+            guard_panel(L);
 #pragma unroll 1
-            for (int j = 0; j < 2; ++j) {
-              const int col = g * 128 + j * 64;
-              const float* wd = p.bias + p.w_dens_off + col;
+            for (int hf = 0; hf < 2; ++hf) {
+              const float* wd = sm.bias + p.w_dens_off + col + hf * 32;
 #pragma unroll
-              for (int c = 0; c < 64; ++c) v[c] = dd * __ldg(wd + c);
-              if (valid) apply_relu_mask64(p.act + ((size_t)L.mask_row + s) * kW, col, v);
-              finish_chunk(L, L.dst_buf * 4 + g * 2 + j, col, v, tile);
+              for (int c = 0; c < 32; ++c) v[c] = dd * wd[c];
+              uint4 mk[4];
+              if (valid) {
+                const uint4* src = reinterpret_cast<const uint4*>(p.act + ((size_t)L.mask_row + s) * kW + col + hf * 32);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mk[c] = __ldg(src + c);
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) mk[c] = make_uint4(0u, 0u, 0u, 0u);
+              }
+              apply_mask32(mk, v);
+              store_half32<false>(panel, row, hf * 4, v);
             }
+            publish(L, pi, col, tile);
             break;
           }
           default: break;
@@ -755,7 +824,12 @@ int tc_create(hugs_handle* h) {
   tc->total_feat_rows = frow; tc->total_save_rows = srow;
   if ((rc = tc_alloc(h, &tc->feat, (size_t)frow * kFeatPad))) return rc;
   if ((rc = tc_alloc(h, &tc->act, (size_t)srow * kW)) || (rc = tc_alloc(h, &tc->dz, (size_t)srow * kW))) return rc;
-  if ((rc = tc_alloc(h, &tc->drgb, (size_t)tc->cap[L - 1] * 16))) return rc;
+  for (int l = 0; l < L; ++l) tc->drgb_rows = std::max(tc->drgb_rows, tc->cap[l]);
+  if ((rc = tc_alloc(h, &tc->drgb, (size_t)tc->drgb_rows * kHeadCols))) return rc;
+  // unused columns (head gradients beyond col 3, view-activation columns 128..255) must read as zero
+  HUGS_CUDA(cudaMemset(tc->drgb, 0, (size_t)tc->drgb_rows * kHeadCols * 2));
+  HUGS_CUDA(cudaMemset(tc->act, 0, (size_t)srow * kW * 2));
+  HUGS_CUDA(cudaMemset(tc->dz, 0, (size_t)srow * kW * 2));
   if ((rc = tc_alloc(h, &tc->viewbias, (size_t)d.max_rays * 128))) return rc;
   if ((rc = make_map(&tc->map_feat, tc->feat, frow, kFeatPad, 128)) ||
       (rc = make_map(&tc->map_act, tc->act, srow, kW, 128)) || (rc = make_map(&tc->map_dz, tc->dz, srow, kW, 128)))
@@ -831,7 +905,7 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
   }
   p.n_tiles = n_tiles; p.n_samples = n_samples; p.S = S; p.feat_row0 = tc->feat_row0[level];
   p.bias = m.bias; p.viewbias = tc->viewbias; p.raw_out = h->raw[level]; p.raw_c = is_prop ? 1 : 4;
-  p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
+  p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off; p.bias_floats = m.bias_floats;
   const int grid = std::min(n_tiles, tc->num_sms);
   ProfScope ps(h, is_prop ? HUGS_K_CHAIN_FWD_PROP : HUGS_K_CHAIN_FWD_NERF, st);
   if (training) mlp_chain_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);
@@ -862,7 +936,7 @@ int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays
   p.n_tiles = n_tiles; p.n_samples = n_samples; p.S = S; p.feat_row0 = tc->feat_row0[level];
   p.bias = m.bias; p.viewbias = tc->viewbias; p.raw_out = nullptr; p.raw_c = is_prop ? 1 : 4;
   p.d_raw = h->d_raw[level]; p.act = tc->act; p.drgb_out = tc->drgb;
-  p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
+  p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off; p.bias_floats = m.bias_floats;
   const int grid = std::min(n_tiles, tc->num_sms);
   {
     ProfScope ps(h, is_prop ? HUGS_K_CHAIN_BWD_PROP : HUGS_K_CHAIN_BWD_NERF, st);

@@ -14,12 +14,15 @@ namespace hugs {
 constexpr int kTileM = 128;             // samples per tile (= TMEM lanes)
 constexpr int kPanelBytes = 16384;      // 128 rows x 64 bf16, SWIZZLE_128B
 constexpr int kNumPanels = 8;           // two activation buffers of 4 K-panels (256 columns) each
-constexpr int kStages = 6;              // TMA ring depth
+constexpr int kStages = 5;              // TMA ring depth
 constexpr int kW = 256;                 // trunk / bottleneck width of this path
 constexpr int kFeatPad = 512;           // IPE features padded to 8 K-panels
 constexpr int kKP = kW + kFeatPad;      // K extent of the packed forward weights
-constexpr int kThreads = 320;
-constexpr int kSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + 512;
+constexpr int kEpiGroups = 4;           // epilogue groups of 128 threads; group q owns output columns [64q, 64q+64)
+constexpr int kThreads = 64 + kEpiGroups * 128;   // producer warp + MMA warp + epilogue warps
+constexpr int kHeadCols = 64;           // columns of the head-gradient tensor (d_r, d_g, d_b, d_density, 0...)
+constexpr int kBiasTab = 3584;          // fp32 bias / head-weight table staged in shared memory
+constexpr int kSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTab * 4 + 512;
 
 enum Epi : int {
   EPI_RELU = 0,      // bias + ReLU -> bf16 panels            (trunk)
@@ -58,8 +61,9 @@ struct alignas(64) TcParams {
   float* raw_out; int raw_c;         // [n_samples, raw_c]
   const float* d_raw;                // bwd: [n_samples, raw_c]
   const __nv_bfloat16* act;          // bwd: saved forward activations [rows, 256]
-  __nv_bfloat16* drgb_out;           // bwd: [n_samples, 16] bf16 (d raw rgb, padded) for the rgb-head wgrad
+  __nv_bfloat16* drgb_out;           // bwd: [rows, kHeadCols] bf16 head gradients for the head wgrad GEMMs
   int w_dens_off, w_rgb_off;         // float offsets of head weights inside `bias`
+  int bias_floats;                   // size of the bias table
 };
 
 struct TcMlp {
@@ -84,7 +88,8 @@ struct TcState {
   __nv_bfloat16* feat = nullptr;     // per level region [cap_l, 512]
   __nv_bfloat16* act = nullptr;      // saved forward activations
   __nv_bfloat16* dz = nullptr;       // saved backward dZ
-  __nv_bfloat16* drgb = nullptr;     // [cap, 16]
+  __nv_bfloat16* drgb = nullptr;     // [max cap, kHeadCols]
+  int drgb_rows = 0;
   float* viewbias = nullptr;
   CUtensorMap map_feat, map_act, map_dz;
   std::vector<int> cap, feat_row0, save_row0;   // per level

@@ -33,11 +33,14 @@ struct WgItem {
   long long koff;   // kernel offset in the flat gradient
   int in_base;      // kernel row of A column a_col0 (feature mode: first feature row)
   int feat_mode;    // 1: A columns are features in engine order -> permute rows on flush
-  int pad;
+  int b_map;        // 0: dZ tensor, 1: head-gradient tensor (kHeadCols wide)
+  int flush_mode;   // 0: kernel tile; 1: density head (column 3 -> [in,1]); 2: rgb head (columns 0..2 -> [in,3])
+  int bias_mode;    // 0: none; 1: all n columns -> boff + c; 2: column 3 -> boff; 3: columns 0..2 -> boff + c
+  long long boff;   // bias offset in the flat gradient
 };
 
 struct WgState {
-  CUtensorMap map_act64, map_feat64, map_dz64;
+  CUtensorMap map_act64, map_feat64, map_dz64, map_dh64;
   std::vector<std::vector<WgItem>> host;   // per level
   std::vector<WgItem*> dev;                // per level
   std::vector<int> built_for;              // n_samples the list was built for
@@ -52,7 +55,7 @@ constexpr int kWgThreads = 192;
 constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 256;
 
 struct alignas(64) WgParams {
-  CUtensorMap map_act64, map_feat64, map_dz64;
+  CUtensorMap map_act64, map_feat64, map_dz64, map_dh64;
   const WgItem* items;
   int n_items, nb, ndeg, feat_dim;
   float* grad;
@@ -68,7 +71,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.map_act64); ptx::prefetch_tmap(&p.map_feat64); ptx::prefetch_tmap(&p.map_dz64);
-    for (int i = 0; i < kWgStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    ptx::prefetch_tmap(&p.map_dh64);
+    // a stage is released by the MMA commit and by the four epilogue warps (bias column sums read B)
+    for (int i = 0; i < kWgStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 5); }
     ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_empty, 128);
     ptx::fence_mbar_init();
   }
@@ -91,8 +96,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           ptx::mbar_expect_tx(&full[stage], (4 + nb_atoms) * 8192);
           for (int a = 0; a < 4; ++a)
             ptx::tma_load_2d(s + a * 8192, amap, &full[stage], w.a_col0 + a * 64, w.a_row0 + st * 64);
+          const CUtensorMap* bmap = w.b_map ? &p.map_dh64 : &p.map_dz64;
           for (int a = 0; a < nb_atoms; ++a)
-            ptx::tma_load_2d(s + 32768 + a * 8192, &p.map_dz64, &full[stage], a * 64, w.b_row0 + st * 64);
+            ptx::tma_load_2d(s + 32768 + a * 8192, bmap, &full[stage], a * 64, w.b_row0 + st * 64);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -129,33 +135,84 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
+    const int t = (warp - 2) * 32 + lane;          // 0..127: owns B columns 2t, 2t+1 for the bias sums
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t af_phase = 0;
+    int stage = 0; uint32_t phase = 0;
     for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
       const WgItem w = p.items[it];
+      // ---- main loop: bias gradients = column sums of the dZ stage while the tensor core consumes it ----
+      float s0 = 0.f, s1 = 0.f;
+      const int cc = (2 * t) & 63, atom = (2 * t) >> 6;
+      const bool sum_cols = w.bias_mode != 0 && 2 * t < w.n;
+      for (int st = w.st0; st < w.st1; ++st) {
+        if (w.bias_mode == 0) {
+          // nothing to read from this stage: one lane observes `full` and releases the warp's share
+          if (lane == 0) { ptx::mbar_wait(&full[stage], phase); ptx::mbar_arrive(&empty[stage]); }
+          if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+          continue;
+        }
+        if (lane == 0) ptx::mbar_wait(&full[stage], phase);
+        __syncwarp();
+        if (sum_cols) {
+          const uint8_t* bs = base + stage * kWgStageBytes + 32768 + atom * 8192 + (cc & 7) * 2;
+#pragma unroll 8
+          for (int k = 0; k < 64; ++k) {
+            const uint32_t pr = *reinterpret_cast<const uint32_t*>(bs + k * 128 + (((cc >> 3) ^ (k & 7)) << 4));
+            s0 += __uint_as_float(pr << 16);
+            s1 += __uint_as_float(pr & 0xFFFF0000u);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&empty[stage]);
+        if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+      }
+      if (sum_cols && w.st1 > w.st0) {
+        const int c = 2 * t;
+        if (w.bias_mode == 1) { atomicAdd(p.grad + w.boff + c, s0); atomicAdd(p.grad + w.boff + c + 1, s1); }
+        else if (w.bias_mode == 2) { if (c == 2) atomicAdd(p.grad + w.boff, s1); }
+        else if (w.bias_mode == 3) {
+          if (c == 0) { atomicAdd(p.grad + w.boff, s0); atomicAdd(p.grad + w.boff + 1, s1); }
+          if (c == 2) atomicAdd(p.grad + w.boff + 2, s0);
+        }
+      }
+      // ---- flush the accumulators ----
       ptx::mbar_wait(acc_full, af_phase); af_phase ^= 1;
       ptx::tc_fence_after();
       if (w.st1 > w.st0) {
 #pragma unroll 1
         for (int mb = 0; mb < 2; ++mb) {
           const int m = mb * 128 + row;
-          int krow;
-          if (w.feat_mode) {
-            const int fp = w.a_col0 + m;
-            krow = fp < p.feat_dim ? w.in_base + ref_feature_col(fp, p.nb, p.ndeg) : -1;
-          } else {
-            krow = w.in_base + m;
-          }
+          if (w.flush_mode == 0) {
+            int krow;
+            if (w.feat_mode) {
+              const int fp = w.a_col0 + m;
+              krow = fp < p.feat_dim ? w.in_base + ref_feature_col(fp, p.nb, p.ndeg) : -1;
+            } else {
+              krow = w.in_base + m;
+            }
 #pragma unroll 1
-          for (int c = 0; c < w.n; c += 32) {
-            uint32_t r[32];
-            ptx::tmem_ld32(lane_addr + (uint32_t)(mb * 256 + c), r);
-            ptx::tmem_ld_wait();
-            if (krow >= 0) {
-              float* dst = p.grad + w.koff + (long long)krow * w.out + c;
+            for (int c = 0; c < w.n; c += 32) {
+              uint32_t r[32];
+              ptx::tmem_ld32(lane_addr + (uint32_t)(mb * 256 + c), r);
+              ptx::tmem_ld_wait();
+              if (krow >= 0) {
+                float* dst = p.grad + w.koff + (long long)krow * w.out + c;
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (c + j < w.out) atomicAdd(dst + j, __uint_as_float(r[j]));
+                for (int j = 0; j < 32; ++j)
+                  if (c + j < w.out) atomicAdd(dst + j, __uint_as_float(r[j]));
+              }
+            }
+          } else {
+            uint32_t r4[4];
+            ptx::tmem_ld4(lane_addr + (uint32_t)(mb * 256), r4);
+            ptx::tmem_ld_wait();
+            if (w.flush_mode == 1) {
+              atomicAdd(p.grad + w.koff + m, __uint_as_float(r4[3]));
+            } else if (m < 128) {
+              atomicAdd(p.grad + w.koff + m * 3 + 0, __uint_as_float(r4[0]));
+              atomicAdd(p.grad + w.koff + m * 3 + 1, __uint_as_float(r4[1]));
+              atomicAdd(p.grad + w.koff + m * 3 + 2, __uint_as_float(r4[2]));
             }
           }
         }
@@ -169,67 +226,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
 }
 
-// ---------------------------------------------------------------- CUDA-core reductions
-struct ColsumJob { int row0; int cols; long long boff; };
-struct ColsumArgs { ColsumJob jobs[16]; int n_jobs; int n_rows; const __nv_bfloat16* dz; float* grad; };
-
-// grad[boff + c] += sum_s dz[row0 + s][c]     (bias gradients)
-__global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs a) {
-  const ColsumJob j = a.jobs[blockIdx.y];
-  const int c = threadIdx.x;
-  const int chunk = (a.n_rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * chunk, r1 = min(r0 + chunk, a.n_rows);
-  if (c >= j.cols) return;
-  float acc = 0.f;
-  const __nv_bfloat16* src = a.dz + (size_t)j.row0 * kW + c;
-  for (int r = r0; r < r1; ++r) acc += __bfloat162float(src[(size_t)r * kW]);
-  if (r1 > r0) atomicAdd(a.grad + j.boff + c, acc);
-}
-
-struct HeadArgs {
-  const __nv_bfloat16* a_last;   // [n, 256] last trunk activation (density head input)
-  const __nv_bfloat16* v_act;    // [n, 256] view activation in cols [0,128) (nullptr: proposal MLP)
-  const __nv_bfloat16* dhead;    // [n, 16]: (d_r, d_g, d_b, d_density, 0...)
-  int n_rows;
-  long long dens_koff, dens_boff, rgb_koff, rgb_boff;
-  float* grad;
-};
-
-__global__ void __launch_bounds__(256) head_wgrad_kernel(HeadArgs a) {
-  const int c = threadIdx.x;
-  const int chunk = (a.n_rows + gridDim.x - 1) / gridDim.x;
-  const int r0 = blockIdx.x * chunk, r1 = min(r0 + chunk, a.n_rows);
-  float wd = 0.f, w0 = 0.f, w1 = 0.f, w2 = 0.f, bd = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f;
-  for (int r = r0; r < r1; ++r) {
-    const __nv_bfloat16* dh = a.dhead + (size_t)r * 16;
-    const float dd = __bfloat162float(dh[3]);
-    wd += __bfloat162float(a.a_last[(size_t)r * kW + c]) * dd;
-    if (c == 0) bd += dd;
-    if (a.v_act) {
-      const float d0 = __bfloat162float(dh[0]), d1 = __bfloat162float(dh[1]), d2 = __bfloat162float(dh[2]);
-      if (c < 128) {
-        const float v = __bfloat162float(a.v_act[(size_t)r * kW + c]);
-        w0 += v * d0; w1 += v * d1; w2 += v * d2;
-      }
-      if (c == 0) { b0 += d0; b1 += d1; b2 += d2; }
-    }
-  }
-  if (r1 <= r0) return;
-  atomicAdd(a.grad + a.dens_koff + c, wd);
-  if (c == 0) atomicAdd(a.grad + a.dens_boff, bd);
-  if (a.v_act) {
-    if (c < 128) {
-      atomicAdd(a.grad + a.rgb_koff + c * 3 + 0, w0);
-      atomicAdd(a.grad + a.rgb_koff + c * 3 + 1, w1);
-      atomicAdd(a.grad + a.rgb_koff + c * 3 + 2, w2);
-    }
-    if (c == 0) {
-      atomicAdd(a.grad + a.rgb_boff + 0, b0); atomicAdd(a.grad + a.rgb_boff + 1, b1);
-      atomicAdd(a.grad + a.rgb_boff + 2, b2);
-    }
-  }
-}
-
+// ---------------------------------------------------------------- CUDA-core reductions (view layer extras)
 // dzv_ray[ray][c] = sum over the ray's samples of dZ_view[s][c]
 __global__ void __launch_bounds__(128) ray_sum_kernel(const __nv_bfloat16* dzv, int n_rays, int S, float* out) {
   const int ray = blockIdx.x, c = threadIdx.x;
@@ -245,8 +242,11 @@ __global__ void __launch_bounds__(128) view_extra_wgrad_kernel(const float* view
                                                                const float* dzv_ray, int n_rays, long long koff,
                                                                int bott_w, float* grad) {
   const int j = blockIdx.x, c = threadIdx.x;
+  const int chunk = (n_rays + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * chunk, r1 = min(r0 + chunk, n_rays);
+  if (r1 <= r0) return;
   float acc = 0.f;
-  for (int r = 0; r < n_rays; ++r)
+  for (int r = r0; r < r1; ++r)
     acc = fmaf(__bfloat162float(__float2bfloat16(view_in[(size_t)r * view_in_dim + j])), dzv_ray[(size_t)r * 128 + c], acc);
   atomicAdd(grad + koff + (long long)(bott_w + j) * 128 + c, acc);
 }
@@ -275,7 +275,8 @@ int wgrad_create(hugs_handle* h) {
   int rc;
   if ((rc = make_map(&w->map_act64, tc->act, tc->total_save_rows, kW, 64)) ||
       (rc = make_map(&w->map_dz64, tc->dz, tc->total_save_rows, kW, 64)) ||
-      (rc = make_map(&w->map_feat64, tc->feat, tc->total_feat_rows, kFeatPad, 64)))
+      (rc = make_map(&w->map_feat64, tc->feat, tc->total_feat_rows, kFeatPad, 64)) ||
+      (rc = make_map(&w->map_dh64, tc->drgb, tc->drgb_rows, kHeadCols, 64)))
     return rc;
   const int L = h->d.num_levels;
   w->host.resize(L); w->dev.assign(L, nullptr); w->built_for.assign(L, -1);
@@ -307,26 +308,40 @@ static void build_items(hugs_handle* h, int level, int n_tiles, std::vector<WgIt
   const int T = n_tiles * 2;   // 64-sample stages
   struct Unit { WgItem w; float cost; };
   std::vector<Unit> units;
-  auto add = [&](int a_map, int a_row0, int a_col0, int b_slot, int n, const DenseView& v, int in_base, int feat_mode) {
+  auto add = [&](int a_map, int a_row0, int a_col0, int b_slot, int n, const DenseView& v, int in_base, int feat_mode,
+                 bool first_of_layer) {
     WgItem w{};
     w.a_map = a_map; w.a_row0 = a_row0; w.a_col0 = a_col0; w.b_row0 = srow + b_slot * cap; w.n = n;
     w.out = v.out; w.koff = v.kernel_off; w.in_base = in_base; w.feat_mode = feat_mode;
+    w.bias_mode = first_of_layer ? 1 : 0; w.boff = v.bias_off;
     units.push_back({w, n / 256.f});
   };
   bool cat = false;
   for (int l = 0; l < D; ++l) {
     const DenseView& v = mv.dense[l];
     if (l == 0) {
-      for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, 0, 256, v, 0, 1);
+      for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, 0, 256, v, 0, 1, sb == 0);
     } else {
-      add(0, srow + (l - 1) * cap, 0, l, 256, v, 0, 0);
-      if (cat) for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, l, 256, v, kW, 1);
+      add(0, srow + (l - 1) * cap, 0, l, 256, v, 0, 0, true);
+      if (cat) for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, l, 256, v, kW, 1, false);
     }
     cat = (l % d.skip_layer == 0 && l > 0);
   }
   if (mv.has_rgb) {
-    add(0, srow + (D - 1) * cap, 0, D, 256, mv.dense[D + 1], 0, 0);        // bottleneck
-    add(0, srow + D * cap, 0, D + 1, 128, mv.dense[D + 2], 0, 0);          // view layer (bottleneck rows)
+    add(0, srow + (D - 1) * cap, 0, D, 256, mv.dense[D + 1], 0, 0, true);        // bottleneck
+    add(0, srow + D * cap, 0, D + 1, 128, mv.dense[D + 2], 0, 0, true);          // view layer (bottleneck rows)
+  }
+  {  // density head: A = last trunk activation, B = head gradients (column 3)
+    WgItem w{};
+    w.a_map = 0; w.a_row0 = srow + (D - 1) * cap; w.a_col0 = 0; w.b_map = 1; w.b_row0 = 0; w.n = kHeadCols;
+    w.out = 1; w.koff = mv.dense[D].kernel_off; w.flush_mode = 1; w.bias_mode = 2; w.boff = mv.dense[D].bias_off;
+    units.push_back({w, 0.35f});
+  }
+  if (mv.has_rgb) {  // rgb head: A = view activation (columns 128..255 are zero), B = head gradients (columns 0..2)
+    WgItem w{};
+    w.a_map = 0; w.a_row0 = srow + (D + 1) * cap; w.a_col0 = 0; w.b_map = 1; w.b_row0 = 0; w.n = kHeadCols;
+    w.out = 3; w.koff = mv.dense[D + 3].kernel_off; w.flush_mode = 2; w.bias_mode = 3; w.boff = mv.dense[D + 3].bias_off;
+    units.push_back({w, 0.35f});
   }
   float total = 0.f;
   for (auto& u : units) total += u.cost;
@@ -364,7 +379,7 @@ int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t s
   }
   WgParams p;
   memset(&p, 0, sizeof(p));
-  p.map_act64 = w->map_act64; p.map_feat64 = w->map_feat64; p.map_dz64 = w->map_dz64;
+  p.map_act64 = w->map_act64; p.map_feat64 = w->map_feat64; p.map_dz64 = w->map_dz64; p.map_dh64 = w->map_dh64;
   p.items = w->dev[level]; p.n_items = (int)w->host[level].size();
   p.nb = d.num_basis; p.ndeg = d.max_deg_point - d.min_deg_point; p.feat_dim = h->feat_dim; p.grad = grad;
   {
@@ -374,36 +389,11 @@ int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t s
   }
   ProfScope ps_red(h, HUGS_K_REDUCTIONS, st);
 
-  // biases: column sums of the saved dZ slots
-  ColsumArgs ca;
-  memset(&ca, 0, sizeof(ca));
-  for (int l = 0; l < D; ++l) ca.jobs[ca.n_jobs++] = ColsumJob{srow + l * cap, 256, mv.dense[l].bias_off};
-  if (mv.has_rgb) {
-    ca.jobs[ca.n_jobs++] = ColsumJob{srow + D * cap, 256, mv.dense[D + 1].bias_off};
-    ca.jobs[ca.n_jobs++] = ColsumJob{srow + (D + 1) * cap, 128, mv.dense[D + 2].bias_off};
-  }
-  ca.n_rows = n_rows; ca.dz = tc->dz; ca.grad = grad;
-  const int chunks = std::max(1, std::min(64, n_rows / 256));
-  colsum_kernel<<<dim3(chunks, ca.n_jobs), 256, 0, st>>>(ca);
-  HUGS_LAUNCH_CHECK();
-
-  // density / rgb heads
-  HeadArgs ha;
-  memset(&ha, 0, sizeof(ha));
-  ha.a_last = tc->act + (size_t)(srow + (D - 1) * cap) * kW;
-  ha.v_act = mv.has_rgb ? tc->act + (size_t)(srow + (D + 1) * cap) * kW : nullptr;
-  ha.dhead = tc->drgb; ha.n_rows = n_samples;
-  ha.dens_koff = mv.dense[D].kernel_off; ha.dens_boff = mv.dense[D].bias_off;
-  if (mv.has_rgb) { ha.rgb_koff = mv.dense[D + 3].kernel_off; ha.rgb_boff = mv.dense[D + 3].bias_off; }
-  ha.grad = grad;
-  head_wgrad_kernel<<<std::max(1, std::min(296, n_samples / 128)), 256, 0, st>>>(ha);
-  HUGS_LAUNCH_CHECK();
-
   if (mv.has_rgb) {
     const DenseView& vv = mv.dense[D + 2];
     ray_sum_kernel<<<n_rays, 128, 0, st>>>(tc->dz + (size_t)(srow + (D + 1) * cap) * kW, n_rays, S, w->dzv_ray);
     HUGS_LAUNCH_CHECK();
-    view_extra_wgrad_kernel<<<h->view_in_dim, 128, 0, st>>>(h->view_in, h->view_in_dim, w->dzv_ray, n_rays,
+    view_extra_wgrad_kernel<<<dim3(h->view_in_dim, 32), 128, 0, st>>>(h->view_in, h->view_in_dim, w->dzv_ray, n_rays,
                                                            vv.kernel_off, d.bottleneck_width, grad);
     HUGS_LAUNCH_CHECK();
     if (d.num_glo_features > 0) {
