@@ -20,6 +20,7 @@ SOURCES = [
     ('mlp_simt.cu', ['-fmad=false']),
     ('mlp_tc.cu', []),
     ('wgrad_tc.cu', []),
+    ('tc_microbench.cu', []),
     ('optim.cu', []),
 ]
 

@@ -60,6 +60,7 @@ struct hugs_handle {
     cudaEvent_t e; cudaEventCreate(&e); return e;
   }
 
+  long long* dbg_counters = nullptr;          // development instrumentation (hugs_debug_counters)
   const float* cur_params = nullptr;          // parameters of the call in flight
   const int32_t* cur_embed_idx = nullptr;
 

@@ -190,12 +190,15 @@ __global__ void pack_params_kernel(PackArgs a) {
 struct Smem {
   uint8_t* panels;          // [kNumPanels][kPanelBytes]
   uint8_t* ring;            // [kStages][kPanelBytes]
+  float* bias;              // [kBiasTab]
+  uint4* steps;             // [kMaxSteps] precomputed MMA issue list
   uint64_t* full;           // [kStages]
   uint64_t* empty;          // [kStages]
-  uint64_t* panel_ready;    // [kNumPanels]
-  uint64_t* acc_full;       // [8]
+  uint64_t* panel_ready;    // [kNumPanels]  (count 128: one epilogue group per panel)
+  uint64_t* feat_ready;     // [kNumPanels]  (count 1 + tx: layer-0 features TMA-loaded into the panels)
+  uint64_t* acc_full;       // [8]           ([7] = tile_done)
+  uint64_t* panels_free;    // [1]           (count kEpiGroups: no TMA store still reads the panels)
   uint32_t* tmem_ptr;
-  float* bias;              // [kBiasTab]
 };
 
 __device__ __forceinline__ Smem carve(uint8_t* raw) {
@@ -204,10 +207,13 @@ __device__ __forceinline__ Smem carve(uint8_t* raw) {
   s.panels = base;
   s.ring = base + kNumPanels * kPanelBytes;
   s.bias = reinterpret_cast<float*>(s.ring + kStages * kPanelBytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s.bias + kBiasTab);
+  s.steps = reinterpret_cast<uint4*>(s.bias + kBiasTab);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.steps + kMaxSteps);
   s.full = bars; s.empty = bars + kStages; s.panel_ready = bars + 2 * kStages;
-  s.acc_full = s.panel_ready + kNumPanels;
-  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.acc_full + 8);
+  s.feat_ready = s.panel_ready + kNumPanels;
+  s.acc_full = s.feat_ready + kNumPanels;
+  s.panels_free = s.acc_full + 8;
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.panels_free + 1);
   return s;
 }
 
@@ -261,118 +267,185 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
   Smem sm = carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (warp == 0 && lane == 0) {
+  const uint32_t panels_u32 = ptx::smem_u32(sm.panels), ring_u32 = ptx::smem_u32(sm.ring);
+  const uint32_t full_u32 = ptx::smem_u32(sm.full), empty_u32 = ptx::smem_u32(sm.empty);
+  const uint32_t waitbar_u32 = ptx::smem_u32(sm.panel_ready);   // panel_ready[0..7] ++ feat_ready[0..7]
+  const uint32_t featready_u32 = ptx::smem_u32(sm.feat_ready), accfull_u32 = ptx::smem_u32(sm.acc_full);
+  const uint32_t pfree_u32 = ptx::smem_u32(sm.panels_free);
+
+  constexpr int kProducerWarp = kEpiGroups * 4, kMmaWarp = kEpiGroups * 4 + 1;
+  if (warp == kProducerWarp && lane == 0) {
     ptx::prefetch_tmap(&p.map_w128); ptx::prefetch_tmap(&p.map_w16);
     ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&sm.full[i], 1); ptx::mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < kNumPanels; ++i) ptx::mbar_init(&sm.panel_ready[i], 128);   // one epilogue group per panel
+    for (int i = 0; i < kNumPanels; ++i) { ptx::mbar_init(&sm.panel_ready[i], 128); ptx::mbar_init(&sm.feat_ready[i], 1); }
     for (int i = 0; i < 8; ++i) ptx::mbar_init(&sm.acc_full[i], 1);
+    ptx::mbar_init(sm.panels_free, kEpiGroups);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(sm.tmem_ptr, 512);
+  int n_steps = 0;
+  if (warp == kMmaWarp) {
+    ptx::tmem_alloc(sm.tmem_ptr, 512);
+    // Precompute the per-tile MMA issue list (identical for every tile):
+    //   x = smem address of the resident A panel (0: A is streamed through the ring)
+    //   y = TMEM column of the accumulator        z = instruction descriptor
+    //   w = [0,5) barrier to wait for (1..8 panel_ready, 9..16 feat_ready, 0 none) | bit 5 accumulate
+    //       | bit 6 two N-halves | [8,12) acc_full barrier to commit to + 1 (0: none)
+    for (int l = 0; l < p.n_layers; ++l) {
+      const TcLayer& L = p.layers[l];
+      if (!layer_has_mma(L)) continue;
+      const int kps = L.a_res + L.a_str;
+      for (int kp = 0; kp < kps; ++kp, ++n_steps) {
+        if (lane != 0) continue;
+        uint4 e;
+        const int pi = L.a_buf * 4 + kp;
+        e.x = kp < L.a_res ? panels_u32 + pi * kPanelBytes : 0u;
+        e.y = (uint32_t)L.acc_col;
+        e.z = ptx::make_idesc_bf16(128, L.n_mma, 0, 0);
+        uint32_t wi = 0;
+        if (kp < L.a_res && L.wait_panels) wi = (L.a_feat ? 9 : 1) + pi;
+        e.w = wi | (kp > 0 ? 32u : 0u) | (L.n_halves == 2 ? 64u : 0u) |
+              (kp == kps - 1 ? (uint32_t)(L.acc_bar + 1) << 8 : 0u);
+        sm.steps[n_steps] = e;
+      }
+    }
+  }
   for (int i = threadIdx.x; i < p.bias_floats; i += kThreads) sm.bias[i] = p.bias[i];
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_ptr;
+  const bool feat_resident = p.layers[0].a_feat != 0;
 
-  const uint32_t panels_u32 = ptx::smem_u32(sm.panels), ring_u32 = ptx::smem_u32(sm.ring);
-  const uint32_t full_u32 = ptx::smem_u32(sm.full), empty_u32 = ptx::smem_u32(sm.empty);
-  const uint32_t pready_u32 = ptx::smem_u32(sm.panel_ready), accfull_u32 = ptx::smem_u32(sm.acc_full);
-
-  if (warp == 0) {
-    // =============================== TMA producer (whole warp converged, one elected lane issues) =====
-    int stage = 0; uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int feat_row = p.feat_row0 + tile * kTileM;
-      for (int l = 0; l < p.n_layers; ++l) {
-        const TcLayer& L = p.layers[l];
-        if (!layer_has_mma(L)) continue;
-        const int a_res = L.a_res, kps = L.a_res + L.a_str, n_halves = L.n_halves;
-        const uint32_t w_bytes = (uint32_t)L.n_mma * 128u;
-        const CUtensorMap* wmap = L.w_map ? &p.map_w16 : &p.map_w128;
-        const int w_row = L.w_row;
-        for (int h = 0; h < n_halves; ++h) {
+  if (warp == kProducerWarp) {
+    // =============================== TMA producer (one lane) ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int tile_iter = 0;
+      long long c_empty = 0, c_tile = 0;
+      const long long c_start = clock64();
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tile_iter) {
+        const int feat_row = p.feat_row0 + tile * kTileM;
+        if (feat_resident) {
+          // the tile's 512 IPE feature columns go straight into the eight activation panels, which are
+          // free between tiles: every MMA of the previous tile has completed and no TMA store reads them
+          if (tile_iter > 0) {
+            const long long c0 = clock64();
+            ptx::mbar_wait_u32(accfull_u32 + 7 * 8, (uint32_t)((tile_iter - 1) & 1));
+            ptx::mbar_wait_u32(pfree_u32, (uint32_t)((tile_iter - 1) & 1));
+            c_tile += clock64() - c0;
+          }
+          for (int kp = 0; kp < kNumPanels; ++kp) {
+            ptx::mbar_expect_tx_u32(featready_u32 + kp * 8, kPanelBytes);
+            ptx::tma_load_2d_u32(panels_u32 + kp * kPanelBytes, &p.map_feat, featready_u32 + kp * 8, kp * 64, feat_row);
+          }
+        }
+        for (int l = 0; l < p.n_layers; ++l) {
+          const TcLayer& L = p.layers[l];
+          if (!layer_has_mma(L)) continue;
+          const int a_res = L.a_res, kps = L.a_res + L.a_str, n_halves = L.n_halves;
+          const uint32_t w_bytes = (uint32_t)L.n_mma * 128u;
+          const CUtensorMap* wmap = L.w_map ? &p.map_w16 : &p.map_w128;
+          const int w_row = L.w_row;
           for (int kp = 0; kp < kps; ++kp) {
             if (kp >= a_res) {
               ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-              if (ptx::elect_one()) {
-                ptx::mbar_expect_tx_u32(full_u32 + stage * 8, kPanelBytes);
-                ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, &p.map_feat, full_u32 + stage * 8,
-                                     (kp - a_res) * 64, feat_row);
-              }
-              __syncwarp();
+              ptx::mbar_expect_tx_u32(full_u32 + stage * 8, kPanelBytes);
+              ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, &p.map_feat, full_u32 + stage * 8,
+                                   (kp - a_res) * 64, feat_row);
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-            if (ptx::elect_one()) {
+            for (int h = 0; h < n_halves; ++h) {
+              const long long c0 = clock64();
+              ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+              c_empty += clock64() - c0;
               ptx::mbar_expect_tx_u32(full_u32 + stage * 8, w_bytes);
               ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, wmap, full_u32 + stage * 8, kp * 64,
                                    w_row + h * 128);
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-          }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // =============================== MMA issuer (whole warp converged, one elected lane issues) ========
-    constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
-    int stage = 0; uint32_t phase = 0;
-    uint32_t panel_phase = 0;   // bit i: parity to wait for on panel_ready[i]
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      for (int l = 0; l < p.n_layers; ++l) {
-        const TcLayer& L = p.layers[l];
-        if (!layer_has_mma(L)) continue;
-        const int a_res = L.a_res, kps = L.a_res + L.a_str, n_halves = L.n_halves;
-        const int a_panel0 = L.a_buf * 4;
-        const bool wait_panels = L.wait_panels != 0;
-        const uint32_t idesc = ptx::make_idesc_bf16(128, L.n_mma, 0, 0);
-        const uint32_t acc_bar = accfull_u32 + L.acc_bar * 8;
-        const uint32_t acc_tmem = tmem_base + (uint32_t)L.acc_col;
-        for (int h = 0; h < n_halves; ++h) {
-          const uint32_t d_tmem = acc_tmem + (uint32_t)(h * 128);
-          for (int kp = 0; kp < kps; ++kp) {
-            uint32_t a_addr, a_empty = 0;
-            if (kp < a_res) {
-              const int pi = a_panel0 + kp;
-              if (h == 0 && wait_panels) {
-                ptx::mbar_wait_u32(pready_u32 + pi * 8, (panel_phase >> pi) & 1u);
-                panel_phase ^= 1u << pi;
-              }
-              a_addr = panels_u32 + pi * kPanelBytes;
-            } else {
-              ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
-              a_addr = ring_u32 + stage * kPanelBytes;
-              a_empty = empty_u32 + stage * 8;
               if (++stage == kStages) { stage = 0; phase ^= 1; }
             }
-            ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
-            const uint32_t b_addr = ring_u32 + stage * kPanelBytes;
-            ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint64_t da = ptx::desc_from(kDescHi, a_addr), db = ptx::desc_from(kDescHi, b_addr);
-              // advancing K by 16 bf16 (32 bytes) inside the 128B swizzle atom = +2 in the address field
-              ptx::mma_bf16_ss(d_tmem, da, db, idesc, kp > 0 ? 1u : 0u);
-              ptx::mma_bf16_ss(d_tmem, da + 2, db + 2, idesc, 1u);
-              ptx::mma_bf16_ss(d_tmem, da + 4, db + 4, idesc, 1u);
-              ptx::mma_bf16_ss(d_tmem, da + 6, db + 6, idesc, 1u);
-              ptx::mma_commit_u32(empty_u32 + stage * 8);
-              if (a_empty) ptx::mma_commit_u32(a_empty);
-              if (kp == kps - 1) ptx::mma_commit_u32(acc_bar + h * 8);
-            }
-            __syncwarp();
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
-      if (ptx::elect_one()) ptx::mma_commit_u32(accfull_u32 + 7 * 8);   // tile_done: every MMA of this tile completed
-      __syncwarp();
+      if (p.dbg) {
+        long long* d = p.dbg + blockIdx.x * 16;
+        d[0] = clock64() - c_start; d[1] = c_empty; d[2] = c_tile;
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // =============================== MMA issuer (one lane walks the step list) ===============================
+    if (lane == 0) {
+      constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t wait_phase = 0;    // bit i: parity to wait for on barrier i of {panel_ready, feat_ready}
+      long long c_panel = 0, c_full = 0, c_issue = 0;
+      const long long c_start = clock64();
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+#pragma unroll 1
+        for (int i = 0; i < n_steps; ++i) {
+          const uint4 e = sm.steps[i];
+          const uint32_t wi = e.w & 31u;
+          if (wi) {
+            const uint32_t idx = wi - 1;
+            const long long c0 = clock64();
+            ptx::mbar_wait_u32(waitbar_u32 + idx * 8, (wait_phase >> idx) & 1u);
+            c_panel += clock64() - c0;
+            wait_phase ^= 1u << idx;
+          }
+          uint32_t a_addr = e.x, a_empty = 0;
+          if (a_addr == 0) {
+            ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+            a_addr = ring_u32 + stage * kPanelBytes;
+            a_empty = empty_u32 + stage * 8;
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          long long c1 = clock64();
+          ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+          long long c2 = clock64();
+          c_full += c2 - c1;
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::desc_from(kDescHi, a_addr);
+          const uint32_t d_tmem = tmem_base + e.y;
+          {
+            // advancing K by 16 bf16 (32 bytes) inside the 128B swizzle atom = +2 in the address field
+            const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kPanelBytes);
+            ptx::mma_bf16_ss(d_tmem, da, db, e.z, (e.w >> 5) & 1u);
+            ptx::mma_bf16_ss(d_tmem, da + 2, db + 2, e.z, 1u);
+            ptx::mma_bf16_ss(d_tmem, da + 4, db + 4, e.z, 1u);
+            ptx::mma_bf16_ss(d_tmem, da + 6, db + 6, e.z, 1u);
+            ptx::mma_commit_u32(empty_u32 + stage * 8);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+          c_issue += clock64() - c2;
+          if (e.w & 64u) {
+            c1 = clock64();
+            ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+            c2 = clock64();
+            c_full += c2 - c1;
+            ptx::tc_fence_after();
+            const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kPanelBytes);
+            ptx::mma_bf16_ss(d_tmem + 128, da, db, e.z, (e.w >> 5) & 1u);
+            ptx::mma_bf16_ss(d_tmem + 128, da + 2, db + 2, e.z, 1u);
+            ptx::mma_bf16_ss(d_tmem + 128, da + 4, db + 4, e.z, 1u);
+            ptx::mma_bf16_ss(d_tmem + 128, da + 6, db + 6, e.z, 1u);
+            ptx::mma_commit_u32(empty_u32 + stage * 8);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            c_issue += clock64() - c2;
+          }
+          if (a_empty) ptx::mma_commit_u32(a_empty);
+          const uint32_t ci = (e.w >> 8) & 15u;
+          if (ci) ptx::mma_commit_u32(accfull_u32 + (ci - 1) * 8);
+        }
+        ptx::mma_commit_u32(accfull_u32 + 7 * 8);   // tile_done: every MMA of this tile has completed
+      }
+      if (p.dbg) {
+        long long* d = p.dbg + blockIdx.x * 16;
+        d[4] = clock64() - c_start; d[5] = c_panel; d[6] = c_full; d[7] = c_issue;
+      }
     }
   } else {
     // =============================== epilogue groups ===============================
-    const int ew = warp - 2;               // 0..15
+    const int ew = warp;                   // 0..15 (the scheduler favours high warp ids: issuer warps come last)
     const int q = ew >> 2;                 // group: owns output columns [64q, 64q+64) of a 256-wide layer
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;   // tile row == TMEM lane
@@ -382,6 +455,8 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
     uint32_t acc_phase = 0;
     int tile_iter = 0;
     float v[32];
+    long long c_acc = 0, c_guard = 0, c_ld = 0, c_math = 0, c_pub = 0;
+    const long long c_epi_start = clock64();
 
     // Publish a finished panel: optional TMA store (saved activations / dZ), then signal the MMA issuer.
     auto publish = [&](const TcLayer& L, int pi, int col, int tile) {
@@ -399,12 +474,16 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
     // The panel this group is about to overwrite was TMA-stored two layers ago: that read must be done.
     auto guard_panel = [&](const TcLayer& L) {
       if (kTrain && L.save_row >= 0) {
+        const long long c0 = clock64();
         if (group_leader) ptx::tma_wait_group_read<1>();
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        c_guard += clock64() - c0;
       }
     };
     auto wait_acc = [&](int bar) {
+      const long long c0 = clock64();
       ptx::mbar_wait(&sm.acc_full[bar], (acc_phase >> bar) & 1u);
+      c_acc += clock64() - c0;
       acc_phase ^= 1u << bar;
       ptx::tc_fence_after();
     };
@@ -424,10 +503,13 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
             const int col = q * 64, pi = L.dst_buf * 4 + q;
             uint8_t* panel = sm.panels + pi * kPanelBytes;
             guard_panel(L);
-            wait_acc(L.acc_bar + (q >> 1));
+            wait_acc(L.acc_bar);
 #pragma unroll 1
             for (int hf = 0; hf < 2; ++hf) {
+              const long long c0 = clock64();
               load_acc32(lane_addr + (uint32_t)(L.acc_col + col + hf * 32), v);
+              const long long c1 = clock64();
+              c_ld += c1 - c0;
               const float4* b4 = reinterpret_cast<const float4*>(sm.bias + L.bias_off + col + hf * 32);
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
@@ -436,8 +518,11 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
               }
               if (L.epi == EPI_RELU) store_half32<true>(panel, row, hf * 4, v);
               else store_half32<false>(panel, row, hf * 4, v);
+              c_math += clock64() - c1;
             }
+            const long long c2 = clock64();
             publish(L, pi, col, tile);
+            c_pub += clock64() - c2;
             break;
           }
           case EPI_BWD_LINEAR: case EPI_BWD_RELU: case EPI_BWD_RELU_D: {
@@ -459,7 +544,7 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
                 dd = valid ? __bfloat162float(__float2bfloat16(p.d_raw[(size_t)s * p.raw_c])) : 0.f;
             }
             guard_panel(L);
-            wait_acc(L.acc_bar + (q >> 1));
+            wait_acc(L.acc_bar);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
               load_acc32(lane_addr + (uint32_t)(L.acc_col + col + hf * 32), v);
@@ -591,12 +676,22 @@ __global__ void __launch_bounds__(kThreads, 1) mlp_chain_kernel(const __grid_con
           default: break;
         }
       }
+      if (feat_resident && group_leader) {
+        // the producer refills the panels with the next tile's features once no TMA store reads them
+        if (kTrain) ptx::tma_wait_group_read<0>();
+        ptx::mbar_arrive(sm.panels_free);
+      }
     }
     if (group_leader) ptx::tma_wait_group<0>();
+    if (p.dbg && (threadIdx.x == 0 || threadIdx.x == 3 * 128)) {
+      long long* d = p.dbg + blockIdx.x * 16 + (threadIdx.x == 0 ? 8 : 12);
+      d[0] = clock64() - c_epi_start; d[1] = c_acc; d[2] = c_guard;
+      if (threadIdx.x == 0) { long long* e = p.dbg + blockIdx.x * 16; e[3] = c_ld; e[11] = c_math; e[15] = c_pub; }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -682,9 +777,10 @@ int build_mlp_schedule(hugs_handle* h, const MlpViews& mv, TcMlp* m, int save_la
   // ---- forward schedule ----
   auto trunk_layer = [&](int i, bool first, bool cat) {
     TcLayer L{};
-    L.a_res = first ? 0 : 4; L.a_str = (first || cat) ? kFeatPad / 64 : 0;
-    L.a_buf = i % 2; L.wait_panels = 1; L.n_halves = 2; L.n_mma = 128;
-    L.acc_col = (i % 2) * 256; L.acc_bar = (i % 2) * 2;
+    L.a_res = first ? kFeatPad / 64 : 4; L.a_str = (!first && cat) ? kFeatPad / 64 : 0;
+    L.a_feat = first ? 1 : 0;
+    L.a_buf = first ? 0 : i % 2; L.wait_panels = 1; L.n_halves = 2; L.n_mma = 128;
+    L.acc_col = (i % 2) * 256; L.acc_bar = i % 2;
     L.w_row = layer_w_row[i]; L.w_map = 0; L.epi = EPI_RELU; L.dst_buf = (i + 1) % 2; L.bias_off = layer_bias[i];
     L.save_row = -1; L.mask_row = -1;
     return L;
@@ -708,7 +804,7 @@ int build_mlp_schedule(hugs_handle* h, const MlpViews& mv, TcMlp* m, int save_la
     const int other = (D + 1) % 2;        // accumulator / buffer parity not used by the bottleneck
     TcLayer B{};                          // bottleneck (linear)
     B.a_res = 4; B.a_buf = head_buf; B.wait_panels = 1; B.n_halves = 2; B.n_mma = 128;
-    B.acc_col = (D % 2) * 256; B.acc_bar = (D % 2) * 2; B.w_row = layer_w_row[D + 1]; B.w_map = 0;
+    B.acc_col = (D % 2) * 256; B.acc_bar = D % 2; B.w_row = layer_w_row[D + 1]; B.w_map = 0;
     B.epi = EPI_LINEAR; B.dst_buf = other; B.bias_off = layer_bias[D + 1]; B.save_row = -1; B.mask_row = -1;
     m->fwd.push_back(B);
     TcLayer Dn{};                         // density head reads the same activation (already waited for)
@@ -736,7 +832,7 @@ int build_mlp_schedule(hugs_handle* h, const MlpViews& mv, TcMlp* m, int save_la
   auto mma_op = [&](int k, int a_res, int w_row, int epi, int save_slot, int mask_slot) {
     TcLayer L{};
     L.a_res = a_res; L.a_str = 0; L.a_buf = (k - 1) % 2; L.wait_panels = 1; L.n_halves = 2; L.n_mma = 128;
-    L.acc_col = ((k - 1) % 2) * 256; L.acc_bar = ((k - 1) % 2) * 2; L.w_row = w_row; L.w_map = 0; L.epi = epi;
+    L.acc_col = ((k - 1) % 2) * 256; L.acc_bar = (k - 1) % 2; L.w_row = w_row; L.w_map = 0; L.epi = epi;
     L.dst_buf = k % 2; L.bias_off = 0; L.save_row = save_slot; L.mask_row = mask_slot;
     return L;
   };
@@ -906,6 +1002,7 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
   p.n_tiles = n_tiles; p.n_samples = n_samples; p.S = S; p.feat_row0 = tc->feat_row0[level];
   p.bias = m.bias; p.viewbias = tc->viewbias; p.raw_out = h->raw[level]; p.raw_c = is_prop ? 1 : 4;
   p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off; p.bias_floats = m.bias_floats;
+  p.dbg = (!is_prop) ? h->dbg_counters : nullptr;
   const int grid = std::min(n_tiles, tc->num_sms);
   ProfScope ps(h, is_prop ? HUGS_K_CHAIN_FWD_PROP : HUGS_K_CHAIN_FWD_NERF, st);
   if (training) mlp_chain_kernel<true><<<grid, kThreads, kSmemBytes, st>>>(p);

@@ -32,25 +32,30 @@ __device__ __forceinline__ bool mbar_try_wait_u32(uint32_t bar_addr, uint32_t pa
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(bar_addr), "r"(parity)
+      : "r"(bar_addr), "r"(parity), "r"(0x989680u)   // suspend-time hint (ns), as CUTLASS passes
       : "memory");
   return ok != 0;
 }
-static __device__ __noinline__ void mbar_wait_slow(uint32_t bar_addr, uint32_t parity) {
-  const long long t0 = clock64();
+static __device__ __noinline__ void mbar_wait_timeout(uint32_t bar_addr, uint32_t parity) {
+  printf("hugs_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x, threadIdx.x,
+         bar_addr, parity);
+  __trap();
+}
+// try_wait suspends the thread in hardware until the phase completes or a time limit expires, so the
+// loop body is two instructions; the watchdog only looks at the clock every 64K wake-ups.
+__device__ __forceinline__ void mbar_wait_u32(uint32_t bar_addr, uint32_t parity) {
+  uint32_t spins = 0;
+  long long t0 = 0;
   while (!mbar_try_wait_u32(bar_addr, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
-      printf("hugs_b200: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n", blockIdx.x,
-             threadIdx.x, bar_addr, parity);
-      __trap();
+    if ((++spins & 0xFFFFu) == 0u) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) mbar_wait_timeout(bar_addr, parity);   // ~2 s: protocol bug -> trap
     }
   }
-}
-__device__ __forceinline__ void mbar_wait_u32(uint32_t bar_addr, uint32_t parity) {
-  if (!mbar_try_wait_u32(bar_addr, parity)) mbar_wait_slow(bar_addr, parity);
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_u32(smem_u32(bar), parity); }
 

@@ -21,8 +21,9 @@ constexpr int kKP = kW + kFeatPad;      // K extent of the packed forward weight
 constexpr int kEpiGroups = 4;           // epilogue groups of 128 threads; group q owns output columns [64q, 64q+64)
 constexpr int kThreads = 64 + kEpiGroups * 128;   // producer warp + MMA warp + epilogue warps
 constexpr int kHeadCols = 64;           // columns of the head-gradient tensor (d_r, d_g, d_b, d_density, 0...)
-constexpr int kBiasTab = 3584;          // fp32 bias / head-weight table staged in shared memory
-constexpr int kSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTab * 4 + 512;
+constexpr int kBiasTab = 3136;          // fp32 bias / head-weight table staged in shared memory
+constexpr int kMaxSteps = 64;           // MMA issue steps per tile (precomputed list in shared memory)
+constexpr int kSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTab * 4 + kMaxSteps * 16 + 512;
 
 enum Epi : int {
   EPI_RELU = 0,      // bias + ReLU -> bf16 panels            (trunk)
@@ -40,6 +41,7 @@ enum Epi : int {
 
 struct TcLayer {
   int a_res, a_str, a_buf, wait_panels;
+  int a_feat;        // 1: the resident A panels are the tile's IPE features, TMA-loaded into panels 0..7 (layer 0)
   int n_halves, n_mma, acc_col, acc_bar;
   int w_row, w_map;
   int epi, dst_buf, bias_off;
@@ -64,6 +66,7 @@ struct alignas(64) TcParams {
   __nv_bfloat16* drgb_out;           // bwd: [rows, kHeadCols] bf16 head gradients for the head wgrad GEMMs
   int w_dens_off, w_rgb_off;         // float offsets of head weights inside `bias`
   int bias_floats;                   // size of the bias table
+  long long* dbg;                    // optional [gridDim.x][16] cycle counters (development instrumentation)
 };
 
 struct TcMlp {

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   uint64_t* acc_full = bars + 2 * kWgStages; uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&p.map_act64); ptx::prefetch_tmap(&p.map_feat64); ptx::prefetch_tmap(&p.map_dz64);
     ptx::prefetch_tmap(&p.map_dh64);
     // a stage is released by the MMA commit and by the four epilogue warps (bias column sums read B)
@@ -77,13 +77,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
     ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_empty, 128);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) ptx::tmem_alloc(tmem_ptr, 512);
+  if (warp == 5) ptx::tmem_alloc(tmem_ptr, 512);
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  if (warp == 0) {
+  if (warp == 4) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0, ae_phase = 0;
       bool first_item = true;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   } else {
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
-    const int t = (warp - 2) * 32 + lane;          // 0..127: owns B columns 2t, 2t+1 for the bias sums
+    const int t = warp * 32 + lane;                // 0..127: owns B columns 2t, 2t+1 for the bias sums
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     uint32_t af_phase = 0;
     int stage = 0; uint32_t phase = 0;
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) ptx::tmem_dealloc(tmem_base, 512);
+  if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
 }
 
 // ---------------------------------------------------------------- CUDA-core reductions (view layer extras)
