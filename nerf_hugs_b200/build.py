@@ -19,6 +19,7 @@ SOURCES = [
     ('composite.cu', ['-fmad=false']),
     ('mlp_simt.cu', ['-fmad=false']),
     ('mlp_tc.cu', []),
+    ('mlp_pp.cu', []),
     ('wgrad_tc.cu', []),
     ('tc_microbench.cu', []),
     ('optim.cu', []),

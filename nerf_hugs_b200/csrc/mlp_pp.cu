@@ -1,0 +1,555 @@
+// Ping-pong MLP chain kernel (sm_100a): two 128-sample tiles in flight per CTA.
+//
+// While the epilogue warps turn tile A's accumulator into the next layer's A operand, the tensor core
+// already runs tile B's MMAs of the same layer, and vice versa — MMA, epilogue and TMA latencies of one
+// tile hide behind the other tile (profiles/r01_microbench_and_counters.md shows they were serialised
+// in the single-tile kernel).
+//
+//   shared memory  panels[8]  : tile t owns panels 4t..4t+3 = its 128 x 256 bf16 activation, updated IN PLACE
+//                               (a layer's epilogue starts only after all MMAs of that layer have completed)
+//                  ring[5]    : 16 KB weight stages ([128 out x 64 in] bf16, SWIZZLE_128B), TMA-fed
+//                  bias table, head partial sums, mbarriers
+//   tensor memory  tile t accumulates in columns [256t, 256t+256)
+//   warps          0-15 epilogue (group q = warp/4 owns output columns [64q, 64q+64)),
+//                  16 weight producer, 17 feature producer, 18 MMA issuer
+//
+// A layer is a sequence of *segments* of <= 4 K-panels (K <= 256).  IPE features (layer 0 and the skip
+// connection) are TMA-loaded straight into the tile's own panels once the previous segment has been
+// consumed; the N = 1 / N = 3 heads are evaluated on CUDA cores inside the producing epilogue.
+#include <algorithm>
+
+#include "tc_device.cuh"
+#include "tc_internal.h"
+
+namespace hugs {
+namespace {
+
+constexpr int kPpThreads = (kEpiGroups * 4 + 3) * 32;
+constexpr int kPartFloats = 768;     // head partial sums: [2 tiles][3][128]
+constexpr int kPpSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTab * 4 + kPartFloats * 4 + 512;
+
+struct PpSmem {
+  uint8_t* panels; uint8_t* ring; float* bias; float* part;
+  uint64_t *full, *empty, *panel_ready, *feat_ready, *acc_full, *consumed, *epi_done;
+  uint32_t* tmem_ptr;
+};
+
+__device__ __forceinline__ PpSmem pp_carve(uint8_t* raw) {
+  PpSmem s;
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  s.panels = base;
+  s.ring = base + kNumPanels * kPanelBytes;
+  s.bias = reinterpret_cast<float*>(s.ring + kStages * kPanelBytes);
+  s.part = s.bias + kBiasTab;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.part + kPartFloats);
+  s.full = bars; s.empty = bars + kStages;
+  s.panel_ready = bars + 2 * kStages;        // [8]
+  s.feat_ready = s.panel_ready + 8;          // [8]
+  s.acc_full = s.feat_ready + 8;             // [2]
+  s.consumed = s.acc_full + 2;               // [2]
+  s.epi_done = s.consumed + 2;               // [2]
+  s.tmem_ptr = reinterpret_cast<uint32_t*>(s.epi_done + 2);
+  return s;
+}
+
+template <bool kTrain>
+__global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_constant__ PpParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  PpSmem sm = pp_carve(smem_raw);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWProd = kEpiGroups * 4, kFProd = kWProd + 1, kMma = kWProd + 2;
+
+  const uint32_t panels_u32 = ptx::smem_u32(sm.panels), ring_u32 = ptx::smem_u32(sm.ring);
+  const uint32_t full_u32 = ptx::smem_u32(sm.full), empty_u32 = ptx::smem_u32(sm.empty);
+  const uint32_t pready_u32 = ptx::smem_u32(sm.panel_ready), fready_u32 = ptx::smem_u32(sm.feat_ready);
+  const uint32_t accfull_u32 = ptx::smem_u32(sm.acc_full), consumed_u32 = ptx::smem_u32(sm.consumed);
+  const uint32_t epidone_u32 = ptx::smem_u32(sm.epi_done);
+
+  if (warp == kWProd && lane == 0) {
+    ptx::prefetch_tmap(&p.map_w); ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
+    for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&sm.full[i], 1); ptx::mbar_init(&sm.empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { ptx::mbar_init(&sm.panel_ready[i], 128); ptx::mbar_init(&sm.feat_ready[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&sm.acc_full[i], 1); ptx::mbar_init(&sm.consumed[i], 1); ptx::mbar_init(&sm.epi_done[i], kEpiGroups);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == kMma) ptx::tmem_alloc(sm.tmem_ptr, 512);
+  for (int i = threadIdx.x; i < p.bias_floats; i += kPpThreads) sm.bias[i] = p.bias[i];
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *sm.tmem_ptr;
+
+  if (warp == kWProd) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+        for (int si = 0; si < p.n_segs; ++si) {
+          const PpSeg& S = p.segs[si];
+          if (S.kps == 0) continue;
+          const int kps = S.kps, n_halves = S.n_halves, w_row = S.w_row, w_col0 = S.w_col0;
+          for (int t = 0; t < 2; ++t)
+            for (int kp = 0; kp < kps; ++kp)
+              for (int h = 0; h < n_halves; ++h) {
+                ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                ptx::mbar_expect_tx_u32(full_u32 + stage * 8, kPanelBytes);
+                ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, &p.map_w, full_u32 + stage * 8,
+                                     w_col0 + kp * 64, w_row + h * 128);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
+        }
+      }
+    }
+  } else if (warp == kFProd) {
+    // =============================== feature producer ===============================
+    // Walks the MMA segments in issue order and waits for every `consumed` phase exactly once (no phase is
+    // ever skipped, so parity waits cannot alias); refills a tile's panels with IPE feature columns as soon
+    // as the segment that last read those panels has completed.
+    if (lane == 0 && p.any_feat) {
+      uint32_t cons_phase = 0;   // bit t: parity of the next `consumed[t]` phase to wait for
+      bool first = true;
+      int pair_iter = 0;
+      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++pair_iter) {
+        bool first_in_pair = true;
+        for (int si = 0; si < p.n_segs; ++si) {
+          const PpSeg& S = p.segs[si];
+          if (S.kps == 0) continue;
+          for (int t = 0; t < 2; ++t) {
+            if (!(first && first_in_pair)) {       // every segment but the very first has a predecessor on tile t
+              ptx::mbar_wait_u32(consumed_u32 + t * 8, (cons_phase >> t) & 1u);
+              cons_phase ^= 1u << t;
+            }
+            if (S.a_feat) {
+              if (first_in_pair && pair_iter > 0)   // previous pair's last epilogue (and its TMA store) is done
+                ptx::mbar_wait_u32(epidone_u32 + t * 8, (uint32_t)((pair_iter - 1) & 1));
+              const int row = p.feat_row0 + (pair * 2 + t) * kTileM;
+              for (int kp = 0; kp < S.kps; ++kp) {
+                const uint32_t bar = fready_u32 + (t * 4 + kp) * 8;
+                ptx::mbar_expect_tx_u32(bar, kPanelBytes);
+                ptx::tma_load_2d_u32(panels_u32 + (t * 4 + kp) * kPanelBytes, &p.map_feat, bar,
+                                     S.feat_col0 + kp * 64, row);
+              }
+            }
+          }
+          first_in_pair = false;
+        }
+        first = false;
+      }
+    }
+  } else if (warp == kMma) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
+      const uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t wait_phase = 0;   // bits 0-7 panel_ready, 8-15 feat_ready
+      long long c_panel = 0, c_feat = 0, c_full = 0;
+      const long long c_start = clock64();
+      const bool dbg = p.dbg != nullptr;
+      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+        for (int si = 0; si < p.n_segs; ++si) {
+          const PpSeg& S = p.segs[si];
+          if (S.kps == 0) continue;
+          const int kps = S.kps, n_halves = S.n_halves, a_feat = S.a_feat, acc0 = S.accumulate;
+          const bool has_epi = S.epi != EPI_NONE;
+          for (int t = 0; t < 2; ++t) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
+            if (!a_feat) {
+              // in-place accumulator: every epilogue group must have drained the previous layer before the
+              // first MMA of this one overwrites it, so wait for all consumed panels up front
+              const long long c0 = dbg ? clock64() : 0;
+              for (int kp = 0; kp < kps; ++kp) {
+                const uint32_t idx = (uint32_t)(t * 4 + kp);
+                ptx::mbar_wait_u32(pready_u32 + idx * 8, (wait_phase >> idx) & 1u);
+                wait_phase ^= 1u << idx;
+              }
+              if (dbg) c_panel += clock64() - c0;
+            }
+            for (int kp = 0; kp < kps; ++kp) {
+              if (a_feat) {
+                const uint32_t idx = (uint32_t)(8 + t * 4 + kp);
+                const long long c0 = dbg ? clock64() : 0;
+                ptx::mbar_wait_u32(fready_u32 + (t * 4 + kp) * 8, (wait_phase >> idx) & 1u);
+                if (dbg) c_feat += clock64() - c0;
+                wait_phase ^= 1u << idx;
+              }
+              const uint64_t da = ptx::desc_from(kDescHi, panels_u32 + (t * 4 + kp) * kPanelBytes);
+              const uint32_t accum = (acc0 || kp > 0) ? 1u : 0u;
+              for (int h = 0; h < n_halves; ++h) {
+                const long long c0 = dbg ? clock64() : 0;
+                ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+                if (dbg) c_full += clock64() - c0;
+                ptx::tc_fence_after();
+                const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kPanelBytes);
+                const uint32_t d = d_tmem + (uint32_t)(h * 128);
+                ptx::mma_bf16_ss(d, da, db, idesc, accum);
+                ptx::mma_bf16_ss(d, da + 2, db + 2, idesc, 1u);
+                ptx::mma_bf16_ss(d, da + 4, db + 4, idesc, 1u);
+                ptx::mma_bf16_ss(d, da + 6, db + 6, idesc, 1u);
+                ptx::mma_commit_u32(empty_u32 + stage * 8);
+                if (++stage == kStages) { stage = 0; phase ^= 1; }
+              }
+            }
+            ptx::mma_commit_u32(consumed_u32 + t * 8);
+            if (has_epi) ptx::mma_commit_u32(accfull_u32 + t * 8);
+          }
+        }
+      }
+      if (dbg) {
+        long long* d = p.dbg + blockIdx.x * 16;
+        d[4] = clock64() - c_start; d[5] = c_panel; d[6] = c_full; d[7] = c_feat;
+      }
+    }
+  } else {
+    // =============================== epilogue groups ===============================
+    const int q = warp >> 2;               // group: output columns [64q, 64q+64)
+    const int quarter = warp & 3;          // TMEM lane quarter of this warp
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool group_leader = (warp & 3) == 0 && lane == 0;
+    const int bar_id = 1 + q;
+    uint32_t acc_phase = 0;
+    float v[32];
+    float raw_keep[2] = {0.f, 0.f};
+    const int col = q * 64;
+
+    // make the freshly written panel visible to the async proxy, optionally TMA-store it (its smem read is
+    // complete before panel_ready completes, so later in-place overwrites / feature refills are safe),
+    // then hand it to the MMA issuer
+    auto publish = [&](const PpSeg& S, int pi, int tile, bool tile_ok) {
+      ptx::fence_proxy_async();
+      if (kTrain && S.save_row >= 0) {
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (group_leader && tile_ok) {
+          ptx::tma_store_2d(&p.map_save, sm.panels + pi * kPanelBytes, col, S.save_row + tile * kTileM);
+          ptx::tma_commit_group();
+          ptx::tma_wait_group_read<0>();
+        }
+      }
+      ptx::tc_fence_before();
+      if (!S.no_signal) ptx::mbar_arrive(&sm.panel_ready[pi]);
+    };
+
+    for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+      for (int si = 0; si < p.n_segs; ++si) {
+        const PpSeg& S = p.segs[si];
+        if (S.epi == EPI_NONE) continue;
+        for (int t = 0; t < 2; ++t) {
+          const int tile = pair * 2 + t;
+          const bool tile_ok = tile < p.n_tiles;
+          const int s = tile * kTileM + row;
+          const bool valid = s < p.n_samples;
+          const int pi = t * 4 + q;
+          uint8_t* panel = sm.panels + pi * kPanelBytes;
+          const uint32_t acc_addr = lane_addr + (uint32_t)(t * 256 + col);
+          const bool participates = !((S.epi == EPI_VIEW || S.epi == EPI_BWD_START) && q >= 2);
+
+          // side inputs that do not depend on the accumulator are fetched before waiting for the MMAs
+          uint4 mk[8];
+          float dd = 0.f;
+          const bool need_mask = S.epi == EPI_BWD_RELU || S.epi == EPI_BWD_RELU_D || S.epi == EPI_BWD_START ||
+                                 S.epi == EPI_BWD_START_PROP;
+          if (need_mask && participates) {
+            if (valid) {
+              const uint4* src = reinterpret_cast<const uint4*>(p.act + ((size_t)S.mask_row + s) * kW + col);
+#pragma unroll
+              for (int c = 0; c < 8; ++c) mk[c] = __ldg(src + c);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 8; ++c) mk[c] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+          if (S.epi == EPI_BWD_RELU_D) dd = valid ? __bfloat162float(__float2bfloat16(p.d_raw[(size_t)s * p.raw_c])) : 0.f;
+
+          if (S.kps > 0) {
+            if (participates) ptx::mbar_wait_u32(accfull_u32 + t * 8, (acc_phase >> t) & 1u);
+            acc_phase ^= 1u << t;             // the phase advances whether or not this group takes part
+            ptx::tc_fence_after();
+          }
+
+          switch (S.epi) {
+            case EPI_RELU: case EPI_LINEAR: {
+              float head = 0.f;
+#pragma unroll 1
+              for (int hf = 0; hf < 2; ++hf) {
+                load_acc32(acc_addr + (uint32_t)(hf * 32), v);
+                const float4* b4 = reinterpret_cast<const float4*>(sm.bias + S.bias_off + col + hf * 32);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b = b4[c];
+                  v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                }
+                if (S.head) {   // density head: dot of the bf16-rounded activation with the bf16-rounded kernel
+                  const float* wd = sm.bias + p.w_dens_off + col + hf * 32;
+#pragma unroll
+                  for (int c = 0; c < 32; ++c)
+                    head = fmaf(__bfloat162float(__float2bfloat16(fmaxf(v[c], 0.f))), wd[c], head);
+                }
+                if (S.epi == EPI_RELU) store_half32<true>(panel, row, hf * 4, v);
+                else store_half32<false>(panel, row, hf * 4, v);
+              }
+              if (S.head) {
+                float* part = sm.part + t * 384;
+                if (q > 0) part[(q - 1) * 128 + row] = head;
+                asm volatile("bar.sync 5, 512;" ::: "memory");
+                if (q == 0) {
+                  const float rd = ((head + part[row]) + part[128 + row]) + part[256 + row] + sm.bias[p.dens_bias_off];
+                  raw_keep[t] = rd;
+                  if (p.raw_c == 1 && valid) p.raw_out[s] = rd;
+                }
+              }
+              publish(S, pi, tile, tile_ok);
+              break;
+            }
+            case EPI_VIEW: {
+              if (q < 2) {
+                float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+                  load_acc32(acc_addr + (uint32_t)(hf * 32), v);
+                  if (valid) {
+                    const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(s / p.S) * 128 + col + hf * 32);
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                      const float4 b = __ldg(b4 + c);
+                      v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                    }
+                  }
+                  const float* wr = sm.bias + p.w_rgb_off + (col + hf * 32) * 3;
+#pragma unroll
+                  for (int c = 0; c < 32; ++c) {
+                    const float a = __bfloat162float(__float2bfloat16(fmaxf(v[c], 0.f)));
+                    h0 = fmaf(a, wr[c * 3], h0); h1 = fmaf(a, wr[c * 3 + 1], h1); h2 = fmaf(a, wr[c * 3 + 2], h2);
+                  }
+                  if (kTrain) store_half32<true>(panel, row, hf * 4, v);
+                }
+                float* part = sm.part + t * 384;
+                if (q == 1) { part[row * 3] = h0; part[row * 3 + 1] = h1; part[row * 3 + 2] = h2; }
+                asm volatile("bar.sync 6, 256;" ::: "memory");
+                if (q == 0 && valid) {
+                  float4 o;
+                  o.x = raw_keep[t];
+                  o.y = h0 + part[row * 3] + sm.bias[p.rgb_bias_off];
+                  o.z = h1 + part[row * 3 + 1] + sm.bias[p.rgb_bias_off + 1];
+                  o.w = h2 + part[row * 3 + 2] + sm.bias[p.rgb_bias_off + 2];
+                  reinterpret_cast<float4*>(p.raw_out)[s] = o;
+                }
+                publish(S, pi, tile, tile_ok);
+              }
+              break;
+            }
+            case EPI_BWD_LINEAR: case EPI_BWD_RELU: case EPI_BWD_RELU_D: {
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                load_acc32(acc_addr + (uint32_t)(hf * 32), v);
+                if (S.epi == EPI_BWD_RELU_D) {
+                  const float4* w4 = reinterpret_cast<const float4*>(sm.bias + p.w_dens_off + col + hf * 32);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 w = w4[c];
+                    v[c * 4 + 0] = fmaf(dd, w.x, v[c * 4 + 0]); v[c * 4 + 1] = fmaf(dd, w.y, v[c * 4 + 1]);
+                    v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
+                  }
+                }
+                if (S.epi != EPI_BWD_LINEAR) {
+                  const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
+                  apply_mask32(half, v);
+                }
+                store_half32<false>(panel, row, hf * 4, v);
+              }
+              publish(S, pi, tile, tile_ok);
+              break;
+            }
+            case EPI_BWD_START: {
+              // dV = W_rgb^T d_rgb (CUDA cores), gated by the saved view activation; 128 columns: groups 0, 1
+              if (q < 2) {
+                const float4 dr = valid ? reinterpret_cast<const float4*>(p.d_raw)[s] : make_float4(0, 0, 0, 0);
+                const float d0 = __bfloat162float(__float2bfloat16(dr.y)), d1 = __bfloat162float(__float2bfloat16(dr.z)),
+                            d2 = __bfloat162float(__float2bfloat16(dr.w));
+                if (q == 0 && tile_ok) {   // padding rows of a real tile get zeros
+                  uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * kHeadCols);
+                  dst[0] = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
+                }
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                  const float* wr = sm.bias + p.w_rgb_off + (col + hf * 32) * 3;
+#pragma unroll
+                  for (int c = 0; c < 32; ++c) v[c] = d0 * wr[c * 3] + d1 * wr[c * 3 + 1] + d2 * wr[c * 3 + 2];
+                  const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
+                  apply_mask32(half, v);
+                  store_half32<false>(panel, row, hf * 4, v);
+                }
+                publish(S, pi, tile, tile_ok);
+              }
+              break;
+            }
+            case EPI_BWD_START_PROP: {
+              const float dd0 = valid ? p.d_raw[s] : 0.f;
+              const float ddq = __bfloat162float(__float2bfloat16(dd0));
+              if (q == 0 && tile_ok) {
+                uint4* dst = reinterpret_cast<uint4*>(p.drgb_out + (size_t)s * kHeadCols);
+                dst[0] = make_uint4(0u, ptx::pack_bf16x2(0.f, dd0), 0u, 0u);
+              }
+#pragma unroll
+              for (int hf = 0; hf < 2; ++hf) {
+                const float* wd = sm.bias + p.w_dens_off + col + hf * 32;
+#pragma unroll
+                for (int c = 0; c < 32; ++c) v[c] = ddq * wd[c];
+                const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
+                apply_mask32(half, v);
+                store_half32<false>(panel, row, hf * 4, v);
+              }
+              publish(S, pi, tile, tile_ok);
+              break;
+            }
+            default: break;
+          }
+          if (S.last_epi) {
+            // every warp of the group is past its TMEM reads / panel writes before the panels are released
+            asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+            if (group_leader) ptx::mbar_arrive(&sm.epi_done[t]);
+          }
+        }
+      }
+    }
+    if (group_leader) ptx::tma_wait_group<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == kMma) ptx::tmem_dealloc(tmem_base, 512);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// host side: segment programs
+// ------------------------------------------------------------------------------------------
+int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
+  const hugs_model_desc& d = h->d;
+  const int D = mv.depth;
+  auto base_seg = [] {
+    PpSeg s{};
+    s.kps = 4; s.n_halves = 2; s.epi = EPI_NONE; s.save_row = -1; s.mask_row = -1;
+    return s;
+  };
+  // ---- forward ----
+  bool cat = false;
+  for (int i = 0; i < D; ++i) {
+    const auto& P = m->pack[i];
+    const bool last = i == D - 1;
+    auto finish = [&](PpSeg& s) {
+      s.epi = EPI_RELU; s.bias_off = P.bias_off; s.save_row = i;
+      if (last) { s.head = 1; if (!mv.has_rgb) s.no_signal = 1; }
+    };
+    if (i == 0) {
+      for (int part = 0; part < kFeatPad / 256; ++part) {
+        PpSeg s = base_seg();
+        s.a_feat = 1; s.feat_col0 = part * 256; s.w_row = P.row0; s.w_col0 = part * 256; s.accumulate = part > 0;
+        if (part == kFeatPad / 256 - 1) finish(s);
+        m->pp_fwd.push_back(s);
+      }
+    } else {
+      PpSeg s = base_seg();
+      s.w_row = P.row0; s.w_col0 = 0;
+      if (!cat) finish(s);
+      m->pp_fwd.push_back(s);
+      if (cat) {
+        for (int part = 0; part < kFeatPad / 256; ++part) {
+          PpSeg f = base_seg();
+          f.a_feat = 1; f.feat_col0 = part * 256; f.w_row = P.row0; f.w_col0 = kW + part * 256; f.accumulate = 1;
+          if (part == kFeatPad / 256 - 1) finish(f);
+          m->pp_fwd.push_back(f);
+        }
+      }
+    }
+    cat = (i % d.skip_layer == 0 && i > 0);
+  }
+  if (mv.has_rgb) {
+    PpSeg b = base_seg();                       // bottleneck (linear)
+    b.w_row = m->pack[D + 1].row0; b.epi = EPI_LINEAR; b.bias_off = m->pack[D + 1].bias_off; b.save_row = D;
+    m->pp_fwd.push_back(b);
+    PpSeg v = base_seg();                       // view layer (N = 128) + rgb head
+    v.n_halves = 1; v.w_row = m->pack[D + 2].row0; v.epi = EPI_VIEW; v.save_row = D + 1; v.no_signal = 1;
+    m->pp_fwd.push_back(v);
+  }
+  m->pp_fwd.back().last_epi = 1;
+  HUGS_REQUIRE((int)m->pp_fwd.size() <= kMaxSegs, "ping-pong schedule: too many segments (%zu)", m->pp_fwd.size());
+  // a feature refill must never directly follow an epilogue of the same tile (the epilogue writes the panels)
+  for (size_t i = 1; i < m->pp_fwd.size(); ++i)
+    HUGS_REQUIRE(!(m->pp_fwd[i].a_feat && m->pp_fwd[i - 1].epi != EPI_NONE), "unsupported segment order at %zu", i);
+
+  // ---- backward (dgrad chain) ----
+  auto mma_seg = [&](int kps, int w_row, int epi, int save_slot, int mask_slot) {
+    PpSeg s = base_seg();
+    s.kps = kps; s.w_row = w_row; s.epi = epi; s.save_row = save_slot; s.mask_row = mask_slot;
+    return s;
+  };
+  PpSeg st = base_seg();
+  st.kps = 0;
+  if (mv.has_rgb) {
+    st.epi = EPI_BWD_START; st.save_row = D + 1; st.mask_row = D + 1;
+    m->pp_bwd.push_back(st);
+    m->pp_bwd.push_back(mma_seg(2, m->pack[D + 2].brow0, EPI_BWD_LINEAR, D, -1));
+    m->pp_bwd.push_back(mma_seg(4, m->pack[D + 1].brow0, EPI_BWD_RELU_D, D - 1, D - 1));
+  } else {
+    st.epi = EPI_BWD_START_PROP; st.save_row = D - 1; st.mask_row = D - 1;
+    m->pp_bwd.push_back(st);
+  }
+  for (int l = D - 1; l >= 1; --l) m->pp_bwd.push_back(mma_seg(4, m->pack[l].brow0, EPI_BWD_RELU, l - 1, l - 1));
+  m->pp_bwd.back().no_signal = 1;
+  m->pp_bwd.back().last_epi = 1;
+  HUGS_REQUIRE((int)m->pp_bwd.size() <= kMaxSegs, "ping-pong schedule: too many backward segments");
+  return HUGS_OK;
+}
+
+int pp_init(hugs_handle* h) {
+  (void)h;
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  return HUGS_OK;
+}
+
+// direction: 0 forward (render), 1 forward (training, saves activations), 2 backward dgrad chain
+int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t st) {
+  TcState* tc = h->tc;
+  const hugs_model_desc& d = h->d;
+  const bool is_prop = level < d.num_levels - 1;
+  const TcMlp& m = is_prop ? tc->prop : tc->nerf;
+  const MlpViews& mv = is_prop ? h->prop : h->nerf;
+  const int S = h->samples(level);
+  const int n_samples = n_rays * S;
+  const int n_tiles = (n_samples + kTileM - 1) / kTileM;
+  const int cap = tc->cap[level], srow = tc->save_row0[level];
+  const std::vector<PpSeg>& prog = direction == 2 ? m.pp_bwd : m.pp_fwd;
+  PpParams p;
+  memset(&p, 0, sizeof(p));
+  p.map_w = direction == 2 ? m.map_wn128 : m.map_wt128;
+  p.map_feat = tc->map_feat;
+  p.map_save = direction == 2 ? tc->map_dz : tc->map_act;
+  p.n_segs = (int)prog.size();
+  for (int i = 0; i < p.n_segs; ++i) {
+    p.segs[i] = prog[i];
+    if (direction == 0) p.segs[i].save_row = -1;
+    if (p.segs[i].save_row >= 0) p.segs[i].save_row = srow + p.segs[i].save_row * cap;
+    if (p.segs[i].mask_row >= 0) p.segs[i].mask_row = srow + p.segs[i].mask_row * cap;
+    if (p.segs[i].a_feat) p.any_feat = 1;
+  }
+  p.n_tiles = n_tiles; p.n_pairs = (n_tiles + 1) / 2; p.n_samples = n_samples; p.S = S;
+  p.feat_row0 = tc->feat_row0[level];
+  p.bias = m.bias; p.bias_floats = m.bias_floats; p.viewbias = tc->viewbias;
+  p.raw_out = h->raw[level]; p.raw_c = is_prop ? 1 : 4;
+  p.d_raw = h->d_raw[level]; p.act = tc->act; p.drgb_out = tc->drgb;
+  p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
+  p.dbg = (!is_prop && direction != 2) ? h->dbg_counters : nullptr;
+  p.dens_bias_off = m.pack[mv.depth].bias_off;
+  p.rgb_bias_off = mv.has_rgb ? m.pack[mv.depth + 3].bias_off : 0;
+  const int grid = std::min(p.n_pairs, tc->num_sms);
+  if (direction == 0) mlp_pp_kernel<false><<<grid, kPpThreads, kPpSmemBytes, st>>>(p);
+  else mlp_pp_kernel<true><<<grid, kPpThreads, kPpSmemBytes, st>>>(p);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+}  // namespace hugs

@@ -18,10 +18,12 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <stdlib.h>
 #include <vector>
 
 #include "encode.cuh"
 #include "ptx.cuh"
+#include "tc_device.cuh"
 #include "tc_internal.h"
 
 namespace hugs {
@@ -31,7 +33,6 @@ namespace {
 // ------------------------------------------------------------------------------------------
 // small helpers
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t swz_chunk(uint32_t row, uint32_t chunk) { return chunk ^ (row & 7u); }
 
 // ------------------------------------------------------------------------------------------
 // bf16 feature encoder (throughput mode): one thread = (sample, half of the basis directions)
@@ -219,46 +220,6 @@ __device__ __forceinline__ Smem carve(uint8_t* raw) {
 
 __device__ __forceinline__ bool layer_has_mma(const TcLayer& L) {
   return L.epi != EPI_BWD_START && L.epi != EPI_BWD_START_PROP;
-}
-
-// One 32-column half of a chunk: TMEM -> registers (fp32).
-__device__ __forceinline__ void load_acc32(uint32_t taddr, float (&v)[32]) {
-  uint32_t r[32];
-  ptx::tmem_ld32(taddr, r);
-  ptx::tmem_ld_wait();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-}
-
-// 32 values of one row -> bf16 -> four 16-byte chunks (chunk0 .. chunk0+3) of a swizzled panel row.
-template <bool kRelu>
-__device__ __forceinline__ void store_half32(uint8_t* panel, int row, int chunk0, const float (&v)[32]) {
-  uint4* prow = reinterpret_cast<uint4*>(panel + row * 128);
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    uint4 q;
-    if (kRelu) {
-      q.x = ptx::pack_bf16x2_relu(v[c * 8 + 0], v[c * 8 + 1]); q.y = ptx::pack_bf16x2_relu(v[c * 8 + 2], v[c * 8 + 3]);
-      q.z = ptx::pack_bf16x2_relu(v[c * 8 + 4], v[c * 8 + 5]); q.w = ptx::pack_bf16x2_relu(v[c * 8 + 6], v[c * 8 + 7]);
-    } else {
-      q.x = ptx::pack_bf16x2(v[c * 8 + 0], v[c * 8 + 1]); q.y = ptx::pack_bf16x2(v[c * 8 + 2], v[c * 8 + 3]);
-      q.z = ptx::pack_bf16x2(v[c * 8 + 4], v[c * 8 + 5]); q.w = ptx::pack_bf16x2(v[c * 8 + 6], v[c * 8 + 7]);
-    }
-    prow[swz_chunk(row, chunk0 + c)] = q;
-  }
-}
-
-// ReLU gate from four 16-byte words of the saved (post-ReLU, hence >= 0) bf16 activation row.
-__device__ __forceinline__ void apply_mask32(const uint4 (&mk)[4], float (&v)[32]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const uint32_t w[4] = {mk[c].x, mk[c].y, mk[c].z, mk[c].w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if ((w[j] & 0xFFFFu) == 0u) v[c * 8 + j * 2] = 0.f;
-      if ((w[j] >> 16) == 0u) v[c * 8 + j * 2 + 1] = 0.f;
-    }
-  }
 }
 
 template <bool kTrain>
@@ -851,7 +812,7 @@ int build_mlp_schedule(hugs_handle* h, const MlpViews& mv, TcMlp* m, int save_la
   for (int l = D - 1; l >= 1; --l) m->bwd.push_back(mma_op(k++, 4, layer_b_row[l], EPI_BWD_RELU, l - 1, l - 1));
   m->bwd.back().no_signal = 1;   // dZ of the first layer feeds only the weight-gradient pass
   HUGS_REQUIRE((int)m->bwd.size() <= kMaxLayers, "tensor-core path: too many backward ops (%zu)", m->bwd.size());
-  return HUGS_OK;
+  return pp_build(h, mv, m);
 }
 
 int fill_pack_args(hugs_handle* h, const MlpViews& mv, const TcMlp& m, const float* params, PackArgs* a) {
@@ -932,6 +893,12 @@ int tc_create(hugs_handle* h) {
     return rc;
   HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  {
+    const char* e = getenv("HUGS_CHAIN");
+    tc->use_pp = !(e && strcmp(e, "single") == 0);
+  }
+  int rc2 = pp_init(h);
+  if (rc2) return rc2;
   return wgrad_create(h);
 }
 
@@ -982,6 +949,10 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
     HUGS_LAUNCH_CHECK();
   }
   // 3. fused chain
+  if (tc->use_pp) {
+    ProfScope ps(h, is_prop ? HUGS_K_CHAIN_FWD_PROP : HUGS_K_CHAIN_FWD_NERF, st);
+    return pp_launch(h, level, n_rays, training ? 1 : 0, st);
+  }
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.map_w128 = m.map_wt128; p.map_w16 = m.map_wt16; p.map_feat = tc->map_feat; p.map_save = tc->map_act;
@@ -1021,6 +992,14 @@ int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays
   const int n_samples = n_rays * S;
   const int n_tiles = (n_samples + kTileM - 1) / kTileM;
   const int cap = tc->cap[level], srow = tc->save_row0[level];
+  if (tc->use_pp) {
+    {
+      ProfScope ps(h, is_prop ? HUGS_K_CHAIN_BWD_PROP : HUGS_K_CHAIN_BWD_NERF, st);
+      int rc = pp_launch(h, level, n_rays, 2, st);
+      if (rc) return rc;
+    }
+    return wgrad_run(h, level, n_rays, grad, st);
+  }
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.map_w128 = m.map_wn128; p.map_w16 = m.map_wn128; p.map_feat = tc->map_feat; p.map_save = tc->map_dz;

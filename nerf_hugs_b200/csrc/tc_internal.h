@@ -1,6 +1,7 @@
 // Internal declarations shared by the tensor-core translation units (mlp_tc.cu, wgrad_tc.cu).
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include <vector>
 
@@ -69,6 +70,42 @@ struct alignas(64) TcParams {
   long long* dbg;                    // optional [gridDim.x][16] cycle counters (development instrumentation)
 };
 
+constexpr int EPI_NONE = -1;
+constexpr int kMaxSegs = 20;
+
+// One segment of the ping-pong kernel's per-tile program (mlp_pp.cu): <= 4 K-panels of one layer.
+struct PpSeg {
+  int kps;          // K panels (64 columns each); 0: epilogue-only start op (backward)
+  int a_feat;       // 1: A = IPE feature columns [feat_col0, feat_col0 + 64*kps), TMA-loaded into the tile's panels
+  int feat_col0;
+  int n_halves;     // 2: N = 256, 1: N = 128
+  int w_row, w_col0;
+  int accumulate;   // 1: keep accumulating into the tile's TMEM accumulator
+  int epi;          // EPI_NONE: more segments of the same layer follow
+  int bias_off;
+  int save_row;     // slot index in the schedule, row base in the launch parameters; -1: do not save
+  int mask_row;     // same convention; saved forward activation gating a backward epilogue
+  int no_signal;    // the produced panels feed no MMA
+  int head;         // forward: this epilogue also evaluates the density head on CUDA cores
+  int last_epi;     // last epilogue of the tile: release the panels for the next pair's features
+};
+
+struct alignas(64) PpParams {
+  CUtensorMap map_w, map_feat, map_save;
+  PpSeg segs[kMaxSegs];
+  int n_segs, any_feat;
+  int n_tiles, n_pairs, n_samples, S;
+  int feat_row0;
+  const float* bias; int bias_floats;
+  const float* viewbias;
+  float* raw_out; int raw_c;
+  const float* d_raw;
+  const __nv_bfloat16* act;
+  __nv_bfloat16* drgb_out;
+  int w_dens_off, w_rgb_off, dens_bias_off, rgb_bias_off;
+  long long* dbg;                    // optional [gridDim.x][16] cycle counters (development instrumentation)
+};
+
 struct TcMlp {
   bool present = false, has_rgb = false;
   int depth = 0;
@@ -77,6 +114,7 @@ struct TcMlp {
   float* bias = nullptr; int bias_floats = 0;
   int w_dens_off = 0, w_rgb_off = 0, view_bias_off = 0, view_w_row = 0;
   std::vector<TcLayer> fwd, bwd;
+  std::vector<PpSeg> pp_fwd, pp_bwd;
   CUtensorMap map_wt128, map_wt16, map_wn128;
   // packing tables
   struct PackLayer { int row0, rows_pad, out, in, x_in, feat_in; long long koff, boff; int bias_off, brow0, b_out_pad; };
@@ -98,6 +136,7 @@ struct TcState {
   std::vector<int> cap, feat_row0, save_row0;   // per level
   int total_feat_rows = 0, total_save_rows = 0;
   int num_sms = 148;
+  bool use_pp = true;                // two-tile ping-pong chain kernel (HUGS_CHAIN=single selects the older one)
   void* pack_tables = nullptr;
 };
 
@@ -110,6 +149,11 @@ __host__ __device__ inline int ref_feature_col(int fp, int nb, int ndeg) {
   int s = fp & 1, bk = fp >> 1, b = bk / ndeg, k = bk % ndeg;
   return s * (nb * ndeg) + k * nb + b;
 }
+
+// mlp_pp.cu
+int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m);
+int pp_init(hugs_handle* h);
+int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t st);
 
 // wgrad_tc.cu
 int wgrad_create(hugs_handle* h);

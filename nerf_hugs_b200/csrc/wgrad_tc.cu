@@ -314,7 +314,7 @@ static void build_items(hugs_handle* h, int level, int n_tiles, std::vector<WgIt
     w.a_map = a_map; w.a_row0 = a_row0; w.a_col0 = a_col0; w.b_row0 = srow + b_slot * cap; w.n = n;
     w.out = v.out; w.koff = v.kernel_off; w.in_base = in_base; w.feat_mode = feat_mode;
     w.bias_mode = first_of_layer ? 1 : 0; w.boff = v.bias_off;
-    units.push_back({w, n / 256.f});
+    units.push_back({w, (512.f + 2.f * n) / 1024.f});   // the kernel is HBM-bound: cost = bytes streamed per sample
   };
   bool cat = false;
   for (int l = 0; l < D; ++l) {
@@ -335,24 +335,34 @@ static void build_items(hugs_handle* h, int level, int n_tiles, std::vector<WgIt
     WgItem w{};
     w.a_map = 0; w.a_row0 = srow + (D - 1) * cap; w.a_col0 = 0; w.b_map = 1; w.b_row0 = 0; w.n = kHeadCols;
     w.out = 1; w.koff = mv.dense[D].kernel_off; w.flush_mode = 1; w.bias_mode = 2; w.boff = mv.dense[D].bias_off;
-    units.push_back({w, 0.35f});
+    units.push_back({w, (512.f + 2.f * kHeadCols) / 1024.f});
   }
   if (mv.has_rgb) {  // rgb head: A = view activation (columns 128..255 are zero), B = head gradients (columns 0..2)
     WgItem w{};
     w.a_map = 0; w.a_row0 = srow + (D + 1) * cap; w.a_col0 = 0; w.b_map = 1; w.b_row0 = 0; w.n = kHeadCols;
     w.out = 3; w.koff = mv.dense[D + 3].kernel_off; w.flush_mode = 2; w.bias_mode = 3; w.boff = mv.dense[D + 3].bias_off;
-    units.push_back({w, 0.35f});
+    units.push_back({w, (512.f + 2.f * kHeadCols) / 1024.f});
   }
   float total = 0.f;
   for (auto& u : units) total += u.cost;
   items->clear();
-  for (auto& u : units) {
-    int splits = std::max(1, (int)(tc->num_sms * u.cost / total));
-    splits = std::min(splits, std::max(1, T / 4));
-    for (int k = 0; k < splits; ++k) {
-      WgItem w = u.w;
-      w.st0 = (int)((long long)T * k / splits);
-      w.st1 = (int)((long long)T * (k + 1) / splits);
+  // one wave of CTAs: splits proportional to cost (at least 1, at most one split per 4 stages)
+  std::vector<int> splits(units.size());
+  int used = 0;
+  for (size_t i = 0; i < units.size(); ++i) {
+    splits[i] = std::max(1, (int)(tc->num_sms * units[i].cost / total));
+    splits[i] = std::min(splits[i], std::max(1, T / 4));
+    used += splits[i];
+  }
+  for (size_t i = 0; used < tc->num_sms && i < units.size() * 4; ++i) {   // hand out the remainder round-robin
+    const size_t k = i % units.size();
+    if (splits[k] < std::max(1, T / 4)) { ++splits[k]; ++used; }
+  }
+  for (size_t i = 0; i < units.size(); ++i) {
+    for (int k = 0; k < splits[i]; ++k) {
+      WgItem w = units[i].w;
+      w.st0 = (int)((long long)T * k / splits[i]);
+      w.st1 = (int)((long long)T * (k + 1) / splits[i]);
       if (w.st1 > w.st0) items->push_back(w);
     }
   }
