@@ -36,6 +36,17 @@ def _world():
   return (dist.get_rank(), dist.get_world_size()) if dist.is_available() and dist.is_initialized() else (0, 1)
 
 
+def allreduce_sum_(tensors):
+  """In-place all-reduce(SUM) of the flat gradient and the stats vector across ranks; together with
+  grad_scale = 1/world in hugs_adam_step (and the 1/world of _LazyStats) this is jax.lax.pmean of
+  train_utils.py:457-459.  Returns the world size.  No-op on a single process."""
+  rank, world = _world()
+  if world > 1:
+    for t in tensors:
+      dist.all_reduce(t, op=dist.ReduceOp.SUM)
+  return world
+
+
 def loss_cfg_from(config, is_finetune: bool = False) -> '_lib.LossCfg':
   c = _lib.LossCfg()
   c.data_loss_type = {'charb': 0, 'mse': 1}[config.data_loss_type]
@@ -94,9 +105,7 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
       jitter = torch.rand(L, n, generator=rng, device=dev)
     model._ensure_packed(state.params)
     eng.loss_and_grad(state.params, rays, rgb[..., :3], float(train_frac), jitter, lcfg, grad, stats_dev)
-    if world > 1:                                   # pmean(grad), pmean(stats)  (train_utils.py:457-459)
-      dist.all_reduce(grad, op=dist.ReduceOp.SUM)
-      dist.all_reduce(stats_dev, op=dist.ReduceOp.SUM)
+    allreduce_sum_([grad, stats_dev])               # pmean(grad), pmean(stats)  (train_utils.py:457-459)
     a = _lib.AdamCfg()
     a.lr = float(lr_fn(state.step))
     a.beta1, a.beta2, a.eps = config.adam_beta1, config.adam_beta2, config.adam_eps

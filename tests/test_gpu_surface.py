@@ -1,0 +1,61 @@
+"""The reference-facing call surface on the GPU: configs -> train_utils.setup_model -> train_pstep ->
+models.render_image, as MipNeRF360/train.py and eval.py drive it (train.py:51-142, eval.py:95-104)."""
+import numpy as np
+import pytest
+import torch
+
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+def _config(batch, glo=0, transient=None):
+  from nerf_hugs_b200.internal import configs
+  b = [f'Config.batch_size = {batch}', 'Config.near = 0.2', 'Config.far = 1e6', 'Config.render_chunk_size = 256',
+       'Model.raydist_fn = @jnp.reciprocal', 'Model.opaque_background = True', 'Model.num_levels = 2',
+       'Model.num_prop_samples = 64', 'Model.num_nerf_samples = 128', f'Model.num_glo_features = {glo}',
+       'Model.num_embeddings = 16', 'PropMLP.warp_fn = @coord.contract', 'PropMLP.net_depth = 4',
+       'PropMLP.disable_rgb = True', 'NerfMLP.warp_fn = @coord.contract', 'NerfMLP.net_width = 256']
+  if transient:
+    b.append(f"Config.transient_type = '{transient}'")
+  return configs.load_config([], b, save_config=False)
+
+
+@pytest.mark.parametrize('glo,transient', [(0, None), (4, 'withmask')])
+def test_setup_model_train_and_render(glo, transient):
+  from nerf_hugs_b200.internal import models, train_utils, utils
+  config = _config(128, glo, transient)
+  model, state, render_eval_pfn, train_pstep, lr_fn = train_utils.setup_model(config, rng=0)
+  assert abs(lr_fn(0) - 2e-5) < 1e-12 and state.params.numel() == model.engine.n_params
+  tree = state.tree(model)['params']
+  assert tree['NerfMLP_0']['Dense_0']['kernel'].shape == (504, 256)
+  assert tree['PropMLP_0']['Dense_4']['kernel'].shape == (256, 1)
+  rays, gt = H.make_rays(128, seed=2)
+  batch = utils.Batch(rays=utils.Rays(**{k: v.pin_memory() for k, v in rays.items()}), rgb=gt.pin_memory())
+  gen = torch.Generator(device=model.engine.device); gen.manual_seed(0)
+  losses = []
+  for step in range(8):
+    state, stats, gen = train_pstep(gen, state, batch, (step + 1) / 100, None)
+    losses.append(stats['loss'])
+  assert state.step == 8 and all(np.isfinite(losses)) and losses[-1] < losses[0]
+  for k in ('loss', 'losses', 'mses', 'psnrs', 'psnr', 'grad_norms', 'grad_maxes'):
+    assert k in stats.keys()
+  assert set(stats['losses']) == {'data', 'interlevel', 'distortion'}
+  # full-frame render through render_image with the reference's chunk / shard / gather plumbing
+  H_, W_ = 9, 31
+  r2, _ = H.make_rays(H_ * W_, seed=3)
+  img_rays = utils.Rays(**{k: v.reshape(H_, W_, -1) for k, v in r2.items()})
+  rendering = models.render_image(lambda rng, rr: render_eval_pfn(state.params, 0.5, None, rr), img_rays, None,
+                                  config, verbose=False)
+  assert rendering['rgb'].shape == (H_, W_, 3) and rendering['distance_median'].shape == (H_, W_)
+  assert len(rendering['ray_sdist']) == 2 and rendering['ray_sdist'][1].shape == (config.vis_num_rays, 129)
+  direct, _ = model.apply(state.params, None, r2, 0.5, True, zero_glo=False)
+  np.testing.assert_allclose(rendering['rgb'].reshape(-1, 3).cpu().numpy(), direct[-1]['rgb'].cpu().numpy(),
+                             rtol=0, atol=1e-6)
+
+
+def test_unsupported_transient_type_is_loud():
+  from nerf_hugs_b200.internal import train_utils
+  config = _config(128, transient='robustnerf')
+  with pytest.raises(NotImplementedError, match='robustnerf'):
+    train_utils.setup_model(config, rng=0)
