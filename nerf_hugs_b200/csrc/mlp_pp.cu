@@ -264,8 +264,10 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
           if (S.epi == EPI_BWD_RELU_D) dd = valid ? __bfloat162float(__float2bfloat16(p.d_raw[(size_t)s * p.raw_c])) : 0.f;
 
           if (S.kps > 0) {
-            if (participates) ptx::mbar_wait_u32(accfull_u32 + t * 8, (acc_phase >> t) & 1u);
-            acc_phase ^= 1u << t;             // the phase advances whether or not this group takes part
+            // every group waits for every phase, also when it has no columns in this layer: a parity wait
+            // that skipped a phase could be satisfied by an older phase of the same parity
+            ptx::mbar_wait_u32(accfull_u32 + t * 8, (acc_phase >> t) & 1u);
+            acc_phase ^= 1u << t;
             ptx::tc_fence_after();
           }
 

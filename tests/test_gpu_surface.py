@@ -25,7 +25,7 @@ def _config(batch, glo=0, transient=None):
 def test_setup_model_train_and_render(glo, transient):
   from nerf_hugs_b200.internal import models, train_utils, utils
   config = _config(128, glo, transient)
-  model, state, render_eval_pfn, train_pstep, lr_fn = train_utils.setup_model(config, rng=0)
+  model, state, render_eval_pfn, train_pstep, lr_fn = train_utils.setup_model(config, rng=0, max_rays=512)
   assert abs(lr_fn(0) - 2e-5) < 1e-12 and state.params.numel() == model.engine.n_params
   tree = state.tree(model)['params']
   assert tree['NerfMLP_0']['Dense_0']['kernel'].shape == (504, 256)
