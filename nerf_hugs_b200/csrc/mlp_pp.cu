@@ -16,6 +16,12 @@
 // A layer is a sequence of *segments* of <= 4 K-panels (K <= 256).  IPE features (layer 0 and the skip
 // connection) are TMA-loaded straight into the tile's own panels once the previous segment has been
 // consumed; the N = 1 / N = 3 heads are evaluated on CUDA cores inside the producing epilogue.
+//
+// kCg2 = true runs the same program on a CTA *pair* (cluster of 2, tcgen05 cta_group::2): every MMA is
+// M = 256 (128 rows per CTA) x N = 256, each CTA stages only its half of the weight rows, so per-SM weight
+// traffic (L2 -> shared memory, and shared memory -> tensor core) is halved.  The leader CTA issues all MMAs;
+// barriers the issuer waits on live in the leader and receive the peer's TMA completions / epilogue arrivals
+// through the cluster address space, barriers signalled by the tensor core are multicast to both CTAs.
 #include <algorithm>
 
 #include "tc_device.cuh"
@@ -52,12 +58,17 @@ __device__ __forceinline__ PpSmem pp_carve(uint8_t* raw) {
   return s;
 }
 
-template <bool kTrain>
+template <bool kTrain, bool kCg2>
 __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_constant__ PpParams p) {
   extern __shared__ uint8_t smem_raw[];
   PpSmem sm = pp_carve(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWProd = kEpiGroups * 4, kFProd = kWProd + 1, kMma = kWProd + 2;
+  // work distribution: a *unit* is one pass of the segment program over `kCtas` x 2 tiles
+  constexpr int kCtas = kCg2 ? 2 : 1;
+  const int rank = kCg2 ? (int)ptx::cluster_ctarank() : 0;
+  const int unit0 = kCg2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int unit_stride = kCg2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   const uint32_t panels_u32 = ptx::smem_u32(sm.panels), ring_u32 = ptx::smem_u32(sm.ring);
   const uint32_t full_u32 = ptx::smem_u32(sm.full), empty_u32 = ptx::smem_u32(sm.empty);
@@ -68,37 +79,55 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
   if (warp == kWProd && lane == 0) {
     ptx::prefetch_tmap(&p.map_w); ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&sm.full[i], 1); ptx::mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 8; ++i) { ptx::mbar_init(&sm.panel_ready[i], 128); ptx::mbar_init(&sm.feat_ready[i], 1); }
+    for (int i = 0; i < 8; ++i) { ptx::mbar_init(&sm.panel_ready[i], kCg2 ? 2 : 128); ptx::mbar_init(&sm.feat_ready[i], 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&sm.acc_full[i], 1); ptx::mbar_init(&sm.consumed[i], 1); ptx::mbar_init(&sm.epi_done[i], kEpiGroups);
     }
     ptx::fence_mbar_init();
   }
-  if (warp == kMma) ptx::tmem_alloc(sm.tmem_ptr, 512);
+  if (warp == kMma) { if (kCg2) ptx::tmem_alloc_cg2(sm.tmem_ptr, 512); else ptx::tmem_alloc(sm.tmem_ptr, 512); }
   for (int i = threadIdx.x; i < p.bias_floats; i += kPpThreads) sm.bias[i] = p.bias[i];
   ptx::tc_fence_before();
   __syncthreads();
+  if (kCg2) ptx::cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *sm.tmem_ptr;
 
   if (warp == kWProd) {
     // =============================== weight producer ===============================
+    // cg2: this CTA stages rows [rank * N/2, (rank + 1) * N/2) of every weight tile; the transaction bytes of
+    // both CTAs are accounted on the leader's `full` barrier
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+      for (int unit = unit0; unit < p.n_units; unit += unit_stride) {
         for (int si = 0; si < p.n_segs; ++si) {
           const PpSeg& S = p.segs[si];
           if (S.kps == 0) continue;
-          const int kps = S.kps, n_halves = S.n_halves, w_row = S.w_row, w_col0 = S.w_col0;
-          for (int t = 0; t < 2; ++t)
-            for (int kp = 0; kp < kps; ++kp)
-              for (int h = 0; h < n_halves; ++h) {
+          const int kps = S.kps, n_halves = S.n_halves, w_col0 = S.w_col0;
+          if (kCg2) {
+            const int w_row = S.w_row + rank * n_halves * 64;
+            const CUtensorMap* map = n_halves == 2 ? &p.map_w : &p.map_w_half;
+            const uint32_t bytes = (uint32_t)n_halves * (kPanelBytes / 2);
+            for (int t = 0; t < 2; ++t)
+              for (int kp = 0; kp < kps; ++kp) {
                 ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-                ptx::mbar_expect_tx_u32(full_u32 + stage * 8, kPanelBytes);
-                ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, &p.map_w, full_u32 + stage * 8,
-                                     w_col0 + kp * 64, w_row + h * 128);
+                if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
+                ptx::tma_load_2d_cg2(ring_u32 + stage * kPanelBytes, map, ptx::mapa_u32(full_u32 + stage * 8, 0),
+                                     w_col0 + kp * 64, w_row);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
               }
+          } else {
+            const int w_row = S.w_row;
+            for (int t = 0; t < 2; ++t)
+              for (int kp = 0; kp < kps; ++kp)
+                for (int h = 0; h < n_halves; ++h) {
+                  ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                  ptx::mbar_expect_tx_u32(full_u32 + stage * 8, kPanelBytes);
+                  ptx::tma_load_2d_u32(ring_u32 + stage * kPanelBytes, &p.map_w, full_u32 + stage * 8,
+                                       w_col0 + kp * 64, w_row + h * 128);
+                  if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+          }
         }
       }
     }
@@ -110,45 +139,56 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     if (lane == 0 && p.any_feat) {
       uint32_t cons_phase = 0;   // bit t: parity of the next `consumed[t]` phase to wait for
       bool first = true;
-      int pair_iter = 0;
-      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x, ++pair_iter) {
-        bool first_in_pair = true;
+      int unit_iter = 0;
+      for (int unit = unit0; unit < p.n_units; unit += unit_stride, ++unit_iter) {
+        bool first_in_unit = true;
         for (int si = 0; si < p.n_segs; ++si) {
           const PpSeg& S = p.segs[si];
           if (S.kps == 0) continue;
           for (int t = 0; t < 2; ++t) {
-            if (!(first && first_in_pair)) {       // every segment but the very first has a predecessor on tile t
+            if (!(first && first_in_unit)) {       // every segment but the very first has a predecessor on tile t
               ptx::mbar_wait_u32(consumed_u32 + t * 8, (cons_phase >> t) & 1u);
               cons_phase ^= 1u << t;
             }
             if (S.a_feat) {
-              if (first_in_pair && pair_iter > 0)   // previous pair's last epilogue (and its TMA store) is done
-                ptx::mbar_wait_u32(epidone_u32 + t * 8, (uint32_t)((pair_iter - 1) & 1));
-              const int row = p.feat_row0 + (pair * 2 + t) * kTileM;
+              if (first_in_unit && unit_iter > 0)   // previous unit's last epilogue (and its TMA store) is done
+                ptx::mbar_wait_u32(epidone_u32 + t * 8, (uint32_t)((unit_iter - 1) & 1));
+              const int row = p.feat_row0 + ((unit * 2 + t) * kCtas + rank) * kTileM;
               for (int kp = 0; kp < S.kps; ++kp) {
                 const uint32_t bar = fready_u32 + (t * 4 + kp) * 8;
-                ptx::mbar_expect_tx_u32(bar, kPanelBytes);
-                ptx::tma_load_2d_u32(panels_u32 + (t * 4 + kp) * kPanelBytes, &p.map_feat, bar,
-                                     S.feat_col0 + kp * 64, row);
+                if (kCg2) {
+                  if (rank == 0) ptx::mbar_expect_tx_u32(bar, 2 * kPanelBytes);
+                  ptx::tma_load_2d_cg2(panels_u32 + (t * 4 + kp) * kPanelBytes, &p.map_feat, ptx::mapa_u32(bar, 0),
+                                       S.feat_col0 + kp * 64, row);
+                } else {
+                  ptx::mbar_expect_tx_u32(bar, kPanelBytes);
+                  ptx::tma_load_2d_u32(panels_u32 + (t * 4 + kp) * kPanelBytes, &p.map_feat, bar,
+                                       S.feat_col0 + kp * 64, row);
+                }
               }
             }
           }
-          first_in_pair = false;
+          first_in_unit = false;
         }
         first = false;
       }
     }
   } else if (warp == kMma) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
-      const uint32_t idesc = ptx::make_idesc_bf16(128, 128, 0, 0);
+      const uint32_t idesc128 = ptx::make_idesc_bf16(kCg2 ? 256 : 128, 128, 0, 0);
+      const uint32_t idesc256 = ptx::make_idesc_bf16(kCg2 ? 256 : 128, 256, 0, 0);
+      auto wait = [](uint32_t bar, uint32_t parity) {
+        if (kCg2) ptx::mbar_wait_cluster_u32(bar, parity); else ptx::mbar_wait_u32(bar, parity);
+      };
+      auto commit = [](uint32_t bar) { if (kCg2) ptx::mma_commit_mc2_u32(bar); else ptx::mma_commit_u32(bar); };
       int stage = 0; uint32_t phase = 0;
       uint32_t wait_phase = 0;   // bits 0-7 panel_ready, 8-15 feat_ready
       long long c_panel = 0, c_feat = 0, c_full = 0;
       const long long c_start = clock64();
       const bool dbg = p.dbg != nullptr;
-      for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+      for (int unit = unit0; unit < p.n_units; unit += unit_stride) {
         for (int si = 0; si < p.n_segs; ++si) {
           const PpSeg& S = p.segs[si];
           if (S.kps == 0) continue;
@@ -162,7 +202,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               const long long c0 = dbg ? clock64() : 0;
               for (int kp = 0; kp < kps; ++kp) {
                 const uint32_t idx = (uint32_t)(t * 4 + kp);
-                ptx::mbar_wait_u32(pready_u32 + idx * 8, (wait_phase >> idx) & 1u);
+                wait(pready_u32 + idx * 8, (wait_phase >> idx) & 1u);
                 wait_phase ^= 1u << idx;
               }
               if (dbg) c_panel += clock64() - c0;
@@ -171,34 +211,50 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               if (a_feat) {
                 const uint32_t idx = (uint32_t)(8 + t * 4 + kp);
                 const long long c0 = dbg ? clock64() : 0;
-                ptx::mbar_wait_u32(fready_u32 + (t * 4 + kp) * 8, (wait_phase >> idx) & 1u);
+                wait(fready_u32 + (t * 4 + kp) * 8, (wait_phase >> idx) & 1u);
                 if (dbg) c_feat += clock64() - c0;
                 wait_phase ^= 1u << idx;
               }
               const uint64_t da = ptx::desc_from(kDescHi, panels_u32 + (t * 4 + kp) * kPanelBytes);
               const uint32_t accum = (acc0 || kp > 0) ? 1u : 0u;
-              for (int h = 0; h < n_halves; ++h) {
+              if (kCg2) {
+                // one stage = this K panel of all N columns (each CTA holds its half of the rows)
                 const long long c0 = dbg ? clock64() : 0;
-                ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+                wait(full_u32 + stage * 8, phase);
                 if (dbg) c_full += clock64() - c0;
                 ptx::tc_fence_after();
                 const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kPanelBytes);
-                const uint32_t d = d_tmem + (uint32_t)(h * 128);
-                ptx::mma_bf16_ss(d, da, db, idesc, accum);
-                ptx::mma_bf16_ss(d, da + 2, db + 2, idesc, 1u);
-                ptx::mma_bf16_ss(d, da + 4, db + 4, idesc, 1u);
-                ptx::mma_bf16_ss(d, da + 6, db + 6, idesc, 1u);
-                ptx::mma_commit_u32(empty_u32 + stage * 8);
+                const uint32_t idesc = n_halves == 2 ? idesc256 : idesc128;
+                ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, accum);
+                ptx::mma_bf16_ss_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
+                ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
+                ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
+                commit(empty_u32 + stage * 8);
                 if (++stage == kStages) { stage = 0; phase ^= 1; }
+              } else {
+                for (int h = 0; h < n_halves; ++h) {
+                  const long long c0 = dbg ? clock64() : 0;
+                  wait(full_u32 + stage * 8, phase);
+                  if (dbg) c_full += clock64() - c0;
+                  ptx::tc_fence_after();
+                  const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kPanelBytes);
+                  const uint32_t d = d_tmem + (uint32_t)(h * 128);
+                  ptx::mma_bf16_ss(d, da, db, idesc128, accum);
+                  ptx::mma_bf16_ss(d, da + 2, db + 2, idesc128, 1u);
+                  ptx::mma_bf16_ss(d, da + 4, db + 4, idesc128, 1u);
+                  ptx::mma_bf16_ss(d, da + 6, db + 6, idesc128, 1u);
+                  commit(empty_u32 + stage * 8);
+                  if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
               }
             }
-            ptx::mma_commit_u32(consumed_u32 + t * 8);
-            if (has_epi) ptx::mma_commit_u32(accfull_u32 + t * 8);
+            commit(consumed_u32 + t * 8);
+            if (has_epi) commit(accfull_u32 + t * 8);
           }
         }
       }
       if (dbg) {
-        long long* d = p.dbg + blockIdx.x * 16;
+        long long* d = p.dbg + unit0 * 16;
         d[4] = clock64() - c_start; d[5] = c_panel; d[6] = c_full; d[7] = c_feat;
       }
     }
@@ -220,6 +276,24 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     // then hand it to the MMA issuer
     auto publish = [&](const PpSeg& S, int pi, int tile, bool tile_ok) {
       ptx::fence_proxy_async();
+      if (kCg2) {
+        // one elected arrival per CTA (on the leader's barrier) after the group has synchronised
+        ptx::tc_fence_before();
+        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+        if (group_leader) {
+          const bool save = kTrain && S.save_row >= 0 && tile_ok;
+          if (save) {
+            ptx::tma_store_2d(&p.map_save, sm.panels + pi * kPanelBytes, col, S.save_row + tile * kTileM);
+            ptx::tma_commit_group();
+          }
+          if (!S.no_signal) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(pready_u32 + pi * 8, 0));
+          // the store's shared-memory read must be over before the panel is rewritten; this group's next
+          // write to it is behind the bar.sync of the other tile's publish (or of last_epi), which this
+          // thread only reaches after the wait
+          if (save) ptx::tma_wait_group_read<0>();
+        }
+        return;
+      }
       if (kTrain && S.save_row >= 0) {
         asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
         if (group_leader && tile_ok) {
@@ -232,12 +306,12 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       if (!S.no_signal) ptx::mbar_arrive(&sm.panel_ready[pi]);
     };
 
-    for (int pair = blockIdx.x; pair < p.n_pairs; pair += gridDim.x) {
+    for (int unit = unit0; unit < p.n_units; unit += unit_stride) {
       for (int si = 0; si < p.n_segs; ++si) {
         const PpSeg& S = p.segs[si];
         if (S.epi == EPI_NONE) continue;
         for (int t = 0; t < 2; ++t) {
-          const int tile = pair * 2 + t;
+          const int tile = (unit * 2 + t) * kCtas + rank;
           const bool tile_ok = tile < p.n_tiles;
           const int s = tile * kTileM + row;
           const bool valid = s < p.n_samples;
@@ -420,7 +494,8 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
   }
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == kMma) ptx::tmem_dealloc(tmem_base, 512);
+  if (kCg2) ptx::cluster_sync_all();   // neither CTA retires (or frees TMEM) while the pair's MMAs / arrivals are in flight
+  if (warp == kMma) { if (kCg2) ptx::tmem_dealloc_cg2(tmem_base, 512); else ptx::tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace
@@ -508,8 +583,10 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
 
 int pp_init(hugs_handle* h) {
   (void)h;
-  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
-  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
+  HUGS_CUDA(cudaFuncSetAttribute(mlp_pp_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPpSmemBytes));
   return HUGS_OK;
 }
 
@@ -528,6 +605,7 @@ int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t
   PpParams p;
   memset(&p, 0, sizeof(p));
   p.map_w = direction == 2 ? m.map_wn128 : m.map_wt128;
+  p.map_w_half = m.map_wt64;         // only forward programs contain N = 128 segments
   p.map_feat = tc->map_feat;
   p.map_save = direction == 2 ? tc->map_dz : tc->map_act;
   p.n_segs = (int)prog.size();
@@ -538,7 +616,9 @@ int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t
     if (p.segs[i].mask_row >= 0) p.segs[i].mask_row = srow + p.segs[i].mask_row * cap;
     if (p.segs[i].a_feat) p.any_feat = 1;
   }
-  p.n_tiles = n_tiles; p.n_pairs = (n_tiles + 1) / 2; p.n_samples = n_samples; p.S = S;
+  const bool cg2 = tc->use_cg2;
+  const int tiles_per_unit = cg2 ? 4 : 2;
+  p.n_tiles = n_tiles; p.n_units = (n_tiles + tiles_per_unit - 1) / tiles_per_unit; p.n_samples = n_samples; p.S = S;
   p.feat_row0 = tc->feat_row0[level];
   p.bias = m.bias; p.bias_floats = m.bias_floats; p.viewbias = tc->viewbias;
   p.raw_out = h->raw[level]; p.raw_c = is_prop ? 1 : 4;
@@ -547,9 +627,25 @@ int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t
   p.dbg = (!is_prop && direction != 2) ? h->dbg_counters : nullptr;
   p.dens_bias_off = m.pack[mv.depth].bias_off;
   p.rgb_bias_off = mv.has_rgb ? m.pack[mv.depth + 3].bias_off : 0;
-  const int grid = std::min(p.n_pairs, tc->num_sms);
-  if (direction == 0) mlp_pp_kernel<false><<<grid, kPpThreads, kPpSmemBytes, st>>>(p);
-  else mlp_pp_kernel<true><<<grid, kPpThreads, kPpSmemBytes, st>>>(p);
+  if (cg2) {
+    for (int i = 0; i < p.n_segs; ++i)
+      HUGS_REQUIRE(direction != 2 || p.segs[i].n_halves == 2, "CTA-pair backward program must be N = 256 throughout");
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(2 * std::min(p.n_units, tc->num_sms / 2));
+    cfg.blockDim = dim3(kPpThreads);
+    cfg.dynamicSmemBytes = kPpSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr; cfg.numAttrs = 1;
+    if (direction == 0) HUGS_CUDA(cudaLaunchKernelEx(&cfg, mlp_pp_kernel<false, true>, p));
+    else HUGS_CUDA(cudaLaunchKernelEx(&cfg, mlp_pp_kernel<true, true>, p));
+    return HUGS_OK;
+  }
+  const int grid = std::min(p.n_units, tc->num_sms);
+  if (direction == 0) mlp_pp_kernel<false, false><<<grid, kPpThreads, kPpSmemBytes, st>>>(p);
+  else mlp_pp_kernel<true, false><<<grid, kPpThreads, kPpSmemBytes, st>>>(p);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
 }

@@ -864,7 +864,8 @@ int tc_create(hugs_handle* h) {
       return rc;
     if ((rc = make_map(&m->map_wt128, m->wt, m->rows_f, kKP, 128)) ||
         (rc = make_map(&m->map_wt16, m->wt, m->rows_f, kKP, 16)) ||
-        (rc = make_map(&m->map_wn128, m->wn, m->rows_b, kW, 128)))
+        (rc = make_map(&m->map_wn128, m->wn, m->rows_b, kW, 128)) ||
+        (rc = make_map(&m->map_wt64, m->wt, m->rows_f, kKP, 64)))
       return rc;
   }
   // per-level feature / saved-activation regions
@@ -896,6 +897,7 @@ int tc_create(hugs_handle* h) {
   {
     const char* e = getenv("HUGS_CHAIN");
     tc->use_pp = !(e && strcmp(e, "single") == 0);
+    tc->use_cg2 = tc->use_pp && !(e && strcmp(e, "pp") == 0);
   }
   int rc2 = pp_init(h);
   if (rc2) return rc2;

@@ -92,9 +92,10 @@ struct PpSeg {
 
 struct alignas(64) PpParams {
   CUtensorMap map_w, map_feat, map_save;
+  CUtensorMap map_w_half;            // CTA-pair kernel, N = 128 layers: box of 64 weight rows per CTA
   PpSeg segs[kMaxSegs];
   int n_segs, any_feat;
-  int n_tiles, n_pairs, n_samples, S;
+  int n_tiles, n_units, n_samples, S;   // unit = 2 tiles (one CTA) or 4 tiles (CTA pair)
   int feat_row0;
   const float* bias; int bias_floats;
   const float* viewbias;
@@ -115,7 +116,7 @@ struct TcMlp {
   int w_dens_off = 0, w_rgb_off = 0, view_bias_off = 0, view_w_row = 0;
   std::vector<TcLayer> fwd, bwd;
   std::vector<PpSeg> pp_fwd, pp_bwd;
-  CUtensorMap map_wt128, map_wt16, map_wn128;
+  CUtensorMap map_wt128, map_wt16, map_wn128, map_wt64;
   // packing tables
   struct PackLayer { int row0, rows_pad, out, in, x_in, feat_in; long long koff, boff; int bias_off, brow0, b_out_pad; };
   std::vector<PackLayer> pack;
@@ -137,6 +138,7 @@ struct TcState {
   int total_feat_rows = 0, total_save_rows = 0;
   int num_sms = 148;
   bool use_pp = true;                // two-tile ping-pong chain kernel (HUGS_CHAIN=single selects the older one)
+  bool use_cg2 = true;               // ... on CTA pairs with tcgen05 cta_group::2 (HUGS_CHAIN=pp selects one CTA per unit)
   void* pack_tables = nullptr;
 };
 

@@ -20,8 +20,10 @@ assert fn(eng._h, 1, None) == 0
 eng.forward(flat, rays, 0.5, None, compute_extras=False, want_history=False)
 buf = np.zeros((148, 16), np.int64)
 assert fn(eng._h, 0, buf.ctypes.data_as(C.c_void_p)) == 0
-m = buf.mean(0)
-tiles = 4096 / 148
+rows = buf[buf[:, 4] > 0]
+m = rows.mean(0)
+tiles = 4096 / 148   # 128-sample tiles per SM (a CTA pair reports once for its two SMs)
+print('reporting CTAs/clusters:', len(rows))
 print('producer: total %.0f  wait_empty %.0f  wait_tile %.0f' % (m[0], m[1], m[2]))
 print('mma     : total %.0f  wait_panel %.0f  wait_full %.0f  wait_feat/issue %.0f  (per tile: total %.0f panel %.0f full %.0f feat/issue %.0f)' % (m[4], m[5], m[6], m[7], m[4]/tiles, m[5]/tiles, m[6]/tiles, m[7]/tiles))
 print('epi g0  : total %.0f  wait_acc %.0f  guard %.0f  work %.0f (per tile work %.0f)' % (m[8], m[9], m[10], m[8]-m[9]-m[10], (m[8]-m[9]-m[10])/tiles))

@@ -8,7 +8,7 @@ fn.restype = C.c_int; fn.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(
 torch.cuda.init(); torch.zeros(1, device='cuda')
 out = (C.c_int64 * 2)()
 print('N mode n_mmas | issue cyc/MMA | complete cyc/MMA')
-for n in (128, 256):
+for n in (64, 128, 256):
   for mode in (0, 1, 2, 3, 4, 6):
     for cnt in (64, 512):
       rc = fn(n, cnt, mode, out)
