@@ -42,7 +42,9 @@ struct PpSmem {
 
 __device__ __forceinline__ PpSmem pp_carve(uint8_t* raw) {
   PpSmem s;
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ symbol (not an integer round trip) keeps the shared address space, so the
+  // accesses below compile to LDS/STS instead of generic loads and stores
+  uint8_t* base = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);
   s.panels = base;
   s.ring = base + kNumPanels * kPanelBytes;
   s.bias = reinterpret_cast<float*>(s.ring + kStages * kPanelBytes);
@@ -105,17 +107,17 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
           if (S.kps == 0) continue;
           const int kps = S.kps, n_halves = S.n_halves, w_col0 = S.w_col0;
           if (kCg2) {
+            // one stage per K panel, shared by the unit's two tiles (the issuer releases it after tile 1)
             const int w_row = S.w_row + rank * n_halves * 64;
             const CUtensorMap* map = n_halves == 2 ? &p.map_w : &p.map_w_half;
             const uint32_t bytes = (uint32_t)n_halves * (kPanelBytes / 2);
-            for (int t = 0; t < 2; ++t)
-              for (int kp = 0; kp < kps; ++kp) {
-                ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-                if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
-                ptx::tma_load_2d_cg2(ring_u32 + stage * kPanelBytes, map, ptx::mapa_u32(full_u32 + stage * 8, 0),
-                                     w_col0 + kp * 64, w_row);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
-              }
+            for (int kp = 0; kp < kps; ++kp) {
+              ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+              if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
+              ptx::tma_load_2d_cg2(ring_u32 + stage * kPanelBytes, map, ptx::mapa_u32(full_u32 + stage * 8, 0),
+                                   w_col0 + kp * 64, w_row);
+              if (++stage == kStages) { stage = 0; phase ^= 1; }
+            }
           } else {
             const int w_row = S.w_row;
             for (int t = 0; t < 2; ++t)
@@ -179,9 +181,9 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
       const uint32_t idesc128 = ptx::make_idesc_bf16(kCg2 ? 256 : 128, 128, 0, 0);
       const uint32_t idesc256 = ptx::make_idesc_bf16(kCg2 ? 256 : 128, 256, 0, 0);
-      auto wait = [](uint32_t bar, uint32_t parity) {
-        if (kCg2) ptx::mbar_wait_cluster_u32(bar, parity); else ptx::mbar_wait_u32(bar, parity);
-      };
+      // the issuing thread never reads the data behind these barriers itself (the tensor core does, behind
+      // tcgen05.fence::after_thread_sync), so CTA-scope waits suffice also for the peer's arrivals
+      auto wait = [](uint32_t bar, uint32_t parity) { ptx::mbar_wait_u32(bar, parity); };
       auto commit = [](uint32_t bar) { if (kCg2) ptx::mma_commit_mc2_u32(bar); else ptx::mma_commit_u32(bar); };
       int stage = 0; uint32_t phase = 0;
       uint32_t wait_phase = 0;   // bits 0-7 panel_ready, 8-15 feat_ready
@@ -206,6 +208,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 wait_phase ^= 1u << idx;
               }
               if (dbg) c_panel += clock64() - c0;
+              ptx::tc_fence_after();
             }
             for (int kp = 0; kp < kps; ++kp) {
               if (a_feat) {
@@ -214,23 +217,28 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 wait(fready_u32 + (t * 4 + kp) * 8, (wait_phase >> idx) & 1u);
                 if (dbg) c_feat += clock64() - c0;
                 wait_phase ^= 1u << idx;
+                ptx::tc_fence_after();
               }
               const uint64_t da = ptx::desc_from(kDescHi, panels_u32 + (t * 4 + kp) * kPanelBytes);
               const uint32_t accum = (acc0 || kp > 0) ? 1u : 0u;
               if (kCg2) {
-                // one stage = this K panel of all N columns (each CTA holds its half of the rows)
-                const long long c0 = dbg ? clock64() : 0;
-                wait(full_u32 + stage * 8, phase);
-                if (dbg) c_full += clock64() - c0;
-                ptx::tc_fence_after();
-                const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kPanelBytes);
+                // one stage = this K panel of all N columns (each CTA holds its half of the rows); tile 0 waits
+                // for it, tile 1 reuses it and releases it
+                int st_k = stage + kp; uint32_t ph_k = phase;
+                if (st_k >= kStages) { st_k -= kStages; ph_k ^= 1; }
+                if (t == 0) {
+                  const long long c0 = dbg ? clock64() : 0;
+                  wait(full_u32 + st_k * 8, ph_k);
+                  if (dbg) c_full += clock64() - c0;
+                  ptx::tc_fence_after();
+                }
+                const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + st_k * kPanelBytes);
                 const uint32_t idesc = n_halves == 2 ? idesc256 : idesc128;
                 ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, accum);
                 ptx::mma_bf16_ss_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
                 ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
                 ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
-                commit(empty_u32 + stage * 8);
-                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                if (t == 1) commit(empty_u32 + st_k * 8);
               } else {
                 for (int h = 0; h < n_halves; ++h) {
                   const long long c0 = dbg ? clock64() : 0;
@@ -251,6 +259,10 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
             commit(consumed_u32 + t * 8);
             if (has_epi) commit(accfull_u32 + t * 8);
           }
+          if (kCg2) {
+            stage += kps;
+            if (stage >= kStages) { stage -= kStages; phase ^= 1; }
+          }
         }
       }
       if (dbg) {
@@ -270,11 +282,16 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     float v[32];
     float raw_keep[2] = {0.f, 0.f};
     const int col = q * 64;
+    // development counters (group 0 / group 3, first lane of the leader CTA)
+    const bool dbg_t = p.dbg != nullptr && rank == 0 && (threadIdx.x == 0 || threadIdx.x == 3 * 128);
+    long long c_acc = 0, c_work = 0, c_pub = 0, c_t0 = 0, c_t1 = 0, c_ld = 0, c_st = 0, c_view = 0, c_head = 0;
+    const long long c_epi_start = clock64();
 
     // make the freshly written panel visible to the async proxy, optionally TMA-store it (its smem read is
     // complete before panel_ready completes, so later in-place overwrites / feature refills are safe),
     // then hand it to the MMA issuer
     auto publish = [&](const PpSeg& S, int pi, int tile, bool tile_ok) {
+      const long long c_p0 = dbg_t ? clock64() : 0;
       ptx::fence_proxy_async();
       if (kCg2) {
         // one elected arrival per CTA (on the leader's barrier) after the group has synchronised
@@ -292,6 +309,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
           // thread only reaches after the wait
           if (save) ptx::tma_wait_group_read<0>();
         }
+        if (dbg_t) c_pub += clock64() - c_p0;
         return;
       }
       if (kTrain && S.save_row >= 0) {
@@ -304,6 +322,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       }
       ptx::tc_fence_before();
       if (!S.no_signal) ptx::mbar_arrive(&sm.panel_ready[pi]);
+      if (dbg_t) c_pub += clock64() - c_p0;
     };
 
     for (int unit = unit0; unit < p.n_units; unit += unit_stride) {
@@ -340,9 +359,11 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
           if (S.kps > 0) {
             // every group waits for every phase, also when it has no columns in this layer: a parity wait
             // that skipped a phase could be satisfied by an older phase of the same parity
+            if (dbg_t) c_t0 = clock64();
             ptx::mbar_wait_u32(accfull_u32 + t * 8, (acc_phase >> t) & 1u);
             acc_phase ^= 1u << t;
             ptx::tc_fence_after();
+            if (dbg_t) { c_t1 = clock64(); c_acc += c_t1 - c_t0; }
           }
 
           switch (S.epi) {
@@ -350,12 +371,16 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               float head = 0.f;
 #pragma unroll 1
               for (int hf = 0; hf < 2; ++hf) {
-                load_acc32(acc_addr + (uint32_t)(hf * 32), v);
+                const long long c_l0 = dbg_t ? clock64() : 0;
+                if (!(p.dbg_flags & 4)) load_acc32(acc_addr + (uint32_t)(hf * 32), v);
+                if (dbg_t) c_ld += clock64() - c_l0;
                 const float4* b4 = reinterpret_cast<const float4*>(sm.bias + S.bias_off + col + hf * 32);
+                if (!(p.dbg_flags & 1)) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                  const float4 b = b4[c];
-                  v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 b = b4[c];
+                    v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                  }
                 }
                 if (S.head) {   // density head: dot of the bf16-rounded activation with the bf16-rounded kernel
                   const float* wd = sm.bias + p.w_dens_off + col + hf * 32;
@@ -363,8 +388,12 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                   for (int c = 0; c < 32; ++c)
                     head = fmaf(__bfloat162float(__float2bfloat16(fmaxf(v[c], 0.f))), wd[c], head);
                 }
-                if (S.epi == EPI_RELU) store_half32<true>(panel, row, hf * 4, v);
-                else store_half32<false>(panel, row, hf * 4, v);
+                const long long c_s0 = dbg_t ? clock64() : 0;
+                if (!(p.dbg_flags & 2)) {
+                  if (S.epi == EPI_RELU) store_half32<true>(panel, row, hf * 4, v);
+                  else store_half32<false>(panel, row, hf * 4, v);
+                }
+                if (dbg_t) c_st += clock64() - c_s0;
               }
               if (S.head) {
                 float* part = sm.part + t * 384;
@@ -482,6 +511,11 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
             }
             default: break;
           }
+          if (dbg_t && S.kps > 0) {
+            const long long dt = clock64() - c_t1;
+            c_work += dt;
+            if (S.epi == EPI_VIEW) c_view += dt; else if (S.head) c_head += dt;
+          }
           if (S.last_epi) {
             // every warp of the group is past its TMEM reads / panel writes before the panels are released
             asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
@@ -491,6 +525,11 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       }
     }
     if (group_leader) ptx::tma_wait_group<0>();
+    if (dbg_t) {
+      long long* d = p.dbg + unit0 * 16 + (threadIdx.x == 0 ? 8 : 12);
+      d[0] = clock64() - c_epi_start; d[1] = c_acc; d[2] = c_work; d[3] = c_pub;
+      if (threadIdx.x == 0) { long long* e = p.dbg + unit0 * 16; e[0] = c_ld; e[1] = c_st; e[2] = c_view; e[3] = c_head; }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -625,6 +664,7 @@ int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t
   p.d_raw = h->d_raw[level]; p.act = tc->act; p.drgb_out = tc->drgb;
   p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
   p.dbg = (!is_prop && direction != 2) ? h->dbg_counters : nullptr;
+  { const char* e = getenv("HUGS_DBG_FLAGS"); p.dbg_flags = e ? atoi(e) : 0; }
   p.dens_bias_off = m.pack[mv.depth].bias_off;
   p.rgb_bias_off = mv.has_rgb ? m.pack[mv.depth + 3].bias_off : 0;
   if (cg2) {

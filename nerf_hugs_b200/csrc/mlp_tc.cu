@@ -204,7 +204,9 @@ struct Smem {
 
 __device__ __forceinline__ Smem carve(uint8_t* raw) {
   Smem s;
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ symbol (not an integer round trip) keeps the shared address space, so the
+  // accesses below compile to LDS/STS instead of generic loads and stores
+  uint8_t* base = raw + ((1024u - (ptx::smem_u32(raw) & 1023u)) & 1023u);
   s.panels = base;
   s.ring = base + kNumPanels * kPanelBytes;
   s.bias = reinterpret_cast<float*>(s.ring + kStages * kPanelBytes);

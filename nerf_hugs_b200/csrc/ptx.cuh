@@ -184,8 +184,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
   return r;
 }
+// Relaxed on purpose: a release at cluster scope compiles to MEMBAR.ALL.GPU (> 1000 cycles on the critical path).
+// The callers order their shared-memory writes with fence.proxy.async + bar.sync before the elected arrive, and
+// the data itself never crosses CTAs (each tensor core reads its own CTA's shared memory) - only the signal does.
 __device__ __forceinline__ void mbar_arrive_cluster_u32(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");

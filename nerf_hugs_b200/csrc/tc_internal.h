@@ -105,6 +105,7 @@ struct alignas(64) PpParams {
   __nv_bfloat16* drgb_out;
   int w_dens_off, w_rgb_off, dens_bias_off, rgb_bias_off;
   long long* dbg;                    // optional [gridDim.x][16] cycle counters (development instrumentation)
+  int dbg_flags;                     // HUGS_DBG_FLAGS timing experiments (results invalid): 1 no bias, 2 no panel store, 4 no TMEM load
 };
 
 struct TcMlp {

@@ -63,7 +63,9 @@ struct alignas(64) WgParams {
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // offset arithmetic on the __shared__ symbol (not an integer round trip) keeps the shared address space, so the
+  // accesses below compile to LDS/STS instead of generic loads and stores
+  uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + kWgStages * kWgStageBytes);
   uint64_t* full = bars; uint64_t* empty = bars + kWgStages;
   uint64_t* acc_full = bars + 2 * kWgStages; uint64_t* acc_empty = acc_full + 1;

@@ -24,8 +24,10 @@ rows = buf[buf[:, 4] > 0]
 m = rows.mean(0)
 tiles = 4096 / 148   # 128-sample tiles per SM (a CTA pair reports once for its two SMs)
 print('reporting CTAs/clusters:', len(rows))
-print('producer: total %.0f  wait_empty %.0f  wait_tile %.0f' % (m[0], m[1], m[2]))
-print('mma     : total %.0f  wait_panel %.0f  wait_full %.0f  wait_feat/issue %.0f  (per tile: total %.0f panel %.0f full %.0f feat/issue %.0f)' % (m[4], m[5], m[6], m[7], m[4]/tiles, m[5]/tiles, m[6]/tiles, m[7]/tiles))
-print('epi g0  : total %.0f  wait_acc %.0f  guard %.0f  work %.0f (per tile work %.0f)' % (m[8], m[9], m[10], m[8]-m[9]-m[10], (m[8]-m[9]-m[10])/tiles))
-print('epi g3  : total %.0f  wait_acc %.0f  guard %.0f  work %.0f (per tile work %.0f)' % (m[12], m[13], m[14], m[12]-m[13]-m[14], (m[12]-m[13]-m[14])/tiles))
-print('epi g0 detail (per tile): ld %.0f  math+store %.0f  publish %.0f' % (m[3]/tiles, m[11]/tiles, m[15]/tiles))
+units = 4096 / len(rows) / (4 if len(rows) <= 74 else 2)   # program passes per reporting CTA (pair)
+print('per unit (one pass of the segment program):')
+print('mma  : total %.0f  wait_panel %.0f  wait_full %.0f  wait_feat %.0f  issue %.0f' % (m[4]/units, m[5]/units, m[6]/units, m[7]/units, (m[4]-m[5]-m[6]-m[7])/units))
+for nm, o in (('epi g0', 8), ('epi g3', 12)):
+  print('%s: total %.0f  wait_acc %.0f  work(incl publish) %.0f  publish %.0f' % (nm, m[o]/units, m[o+1]/units, m[o+2]/units, m[o+3]/units))
+print('epi g0 relu/linear layers: tcgen05.ld+wait %.0f  cvt+st.shared %.0f' % (m[0]/units, m[1]/units))
+print('epi g0 by type: view layers %.0f  density-head layer %.0f' % (m[2]/units, m[3]/units))

@@ -39,3 +39,12 @@ fl_fwd = n * 251.4e6
 print(f'rays {n}: render fwd {t_fwd:.3f} ms ({n / t_fwd * 1e3:.3e} rays/s, {fl_fwd / t_fwd / 1e9:.1f} TFLOP/s) | '
       f'loss+grad {t_lg:.3f} ms | adam {t_adam:.3f} ms | train step {t_lg + t_adam:.3f} ms '
       f'({n / (t_lg + t_adam) * 1e3:.3e} rays/s, {3 * fl_fwd / (t_lg + t_adam) / 1e9:.1f} TFLOP/s)')
+
+def classes(fn, it=10):
+  eng.profile(True)
+  for _ in range(it): fn()
+  torch.cuda.synchronize()
+  prof = eng.profile_read(); eng.profile(False)
+  return {k: round(v[0] / it, 3) for k, v in prof.items() if v[1] > 0}
+print('render classes ms:', classes(lambda: eng.forward(flat, rays, 0.5, None, compute_extras=True, want_history=False)))
+print('train  classes ms:', classes(lambda: eng.loss_and_grad(flat, rays, gt, 0.5, jit, lc, grad, stats)))
