@@ -33,13 +33,22 @@ namespace {
 constexpr int kPpThreads = (kEpiGroups * 4 + 3) * 32;
 constexpr int kPartFloats = 768;     // head partial sums: [2 tiles][3][128]
 constexpr int kPpSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTab * 4 + kPartFloats * 4 + 512;
+// CTA-pair kernel: the fp32 table shrinks to the head weights / head biases, the layer biases become MMA operands
+constexpr int kBiasImgBytes = kBiasChunks * kBiasChunkElems * 2;
+constexpr int kOnesBytes = 4 * 256;   // variant v: core matrix with 1.0 in K columns 2v, 2v+1, then a zero core matrix
+constexpr int kCg2SmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTailFloats * 4 + kPartFloats * 4 +
+                              kBiasImgBytes + kOnesBytes + 512;
+static_assert(kCg2SmemBytes <= kPpSmemBytes, "CTA-pair layout must fit the common allocation");
+static_assert(kPpSmemBytes <= 232448, "shared memory budget");
 
 struct PpSmem {
   uint8_t* panels; uint8_t* ring; float* bias; float* part;
+  uint8_t* bias_img; uint8_t* ones;     // CTA-pair kernel only
   uint64_t *full, *empty, *panel_ready, *feat_ready, *acc_full, *consumed, *epi_done;
   uint32_t* tmem_ptr;
 };
 
+template <bool kCg2>
 __device__ __forceinline__ PpSmem pp_carve(uint8_t* raw) {
   PpSmem s;
   // offset arithmetic on the __shared__ symbol (not an integer round trip) keeps the shared address space, so the
@@ -48,8 +57,10 @@ __device__ __forceinline__ PpSmem pp_carve(uint8_t* raw) {
   s.panels = base;
   s.ring = base + kNumPanels * kPanelBytes;
   s.bias = reinterpret_cast<float*>(s.ring + kStages * kPanelBytes);
-  s.part = s.bias + kBiasTab;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s.part + kPartFloats);
+  s.part = s.bias + (kCg2 ? kBiasTailFloats : kBiasTab);
+  s.bias_img = reinterpret_cast<uint8_t*>(s.part + kPartFloats);
+  s.ones = s.bias_img + (kCg2 ? kBiasImgBytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s.ones + (kCg2 ? kOnesBytes : 0));
   s.full = bars; s.empty = bars + kStages;
   s.panel_ready = bars + 2 * kStages;        // [8]
   s.feat_ready = s.panel_ready + 8;          // [8]
@@ -63,7 +74,7 @@ __device__ __forceinline__ PpSmem pp_carve(uint8_t* raw) {
 template <bool kTrain, bool kCg2>
 __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_constant__ PpParams p) {
   extern __shared__ uint8_t smem_raw[];
-  PpSmem sm = pp_carve(smem_raw);
+  PpSmem sm = pp_carve<kCg2>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWProd = kEpiGroups * 4, kFProd = kWProd + 1, kMma = kWProd + 2;
   // work distribution: a *unit* is one pass of the segment program over `kCtas` x 2 tiles
@@ -77,6 +88,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
   const uint32_t pready_u32 = ptx::smem_u32(sm.panel_ready), fready_u32 = ptx::smem_u32(sm.feat_ready);
   const uint32_t accfull_u32 = ptx::smem_u32(sm.acc_full), consumed_u32 = ptx::smem_u32(sm.consumed);
   const uint32_t epidone_u32 = ptx::smem_u32(sm.epi_done);
+  const uint32_t ones_u32 = ptx::smem_u32(sm.ones), biasimg_u32 = ptx::smem_u32(sm.bias_img);
 
   if (warp == kWProd && lane == 0) {
     ptx::prefetch_tmap(&p.map_w); ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
@@ -88,7 +100,21 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     ptx::fence_mbar_init();
   }
   if (warp == kMma) { if (kCg2) ptx::tmem_alloc_cg2(sm.tmem_ptr, 512); else ptx::tmem_alloc(sm.tmem_ptr, 512); }
-  for (int i = threadIdx.x; i < p.bias_floats; i += kPpThreads) sm.bias[i] = p.bias[i];
+  if (kCg2) {
+    // sm.bias holds table entries [bias_tail0, bias_floats): head weights and head biases; the layer biases are
+    // staged as MMA operands (this CTA's half of the output rows)
+    for (int i = p.bias_tail0 + threadIdx.x; i < p.bias_floats; i += kPpThreads) sm.bias[i - p.bias_tail0] = p.bias[i];
+    const uint4* src = reinterpret_cast<const uint4*>(p.bias_img + (size_t)rank * kBiasChunks * kBiasChunkElems);
+    for (int i = threadIdx.x; i < kBiasImgBytes / 16; i += kPpThreads) reinterpret_cast<uint4*>(sm.bias_img)[i] = src[i];
+    for (int i = threadIdx.x; i < kOnesBytes / 4; i += kPpThreads) {
+      // 32-bit word i: variant v = i / 64, word w = i % 64; core matrix 0 = words 0..31 (row r = w / 4, K pair w % 4)
+      const int v = i >> 6, w = i & 63;
+      reinterpret_cast<uint32_t*>(sm.ones)[i] = (w < 32 && (w & 3) == v) ? 0x3F803F80u : 0u;
+    }
+    ptx::fence_proxy_async();
+  } else {
+    for (int i = threadIdx.x; i < p.bias_floats; i += kPpThreads) sm.bias[i] = p.bias[i];
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (kCg2) ptx::cluster_sync_all();   // the peer's barriers are initialised before any remote arrive / TMA signal
@@ -210,6 +236,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               if (dbg) c_panel += clock64() - c0;
               ptx::tc_fence_after();
             }
+            bool bias_pending = kCg2 && S.bias_idx >= 0;
             for (int kp = 0; kp < kps; ++kp) {
               if (a_feat) {
                 const uint32_t idx = (uint32_t)(8 + t * 4 + kp);
@@ -220,7 +247,19 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 ptx::tc_fence_after();
               }
               const uint64_t da = ptx::desc_from(kDescHi, panels_u32 + (t * 4 + kp) * kPanelBytes);
-              const uint32_t accum = (acc0 || kp > 0) ? 1u : 0u;
+              uint32_t accum = (acc0 || kp > 0) ? 1u : 0u;
+              if (bias_pending) {
+                // acc = ones[256 x 16] * [bias_hi, bias_lo, ...]^T: initialises the accumulator with the layer bias.
+                // No-swizzle K-major tiles: A = one 8-row core matrix for every row group (SBO 0) followed by a zero
+                // core matrix for K 8..15 (LBO 128); B = 16 row groups of this CTA's outputs (SBO 128), K 8..15
+                // aliasing K 0..7 (LBO 0, multiplied by zeros).
+                const int j = S.bias_idx;
+                const uint64_t oa = ptx::make_desc_nosw(ones_u32 + (uint32_t)(j & 3) * 256u, 128u, 0u);
+                const uint64_t ob = ptx::make_desc_nosw(biasimg_u32 + (uint32_t)(j >> 2) * (kBiasChunkElems * 2), 0u, 128u);
+                ptx::mma_bf16_ss_cg2(d_tmem, oa, ob, idesc256, 0u);
+                accum = 1u;
+                bias_pending = false;
+              }
               if (kCg2) {
                 // one stage = this K panel of all N columns (each CTA holds its half of the rows); tile 0 waits
                 // for it, tile 1 reuses it and releases it
@@ -282,6 +321,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     float v[32];
     float raw_keep[2] = {0.f, 0.f};
     const int col = q * 64;
+    const int tail0 = kCg2 ? p.bias_tail0 : 0;   // sm.bias[i - tail0] == bias table entry i
     // development counters (group 0 / group 3, first lane of the leader CTA)
     const bool dbg_t = p.dbg != nullptr && rank == 0 && (threadIdx.x == 0 || threadIdx.x == 3 * 128);
     long long c_acc = 0, c_work = 0, c_pub = 0, c_t0 = 0, c_t1 = 0, c_ld = 0, c_st = 0, c_view = 0, c_head = 0;
@@ -369,18 +409,50 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
           switch (S.epi) {
             case EPI_RELU: case EPI_LINEAR: {
               float head = 0.f;
+              if (kCg2) {
+                // bias already in the accumulator: TMEM -> registers -> bf16 -> swizzled panel, one LDTM wait
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld32(acc_addr, r0);
+                ptx::tmem_ld32(acc_addr + 32u, r1);
+                ptx::tmem_ld_wait();
+                uint32_t pk[32];
+                if (S.epi == EPI_RELU) {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    pk[j] = ptx::pack_bf16x2_relu(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                    pk[16 + j] = ptx::pack_bf16x2_relu(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) {
+                    pk[j] = ptx::pack_bf16x2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                    pk[16 + j] = ptx::pack_bf16x2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+                  }
+                }
+                uint4* prow = reinterpret_cast<uint4*>(panel + row * 128);
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                  prow[swz_chunk(row, c)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                if (S.head) {   // density head: dot of the bf16 activation with the bf16-rounded kernel
+                  const float4* wd4 = reinterpret_cast<const float4*>(sm.bias + (p.w_dens_off - p.bias_tail0) + col);
+#pragma unroll
+                  for (int c = 0; c < 16; ++c) {
+                    const float4 w = wd4[c];
+                    head = fmaf(__uint_as_float(pk[2 * c] << 16), w.x, head);
+                    head = fmaf(__uint_as_float(pk[2 * c] & 0xFFFF0000u), w.y, head);
+                    head = fmaf(__uint_as_float(pk[2 * c + 1] << 16), w.z, head);
+                    head = fmaf(__uint_as_float(pk[2 * c + 1] & 0xFFFF0000u), w.w, head);
+                  }
+                }
+              } else {
 #pragma unroll 1
               for (int hf = 0; hf < 2; ++hf) {
-                const long long c_l0 = dbg_t ? clock64() : 0;
-                if (!(p.dbg_flags & 4)) load_acc32(acc_addr + (uint32_t)(hf * 32), v);
-                if (dbg_t) c_ld += clock64() - c_l0;
+                load_acc32(acc_addr + (uint32_t)(hf * 32), v);
                 const float4* b4 = reinterpret_cast<const float4*>(sm.bias + S.bias_off + col + hf * 32);
-                if (!(p.dbg_flags & 1)) {
 #pragma unroll
-                  for (int c = 0; c < 8; ++c) {
-                    const float4 b = b4[c];
-                    v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
-                  }
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b = b4[c];
+                  v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
                 }
                 if (S.head) {   // density head: dot of the bf16-rounded activation with the bf16-rounded kernel
                   const float* wd = sm.bias + p.w_dens_off + col + hf * 32;
@@ -388,19 +460,16 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                   for (int c = 0; c < 32; ++c)
                     head = fmaf(__bfloat162float(__float2bfloat16(fmaxf(v[c], 0.f))), wd[c], head);
                 }
-                const long long c_s0 = dbg_t ? clock64() : 0;
-                if (!(p.dbg_flags & 2)) {
-                  if (S.epi == EPI_RELU) store_half32<true>(panel, row, hf * 4, v);
-                  else store_half32<false>(panel, row, hf * 4, v);
-                }
-                if (dbg_t) c_st += clock64() - c_s0;
+                if (S.epi == EPI_RELU) store_half32<true>(panel, row, hf * 4, v);
+                else store_half32<false>(panel, row, hf * 4, v);
+              }
               }
               if (S.head) {
                 float* part = sm.part + t * 384;
                 if (q > 0) part[(q - 1) * 128 + row] = head;
                 asm volatile("bar.sync 5, 512;" ::: "memory");
                 if (q == 0) {
-                  const float rd = ((head + part[row]) + part[128 + row]) + part[256 + row] + sm.bias[p.dens_bias_off];
+                  const float rd = ((head + part[row]) + part[128 + row]) + part[256 + row] + sm.bias[p.dens_bias_off - tail0];
                   raw_keep[t] = rd;
                   if (p.raw_c == 1 && valid) p.raw_out[s] = rd;
                 }
@@ -422,7 +491,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                       v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
                     }
                   }
-                  const float* wr = sm.bias + p.w_rgb_off + (col + hf * 32) * 3;
+                  const float* wr = sm.bias + (p.w_rgb_off - tail0) + (col + hf * 32) * 3;
 #pragma unroll
                   for (int c = 0; c < 32; ++c) {
                     const float a = __bfloat162float(__float2bfloat16(fmaxf(v[c], 0.f)));
@@ -436,9 +505,9 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 if (q == 0 && valid) {
                   float4 o;
                   o.x = raw_keep[t];
-                  o.y = h0 + part[row * 3] + sm.bias[p.rgb_bias_off];
-                  o.z = h1 + part[row * 3 + 1] + sm.bias[p.rgb_bias_off + 1];
-                  o.w = h2 + part[row * 3 + 2] + sm.bias[p.rgb_bias_off + 2];
+                  o.y = h0 + part[row * 3] + sm.bias[p.rgb_bias_off - tail0];
+                  o.z = h1 + part[row * 3 + 1] + sm.bias[p.rgb_bias_off + 1 - tail0];
+                  o.w = h2 + part[row * 3 + 2] + sm.bias[p.rgb_bias_off + 2 - tail0];
                   reinterpret_cast<float4*>(p.raw_out)[s] = o;
                 }
                 publish(S, pi, tile, tile_ok);
@@ -450,7 +519,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               for (int hf = 0; hf < 2; ++hf) {
                 load_acc32(acc_addr + (uint32_t)(hf * 32), v);
                 if (S.epi == EPI_BWD_RELU_D) {
-                  const float4* w4 = reinterpret_cast<const float4*>(sm.bias + p.w_dens_off + col + hf * 32);
+                  const float4* w4 = reinterpret_cast<const float4*>(sm.bias + (p.w_dens_off - tail0) + col + hf * 32);
 #pragma unroll
                   for (int c = 0; c < 8; ++c) {
                     const float4 w = w4[c];
@@ -479,7 +548,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 }
 #pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-                  const float* wr = sm.bias + p.w_rgb_off + (col + hf * 32) * 3;
+                  const float* wr = sm.bias + (p.w_rgb_off - tail0) + (col + hf * 32) * 3;
 #pragma unroll
                   for (int c = 0; c < 32; ++c) v[c] = d0 * wr[c * 3] + d1 * wr[c * 3 + 1] + d2 * wr[c * 3 + 2];
                   const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
@@ -499,7 +568,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               }
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
-                const float* wd = sm.bias + p.w_dens_off + col + hf * 32;
+                const float* wd = sm.bias + (p.w_dens_off - tail0) + col + hf * 32;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = ddq * wd[c];
                 const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
@@ -547,7 +616,7 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
   const int D = mv.depth;
   auto base_seg = [] {
     PpSeg s{};
-    s.kps = 4; s.n_halves = 2; s.epi = EPI_NONE; s.save_row = -1; s.mask_row = -1;
+    s.kps = 4; s.n_halves = 2; s.epi = EPI_NONE; s.save_row = -1; s.mask_row = -1; s.bias_idx = -1;
     return s;
   };
   // ---- forward ----
@@ -563,12 +632,13 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
       for (int part = 0; part < kFeatPad / 256; ++part) {
         PpSeg s = base_seg();
         s.a_feat = 1; s.feat_col0 = part * 256; s.w_row = P.row0; s.w_col0 = part * 256; s.accumulate = part > 0;
+        if (part == 0) s.bias_idx = i;
         if (part == kFeatPad / 256 - 1) finish(s);
         m->pp_fwd.push_back(s);
       }
     } else {
       PpSeg s = base_seg();
-      s.w_row = P.row0; s.w_col0 = 0;
+      s.w_row = P.row0; s.w_col0 = 0; s.bias_idx = i;
       if (!cat) finish(s);
       m->pp_fwd.push_back(s);
       if (cat) {
@@ -585,6 +655,7 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
   if (mv.has_rgb) {
     PpSeg b = base_seg();                       // bottleneck (linear)
     b.w_row = m->pack[D + 1].row0; b.epi = EPI_LINEAR; b.bias_off = m->pack[D + 1].bias_off; b.save_row = D;
+    b.bias_idx = D;
     m->pp_fwd.push_back(b);
     PpSeg v = base_seg();                       // view layer (N = 128) + rgb head
     v.n_halves = 1; v.w_row = m->pack[D + 2].row0; v.epi = EPI_VIEW; v.save_row = D + 1; v.no_signal = 1;
@@ -666,6 +737,9 @@ int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t
   p.dbg = (!is_prop && direction != 2) ? h->dbg_counters : nullptr;
   { const char* e = getenv("HUGS_DBG_FLAGS"); p.dbg_flags = e ? atoi(e) : 0; }
   p.dens_bias_off = m.pack[mv.depth].bias_off;
+  p.bias_img = m.bias_img;
+  p.bias_tail0 = cg2 ? m.pack[mv.depth].bias_off : 0;
+  HUGS_REQUIRE(!cg2 || m.bias_floats - p.bias_tail0 <= kBiasTailFloats, "head table too large for the CTA-pair kernel");
   p.rgb_bias_off = mv.has_rgb ? m.pack[mv.depth + 3].bias_off : 0;
   if (cg2) {
     for (int i = 0; i < p.n_segs; ++i)

@@ -132,14 +132,35 @@ struct PackArgs {
   const float* params;
   __nv_bfloat16* wt; __nv_bfloat16* wn; float* bias;
   int w_dens_off, w_rgb_off; long long dens_koff, rgb_koff; int dens_in, rgb_in;
+  __nv_bfloat16* bias_img; int n_bias_layers; int bias_layer[4 * kBiasChunks];   // dense-layer index of biased layer j
 };
 
 __global__ void pack_params_kernel(PackArgs a) {
   const long long nf = (long long)a.rows_f * kKP, nbk = (long long)a.rows_b * kW;
-  const long long total = nf + nbk + a.bias_floats;
+  const long long nimg = 2LL * kBiasChunks * kBiasChunkElems;
+  const long long total = nf + nbk + a.bias_floats + nimg;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    if (e < nf) {
+    if (e >= nf + nbk + a.bias_floats) {
+      // bias image of the CTA-pair kernel: element (n, k) of chunk c lives at (n / 8) * 64 + (n % 8) * 8 + k
+      // (8 x 16-byte core matrices, no swizzle); K columns 2j', 2j'+1 = bf16 hi / lo parts of layer 4c + j'
+      const int q = (int)(e - nf - nbk - a.bias_floats);
+      const int rank = q / (kBiasChunks * kBiasChunkElems), w = q % (kBiasChunks * kBiasChunkElems);
+      const int c = w / kBiasChunkElems, o = w % kBiasChunkElems;
+      const int n = (o / 64) * 8 + (o % 64) / 8, k = o % 8;
+      const int j = c * 4 + k / 2;
+      float v = 0.f;
+      if (j < a.n_bias_layers) {
+        const auto& L = a.layers[a.bias_layer[j]];
+        const int f = rank * 128 + n;
+        if (f < L.out) {
+          const float b = a.params[L.boff + f];
+          const float hi = __bfloat162float(__float2bfloat16(b));
+          v = (k & 1) ? (b - hi) : hi;
+        }
+      }
+      a.bias_img[q] = __float2bfloat16(v);
+    } else if (e < nf) {
       const int r = (int)(e / kKP), k = (int)(e % kKP);
       float v = 0.f;
       for (int l = 0; l < a.n_layers; ++l) {
@@ -827,6 +848,12 @@ int fill_pack_args(hugs_handle* h, const MlpViews& mv, const TcMlp& m, const flo
   a->w_dens_off = m.w_dens_off; a->w_rgb_off = m.w_rgb_off;
   a->dens_koff = mv.dense[mv.depth].kernel_off; a->dens_in = mv.dense[mv.depth].in;
   if (mv.has_rgb) { a->rgb_koff = mv.dense[mv.depth + 3].kernel_off; a->rgb_in = mv.dense[mv.depth + 3].in; }
+  // biased layers of the CTA-pair kernel: trunk layer i -> j = i, bottleneck -> j = depth (see pp_build)
+  a->bias_img = m.bias_img;
+  a->n_bias_layers = mv.depth + (mv.has_rgb ? 1 : 0);
+  HUGS_REQUIRE(a->n_bias_layers <= 4 * kBiasChunks, "too many biased layers (%d)", a->n_bias_layers);
+  for (int i = 0; i < mv.depth; ++i) a->bias_layer[i] = i;
+  if (mv.has_rgb) a->bias_layer[mv.depth] = mv.depth + 1;
   return HUGS_OK;
 }
 
@@ -862,7 +889,8 @@ int tc_create(hugs_handle* h) {
   for (TcMlp* m : {&tc->nerf, &tc->prop}) {
     if (!m->present) continue;
     if ((rc = tc_alloc(h, &m->wt, (size_t)m->rows_f * kKP)) || (rc = tc_alloc(h, &m->wn, (size_t)m->rows_b * kW)) ||
-        (rc = tc_alloc(h, &m->bias, (size_t)m->bias_floats)))
+        (rc = tc_alloc(h, &m->bias, (size_t)m->bias_floats)) ||
+        (rc = tc_alloc(h, &m->bias_img, (size_t)2 * kBiasChunks * kBiasChunkElems)))
       return rc;
     if ((rc = make_map(&m->map_wt128, m->wt, m->rows_f, kKP, 128)) ||
         (rc = make_map(&m->map_wt16, m->wt, m->rows_f, kKP, 16)) ||

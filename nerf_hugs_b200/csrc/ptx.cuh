@@ -268,6 +268,16 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr, uint32_t lbo
   d |= 2ull << 61;
   return d;
 }
+// No-swizzle K-major descriptor: 8-row x 16-byte core matrices (128 contiguous bytes each); LBO = byte distance between
+// the two core matrices of a K = 16 step, SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= 1ull << 46;
+  return d;
+}
 // Instruction descriptor for kind::f16, bf16 A/B, fp32 D.
 //   [4,6) D fmt (1=f32)  [7,10) A fmt (1=bf16)  [10,13) B fmt (1=bf16)  [15] A major (1 = MN)  [16] B major
 //   [17,23) N>>3         [24,29) M>>4

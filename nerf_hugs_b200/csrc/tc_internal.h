@@ -88,7 +88,14 @@ struct PpSeg {
   int no_signal;    // the produced panels feed no MMA
   int head;         // forward: this epilogue also evaluates the density head on CUDA cores
   int last_epi;     // last epilogue of the tile: release the panels for the next pair's features
+  int bias_idx;     // CTA-pair kernel: >= 0 on the first segment of a layer whose bias is applied by a K = 16 MMA
+                    // (ones x [bias_hi, bias_lo]) that also initialises the accumulator; -1: none
 };
+
+// CTA-pair kernel: biases as bf16 (hi, lo) column pairs of no-swizzle K-major B tiles, 4 layers per 8-column chunk
+constexpr int kBiasChunks = 3;            // <= 12 biased layers
+constexpr int kBiasChunkElems = 1024;     // 128 rows (this CTA's half of the outputs) x 8 K columns
+constexpr int kBiasTailFloats = 1280;     // fp32 table kept in shared memory by the CTA-pair kernel (heads + head biases)
 
 struct alignas(64) PpParams {
   CUtensorMap map_w, map_feat, map_save;
@@ -104,6 +111,8 @@ struct alignas(64) PpParams {
   const __nv_bfloat16* act;
   __nv_bfloat16* drgb_out;
   int w_dens_off, w_rgb_off, dens_bias_off, rgb_bias_off;
+  const __nv_bfloat16* bias_img;     // CTA-pair kernel: [2 ranks][kBiasChunks][kBiasChunkElems]
+  int bias_tail0;                    // CTA-pair kernel: first float of `bias` staged in shared memory
   long long* dbg;                    // optional [gridDim.x][16] cycle counters (development instrumentation)
   int dbg_flags;                     // HUGS_DBG_FLAGS timing experiments (results invalid): 1 no bias, 2 no panel store, 4 no TMEM load
 };
@@ -114,6 +123,7 @@ struct TcMlp {
   __nv_bfloat16* wt = nullptr; int rows_f = 0;   // forward pack  [rows_f, kKP]   (K-major rows = outputs)
   __nv_bfloat16* wn = nullptr; int rows_b = 0;   // backward pack [rows_b, kW]    (rows = inputs, cols = outputs)
   float* bias = nullptr; int bias_floats = 0;
+  __nv_bfloat16* bias_img = nullptr;             // see PpParams::bias_img
   int w_dens_off = 0, w_rgb_off = 0, view_bias_off = 0, view_w_row = 0;
   std::vector<TcLayer> fwd, bwd;
   std::vector<PpSeg> pp_fwd, pp_bwd;
