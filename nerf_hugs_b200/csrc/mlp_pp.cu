@@ -365,11 +365,36 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       if (dbg_t) c_pub += clock64() - c_p0;
     };
 
+    // ReLU gate bits of epilogue (unit, e): loaded one epilogue ahead (CTA-pair backward programs)
+    auto load_gate = [&](int unit, int e) -> uint2 {
+      const PpSeg& G = p.segs[p.epi_seg[e >> 1]];
+      if (G.mask_row < 0 || ((G.epi == EPI_BWD_START) && q >= 2)) return make_uint2(0u, 0u);
+      const int s2 = ((unit * 2 + (e & 1)) * kCtas + rank) * kTileM + row;
+      if (s2 >= p.n_samples) return make_uint2(0u, 0u);      // padding rows carry no gradient
+      return __ldg(p.gate + (size_t)G.mask_row * 4 + (size_t)q * p.cap + s2);
+    };
+    const int n_e = 2 * p.n_epi;
+    uint2 gate_next = make_uint2(0u, 0u);
+    if (kCg2 && unit0 < p.n_units) gate_next = load_gate(unit0, 0);
+
+    // 16 packed words (32 columns) -> chunks chunk0 .. chunk0 + 3 of the swizzled panel row
+    auto store_pk16 = [&](uint8_t* panel, int chunk0, const uint32_t* pk) {
+      uint4* prow = reinterpret_cast<uint4*>(panel + row * 128);
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        prow[swz_chunk(row, chunk0 + c)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+    };
+
     for (int unit = unit0; unit < p.n_units; unit += unit_stride) {
-      for (int si = 0; si < p.n_segs; ++si) {
-        const PpSeg& S = p.segs[si];
-        if (S.epi == EPI_NONE) continue;
-        for (int t = 0; t < 2; ++t) {
+      for (int e = 0; e < n_e; ++e) {
+        {
+          const PpSeg& S = p.segs[p.epi_seg[e >> 1]];
+          const int t = e & 1;
+          const uint2 gate = gate_next;
+          if (kCg2) {
+            if (e + 1 < n_e) gate_next = load_gate(unit, e + 1);
+            else if (unit + unit_stride < p.n_units) gate_next = load_gate(unit + unit_stride, 0);
+          }
           const int tile = (unit * 2 + t) * kCtas + rank;
           const bool tile_ok = tile < p.n_tiles;
           const int s = tile * kTileM + row;
@@ -384,7 +409,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
           float dd = 0.f;
           const bool need_mask = S.epi == EPI_BWD_RELU || S.epi == EPI_BWD_RELU_D || S.epi == EPI_BWD_START ||
                                  S.epi == EPI_BWD_START_PROP;
-          if (need_mask && participates) {
+          if (!kCg2 && need_mask && participates) {
             if (valid) {
               const uint4* src = reinterpret_cast<const uint4*>(p.act + ((size_t)S.mask_row + s) * kW + col);
 #pragma unroll
@@ -429,10 +454,9 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                     pk[16 + j] = ptx::pack_bf16x2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
                   }
                 }
-                uint4* prow = reinterpret_cast<uint4*>(panel + row * 128);
-#pragma unroll
-                for (int c = 0; c < 8; ++c)
-                  prow[swz_chunk(row, c)] = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                store_pk16(panel, 0, pk); store_pk16(panel, 4, pk + 16);
+                if (kTrain && S.epi == EPI_RELU && S.save_row >= 0 && tile_ok)   // gates of the backward ReLU
+                  p.gate[(size_t)S.save_row * 4 + (size_t)q * p.cap + s] = make_uint2(gate_bits16(pk), gate_bits16(pk + 16));
                 if (S.head) {   // density head: dot of the bf16 activation with the bf16-rounded kernel
                   const float4* wd4 = reinterpret_cast<const float4*>(sm.bias + (p.w_dens_off - p.bias_tail0) + col);
 #pragma unroll
@@ -480,6 +504,38 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
             case EPI_VIEW: {
               if (q < 2) {
                 float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+                if (kCg2) {
+                  uint32_t g01[2] = {0u, 0u};
+#pragma unroll 1
+                  for (int hf = 0; hf < 2; ++hf) {
+                    load_acc32(acc_addr + (uint32_t)(hf * 32), v);
+                    if (valid) {
+                      const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(s / p.S) * 128 + col + hf * 32);
+#pragma unroll
+                      for (int c = 0; c < 8; ++c) {
+                        const float4 b = __ldg(b4 + c);
+                        v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                      }
+                    }
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16x2_relu(v[2 * j], v[2 * j + 1]);
+                    const float4* wr4 = reinterpret_cast<const float4*>(sm.bias + (p.w_rgb_off - tail0) + (col + hf * 32) * 3);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {   // 4 columns x 3 channels = 3 float4 per step
+                      const float4 wa = wr4[3 * j], wb = wr4[3 * j + 1], wc = wr4[3 * j + 2];
+                      const float a0 = __uint_as_float(pk[2 * j] << 16), a1 = __uint_as_float(pk[2 * j] & 0xFFFF0000u);
+                      const float a2 = __uint_as_float(pk[2 * j + 1] << 16), a3 = __uint_as_float(pk[2 * j + 1] & 0xFFFF0000u);
+                      h0 = fmaf(a0, wa.x, h0); h1 = fmaf(a0, wa.y, h1); h2 = fmaf(a0, wa.z, h2);
+                      h0 = fmaf(a1, wa.w, h0); h1 = fmaf(a1, wb.x, h1); h2 = fmaf(a1, wb.y, h2);
+                      h0 = fmaf(a2, wb.z, h0); h1 = fmaf(a2, wb.w, h1); h2 = fmaf(a2, wc.x, h2);
+                      h0 = fmaf(a3, wc.y, h0); h1 = fmaf(a3, wc.z, h1); h2 = fmaf(a3, wc.w, h2);
+                    }
+                    if (kTrain) { store_pk16(panel, hf * 4, pk); g01[hf] = gate_bits16(pk); }
+                  }
+                  if (kTrain && S.save_row >= 0 && tile_ok)
+                    p.gate[(size_t)S.save_row * 4 + (size_t)q * p.cap + s] = make_uint2(g01[0], g01[1]);
+                } else {
 #pragma unroll 1
                 for (int hf = 0; hf < 2; ++hf) {
                   load_acc32(acc_addr + (uint32_t)(hf * 32), v);
@@ -499,6 +555,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                   }
                   if (kTrain) store_half32<true>(panel, row, hf * 4, v);
                 }
+                }
                 float* part = sm.part + t * 384;
                 if (q == 1) { part[row * 3] = h0; part[row * 3 + 1] = h1; part[row * 3 + 2] = h2; }
                 asm volatile("bar.sync 6, 256;" ::: "memory");
@@ -515,6 +572,37 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               break;
             }
             case EPI_BWD_LINEAR: case EPI_BWD_RELU: case EPI_BWD_RELU_D: {
+              if (kCg2) {
+                uint32_t r0[32], r1[32];
+                ptx::tmem_ld32(acc_addr, r0);
+                ptx::tmem_ld32(acc_addr + 32u, r1);
+                ptx::tmem_ld_wait();
+                if (S.epi == EPI_BWD_RELU_D) {
+                  const float4* w4 = reinterpret_cast<const float4*>(sm.bias + (p.w_dens_off - tail0) + col);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 wa = w4[c], wb = w4[8 + c];
+                    r0[c * 4 + 0] = __float_as_uint(fmaf(dd, wa.x, __uint_as_float(r0[c * 4 + 0])));
+                    r0[c * 4 + 1] = __float_as_uint(fmaf(dd, wa.y, __uint_as_float(r0[c * 4 + 1])));
+                    r0[c * 4 + 2] = __float_as_uint(fmaf(dd, wa.z, __uint_as_float(r0[c * 4 + 2])));
+                    r0[c * 4 + 3] = __float_as_uint(fmaf(dd, wa.w, __uint_as_float(r0[c * 4 + 3])));
+                    r1[c * 4 + 0] = __float_as_uint(fmaf(dd, wb.x, __uint_as_float(r1[c * 4 + 0])));
+                    r1[c * 4 + 1] = __float_as_uint(fmaf(dd, wb.y, __uint_as_float(r1[c * 4 + 1])));
+                    r1[c * 4 + 2] = __float_as_uint(fmaf(dd, wb.z, __uint_as_float(r1[c * 4 + 2])));
+                    r1[c * 4 + 3] = __float_as_uint(fmaf(dd, wb.w, __uint_as_float(r1[c * 4 + 3])));
+                  }
+                }
+                uint32_t pk[32];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  pk[j] = ptx::pack_bf16x2(__uint_as_float(r0[2 * j]), __uint_as_float(r0[2 * j + 1]));
+                  pk[16 + j] = ptx::pack_bf16x2(__uint_as_float(r1[2 * j]), __uint_as_float(r1[2 * j + 1]));
+                }
+                if (S.epi != EPI_BWD_LINEAR) { apply_gate16(gate.x, pk); apply_gate16(gate.y, pk + 16); }
+                store_pk16(panel, 0, pk); store_pk16(panel, 4, pk + 16);
+                publish(S, pi, tile, tile_ok);
+                break;
+              }
 #pragma unroll
               for (int hf = 0; hf < 2; ++hf) {
                 load_acc32(acc_addr + (uint32_t)(hf * 32), v);
@@ -551,9 +639,17 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                   const float* wr = sm.bias + (p.w_rgb_off - tail0) + (col + hf * 32) * 3;
 #pragma unroll
                   for (int c = 0; c < 32; ++c) v[c] = d0 * wr[c * 3] + d1 * wr[c * 3 + 1] + d2 * wr[c * 3 + 2];
+                  if (kCg2) {
+                    uint32_t pk[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                    apply_gate16(hf == 0 ? gate.x : gate.y, pk);
+                    store_pk16(panel, hf * 4, pk);
+                  } else {
                   const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
                   apply_mask32(half, v);
                   store_half32<false>(panel, row, hf * 4, v);
+                  }
                 }
                 publish(S, pi, tile, tile_ok);
               }
@@ -571,9 +667,17 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 const float* wd = sm.bias + (p.w_dens_off - tail0) + col + hf * 32;
 #pragma unroll
                 for (int c = 0; c < 32; ++c) v[c] = ddq * wd[c];
+                if (kCg2) {
+                  uint32_t pk[16];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) pk[j] = ptx::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+                  apply_gate16(hf == 0 ? gate.x : gate.y, pk);
+                  store_pk16(panel, hf * 4, pk);
+                } else {
                 const uint4 (&half)[4] = *reinterpret_cast<const uint4 (*)[4]>(&mk[hf * 4]);
                 apply_mask32(half, v);
                 store_half32<false>(panel, row, hf * 4, v);
+                }
               }
               publish(S, pi, tile, tile_ok);
               break;
@@ -737,6 +841,9 @@ int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t
   p.dbg = (!is_prop && direction != 2) ? h->dbg_counters : nullptr;
   { const char* e = getenv("HUGS_DBG_FLAGS"); p.dbg_flags = e ? atoi(e) : 0; }
   p.dens_bias_off = m.pack[mv.depth].bias_off;
+  p.gate = tc->gate; p.cap = cap;
+  for (int i = 0; i < p.n_segs; ++i)
+    if (p.segs[i].epi != EPI_NONE) p.epi_seg[p.n_epi++] = i;
   p.bias_img = m.bias_img;
   p.bias_tail0 = cg2 ? m.pack[mv.depth].bias_off : 0;
   HUGS_REQUIRE(!cg2 || m.bias_floats - p.bias_tail0 <= kBiasTailFloats, "head table too large for the CTA-pair kernel");

@@ -912,6 +912,8 @@ int tc_create(hugs_handle* h) {
   tc->total_feat_rows = frow; tc->total_save_rows = srow;
   if ((rc = tc_alloc(h, &tc->feat, (size_t)frow * kFeatPad))) return rc;
   if ((rc = tc_alloc(h, &tc->act, (size_t)srow * kW)) || (rc = tc_alloc(h, &tc->dz, (size_t)srow * kW))) return rc;
+  if ((rc = tc_alloc(h, &tc->gate, (size_t)srow * 4))) return rc;
+  HUGS_CUDA(cudaMemset(tc->gate, 0, (size_t)srow * 4 * sizeof(uint2)));
   for (int l = 0; l < L; ++l) tc->drgb_rows = std::max(tc->drgb_rows, tc->cap[l]);
   if ((rc = tc_alloc(h, &tc->drgb, (size_t)tc->drgb_rows * kHeadCols))) return rc;
   // unused columns (head gradients beyond col 3, view-activation columns 128..255) must read as zero

@@ -47,4 +47,18 @@ __device__ __forceinline__ void apply_mask32(const uint4 (&mk)[4], float (&v)[32
   }
 }
 
+// ReLU gate bits of 16 packed bf16x2 words (non-negative halves): bit j = low half of word j is non-zero,
+// bit 16 + j = high half.  (h + 0x7FFF sets bit 15 of a half-word iff h >= 1; no carry between the halves.)
+__device__ __forceinline__ uint32_t gate_bits16(const uint32_t* pk) {
+  uint32_t g = 0;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) g |= ((pk[j] + 0x7FFF7FFFu) >> (15 - j)) & (0x00010001u << j);
+  return g;
+}
+// zero the halves of 16 packed words whose gate bit is clear
+__device__ __forceinline__ void apply_gate16(uint32_t g, uint32_t* pk) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) pk[j] &= ((g >> j) & 0x00010001u) * 0xFFFFu;
+}
+
 }  // namespace hugs

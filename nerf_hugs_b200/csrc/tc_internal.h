@@ -111,6 +111,9 @@ struct alignas(64) PpParams {
   const __nv_bfloat16* act;
   __nv_bfloat16* drgb_out;
   int w_dens_off, w_rgb_off, dens_bias_off, rgb_bias_off;
+  uint2* gate;                       // CTA-pair kernel: ReLU gate bits [save row base * 4 + group * cap + sample] (64 columns each)
+  int cap;                           // rows per save slot of this level
+  int epi_seg[kMaxSegs]; int n_epi;  // segments that carry an epilogue, in program order
   const __nv_bfloat16* bias_img;     // CTA-pair kernel: [2 ranks][kBiasChunks][kBiasChunkElems]
   int bias_tail0;                    // CTA-pair kernel: first float of `bias` staged in shared memory
   long long* dbg;                    // optional [gridDim.x][16] cycle counters (development instrumentation)
@@ -141,6 +144,7 @@ struct TcState {
   __nv_bfloat16* feat = nullptr;     // per level region [cap_l, 512]
   __nv_bfloat16* act = nullptr;      // saved forward activations
   __nv_bfloat16* dz = nullptr;       // saved backward dZ
+  uint2* gate = nullptr;             // ReLU gate bit masks of the saved activations (CTA-pair kernel), 32 B per save row
   __nv_bfloat16* drgb = nullptr;     // [max cap, kHeadCols]
   int drgb_rows = 0;
   float* viewbias = nullptr;
