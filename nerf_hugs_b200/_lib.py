@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libhugs_b200.so')
+# HUGS_LIB selects another build of the same ABI (A/B timing of kernel variants during development)
+LIB_PATH = os.environ.get('HUGS_LIB') or os.path.join(_HERE, 'libhugs_b200.so')
 
 
 class HugsError(RuntimeError):

@@ -31,6 +31,11 @@ namespace hugs {
 namespace {
 
 constexpr int kPpThreads = (kEpiGroups * 4 + 3) * 32;
+#ifdef HUGS_PP_COUNTERS       // per-role cycle counters (scripts/chain_counters.py); off by default: they cost registers
+constexpr bool kCounters = true;
+#else
+constexpr bool kCounters = false;
+#endif
 constexpr int kPartFloats = 768;     // head partial sums: [2 tiles][3][128]
 constexpr int kPpSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTab * 4 + kPartFloats * 4 + 512;
 // CTA-pair kernel: the fp32 table shrinks to the head weights / head biases, the layer biases become MMA operands
@@ -65,8 +70,8 @@ __device__ __forceinline__ PpSmem pp_carve(uint8_t* raw) {
   s.panel_ready = bars + 2 * kStages;        // [8]
   s.feat_ready = s.panel_ready + 8;          // [8]
   s.acc_full = s.feat_ready + 8;             // [2]
-  s.consumed = s.acc_full + 2;               // [2]
-  s.epi_done = s.consumed + 2;               // [2]
+  s.consumed = s.acc_full + 2;               // [8]  per (tile, K panel): the MMAs that read the panel have completed
+  s.epi_done = s.consumed + 8;               // [2]
   s.tmem_ptr = reinterpret_cast<uint32_t*>(s.epi_done + 2);
   return s;
 }
@@ -94,9 +99,8 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     ptx::prefetch_tmap(&p.map_w); ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&sm.full[i], 1); ptx::mbar_init(&sm.empty[i], 1); }
     for (int i = 0; i < 8; ++i) { ptx::mbar_init(&sm.panel_ready[i], kCg2 ? 2 : 128); ptx::mbar_init(&sm.feat_ready[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      ptx::mbar_init(&sm.acc_full[i], 1); ptx::mbar_init(&sm.consumed[i], 1); ptx::mbar_init(&sm.epi_done[i], kEpiGroups);
-    }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.acc_full[i], 1); ptx::mbar_init(&sm.epi_done[i], kEpiGroups); }
+    for (int i = 0; i < 8; ++i) ptx::mbar_init(&sm.consumed[i], 1);
     ptx::fence_mbar_init();
   }
   if (warp == kMma) { if (kCg2) ptx::tmem_alloc_cg2(sm.tmem_ptr, 512); else ptx::tmem_alloc(sm.tmem_ptr, 512); }
@@ -165,40 +169,44 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     // ever skipped, so parity waits cannot alias); refills a tile's panels with IPE feature columns as soon
     // as the segment that last read those panels has completed.
     if (lane == 0 && p.any_feat) {
-      uint32_t cons_phase = 0;   // bit t: parity of the next `consumed[t]` phase to wait for
-      bool first = true;
+      uint32_t cons_phase = 0;   // bit t*4+kp: parity of the next `consumed` phase of that panel to wait for
+      int prev_kps0 = 0, prev_kps1 = 0;   // K panels of the previous MMA segment on tile 0 / 1 (0: none yet)
       int unit_iter = 0;
       for (int unit = unit0; unit < p.n_units; unit += unit_stride, ++unit_iter) {
         bool first_in_unit = true;
         for (int si = 0; si < p.n_segs; ++si) {
           const PpSeg& S = p.segs[si];
           if (S.kps == 0) continue;
+#pragma unroll
           for (int t = 0; t < 2; ++t) {
-            if (!(first && first_in_unit)) {       // every segment but the very first has a predecessor on tile t
-              ptx::mbar_wait_u32(consumed_u32 + t * 8, (cons_phase >> t) & 1u);
-              cons_phase ^= 1u << t;
-            }
-            if (S.a_feat) {
-              if (first_in_unit && unit_iter > 0)   // previous unit's last epilogue (and its TMA store) is done
-                ptx::mbar_wait_u32(epidone_u32 + t * 8, (uint32_t)((unit_iter - 1) & 1));
-              const int row = p.feat_row0 + ((unit * 2 + t) * kCtas + rank) * kTileM;
-              for (int kp = 0; kp < S.kps; ++kp) {
-                const uint32_t bar = fready_u32 + (t * 4 + kp) * 8;
+            const int pk = t == 0 ? prev_kps0 : prev_kps1;
+            const int row = p.feat_row0 + ((unit * 2 + t) * kCtas + rank) * kTileM;
+            const int n_it = S.kps > pk ? S.kps : pk;
+            for (int kp = 0; kp < n_it; ++kp) {
+              const uint32_t idx = (uint32_t)(t * 4 + kp);
+              if (kp < pk) {   // panel kp is free once the previous segment's MMAs on it have completed
+                ptx::mbar_wait_u32(consumed_u32 + idx * 8, (cons_phase >> idx) & 1u);
+                cons_phase ^= 1u << idx;
+              }
+              if (S.a_feat && kp < S.kps) {
+                if (first_in_unit && unit_iter > 0 && kp == 0)   // previous unit's last epilogue (and its TMA store) is done
+                  ptx::mbar_wait_u32(epidone_u32 + t * 8, (uint32_t)((unit_iter - 1) & 1));
+                const uint32_t bar = fready_u32 + idx * 8;
                 if (kCg2) {
                   if (rank == 0) ptx::mbar_expect_tx_u32(bar, 2 * kPanelBytes);
-                  ptx::tma_load_2d_cg2(panels_u32 + (t * 4 + kp) * kPanelBytes, &p.map_feat, ptx::mapa_u32(bar, 0),
+                  ptx::tma_load_2d_cg2(panels_u32 + idx * kPanelBytes, &p.map_feat, ptx::mapa_u32(bar, 0),
                                        S.feat_col0 + kp * 64, row);
                 } else {
                   ptx::mbar_expect_tx_u32(bar, kPanelBytes);
-                  ptx::tma_load_2d_u32(panels_u32 + (t * 4 + kp) * kPanelBytes, &p.map_feat, bar,
-                                       S.feat_col0 + kp * 64, row);
+                  ptx::tma_load_2d_u32(panels_u32 + idx * kPanelBytes, &p.map_feat, bar, S.feat_col0 + kp * 64, row);
                 }
               }
             }
+            const int sig = S.feat_next ? S.kps : 0;
+            if (t == 0) prev_kps0 = sig; else prev_kps1 = sig;
           }
           first_in_unit = false;
         }
-        first = false;
       }
     }
   } else if (warp == kMma) {
@@ -215,7 +223,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       uint32_t wait_phase = 0;   // bits 0-7 panel_ready, 8-15 feat_ready
       long long c_panel = 0, c_feat = 0, c_full = 0;
       const long long c_start = clock64();
-      const bool dbg = p.dbg != nullptr;
+      const bool dbg = kCounters && p.dbg != nullptr;
       for (int unit = unit0; unit < p.n_units; unit += unit_stride) {
         for (int si = 0; si < p.n_segs; ++si) {
           const PpSeg& S = p.segs[si];
@@ -278,6 +286,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
                 ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
                 if (t == 1) commit(empty_u32 + st_k * 8);
+                if (S.feat_next) commit(consumed_u32 + (t * 4 + kp) * 8);
               } else {
                 for (int h = 0; h < n_halves; ++h) {
                   const long long c0 = dbg ? clock64() : 0;
@@ -293,9 +302,9 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                   commit(empty_u32 + stage * 8);
                   if (++stage == kStages) { stage = 0; phase ^= 1; }
                 }
+                if (S.feat_next) commit(consumed_u32 + (t * 4 + kp) * 8);
               }
             }
-            commit(consumed_u32 + t * 8);
             if (has_epi) commit(accfull_u32 + t * 8);
           }
           if (kCg2) {
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     const int col = q * 64;
     const int tail0 = kCg2 ? p.bias_tail0 : 0;   // sm.bias[i - tail0] == bias table entry i
     // development counters (group 0 / group 3, first lane of the leader CTA)
-    const bool dbg_t = p.dbg != nullptr && rank == 0 && (threadIdx.x == 0 || threadIdx.x == 3 * 128);
+    const bool dbg_t = kCounters && p.dbg != nullptr && rank == 0 && (threadIdx.x == 0 || threadIdx.x == 3 * 128);
     long long c_acc = 0, c_work = 0, c_pub = 0, c_t0 = 0, c_t1 = 0, c_ld = 0, c_st = 0, c_view = 0, c_head = 0;
     const long long c_epi_start = clock64();
 
@@ -510,6 +519,8 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                   for (int hf = 0; hf < 2; ++hf) {
                     load_acc32(acc_addr + (uint32_t)(hf * 32), v);
                     if (valid) {
+                      // (prefetching this row before the accumulator wait costs more in registers than the exposed
+                      //  L2 latency: measured, profiles/r01_ab_experiments.md)
                       const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(s / p.S) * 128 + col + hf * 32);
 #pragma unroll
                       for (int c = 0; c < 8; ++c) {
@@ -766,6 +777,11 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
     m->pp_fwd.push_back(v);
   }
   m->pp_fwd.back().last_epi = 1;
+  for (size_t i = 0; i < m->pp_fwd.size(); ++i) {
+    size_t j = (i + 1) % m->pp_fwd.size();
+    while (m->pp_fwd[j].kps == 0) j = (j + 1) % m->pp_fwd.size();
+    m->pp_fwd[i].feat_next = m->pp_fwd[j].a_feat;
+  }
   HUGS_REQUIRE((int)m->pp_fwd.size() <= kMaxSegs, "ping-pong schedule: too many segments (%zu)", m->pp_fwd.size());
   // a feature refill must never directly follow an epilogue of the same tile (the epilogue writes the panels)
   for (size_t i = 1; i < m->pp_fwd.size(); ++i)

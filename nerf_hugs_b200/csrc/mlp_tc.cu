@@ -45,12 +45,13 @@ struct EncArgs {
 };
 
 constexpr int kEncRows = 32;
-__global__ void __launch_bounds__(2 * kEncRows) encode_bf16_kernel(EncArgs a) {
+constexpr int kEncSplit = 4;     // threads per sample (each takes a contiguous range of basis directions)
+__global__ void __launch_bounds__(kEncSplit * kEncRows) encode_bf16_kernel(EncArgs a) {
   __shared__ __align__(16) uint4 tile[kEncRows * 64];   // rows x 64 chunks of 16 B, chunk index swizzled
-  const int tid = threadIdx.x, rl = tid % kEncRows, half = tid / kEncRows;
+  const int tid = threadIdx.x, rl = tid % kEncRows, part = tid / kEncRows;
   const int s = blockIdx.x * kEncRows + rl;
-  const int nb0 = (a.nb + 1) >> 1;
-  const int b_beg = half ? nb0 : 0, b_end = half ? a.nb : nb0;
+  const int b_beg = (a.nb * part) / kEncSplit, b_end = (a.nb * (part + 1)) / kEncSplit;
+  const bool half = part == kEncSplit - 1;      // the last part also clears the padding columns
   const int cpb = a.ndeg >> 2;                    // 16-byte chunks per basis direction
   if (s < a.n_samples) {
     const int ray = s / a.S, i = s % a.S;
@@ -96,13 +97,14 @@ __global__ void __launch_bounds__(2 * kEncRows) encode_bf16_kernel(EncArgs a) {
   } else if (s < a.n_rows_pad) {
     // rows between n_samples and the 128-row tile boundary: finite (zero) features so that the saved
     // activations of padding rows can never poison the weight-gradient reduction
-    for (int c = half * 32; c < half * 32 + 32; ++c) tile[rl * 64 + swz_chunk(rl, c)] = make_uint4(0, 0, 0, 0);
+    for (int c = part * (64 / kEncSplit); c < (part + 1) * (64 / kEncSplit); ++c)
+      tile[rl * 64 + swz_chunk(rl, c)] = make_uint4(0, 0, 0, 0);
   }
   __syncthreads();
   // coalesced copy-out of the block's consecutive rows
   const int rows = min(kEncRows, a.n_rows_pad - blockIdx.x * kEncRows);
   uint4* dst = reinterpret_cast<uint4*>(a.feat) + (size_t)blockIdx.x * kEncRows * 64;
-  for (int e = tid; e < rows * 64; e += 2 * kEncRows) {
+  for (int e = tid; e < rows * 64; e += kEncSplit * kEncRows) {
     int r = e >> 6, c = e & 63;
     dst[e] = tile[r * 64 + swz_chunk(r, c)];
   }
@@ -971,7 +973,7 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
              is_prop ? d.prop_contract : d.nerf_contract, tc->feat + (size_t)tc->feat_row0[level] * kFeatPad};
   {
     ProfScope ps(h, HUGS_K_ENCODE, st);
-    encode_bf16_kernel<<<(n_tiles * kTileM + kEncRows - 1) / kEncRows, 2 * kEncRows, 0, st>>>(ea);
+    encode_bf16_kernel<<<(n_tiles * kTileM + kEncRows - 1) / kEncRows, kEncSplit * kEncRows, 0, st>>>(ea);
     HUGS_LAUNCH_CHECK();
   }
   // 2. per-ray view bias (direction encoding + GLO folded through the view layer)

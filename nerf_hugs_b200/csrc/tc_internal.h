@@ -88,6 +88,8 @@ struct PpSeg {
   int no_signal;    // the produced panels feed no MMA
   int head;         // forward: this epilogue also evaluates the density head on CUDA cores
   int last_epi;     // last epilogue of the tile: release the panels for the next pair's features
+  int feat_next;    // the next MMA segment of the program (cyclically) refills this tile's panels with features:
+                    // signal `consumed` per K panel so that the refill can start panel by panel
   int bias_idx;     // CTA-pair kernel: >= 0 on the first segment of a layer whose bias is applied by a K = 16 MMA
                     // (ones x [bias_hi, bias_lo]) that also initialises the accumulator; -1: none
 };

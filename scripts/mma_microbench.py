@@ -15,6 +15,15 @@ for n in (64, 128, 256):
       assert rc == 0, _lib.lib.hugs_last_error()
       print(f'{n:4d} {mode:2d} {cnt:5d} | {out[0]/cnt:8.1f} | {out[1]/cnt:8.1f}')
 
+f2 = _lib.lib.hugs_debug_mma_rate_cg2
+f2.restype = C.c_int; f2.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+print('cta_group::2 (M=256): N mode n_mmas | issue cyc/MMA | complete cyc/MMA')
+for n in (128, 256):
+  for mode in (0, 1, 4, 5):
+    for cnt in (64, 512):
+      assert f2(n, cnt, mode, out) == 0, _lib.lib.hugs_last_error()
+      print(f'{n:4d} {mode:2d} {cnt:5d} | {out[0]/cnt:8.1f} | {out[1]/cnt:8.1f}')
+
 fl = _lib.lib.hugs_debug_ldtm_rate
 fl.restype = C.c_int; fl.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
 print('tcgen05.ld 32x32b.x32: warps cols | cycles per 128-lane x cols tile-read | bytes/cycle/SM')
