@@ -14,7 +14,8 @@ is available offline).  Rays are sharded over ranks (one process per GPU, weak s
 Printed JSON (rank 0, one line): see the keys below; `value` = whole-job rays/s with inputs resident in HBM,
 `e2e` = the same metric through the reference-facing call (`train_utils.train_pstep`) with HOST batches
 (pinned H2D copy of every batch + D2H read of the loss inside the timed region),
-`roofline` = the dominant kernel (NerfMLP forward chain) against the measured bf16 tensor peak,
+`roofline` = the kernel class with the largest time per step against its measured peak (tensor or HBM), with every
+MLP kernel listed under `roofline.kernels`,
 `cpu_baseline` = the CPU oracle (a port of the reference algorithm) timed on this box's host cores.
 """
 import argparse
@@ -35,6 +36,11 @@ FLOPS_PROP_SAMPLE = 651776          # 2*sum(K*N) over the PropML
 FLOPS_NERF_SAMPLE = 1638400         # NerfMLP(256)
 FLOPS_RAY_FWD = N_PROP * FLOPS_PROP_SAMPLE + N_NERF * FLOPS_NERF_SAMPLE   # 251.4 MFLOP
 METRIC = 'training rays/s (Mip-NeRF 360, 4096-ray batch, 64+128 samples/ray, 256-wide MLPs)'
+# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (bytes)
+NCU_DRAM_BYTES = {'chain_fwd_nerf': 1.087483e9 + 2.648109e9, 'chain_bwd_nerf': 0.183374e9 + 2.510509e9,
+                  'wgrad_nerf': 6.880211e9 + 0.008463e9, 'chain_fwd_prop': 0.272809e9 + 0.512298e9,
+                  'wgrad_prop': 1.463896e9 + 0.004328e9}
+NCU_DRAM_SOURCE = 'profiles/r01_ncu_full_train_step_cg2.json (ncu --set full, one training step, 4096 rays)'
 
 
 def synthetic_batch(n_rays, seed, n_cams=100, hw=800, focal=1111.1):
@@ -90,7 +96,7 @@ class ClockSampler(threading.Thread):
           self.rows.append([c.strip() for c in out.split(',')])
       except Exception:
         pass
-      self._halt.wait(0.2)
+      self._halt.wait(0.05)
 
   def stop(self):
     self._halt.set()
@@ -247,17 +253,48 @@ def run_ours(args):
 
   if rank == 0:
     peaks = measured_peaks()
-    t_dom = kern_ms.get('chain_fwd_nerf')
-    flops_dom = per_gpu * N_NERF * FLOPS_NERF_SAMPLE
-    achieved = flops_dom / (t_dom * 1e-3) / 1e12 if t_dom else None
-    roofline = {'bound': 'tensor', 'kernel': 'mlp_chain_kernel<train> (NerfMLP forward chain, tcgen05)',
-                'achieved': achieved, 'peak': peaks['bf16_sustained'], 'unit': 'TFLOP/s',
-                'frac': (achieved / peaks['bf16_sustained']) if achieved else None, 'traffic': None,
-                'peak_source': f"{peaks['source']} cuBLAS bf16 sustained (MEASURED_PEAKS.json)",
-                'algorithmic_flops_per_launch': flops_dom, 'ms_per_launch': t_dom,
-                'step_tflops_3x_convention': 3 * FLOPS_RAY_FWD * per_gpu / (ms / args.steps * 1e-3) / 1e12,
-                'step_frac_of_peak': 3 * FLOPS_RAY_FWD * per_gpu / (ms / args.steps * 1e-3) / 1e12 / peaks['bf16_sustained'],
-                'kernel_class_ms_per_step': kern_ms}
+    src = f"{peaks['source']} (MEASURED_PEAKS.json)"
+    n_nerf, n_prop = per_gpu * N_NERF, per_gpu * N_PROP
+
+    def tensor_line(cls, kernel, flops):
+      t = kern_ms.get(cls)
+      a = flops / (t * 1e-3) / 1e12 if t else None
+      return {'class': cls, 'kernel': kernel, 'bound': 'tensor', 'achieved': a, 'peak': peaks['bf16_sustained'],
+              'unit': 'TFLOP/s', 'frac': a / peaks['bf16_sustained'] if a else None,
+              'algorithmic_flops_per_launch': flops, 'ms_per_launch': t,
+              'peak_source': 'cuBLAS bf16 sustained, ' + src}
+
+    def hbm_line(cls, kernel, nbytes):
+      t = kern_ms.get(cls)
+      a = nbytes / (t * 1e-3) / 1e9 if t else None
+      return {'class': cls, 'kernel': kernel, 'bound': 'hbm', 'achieved': a, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+              'frac': a / peaks['hbm_gbs'] if a else None, 'algorithmic_bytes_per_launch': nbytes, 'ms_per_launch': t,
+              'peak_source': 'STREAM-style copy, ' + src}
+
+    # algorithmic work per launch (DESIGN.md "Kernels and their bounds"): MLP chains = SURVEY §8d FLOPs per sample;
+    # the weight-gradient GEMMs stream every saved activation / dZ / feature row exactly once (unique bytes).
+    wg_bytes_nerf = n_nerf * ((8 + 2) * 512 * 2 + 1024 + 128)
+    wg_bytes_prop = n_prop * (4 * 512 * 2 + 1024 + 128)
+    lines = [
+        tensor_line('chain_fwd_nerf', 'mlp_pp_kernel<train, cta_pair> NerfMLP forward chain (tcgen05 cta_group::2)',
+                    n_nerf * FLOPS_NERF_SAMPLE),
+        tensor_line('chain_bwd_nerf', 'mlp_pp_kernel<train, cta_pair> NerfMLP dgrad chain',
+                    n_nerf * 2 * (7 * 256 * 256 + 256 * 256 + 256 * 128)),
+        hbm_line('wgrad_nerf', 'wgrad_kernel NerfMLP weight gradients (tcgen05, MN-major operands)', wg_bytes_nerf),
+        tensor_line('chain_fwd_prop', 'mlp_pp_kernel<train, cta_pair> PropMLP forward chain', n_prop * FLOPS_PROP_SAMPLE),
+        hbm_line('wgrad_prop', 'wgrad_kernel PropMLP weight gradients', wg_bytes_prop),
+    ]
+    lines = [l for l in lines if l['ms_per_launch']]
+    dom = max(lines, key=lambda l: l['ms_per_launch'])
+    for l in lines:
+      l['traffic'] = NCU_DRAM_BYTES.get(l['class']) if per_gpu == 4096 else None
+    roofline = dict(dom)
+    roofline['traffic_source'] = NCU_DRAM_SOURCE
+    roofline['dominant_by'] = 'largest CUDA-event time per step among the kernel classes'
+    roofline['step_tflops_3x_convention'] = 3 * FLOPS_RAY_FWD * per_gpu / (ms / args.steps * 1e-3) / 1e12
+    roofline['step_frac_of_tensor_peak'] = roofline['step_tflops_3x_convention'] / peaks['bf16_sustained']
+    roofline['kernels'] = lines
+    roofline['kernel_class_ms_per_step'] = kern_ms
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
       rate, dt, threads = cpu_oracle_rate(args.ref_rays, 3)
@@ -290,8 +327,8 @@ def run_ours(args):
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--gpus', type=int, default=1)
-  ap.add_argument('--steps', type=int, default=50)
-  ap.add_argument('--warmup', type=int, default=5)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=20)
   ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
   ap.add_argument('--rays', type=int, default=4096, help='rays per GPU (weak) or global batch (strong)')
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
