@@ -44,8 +44,14 @@ struct EncArgs {
   __nv_bfloat16* feat;    // [rows, 512] (already offset to the level's first row)
 };
 
-constexpr int kEncRows = 32;
-constexpr int kEncSplit = 4;     // threads per sample (each takes a contiguous range of basis directions)
+#ifndef HUGS_ENC_ROWS
+#define HUGS_ENC_ROWS 8
+#endif
+#ifndef HUGS_ENC_SPLIT
+#define HUGS_ENC_SPLIT 8
+#endif
+constexpr int kEncRows = HUGS_ENC_ROWS;
+constexpr int kEncSplit = HUGS_ENC_SPLIT;     // threads per sample (each takes a contiguous range of basis directions)
 __global__ void __launch_bounds__(kEncSplit * kEncRows) encode_bf16_kernel(EncArgs a) {
   __shared__ __align__(16) uint4 tile[kEncRows * 64];   // rows x 64 chunks of 16 B, chunk index swizzled
   const int tid = threadIdx.x, rl = tid % kEncRows, part = tid / kEncRows;
