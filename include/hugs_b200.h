@@ -190,6 +190,42 @@ int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* ray
 int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
                    const hugs_adam_cfg* cfg, float* norms_out, void* stream);
 
+/* ---- batch assembly on the device (the caller of the path: SURVEY.md §8f item 2) ---- */
+
+/* Device-resident dataset: Dataset.{pixtocams, camtoworlds, heights, widths, images, static_masks, nears, fars,
+ * embed_idxs} (MipNeRF360/internal/datasets.py:310-383,446-482).  Images of different sizes are packed back to back;
+ * camera c's pixel (y, x) is element pixel_offset[c] + y * widths[c] + x of every per-pixel store. */
+typedef struct {
+  const float* pixtocams;      /* [n_cams, 3, 3] inverse intrinsics (camera_utils.get_pixtocam) */
+  const float* camtoworlds;    /* [n_cams, 3, 4] */
+  const int32_t* heights;      /* [n_cams] */
+  const int32_t* widths;       /* [n_cams] */
+  const int64_t* pixel_offset; /* [n_cams] */
+  const float* images;         /* packed [pixels, 3] fp32 in [0,1], or NULL */
+  const uint8_t* images_u8;    /* packed [pixels, 3] uint8 (rgb = u8 / 255), or NULL; takes precedence */
+  const float* static_masks;   /* packed [pixels] HuGS static masks (datasets.py:473), NULL => 1 */
+  const float* nears;          /* packed [pixels] per-pixel near (datasets.py:474), NULL => `near` */
+  const float* fars;           /* packed [pixels], NULL => `far` */
+  const int32_t* embed_idxs;   /* [n_cams], NULL => camera index */
+  float near, far;
+} hugs_camera_set;
+
+/* utils.Rays + Batch.rgb as writable struct-of-arrays device pointers, each [n_rays, C] contiguous. */
+typedef struct {
+  float* origins; float* directions; float* viewdirs;   /* [n,3] */
+  float* radii; float* near; float* far; float* lossmult; float* static_mask;   /* [n,1] */
+  int32_t* embed_idx;          /* [n,1] */
+  int32_t* cam_idx;            /* [n,1] or NULL */
+  float* pix_coords;           /* [n,2] or NULL */
+  float* rgb;                  /* [n,3] or NULL (render paths have no images) */
+} hugs_ray_batch;
+
+/* Dataset._make_ray_batch (datasets.py:446-482) -> camera_utils.cast_ray_batch -> pixels_to_rays
+ * (camera_utils.py:503-607,610-669) for perspective cameras without lens distortion / NDC:
+ * rays, HuGS static mask, near/far and ground-truth colours of pixels (cam_idx[i], pix_y[i], pix_x[i]). */
+int hugs_make_ray_batch(const hugs_camera_set* cams, const int32_t* cam_idx, const int32_t* pix_x,
+                        const int32_t* pix_y, int32_t n_rays, const hugs_ray_batch* out, void* stream);
+
 /* ---- measurement hooks (bench.py): no reference counterpart beyond train.py:162-168 wall-clock ---- */
 
 /* Number of kernels this library has launched in this process (every launch site counts itself). */

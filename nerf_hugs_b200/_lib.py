@@ -61,6 +61,17 @@ class LevelOut(C.Structure):
                                         'distance_p95', 'sdist', 'weights', 'density', 'rgbs')]
 
 
+class CameraSet(C.Structure):
+  _fields_ = [(n, C.c_void_p) for n in ('pixtocams', 'camtoworlds', 'heights', 'widths', 'pixel_offset', 'images',
+                                        'images_u8', 'static_masks', 'nears', 'fars', 'embed_idxs')] + \
+             [('near', C.c_float), ('far', C.c_float)]
+
+
+class RayBatch(C.Structure):
+  _fields_ = [(n, C.c_void_p) for n in ('origins', 'directions', 'viewdirs', 'radii', 'near', 'far', 'lossmult',
+                                        'static_mask', 'embed_idx', 'cam_idx', 'pix_coords', 'rgb')]
+
+
 # every symbol include/hugs_b200.h declares: (name, restype, argtypes)
 _P, _I, _F = C.c_void_p, C.c_int32, C.c_float
 SYMBOLS = {
@@ -79,6 +90,7 @@ SYMBOLS = {
     'hugs_forward': (C.c_int, [_P, _P, C.POINTER(Rays), _I, _F, _P, _I, _I, C.POINTER(LevelOut), _P]),
     'hugs_loss_and_grad': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _F, _P, C.POINTER(LossCfg), _P, _P, _P]),
     'hugs_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P]),
+    'hugs_make_ray_batch': (C.c_int, [C.POINTER(CameraSet), _P, _P, _P, _I, C.POINTER(RayBatch), _P]),
     'hugs_launch_count': (C.c_int64, []),
     'hugs_profile_enable': (C.c_int, [_P, _I]),
     'hugs_profile_read': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

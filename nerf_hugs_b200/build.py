@@ -23,6 +23,7 @@ SOURCES = [
     ('wgrad_tc.cu', []),
     ('tc_microbench.cu', []),
     ('optim.cu', []),
+    ('raygen.cu', []),
 ]
 
 

@@ -1,0 +1,108 @@
+// On-device ray generation and per-pixel batch gather.
+//
+// Reference semantics (paths under /root/reference/MipNeRF360/internal):
+//   camera_utils.py:503-607  pixels_to_rays (perspective camera, no lens distortion, no NDC): three rays per pixel
+//                            (centre, +x, +y) through pixtocam, OpenCV -> OpenGL flip, camtoworld rotation;
+//                            radii = mean distance to the two neighbours * 2 / sqrt(12)
+//   camera_utils.py:655-659  pix_coords = (pixel + 0.5) / (width, height)
+//   datasets.py:446-482      Dataset._make_ray_batch: static_masks[cam][y, x] (the HuGS mask), nears / fars[cam][y, x],
+//                            images[cam][y, x], embed_idxs[cam]
+//
+// The reference's NumPy branch evaluates this in float64 (integer pixel + 0.5 promotes) on float32 cameras and the
+// batch is rounded to float32 when it is put on the device; the kernel does the same (fp64 registers, fp32 stores).
+// One thread per ray; consecutive threads write consecutive rays of every SoA field.
+#include "common.cuh"
+#include "handle.h"
+
+namespace hugs {
+namespace {
+
+struct RayGenArgs {
+  hugs_camera_set cams;
+  const int32_t* cam_idx; const int32_t* pix_x; const int32_t* pix_y;
+  int n;
+  hugs_ray_batch out;
+};
+
+__global__ void __launch_bounds__(128) make_ray_batch_kernel(RayGenArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const int c = a.cam_idx[i], x = a.pix_x[i], y = a.pix_y[i];
+  const float* P = a.cams.pixtocams + (size_t)c * 9;
+  const float* M = a.cams.camtoworlds + (size_t)c * 12;
+  double p[9], m[12];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) p[k] = (double)__ldg(P + k);
+#pragma unroll
+  for (int k = 0; k < 12; ++k) m[k] = (double)__ldg(M + k);
+  double dir[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double px = (double)(x + (r == 1)) + 0.5, py = (double)(y + (r == 2)) + 0.5;
+    double cam[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) cam[k] = p[k * 3] * px + p[k * 3 + 1] * py + p[k * 3 + 2];
+    cam[1] = -cam[1]; cam[2] = -cam[2];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) dir[r][k] = m[k * 4] * cam[0] + m[k * 4 + 1] * cam[1] + m[k * 4 + 2] * cam[2];
+  }
+  const double nrm = sqrt(dir[0][0] * dir[0][0] + dir[0][1] * dir[0][1] + dir[0][2] * dir[0][2]);
+  double dxn = 0.0, dyn = 0.0;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const double ex = dir[1][k] - dir[0][k], ey = dir[2][k] - dir[0][k];
+    dxn += ex * ex; dyn += ey * ey;
+  }
+  const double radius = (0.5 * (sqrt(dxn) + sqrt(dyn))) * 2.0 / sqrt(12.0);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    a.out.origins[(size_t)i * 3 + k] = (float)m[k * 4 + 3];
+    a.out.directions[(size_t)i * 3 + k] = (float)dir[0][k];
+    a.out.viewdirs[(size_t)i * 3 + k] = (float)(dir[0][k] / nrm);
+  }
+  a.out.radii[i] = (float)radius;
+  const int h = a.cams.heights[c], w = a.cams.widths[c];
+  const size_t pix = (size_t)a.cams.pixel_offset[c] + (size_t)y * w + x;
+  if (a.out.pix_coords) {
+    a.out.pix_coords[(size_t)i * 2] = ((float)x + 0.5f) / (float)w;
+    a.out.pix_coords[(size_t)i * 2 + 1] = ((float)y + 0.5f) / (float)h;
+  }
+  a.out.near[i] = a.cams.nears ? __ldg(a.cams.nears + pix) : a.cams.near;
+  a.out.far[i] = a.cams.fars ? __ldg(a.cams.fars + pix) : a.cams.far;
+  a.out.lossmult[i] = 1.f;
+  a.out.static_mask[i] = a.cams.static_masks ? __ldg(a.cams.static_masks + pix) : 1.f;
+  a.out.embed_idx[i] = a.cams.embed_idxs ? a.cams.embed_idxs[c] : c;
+  if (a.out.cam_idx) a.out.cam_idx[i] = c;
+  if (a.out.rgb) {
+    if (a.cams.images_u8) {
+      const uint8_t* s = a.cams.images_u8 + pix * 3;
+      // datasets.py: images are uint8 / 255 in float32
+      a.out.rgb[(size_t)i * 3] = (float)s[0] / 255.f; a.out.rgb[(size_t)i * 3 + 1] = (float)s[1] / 255.f;
+      a.out.rgb[(size_t)i * 3 + 2] = (float)s[2] / 255.f;
+    } else if (a.cams.images) {
+      const float* s = a.cams.images + pix * 3;
+      a.out.rgb[(size_t)i * 3] = __ldg(s); a.out.rgb[(size_t)i * 3 + 1] = __ldg(s + 1); a.out.rgb[(size_t)i * 3 + 2] = __ldg(s + 2);
+    }
+  }
+}
+
+}  // namespace
+}  // namespace hugs
+
+using namespace hugs;
+
+HUGS_API int hugs_make_ray_batch(const hugs_camera_set* cams, const int32_t* cam_idx, const int32_t* pix_x,
+                                 const int32_t* pix_y, int32_t n_rays, const hugs_ray_batch* out, void* stream) {
+  HUGS_REQUIRE(cams && out, "null camera set / output");
+  HUGS_REQUIRE(cams->pixtocams && cams->camtoworlds && cams->heights && cams->widths && cams->pixel_offset,
+               "camera set needs pixtocams, camtoworlds, heights, widths and pixel_offset");
+  HUGS_REQUIRE(n_rays >= 0 && (n_rays == 0 || (cam_idx && pix_x && pix_y)), "null pixel arrays");
+  HUGS_REQUIRE(out->origins && out->directions && out->viewdirs && out->radii && out->near && out->far &&
+               out->lossmult && out->static_mask && out->embed_idx, "null ray output");
+  HUGS_REQUIRE(!out->rgb || cams->images || cams->images_u8, "rgb requested but the camera set holds no images");
+  if (n_rays == 0) return HUGS_OK;
+  RayGenArgs a{*cams, cam_idx, pix_x, pix_y, n_rays, *out};
+  make_ray_batch_kernel<<<(n_rays + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}

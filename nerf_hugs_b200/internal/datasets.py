@@ -1,0 +1,135 @@
+"""Device-resident dataset and batch assembly (MipNeRF360/internal/datasets.py:259-529, camera_utils.py:503-669).
+
+The reference builds every training batch on the host (NumPy gathers + pixels_to_rays in a producer thread,
+`datasets.py:393-407`) and ships 84 B per ray to the device.  Here the images, HuGS static masks, near/far maps and
+cameras live in HBM once, and a batch is produced by one kernel (`hugs_make_ray_batch`) from integer
+(camera, x, y) draws made on the device — same fields, shapes and value semantics as `Dataset._make_ray_batch`.
+
+Out of scope (raise NotImplementedError): lens distortion, fisheye cameras, NDC, spherical render paths.
+"""
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .._lib import check, lib
+from . import utils
+
+
+def _ptr(t):
+  return None if t is None else t.data_ptr()
+
+
+class DeviceDataset:
+  """Holds Dataset.{images, static_masks, nears, fars, pixtocams, camtoworlds, heights, widths, embed_idxs} on the device.
+
+  Args mirror the attributes `datasets.Dataset` fills in `_load_renderings` (datasets.py:310-383):
+    images: list of [H_i, W_i, 3] arrays (float in [0, 1] or uint8), or None for render-only sets;
+    static_masks / nears / fars: lists of [H_i, W_i, 1] (or [H_i, W_i]) float arrays, or None;
+    pixtocams [N, 3, 3], camtoworlds [N, 3, 4]; embed_idxs [N] or None (camera index).
+  """
+
+  def __init__(self, pixtocams, camtoworlds, heights, widths, images: Optional[Sequence] = None,
+               static_masks: Optional[Sequence] = None, nears: Optional[Sequence] = None,
+               fars: Optional[Sequence] = None, embed_idxs=None, near: float = 0.2, far: float = 1e6,
+               distortion_params=None, camtype: str = 'perspective', device=None):
+    if distortion_params is not None and any(d is not None for d in np.atleast_1d(distortion_params)):
+      raise NotImplementedError('lens distortion (camera_utils._radial_and_tangential_undistort) is not supported on the device path')
+    if camtype != 'perspective':
+      raise NotImplementedError(f'camera type {camtype!r} is not supported on the device path')
+    if not torch.cuda.is_available():
+      raise RuntimeError('DeviceDataset needs a CUDA device (the product path has no CPU fallback)')
+    dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
+    self.device = dev
+    self.heights_np = np.asarray(heights, np.int64); self.widths_np = np.asarray(widths, np.int64)
+    self.n_cams = len(self.heights_np)
+    sizes = self.heights_np * self.widths_np
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    f32 = lambda a: torch.as_tensor(np.array(a, np.float32, copy=True), device=dev)
+    self.pixtocams = f32(np.broadcast_to(np.asarray(pixtocams, np.float32), (self.n_cams, 3, 3)))
+    self.camtoworlds = f32(np.asarray(camtoworlds)[..., :3, :4])
+    self.heights = torch.as_tensor(self.heights_np.astype(np.int32), device=dev)
+    self.widths = torch.as_tensor(self.widths_np.astype(np.int32), device=dev)
+    self.pixel_offset = torch.as_tensor(offs.astype(np.int64), device=dev)
+    self.embed_idxs = None if embed_idxs is None else torch.as_tensor(np.asarray(embed_idxs, np.int32), device=dev)
+
+    def pack(store, ch):
+      if store is None:
+        return None
+      flat = [np.asarray(a).reshape(-1, ch) for a in store]
+      for a, n in zip(flat, sizes):
+        assert a.shape[0] == n, 'per-pixel store does not match heights x widths'
+      return np.concatenate(flat, 0)
+    self.images = self.images_u8 = None
+    if images is not None:
+      img = pack(images, 3)
+      if img.dtype == np.uint8:
+        self.images_u8 = torch.as_tensor(np.ascontiguousarray(img), device=dev)
+      else:
+        self.images = f32(img)
+    sm, nn, ff = pack(static_masks, 1), pack(nears, 1), pack(fars, 1)
+    self.static_masks = None if sm is None else f32(sm[:, 0])
+    self.nears = None if nn is None else f32(nn[:, 0])
+    self.fars = None if ff is None else f32(ff[:, 0])
+    self.near, self.far = float(near), float(far)
+    cs = _lib.CameraSet()
+    cs.pixtocams, cs.camtoworlds = _ptr(self.pixtocams), _ptr(self.camtoworlds)
+    cs.heights, cs.widths, cs.pixel_offset = _ptr(self.heights), _ptr(self.widths), _ptr(self.pixel_offset)
+    cs.images, cs.images_u8 = _ptr(self.images), _ptr(self.images_u8)
+    cs.static_masks, cs.nears, cs.fars = _ptr(self.static_masks), _ptr(self.nears), _ptr(self.fars)
+    cs.embed_idxs = _ptr(self.embed_idxs)
+    cs.near, cs.far = self.near, self.far
+    self._cs = cs
+
+  # datasets.py:446-482
+  def make_ray_batch(self, pix_x_int, pix_y_int, cam_idx, want_rgb: bool = True) -> utils.Batch:
+    """Rays + ground truth of pixels (cam_idx, pix_y_int, pix_x_int): int tensors of one common shape."""
+    dev = self.device
+    i32 = lambda t: torch.as_tensor(t, device=dev).to(torch.int32).contiguous()
+    px, py = i32(pix_x_int), i32(pix_y_int)
+    ci = i32(cam_idx).expand_as(px).contiguous() if torch.as_tensor(cam_idx).ndim == 0 else i32(cam_idx)
+    shape = tuple(px.shape)
+    n = px.numel()
+    mk = lambda c, dt=torch.float32: torch.empty(shape + (c,), device=dev, dtype=dt)
+    rays = utils.Rays(pix_coords=mk(2), origins=mk(3), directions=mk(3), viewdirs=mk(3), radii=mk(1), lossmult=mk(1),
+                      static_mask=mk(1), near=mk(1), far=mk(1), embed_idx=mk(1, torch.int32), cam_idx=mk(1, torch.int32))
+    has_img = self.images is not None or self.images_u8 is not None
+    rgb = mk(3) if (want_rgb and has_img) else None
+    out = _lib.RayBatch()
+    for k in ('origins', 'directions', 'viewdirs', 'radii', 'near', 'far', 'lossmult', 'static_mask', 'embed_idx',
+              'cam_idx', 'pix_coords'):
+      setattr(out, k, getattr(rays, k).data_ptr())
+    out.rgb = _ptr(rgb)
+    if n > 0:
+      with torch.cuda.device(dev):
+        check(lib.hugs_make_ray_batch(C.byref(self._cs), ci.data_ptr(), px.data_ptr(), py.data_ptr(), n, C.byref(out),
+                                      torch.cuda.current_stream(dev).cuda_stream))
+    return utils.Batch(rays=rays, rgb=rgb)
+
+  # datasets.py:484-527 (_next_train): random patches of `image_num_per_batch` random cameras
+  def next_train_batch(self, gen: torch.Generator, batch_size: int, patch_size: int = 1, patch_dilation: int = 1,
+                       image_num_per_batch: int = 1, sample_from_half_image: bool = False) -> utils.Batch:
+    dev = self.device
+    n_patch = (batch_size // image_num_per_batch) // patch_size ** 2
+    upper = (patch_size - 1) * patch_dilation
+    cams = torch.randint(0, self.n_cams, (image_num_per_batch,), generator=gen, device=dev)
+    h = self.heights[cams].to(torch.float32); w = self.widths[cams].to(torch.float32)
+    if sample_from_half_image:
+      w = torch.floor(w / 2)
+    u = torch.rand(2, image_num_per_batch, n_patch, generator=gen, device=dev)
+    x0 = torch.floor(u[0] * (w[:, None] - upper)).to(torch.int32)
+    y0 = torch.floor(u[1] * (h[:, None] - upper)).to(torch.int32)
+    d = torch.arange(patch_size, device=dev, dtype=torch.int32) * patch_dilation
+    px = (x0[:, :, None, None] + d[None, None, None, :]).expand(-1, -1, patch_size, -1)     # pixel_coordinates: x varies fastest
+    py = (y0[:, :, None, None] + d[None, None, :, None]).expand(-1, -1, -1, patch_size)
+    ci = cams.to(torch.int32)[:, None, None, None].expand_as(px)
+    flat = lambda t: t.reshape(image_num_per_batch * n_patch, patch_size, patch_size).contiguous()
+    return self.make_ray_batch(flat(px), flat(py), flat(ci))
+
+  # datasets.py:529-560 (generate_ray_batch): every pixel of one camera
+  def generate_ray_batch(self, cam_idx: int) -> utils.Batch:
+    h, w = int(self.heights_np[cam_idx]), int(self.widths_np[cam_idx])
+    ys, xs = torch.meshgrid(torch.arange(h, device=self.device), torch.arange(w, device=self.device), indexing='ij')
+    return self.make_ray_batch(xs, ys, torch.full_like(xs, cam_idx))

@@ -11,6 +11,9 @@ What is importable from the reference without JAX:
                                                             stepfun.sample*, render.compute_alpha_weights)
   * nerfacto/utils/loss_utils.py          (torch)        -> lossfun_outer / lossfun_distortion
   * nerfacto/models/custom_functions.py   (torch)        -> contraction, pos_enc
+  * MipNeRF360/internal/camera_utils.py   (NumPy branch, xnp=np; its jax / internal.* imports are satisfied by empty
+                                           stub modules because pixels_to_rays never touches them with xnp=np)
+                                                         -> pixels_to_rays, get_pixtocam
 """
 import importlib.util
 import os
@@ -31,9 +34,53 @@ def load(path, name):
   return mod
 
 
+def load_camera_utils():
+  class Stub(types.ModuleType):
+    def __getattr__(self, k):
+      if k.startswith('__'):
+        raise AttributeError(k)
+      return type(k, (), {})
+  saved = {}
+  names = ['jax', 'jax.numpy', 'internal', 'internal.configs', 'internal.math', 'internal.stepfun', 'internal.utils']
+  for n in names:
+    saved[n] = sys.modules.get(n)
+    sys.modules[n] = Stub(n)
+  sys.modules['jax'].numpy = sys.modules['jax.numpy']
+  for n in ('configs', 'math', 'stepfun', 'utils'):
+    setattr(sys.modules['internal'], n, sys.modules['internal.' + n])
+  try:
+    return load(f'{REF}/MipNeRF360/internal/camera_utils.py', 'ref_camera_utils')
+  finally:
+    for n in names:
+      if saved[n] is None:
+        sys.modules.pop(n, None)
+      else:
+        sys.modules[n] = saved[n]
+
+
+def camera_golden(rng):
+  """Rays of random pixels of random cameras through the reference's pixels_to_rays (NumPy branch)."""
+  cu = load_camera_utils()
+  n_cams, n = 6, 257
+  hw = rng.integers(40, 90, size=(n_cams, 2))
+  focal = rng.uniform(50., 120., size=n_cams)
+  pixtocams = np.stack([cu.get_pixtocam(focal[i], int(hw[i, 1]), int(hw[i, 0])) for i in range(n_cams)]).astype(np.float32)
+  rot, _ = np.linalg.qr(rng.normal(size=(n_cams, 3, 3)))
+  pos = rng.normal(size=(n_cams, 3, 1)) * 2.0
+  camtoworlds = np.concatenate([rot, pos], -1).astype(np.float32)
+  cam_idx = rng.integers(0, n_cams, size=n)
+  px = (rng.uniform(size=n) * hw[cam_idx, 1]).astype(np.int64)
+  py = (rng.uniform(size=n) * hw[cam_idx, 0]).astype(np.int64)
+  o, d, v, r = cu.pixels_to_rays(px, py, pixtocams[cam_idx], camtoworlds[cam_idx], xnp=np)
+  np.savez(f'{OUT}/camera.npz', heights=hw[:, 0], widths=hw[:, 1], pixtocams=pixtocams, camtoworlds=camtoworlds,
+           cam_idx=cam_idx, pix_x=px, pix_y=py, origins=o, directions=d, viewdirs=v, radii=r)
+
+
 def main():
   torch.manual_seed(0)
   rng = np.random.default_rng(0)
+
+  camera_golden(np.random.default_rng(7))
 
   geopoly = load(f'{REF}/MipNeRF360/internal/geopoly.py', 'ref_geopoly')
   np.savez(f'{OUT}/geopoly_basis.npz',

@@ -1,0 +1,84 @@
+"""hugs_make_ray_batch (on-device pixels_to_rays + HuGS mask / near / far / colour gather) vs the CPU oracle and the
+reference-generated golden rays."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import camera as OC
+
+pytestmark = pytest.mark.gpu
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'camera.npz'))
+
+
+def _dataset(u8=False, seed=0):
+  rng = np.random.default_rng(seed)
+  hs, ws = G['heights'], G['widths']
+  if u8:
+    images = [rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8) for h, w in zip(hs, ws)]
+  else:
+    images = [rng.uniform(size=(h, w, 3)).astype(np.float32) for h, w in zip(hs, ws)]
+  return dict(pixtocams=G['pixtocams'], camtoworlds=G['camtoworlds'], heights=hs, widths=ws, images=images,
+              static_masks=[(rng.uniform(size=(h, w, 1)) < 0.8).astype(np.float32) for h, w in zip(hs, ws)],
+              nears=[rng.uniform(0.1, 0.3, size=(h, w, 1)).astype(np.float32) for h, w in zip(hs, ws)],
+              fars=[rng.uniform(2., 9., size=(h, w, 1)).astype(np.float32) for h, w in zip(hs, ws)],
+              embed_idxs=np.arange(len(hs))[::-1].copy())
+
+
+def _device(ds):
+  from nerf_hugs_b200.internal.datasets import DeviceDataset
+  return DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], images=ds['images'],
+                       static_masks=ds['static_masks'], nears=ds['nears'], fars=ds['fars'], embed_idxs=ds['embed_idxs'])
+
+
+@pytest.mark.parametrize('u8', [False, True])
+def test_make_ray_batch_vs_oracle_and_reference_golden(u8):
+  ds = _dataset(u8)
+  dd = _device(ds)
+  ci, px, py = G['cam_idx'], G['pix_x'], G['pix_y']
+  b = dd.make_ray_batch(torch.tensor(px), torch.tensor(py), torch.tensor(ci))
+  ref_ds = dict(ds)
+  if u8:
+    ref_ds['images'] = [im.astype(np.float32) / 255. for im in ds['images']]      # datasets.py image loading
+  rays, rgb = OC.make_ray_batch(ref_ds, ci, px, py)
+  got = {k: v.cpu().numpy() for k, v in b.rays.as_dict().items()}
+  # gathers and integer fields: bit-exact
+  for k in ('static_mask', 'near', 'far', 'lossmult', 'embed_idx', 'cam_idx', 'origins'):
+    assert np.array_equal(got[k], rays[k]), k
+  assert np.array_equal(b.rgb.cpu().numpy(), rgb)
+  # geometry: float64 arithmetic rounded to float32 on both sides; fused multiply-adds may flip the last bit
+  for k, tol in (('directions', 2e-7), ('viewdirs', 2e-7), ('radii', 2e-7), ('pix_coords', 2e-7)):
+    np.testing.assert_allclose(got[k], rays[k], rtol=tol, atol=1e-9, err_msg=k)
+    assert (got[k] == rays[k]).mean() > 0.99, k
+  # and directly against the reference's own outputs
+  np.testing.assert_allclose(got['directions'], G['directions'].astype(np.float32), rtol=2e-7, atol=1e-9)
+  np.testing.assert_allclose(got['radii'], G['radii'].astype(np.float32), rtol=2e-7)
+
+
+def test_generate_ray_batch_and_patch_sampling():
+  ds = _dataset()
+  dd = _device(ds)
+  cam = 2
+  b = dd.generate_ray_batch(cam)
+  h, w = int(ds['heights'][cam]), int(ds['widths'][cam])
+  assert tuple(b.rays.origins.shape) == (h, w, 3) and tuple(b.rgb.shape) == (h, w, 3)
+  assert np.array_equal(b.rgb.cpu().numpy(), ds['images'][cam])
+  assert np.array_equal(b.rays.static_mask.cpu().numpy(), ds['static_masks'][cam])
+  gen = torch.Generator(device='cuda'); gen.manual_seed(0)
+  tb = dd.next_train_batch(gen, batch_size=512, patch_size=4, patch_dilation=2, image_num_per_batch=2)
+  assert tuple(tb.rays.origins.shape) == (32, 4, 4, 3)           # [patches, patch, patch, 3] as datasets.py:484-527
+  pc = tb.rays.pix_coords.cpu().numpy(); ci = tb.rays.cam_idx.cpu().numpy()[..., 0]
+  assert ((pc > 0) & (pc < 1)).all()
+  x = pc[..., 0] * ds['widths'][ci] - 0.5
+  assert np.allclose(x[:, 0, 1] - x[:, 0, 0], 2.0, atol=1e-3)     # dilation along x inside a patch
+  assert len(np.unique(ci)) <= 2 and (ci[0] == ci[0, 0, 0]).all()
+
+
+def test_unsupported_camera_models_are_loud():
+  from nerf_hugs_b200.internal.datasets import DeviceDataset
+  ds = _dataset()
+  with pytest.raises(NotImplementedError):
+    DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], camtype='fisheye')
+  with pytest.raises(NotImplementedError):
+    DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], distortion_params=[{'k1': 0.1}])
