@@ -116,3 +116,13 @@ def test_forward_tc_ragged_and_glo():
   rend, hist, res, eh = _run_pair('bf16_tc', 'bf16', n=37, glo=4)
   assert res[-1]['rgb'].shape == (37, 3)
   assert _relerr(res[-1]['rgb'], rend[-1]['rgb']) < 2e-2
+
+
+def test_forward_tc_three_levels_repo_default_sampling():
+  """the repo-default 3-level 64 / 64 / 32 sampling (the PropMLP serves two levels, a 128-sample
+  tile of the NeRF level spans 4 rays)."""
+  rend, hist, res, eh = _run_pair('bf16_tc', 'bf16', n=50, num_levels=3, n_prop=64, n_nerf=32)
+  assert len(res) == 3 and res[-1]['rgb'].shape == (50, 3)
+  stats = {k: _relerr(res[-1][k], rend[-1][k]) for k in ('rgb', 'acc', 'distance_mean')}
+  _report('forward_tc_L3', stats)
+  assert stats['rgb'] < 1e-2 and stats['acc'] < 1e-2, stats
