@@ -1,0 +1,117 @@
+"""Measurements of the BASELINE.json parity configs that are not the bench line (one GPU; JSON lines on stdout):
+
+  config 3  Mip-NeRF 360 with HuGS static masks, Phototourism-shape synthetic scene
+            (phototourism_1024_withmask.gin shape: no warp_fn / raydist_fn, per-pixel near/far, patch 16, 48 GLO
+            features, transient_type='withmask', charb loss, distortion 0.001), batches assembled ON THE DEVICE by
+            hugs_make_ray_batch from uint8 images + static masks (DeviceDataset.next_train_batch)
+  config 5  full-frame render sweep through models.render_image (deterministic path, compute_extras=True)
+
+Usage: python scripts/extra_configs.py [hugs] [render] [--steps K]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from nerf_hugs_b200.internal import configs, models, train_utils, utils
+from nerf_hugs_b200.internal.datasets import DeviceDataset
+
+
+def sphere_cameras(rng, n_cams, hw):
+  pos = rng.normal(size=(n_cams, 3)); pos /= np.linalg.norm(pos, axis=-1, keepdims=True)
+  fwd = -pos
+  right = np.cross(fwd, np.array([0., 0., 1.])); right /= np.linalg.norm(right, axis=-1, keepdims=True) + 1e-9
+  up = np.cross(right, fwd)
+  c2w = np.stack([right, up, -fwd, pos], -1).astype(np.float32)                 # OpenGL: camera looks along -z
+  focal = 1111.1 / 800. * hw[:, 1]
+  p2c = np.stack([np.linalg.inv(np.array([[f, 0, w / 2.], [0, f, h / 2.], [0, 0, 1.]])) for f, (h, w) in zip(focal, hw)])
+  return p2c.astype(np.float32), c2w
+
+
+def hugs_dataset(n_cams=64, seed=0):
+  rng = np.random.default_rng(seed)
+  hw = rng.integers(400, 801, size=(n_cams, 2))
+  p2c, c2w = sphere_cameras(rng, n_cams, hw)
+  images, masks, nears, fars = [], [], [], []
+  for h, w in hw:
+    images.append(rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8))
+    blocks = (rng.uniform(size=((h + 31) // 32, (w + 31) // 32)) < 0.8).astype(np.float32)     # 32x32-block Bernoulli(0.8)
+    masks.append(np.kron(blocks, np.ones((32, 32), np.float32))[:h, :w, None])
+    nears.append(np.full((h, w, 1), 1.0 * rng.uniform(0.9, 1.1), np.float32))
+    fars.append(np.full((h, w, 1), 2.0 * rng.uniform(0.9, 1.1), np.float32))
+  return DeviceDataset(p2c, c2w, hw[:, 0], hw[:, 1], images=images, static_masks=masks, nears=nears, fars=fars,
+                       embed_idxs=np.arange(n_cams))
+
+
+def run_hugs(steps, batch=4096):
+  bind = [f'Config.batch_size = {batch}', 'Config.patch_size = 16', f'Config.image_num_per_batch = {max(1, batch // 256)}', "Config.transient_type = 'withmask'",
+          "Config.data_loss_type = 'charb'", 'Config.distortion_loss_mult = 0.001', 'Config.interlevel_loss_mult = 1.0',
+          'Model.opaque_background = True', 'Model.num_levels = 2', 'Model.num_prop_samples = 64',
+          'Model.num_nerf_samples = 128', 'Model.num_glo_features = 48', 'Model.num_embeddings = 64',
+          'PropMLP.net_depth = 4', 'PropMLP.net_width = 256', 'PropMLP.disable_rgb = True', 'NerfMLP.net_depth = 8',
+          'NerfMLP.net_width = 256']
+  config = configs.load_config([], bind, save_config=False)
+  dev = torch.device('cuda', 0)
+  model, state, _, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=batch, device=dev)
+  dd = hugs_dataset()
+  gen = torch.Generator(device=dev); gen.manual_seed(1)
+
+  def step():
+    b = dd.next_train_batch(gen, batch, config.patch_size, config.patch_dilation, config.image_num_per_batch)
+    return train_pstep(gen, state, b, min(1.0, (state.step + 1) / config.max_steps), None)
+
+  for _ in range(10):
+    step()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(steps):
+    _, stats, _ = step()
+  e1.record(); torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / steps
+  b = dd.next_train_batch(gen, batch, config.patch_size, config.patch_dilation, config.image_num_per_batch)
+  print(json.dumps({'config': 'Mip-NeRF 360 + HuGS static masks (Phototourism-shape synthetic, patch 16, GLO 48, no warp / '
+                              'raydist), device-side batch assembly', 'metric': 'training rays/s', 'value': batch / ms * 1e3,
+                    'ms_per_step': ms, 'rays_per_gpu': batch, 'n_gpus': 1, 'steps': steps,
+                    'loss': float(stats['loss']), 'static_fraction': float(b.rays.static_mask.mean()),
+                    'h2d_bytes_per_step': 0}))
+
+
+def run_render(resolutions=((800, 800), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840))):
+  import bench
+  config = configs.load_config([], bench.gin_bindings(4096), save_config=False)
+  config.render_chunk_size = 65536
+  dev = torch.device('cuda', 0)
+  model, state, render_eval_pfn, _, _ = train_utils.setup_model(config, rng=0, max_rays=config.render_chunk_size, device=dev)
+  rng = np.random.default_rng(0)
+  for h, w in resolutions:
+    p2c, c2w = sphere_cameras(rng, 1, np.array([[h, w]]))
+    dd = DeviceDataset(p2c, c2w, [h], [w], near=0.2, far=1e6)
+    rays = dd.generate_ray_batch(0).rays
+    fn = lambda _, chunk: render_eval_pfn(state.params, 1.0, None, chunk)
+    out = models.render_image(fn, rays, None, config, verbose=False)       # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    out = models.render_image(fn, rays, None, config, verbose=False)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert tuple(out['rgb'].shape) == (h, w, 3) and torch.isfinite(out['rgb']).all()
+    print(json.dumps({'config': f'full-frame render {w}x{h} (config A weights, compute_extras, chunk {config.render_chunk_size})',
+                      'metric': 'render rays/s', 'value': h * w / dt, 'frame_s': dt, 'n_gpus': 1,
+                      'outputs': sorted(k for k in out if not k.startswith('ray_'))}))
+
+
+if __name__ == '__main__':
+  ap = argparse.ArgumentParser()
+  ap.add_argument('what', nargs='*', default=['hugs', 'render'])
+  ap.add_argument('--steps', type=int, default=100)
+  a = ap.parse_args()
+  if 'hugs' in a.what:
+    run_hugs(a.steps)
+  if 'render' in a.what:
+    run_render()
