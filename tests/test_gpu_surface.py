@@ -59,3 +59,26 @@ def test_unsupported_transient_type_is_loud():
   config = _config(128, transient='robustnerf')
   with pytest.raises(NotImplementedError, match='robustnerf'):
     train_utils.setup_model(config, rng=0)
+
+
+def test_checkpoint_round_trip_through_the_flax_format(tmp_path):
+  """train.py:121,235: save_checkpoint(state) -> restore_checkpoint into a fresh setup_model gives the same renders."""
+  from nerf_hugs_b200.internal import checkpoints, train_utils, utils
+  config = _config(64, glo=4)
+  model, state, render_eval_pfn, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=128)
+  rays, gt = H.make_rays(64, seed=2, glo=True)
+  batch = utils.Batch(rays=utils.Rays(**rays), rgb=gt)
+  gen = torch.Generator(device=model.engine.device); gen.manual_seed(0)
+  for _ in range(2):
+    state, _, gen = train_pstep(gen, state, batch, 0.1, None)
+  checkpoints.save_checkpoint(str(tmp_path), state, state.step, model=model, keep=100)
+  sd = checkpoints.restore_checkpoint(str(tmp_path), None)
+  assert int(sd['step']) == 2 and 'kernel' in sd['params']['params']['NerfMLP_0']['Dense_0']
+  assert sd['params']['params']['GloEmbed_0']['embedding'].shape == (16, 4)
+  model2, state2, _, _, _ = train_utils.setup_model(config, rng=1, max_rays=128)
+  assert not torch.equal(state2.params, state.params)
+  state2 = checkpoints.restore_checkpoint(str(tmp_path), state2, model=model2)
+  assert state2.step == 2 and torch.equal(state2.params, state.params) and torch.equal(state2.mu, state.mu)
+  a, _ = model.apply(state.params, None, utils.Rays(**rays), 0.5, True)
+  b, _ = model2.apply(state2.params, None, utils.Rays(**rays), 0.5, True)
+  assert torch.equal(a[-1]['rgb'], b[-1]['rgb'])
