@@ -215,11 +215,17 @@ def run_ours(args):
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    loss = 0.0
+    loss, prev = 0.0, None
     for i in range(steps):
       _, stats, _ = train_pstep(gen, state, batches[i % len(batches)], min(1.0, (state.step + 1) / config.max_steps), None)
       if read_loss:
-        loss = stats['loss']           # device -> host read of the step's result
+        # device -> host read of every step's result: train_pstep copies the stats to pinned memory asynchronously,
+        # the host consumes step i-1's loss while step i runs (and the last one before the timer stops)
+        if prev is not None:
+          loss = prev['loss']
+        prev = stats
+    if read_loss and prev is not None:
+      loss = prev['loss']
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)

@@ -93,6 +93,10 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
   stats_dev = torch.empty(16, device=dev)
   norms_dev = torch.empty(9, device=dev)
   L = model.num_levels
+  # every step's stats are copied (asynchronously) into a pinned host ring, so a stats object stays valid after later
+  # steps have been launched and reading it waits only for its own step
+  ring = torch.empty(_STATS_RING, 25).pin_memory()
+  holders = [None] * _STATS_RING
 
   def train_step(rng, state: TrainState, batch: utils.Batch, train_frac, inlier_thresholds=None):
     del inlier_thresholds   # RobustNeRF only (out of scope)
@@ -113,26 +117,40 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
     a.step, a.grad_scale = int(state.step), 1.0 / world
     eng.adam_step(state.params, grad, state.mu, state.nu, a, norms_dev)
     model._packed_version = (state.params.data_ptr(), state.params._version)   # adam_step re-packs bf16 operands
+    slot = state.step % _STATS_RING
+    if holders[slot] is not None:
+      holders[slot]._fetch()                          # about to reuse the slot: materialise its old owner
+    ring[slot, :16].copy_(stats_dev, non_blocking=True)
+    ring[slot, 16:].copy_(norms_dev, non_blocking=True)
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
     state.step += 1
-    stats = _LazyStats(stats_dev, norms_dev, L, world, a.lr)
+    stats = _LazyStats(ring[slot], ev, L, world, a.lr)
+    holders[slot] = stats
     return state, stats, rng
 
   return train_step
 
 
-class _LazyStats(dict):
-  """stats pytree of train_step (train_utils.py:442-476); device values are fetched on first access so
-  that the training loop does not synchronise every step (the reference reads them every print_every)."""
+_STATS_RING = 64
 
-  def __init__(self, stats_dev, norms_dev, L, world, lr):
+
+class _LazyStats(dict):
+  """stats pytree of train_step (train_utils.py:442-476).  The values sit in a pinned host slot filled by an
+  asynchronous copy; the first access waits for that step's event only, so the training loop does not synchronise
+  every step (the reference reads them every print_every)."""
+
+  def __init__(self, host_slot, event, L, world, lr):
     super().__init__()
-    self._s, self._n, self._L, self._world, self._lr, self._done = stats_dev, norms_dev, L, world, lr, False
+    self._h, self._ev, self._L, self._world, self._lr, self._done = host_slot, event, L, world, lr, False
 
   def _fetch(self):
     if self._done:
       return
-    s = (self._s / self._world).cpu().numpy()
-    n = self._n.cpu().numpy()
+    if self._ev is not None:
+      self._ev.synchronize()
+    s = self._h[:16].numpy() / self._world
+    n = self._h[16:].numpy().copy()
     mses = s[4:4 + self._L]
     psnrs = [-10.0 * _pymath.log10(max(float(m), 1e-30)) for m in mses]
     dict.update(self, {

@@ -30,7 +30,7 @@ def _worker(rank, world, port, out_dir):
   stats = torch.tensor([float(rank + 1), 2.0])
   w = train_utils.allreduce_sum_([grad, stats])
   assert w == world
-  st = train_utils._LazyStats(torch.cat([stats, torch.zeros(14)]), torch.zeros(9), 2, w, 1e-3)
+  st = train_utils._LazyStats(torch.cat([stats, torch.zeros(14 + 9)]), None, 2, w, 1e-3)   # host slot: 16 stats + 9 norms
   np.save(os.path.join(out_dir, f'r{rank}.npy'), np.concatenate([(grad / w).numpy(), [st['loss']]]))
   dist.barrier()
   dist.destroy_process_group()
