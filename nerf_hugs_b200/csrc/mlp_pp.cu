@@ -855,7 +855,6 @@ int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t
   p.d_raw = h->d_raw[level]; p.act = tc->act; p.drgb_out = tc->drgb;
   p.w_dens_off = m.w_dens_off; p.w_rgb_off = m.w_rgb_off;
   p.dbg = (!is_prop && direction != 2) ? h->dbg_counters : nullptr;
-  { const char* e = getenv("HUGS_DBG_FLAGS"); p.dbg_flags = e ? atoi(e) : 0; }
   p.dens_bias_off = m.pack[mv.depth].bias_off;
   p.gate = tc->gate; p.cap = cap;
   for (int i = 0; i < p.n_segs; ++i)

@@ -119,7 +119,6 @@ struct alignas(64) PpParams {
   const __nv_bfloat16* bias_img;     // CTA-pair kernel: [2 ranks][kBiasChunks][kBiasChunkElems]
   int bias_tail0;                    // CTA-pair kernel: first float of `bias` staged in shared memory
   long long* dbg;                    // optional [gridDim.x][16] cycle counters (development instrumentation)
-  int dbg_flags;                     // HUGS_DBG_FLAGS timing experiments (results invalid): 1 no bias, 2 no panel store, 4 no TMEM load
 };
 
 struct TcMlp {
