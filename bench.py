@@ -36,6 +36,8 @@ FLOPS_PROP_SAMPLE = 651776          # 2*sum(K*N) over the PropML
 FLOPS_NERF_SAMPLE = 1638400         # NerfMLP(256)
 FLOPS_RAY_FWD = N_PROP * FLOPS_PROP_SAMPLE + N_NERF * FLOPS_NERF_SAMPLE   # 251.4 MFLOP
 METRIC = 'training rays/s (Mip-NeRF 360, 4096-ray batch, 64+128 samples/ray, 256-wide MLPs)'
+WORKLOAD = ('Mip-NeRF 360 config A (SURVEY §8d): 360.gin geometry, num_levels=2, 64 proposal + 128 NeRF samples/ray, '
+            'PropMLP 4x256, NerfMLP 8x256, IPE 504, contract + reciprocal spacing')
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (bytes)
 NCU_DRAM_BYTES = {'chain_fwd_nerf': 1.087483e9 + 2.648109e9, 'chain_bwd_nerf': 0.183374e9 + 2.510509e9,
                   'wgrad_nerf': 6.880211e9 + 0.008463e9, 'chain_fwd_prop': 0.272809e9 + 0.512298e9,
@@ -161,8 +163,9 @@ def run_reference(args):
       'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'rays/s', 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
       'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': f'Mip-NeRF 360 config A: (64+128) samples/ray, 256-wide MLPs; each step = a bounded '
-                             f'sample of {sample} rays of the 4096-ray batch on the host CPU'},
+      'config': {'workload': WORKLOAD, 'rays_per_gpu': args.rays, 'global_batch': args.rays,
+                 'sample': f'each step = a bounded sample of {sample} rays of the {args.rays}-ray batch on the host CPU '
+                           f'(torch fp32 port of the reference JAX path; JAX is not installable offline)'},
       'cpu_baseline': {'value': rate, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
                        'sample': f'{sample} rays x {args.steps} train steps (fwd+bwd+Adam), torch fp32, '
                                  f'os.cpu_count()={os.cpu_count()}'},
@@ -311,9 +314,7 @@ def run_ours(args):
         'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': 'Mip-NeRF 360 config A (SURVEY §8d): 360.gin geometry, num_levels=2, 64 proposal + 128 '
-                               'NeRF samples/ray, PropMLP 4x256, NerfMLP 8x256, IPE 504, contract + reciprocal spacing',
-                   'rays_per_gpu': per_gpu, 'global_batch': global_batch, 'parallelism': f'ray-sharded dp{world}',
+        'config': {'workload': WORKLOAD, 'rays_per_gpu': per_gpu, 'global_batch': global_batch, 'parallelism': f'ray-sharded dp{world}',
                    'l2_policy': 'per-step working set (>5 GB of saved activations) >> 126 MB L2; 4 distinct batches cycled',
                    'precision': 'bf16 operands, fp32 accumulate (tcgen05); fp32 sampling/compositing/losses/Adam'},
         'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 64 + 36,
