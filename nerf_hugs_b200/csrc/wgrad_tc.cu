@@ -52,7 +52,8 @@ namespace {
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 65536;       // A0 16K | A1 16K | B 32K
 constexpr int kWgThreads = 192;
-constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 256;
+constexpr int kWgScratchFloats = 4 * 32 * 33;   // per epilogue warp: 32 x 32 accumulator block (row stride 33) for the transposed flush
+constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 256 + kWgScratchFloats * 4;
 
 struct alignas(64) WgParams {
   CUtensorMap map_act64, map_feat64, map_dz64, map_dh64;
@@ -70,6 +71,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   uint64_t* full = bars; uint64_t* empty = bars + kWgStages;
   uint64_t* acc_full = bars + 2 * kWgStages; uint64_t* acc_empty = acc_full + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 1);
+  float* scratch = reinterpret_cast<float*>(base + kWgStages * kWgStageBytes + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 4 && lane == 0) {
     ptx::prefetch_tmap(&p.map_act64); ptx::prefetch_tmap(&p.map_feat64); ptx::prefetch_tmap(&p.map_dz64);
@@ -193,17 +195,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             } else {
               krow = w.in_base + m;
             }
+            // thread = accumulator row, but the gradient rows are `out` floats apart: transpose each 32 x 32 block
+            // through shared memory so that one warp instruction adds 32 consecutive floats of one row (one 128-byte
+            // L2 transaction instead of 32 scattered ones)
+            float* sc = scratch + warp * (32 * 33);
 #pragma unroll 1
             for (int c = 0; c < w.n; c += 32) {
               uint32_t r[32];
               ptx::tmem_ld32(lane_addr + (uint32_t)(mb * 256 + c), r);
               ptx::tmem_ld_wait();
-              if (krow >= 0) {
-                float* dst = p.grad + w.koff + (long long)krow * w.out + c;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (c + j < w.out) atomicAdd(dst + j, __uint_as_float(r[j]));
+              for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = __uint_as_float(r[j]);
+              __syncwarp();
+              const bool col_ok = c + lane < w.out;
+#pragma unroll 4
+              for (int rr = 0; rr < 32; ++rr) {
+                const int kr = __shfl_sync(0xffffffffu, krow, rr);
+                if (kr >= 0 && col_ok) atomicAdd(p.grad + w.koff + (long long)kr * w.out + c + lane, sc[rr * 33 + lane]);
               }
+              __syncwarp();
             }
           } else {
             uint32_t r4[4];
