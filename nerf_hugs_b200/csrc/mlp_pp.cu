@@ -36,6 +36,16 @@ constexpr bool kCounters = true;
 #else
 constexpr bool kCounters = false;
 #endif
+// CTA-pair kernel: ONE barrier per tile (panel_ready[4t]) collects the elected arrivals of all 4 epilogue groups of both
+// CTAs.  A try_wait costs the issuing thread ~350 cycles under load even on a completed phase (shared-memory pipe queue),
+// and four of them in a row left the tensor pipe idle for ~1 k cycles per tile and layer (event trace,
+// profiles/r01_ab_experiments.md).
+constexpr int kPanelArrivals = 8;
+#ifdef HUGS_EXP_MMA_ONLY      // timing experiment (results invalid): weight producer + MMA issuer only, no epilogue dependency
+constexpr bool kMmaOnly = true;
+#else
+constexpr bool kMmaOnly = false;
+#endif
 constexpr int kPartFloats = 768;     // head partial sums: [2 tiles][3][128]
 constexpr int kPpSmemBytes = 1024 + (kNumPanels + kStages) * kPanelBytes + kBiasTab * 4 + kPartFloats * 4 + 512;
 // CTA-pair kernel: the fp32 table shrinks to the head weights / head biases, the layer biases become MMA operands
@@ -94,11 +104,27 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
   const uint32_t accfull_u32 = ptx::smem_u32(sm.acc_full), consumed_u32 = ptx::smem_u32(sm.consumed);
   const uint32_t epidone_u32 = ptx::smem_u32(sm.epi_done);
   const uint32_t ones_u32 = ptx::smem_u32(sm.ones), biasimg_u32 = ptx::smem_u32(sm.bias_img);
+  // counters build: event trace of cluster 0 (leader CTA): (code, clock) pairs; code = ev << 16 | si << 8 | t << 4 | q
+  __shared__ unsigned int trace_n;
+  if (threadIdx.x == 0) trace_n = 0;
+  auto trace = [&](int ev, int si_, int t_, int q_) {
+    if (kCounters && p.dbg != nullptr && blockIdx.x < 2) {      // both CTAs of cluster 0, %globaltimer (ns) as common clock
+      const unsigned int i = atomicAdd(&trace_n, 1u);
+      if (i < 2048u) {
+        long long* e = p.dbg + 148 * 16 + 74 * 60 + 2 * (i + 2048u * blockIdx.x);
+        unsigned long long gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        e[0] = (long long)((blockIdx.x << 24) | (ev << 16) | (si_ << 8) | (t_ << 4) | q_); e[1] = (long long)gt;
+      }
+    }
+  };
+  __shared__ long long ts_acc[2];     // counters build: clock at which epilogue group 0 saw acc_full of tile t
+  __shared__ long long ts_pub[2][4];  // counters build: clock at which group q's leader arrived on panel_ready of tile t
 
   if (warp == kWProd && lane == 0) {
     ptx::prefetch_tmap(&p.map_w); ptx::prefetch_tmap(&p.map_feat); ptx::prefetch_tmap(&p.map_save);
     for (int i = 0; i < kStages; ++i) { ptx::mbar_init(&sm.full[i], 1); ptx::mbar_init(&sm.empty[i], 1); }
-    for (int i = 0; i < 8; ++i) { ptx::mbar_init(&sm.panel_ready[i], kCg2 ? 2 : 128); ptx::mbar_init(&sm.feat_ready[i], 1); }
+    for (int i = 0; i < 8; ++i) { ptx::mbar_init(&sm.panel_ready[i], kCg2 ? kPanelArrivals : 128); ptx::mbar_init(&sm.feat_ready[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&sm.acc_full[i], 1); ptx::mbar_init(&sm.epi_done[i], kEpiGroups); }
     for (int i = 0; i < 8; ++i) ptx::mbar_init(&sm.consumed[i], 1);
     ptx::fence_mbar_init();
@@ -168,7 +194,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
     // Walks the MMA segments in issue order and waits for every `consumed` phase exactly once (no phase is
     // ever skipped, so parity waits cannot alias); refills a tile's panels with IPE feature columns as soon
     // as the segment that last read those panels has completed.
-    if (lane == 0 && p.any_feat) {
+    if (lane == 0 && p.any_feat && !kMmaOnly) {
       uint32_t cons_phase = 0;   // bit t*4+kp: parity of the next `consumed` phase of that panel to wait for
       int prev_kps0 = 0, prev_kps1 = 0;   // K panels of the previous MMA segment on tile 0 / 1 (0: none yet)
       int unit_iter = 0;
@@ -217,11 +243,21 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       const uint32_t idesc256 = ptx::make_idesc_bf16(kCg2 ? 256 : 128, 256, 0, 0);
       // the issuing thread never reads the data behind these barriers itself (the tensor core does, behind
       // tcgen05.fence::after_thread_sync), so CTA-scope waits suffice also for the peer's arrivals
+#ifdef HUGS_EXP_SLEEPWAIT
       auto wait = [](uint32_t bar, uint32_t parity) { ptx::mbar_wait_u32(bar, parity); };
+#else
+      auto wait = [](uint32_t bar, uint32_t parity) {
+        if (kCg2) ptx::mbar_wait_poll_u32(bar, parity); else ptx::mbar_wait_u32(bar, parity);
+      };
+#endif
       auto commit = [](uint32_t bar) { if (kCg2) ptx::mma_commit_mc2_u32(bar); else ptx::mma_commit_u32(bar); };
       int stage = 0; uint32_t phase = 0;
       uint32_t wait_phase = 0;   // bits 0-7 panel_ready, 8-15 feat_ready
       long long c_panel = 0, c_feat = 0, c_full = 0;
+      long long c_elat = 0, n_elat = 0;   // acc_full seen by epilogue group 0 -> all panels ready (as seen by the issuer)
+      long long c_pubq[4] = {0, 0, 0, 0}, c_after = 0;   // ... -> local group q arrived; last local arrival -> issuer proceeds
+      long long c_seg[kMaxSegs][3];     // counters build: per-segment waits (panel, full, feat)
+      if (kCounters) for (int i = 0; i < kMaxSegs; ++i) c_seg[i][0] = c_seg[i][1] = c_seg[i][2] = 0;
       const long long c_start = clock64();
       const bool dbg = kCounters && p.dbg != nullptr;
       for (int unit = unit0; unit < p.n_units; unit += unit_stride) {
@@ -231,26 +267,40 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
           const int kps = S.kps, n_halves = S.n_halves, a_feat = S.a_feat, acc0 = S.accumulate;
           const bool has_epi = S.epi != EPI_NONE;
           for (int t = 0; t < 2; ++t) {
+            trace(1, si, t, 0);       // issuer reaches (segment, tile)
             const uint32_t d_tmem = tmem_base + (uint32_t)(t * 256);
-            if (!a_feat) {
+            if (!a_feat && !kMmaOnly) {
               // in-place accumulator: every epilogue group must have drained the previous layer before the
               // first MMA of this one overwrites it, so wait for all consumed panels up front
               const long long c0 = dbg ? clock64() : 0;
-              for (int kp = 0; kp < kps; ++kp) {
+              for (int kp = 0; kp < (kCg2 ? 1 : kps); ++kp) {
                 const uint32_t idx = (uint32_t)(t * 4 + kp);
                 wait(pready_u32 + idx * 8, (wait_phase >> idx) & 1u);
                 wait_phase ^= 1u << idx;
+                trace(6, si, t, kp);     // panel kp ready
               }
-              if (dbg) c_panel += clock64() - c0;
+              if (dbg) {
+                const long long now = clock64(), dt = now - c0;
+                c_panel += dt; c_seg[si][0] += dt;
+                const long long ta = *(volatile long long*)&ts_acc[t];
+                c_elat += now - ta; ++n_elat;
+                long long mx = 0;
+                for (int g = 0; g < 4; ++g) {
+                  const long long tp = *(volatile long long*)&ts_pub[t][g];
+                  c_pubq[g] += tp - ta; if (tp > mx) mx = tp;
+                }
+                c_after += now - mx;
+              }
               ptx::tc_fence_after();
             }
+            trace(2, si, t, 0);       // panel waits done
             bool bias_pending = kCg2 && S.bias_idx >= 0;
             for (int kp = 0; kp < kps; ++kp) {
-              if (a_feat) {
+              if (a_feat && !kMmaOnly) {
                 const uint32_t idx = (uint32_t)(8 + t * 4 + kp);
                 const long long c0 = dbg ? clock64() : 0;
                 wait(fready_u32 + (t * 4 + kp) * 8, (wait_phase >> idx) & 1u);
-                if (dbg) c_feat += clock64() - c0;
+                if (dbg) { const long long dt = clock64() - c0; c_feat += dt; c_seg[si][2] += dt; }
                 wait_phase ^= 1u << idx;
                 ptx::tc_fence_after();
               }
@@ -276,7 +326,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                 if (t == 0) {
                   const long long c0 = dbg ? clock64() : 0;
                   wait(full_u32 + st_k * 8, ph_k);
-                  if (dbg) c_full += clock64() - c0;
+                  if (dbg) { const long long dt = clock64() - c0; c_full += dt; c_seg[si][1] += dt; }
                   ptx::tc_fence_after();
                 }
                 const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + st_k * kPanelBytes);
@@ -306,6 +356,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
               }
             }
             if (has_epi) commit(accfull_u32 + t * 8);
+            trace(3, si, t, 0);       // all MMAs of (segment, tile) issued
           }
           if (kCg2) {
             stage += kps;
@@ -316,6 +367,12 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       if (dbg) {
         long long* d = p.dbg + unit0 * 16;
         d[4] = clock64() - c_start; d[5] = c_panel; d[6] = c_full; d[7] = c_feat;
+        if (kCounters) {
+          long long* e = p.dbg + 148 * 16 + unit0 * (kMaxSegs * 3);
+          for (int i = 0; i < kMaxSegs - 3; ++i) { e[i * 3] = c_seg[i][0]; e[i * 3 + 1] = c_seg[i][1]; e[i * 3 + 2] = c_seg[i][2]; }
+          e[57] = c_elat; e[58] = n_elat; e[59] = c_after;
+          for (int g = 0; g < 4; ++g) e[53 + g] = c_pubq[g];
+        }
       }
     }
   } else {
@@ -352,7 +409,11 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
             ptx::tma_store_2d(&p.map_save, sm.panels + pi * kPanelBytes, col, S.save_row + tile * kTileM);
             ptx::tma_commit_group();
           }
-          if (!S.no_signal) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(pready_u32 + pi * 8, 0));
+          if (kCounters && rank == 0) *(volatile long long*)&ts_pub[pi >> 2][pi & 3] = clock64();
+          trace(5, 0, pi >> 2, pi & 3);                              // group arrives on panel_ready
+          if (!S.no_signal) {
+            ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(pready_u32 + (kCg2 ? (pi & ~3) : pi) * 8, 0));
+          }
           // the store's shared-memory read must be over before the panel is rewritten; this group's next
           // write to it is behind the bar.sync of the other tile's publish (or of last_epi), which this
           // thread only reaches after the wait
@@ -382,7 +443,7 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       if (s2 >= p.n_samples) return make_uint2(0u, 0u);      // padding rows carry no gradient
       return __ldg(p.gate + (size_t)G.mask_row * 4 + (size_t)q * p.cap + s2);
     };
-    const int n_e = 2 * p.n_epi;
+    const int n_e = kMmaOnly ? 0 : 2 * p.n_epi;
     uint2 gate_next = make_uint2(0u, 0u);
     if (kCg2 && unit0 < p.n_units) gate_next = load_gate(unit0, 0);
 
@@ -437,7 +498,8 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
             ptx::mbar_wait_u32(accfull_u32 + t * 8, (acc_phase >> t) & 1u);
             acc_phase ^= 1u << t;
             ptx::tc_fence_after();
-            if (dbg_t) { c_t1 = clock64(); c_acc += c_t1 - c_t0; }
+            if (dbg_t) { c_t1 = clock64(); c_acc += c_t1 - c_t0; if (threadIdx.x == 0) *(volatile long long*)&ts_acc[t] = c_t1; }
+            if (group_leader) trace(4, p.epi_seg[e >> 1], t, q);     // acc_full seen
           }
 
           switch (S.epi) {
@@ -663,6 +725,9 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
                   }
                 }
                 publish(S, pi, tile, tile_ok);
+              } else if (kCg2 && !S.no_signal && group_leader) {
+                // the tile barrier counts every group of both CTAs: groups without columns in this op arrive at once
+                ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(pready_u32 + (pi & ~3) * 8, 0));
               }
               break;
             }

@@ -192,14 +192,14 @@ HUGS_API int hugs_debug_counters(hugs_handle* h, int32_t enable, int64_t* out_ho
   HUGS_REQUIRE(h, "null handle");
   if (enable && !h->dbg_counters) {
     void* q = nullptr;
-    HUGS_CUDA(cudaMalloc(&q, 148 * 16 * 8));
-    HUGS_CUDA(cudaMemset(q, 0, 148 * 16 * 8));
+    HUGS_CUDA(cudaMalloc(&q, 148 * 16 * 8 + 74 * 60 * 8 + 8192 * 8));      // + [74 clusters][20 segments][3] per-segment waits
+    HUGS_CUDA(cudaMemset(q, 0, 148 * 16 * 8 + 74 * 60 * 8 + 8192 * 8));
     h->allocs.push_back(q);
     h->dbg_counters = static_cast<long long*>(q);
   }
   if (out_host && h->dbg_counters) {
     HUGS_CUDA(cudaDeviceSynchronize());
-    HUGS_CUDA(cudaMemcpy(out_host, h->dbg_counters, 148 * 16 * 8, cudaMemcpyDeviceToHost));
+    HUGS_CUDA(cudaMemcpy(out_host, h->dbg_counters, 148 * 16 * 8 + 74 * 60 * 8 + 8192 * 8, cudaMemcpyDeviceToHost));
   }
   if (!enable) h->dbg_counters = nullptr;
   return HUGS_OK;
