@@ -39,10 +39,10 @@ METRIC = 'training rays/s (Mip-NeRF 360, 4096-ray batch, 64+128 samples/ray, 256
 WORKLOAD = ('Mip-NeRF 360 config A (SURVEY §8d): 360.gin geometry, num_levels=2, 64 proposal + 128 NeRF samples/ray, '
             'PropMLP 4x256, NerfMLP 8x256, IPE 504, contract + reciprocal spacing')
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (bytes)
-NCU_DRAM_BYTES = {'chain_fwd_nerf': 1.087483e9 + 2.648109e9, 'chain_bwd_nerf': 0.183374e9 + 2.510509e9,
-                  'wgrad_nerf': 6.880211e9 + 0.008463e9, 'chain_fwd_prop': 0.272809e9 + 0.512298e9,
-                  'wgrad_prop': 1.463896e9 + 0.004328e9}
-NCU_DRAM_SOURCE = 'profiles/r01_ncu_full_train_step_cg2.json (ncu --set full, one training step, 4096 rays)'
+NCU_DRAM_BYTES = {'chain_fwd_nerf': 1.087201e9 + 2.650518e9, 'chain_bwd_nerf': 0.182906e9 + 2.507198e9,
+                  'wgrad_nerf': 6.827791e9 + 0.006946e9, 'chain_fwd_prop': 0.272877e9 + 0.512431e9,
+                  'wgrad_prop': 1.463295e9 + 0.004237e9}
+NCU_DRAM_SOURCE = 'profiles/r01_ncu_full_train_step_final.json (ncu --set full, one training step, 4096 rays)'
 
 
 def synthetic_batch(n_rays, seed, n_cams=100, hw=800, focal=1111.1):
