@@ -22,6 +22,8 @@ raw = np.zeros(148 * 16 + 74 * 60 + 8192, np.int64)
 buf = raw[:148 * 16].reshape(148, 16)
 assert fn(eng._h, 0, raw.ctypes.data_as(C.c_void_p)) == 0
 rows = buf[buf[:, 4] > 0]
+if len(rows) == 0:
+  rows = buf[:74]
 m = rows.mean(0)
 tiles = 4096 / 148   # 128-sample tiles per SM (a CTA pair reports once for its two SMs)
 print('reporting CTAs/clusters:', len(rows))
