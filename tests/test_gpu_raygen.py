@@ -82,3 +82,33 @@ def test_unsupported_camera_models_are_loud():
     DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], camtype='fisheye')
   with pytest.raises(NotImplementedError):
     DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], distortion_params=[{'k1': 0.1}])
+
+
+def test_device_batches_drive_the_training_step():
+  """A batch assembled on the device (hugs_make_ray_batch) trains exactly like the same batch handed over from the
+  host: the two train_pstep calls start from identical states and must report identical statistics."""
+  import copy
+  from nerf_hugs_b200.internal import configs, train_utils, utils
+  ds = _dataset(u8=True)
+  dd = _device(ds)
+  bind = ['Config.batch_size = 256', 'Config.patch_size = 8', "Config.transient_type = 'withmask'",
+          'Model.opaque_background = True', 'Model.num_levels = 2', 'Model.num_prop_samples = 64',
+          'Model.num_nerf_samples = 128', 'Model.num_glo_features = 4', 'Model.num_embeddings = 16',
+          'PropMLP.net_depth = 4', 'PropMLP.disable_rgb = True', 'NerfMLP.net_width = 256']
+  config = configs.load_config([], bind, save_config=False)
+  stats = []
+  for mode in ('device', 'host'):
+    model, state, _, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=256)
+    gen = torch.Generator(device='cuda'); gen.manual_seed(3)
+    batch = dd.next_train_batch(gen, 256, patch_size=8, patch_dilation=1, image_num_per_batch=4)
+    assert tuple(batch.rays.origins.shape) == (4, 8, 8, 3)
+    if mode == 'host':
+      batch = utils.Batch(rays=batch.rays.map(lambda t: t.cpu()), rgb=batch.rgb.cpu())
+    g2 = torch.Generator(device='cuda'); g2.manual_seed(5)
+    state, st, _ = train_pstep(g2, state, batch, 0.1, None)
+    stats.append((st['loss'], st['losses']['data'], float(state.params.double().sum())))
+    assert 0.0 < float(batch.rays.static_mask.float().mean()) < 1.0      # the HuGS masks are really in the batch
+  # the forward is deterministic (identical losses); the weight gradients are reduced with fp32 atomics, so the
+  # updated parameters agree to rounding only
+  assert stats[0][:2] == stats[1][:2], stats
+  assert abs(stats[0][2] - stats[1][2]) <= 1e-6 * abs(stats[0][2]) + 1e-6, stats
