@@ -52,13 +52,17 @@ struct EncArgs {
 #endif
 constexpr int kEncRows = HUGS_ENC_ROWS;
 constexpr int kEncSplit = HUGS_ENC_SPLIT;     // threads per sample (each takes a contiguous range of basis directions)
+// kNdeg > 0: number of IPE degrees known at compile time (12 for every shipped config): the per-direction word buffer
+// stays in registers instead of a dynamically indexed local array.
+template <int kNdeg>
 __global__ void __launch_bounds__(kEncSplit * kEncRows) encode_bf16_kernel(EncArgs a) {
   __shared__ __align__(16) uint4 tile[kEncRows * 64];   // rows x 64 chunks of 16 B, chunk index swizzled
   const int tid = threadIdx.x, rl = tid % kEncRows, part = tid / kEncRows;
   const int s = blockIdx.x * kEncRows + rl;
   const int b_beg = (a.nb * part) / kEncSplit, b_end = (a.nb * (part + 1)) / kEncSplit;
   const bool half = part == kEncSplit - 1;      // the last part also clears the padding columns
-  const int cpb = a.ndeg >> 2;                    // 16-byte chunks per basis direction
+  const int ndeg = kNdeg > 0 ? kNdeg : a.ndeg;
+  const int cpb = ndeg >> 2;                      // 16-byte chunks per basis direction
   if (s < a.n_samples) {
     const int ray = s / a.S, i = s % a.S;
     float o[3], d[3];
@@ -79,8 +83,9 @@ __global__ void __launch_bounds__(kEncSplit * kEncRows) encode_bf16_kernel(EncAr
       const float av = -0.5f * 1.4426950408889634f * var;                                  // exp(x)=2^(x log2e)
       float sc = sc0;
       uint32_t w[16];
-#pragma unroll 2
-      for (int k = 0; k < a.ndeg; k += 2) {
+#pragma unroll
+      for (int k = 0; k < (kNdeg > 0 ? kNdeg : 16); k += 2) {
+        if (kNdeg == 0 && k >= ndeg) break;
         float t = r_hi * sc;
         float f = (t - rintf(t)) + r_lo * sc;
         float x = f * 6.283185307179586f;
@@ -92,7 +97,9 @@ __global__ void __launch_bounds__(kEncSplit * kEncRows) encode_bf16_kernel(EncAr
         w[k + 1] = ptx::pack_bf16x2(e2 * sn2, e2 * cs2);
         sc *= 4.f;
       }
-      for (int c = 0; c < cpb; ++c) {
+#pragma unroll
+      for (int c = 0; c < (kNdeg > 0 ? kNdeg / 4 : 4); ++c) {
+        if (kNdeg == 0 && c >= cpb) break;
         uint4 v = make_uint4(w[c * 4], w[c * 4 + 1], w[c * 4 + 2], w[c * 4 + 3]);
         tile[rl * 64 + swz_chunk(rl, b * cpb + c)] = v;
       }
@@ -979,7 +986,9 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
              is_prop ? d.prop_contract : d.nerf_contract, tc->feat + (size_t)tc->feat_row0[level] * kFeatPad};
   {
     ProfScope ps(h, HUGS_K_ENCODE, st);
-    encode_bf16_kernel<<<(n_tiles * kTileM + kEncRows - 1) / kEncRows, kEncSplit * kEncRows, 0, st>>>(ea);
+    const int eg = (n_tiles * kTileM + kEncRows - 1) / kEncRows;
+    if (ea.ndeg == 12) encode_bf16_kernel<12><<<eg, kEncSplit * kEncRows, 0, st>>>(ea);
+    else encode_bf16_kernel<0><<<eg, kEncSplit * kEncRows, 0, st>>>(ea);
     HUGS_LAUNCH_CHECK();
   }
   // 2. per-ray view bias (direction encoding + GLO folded through the view layer)
