@@ -254,7 +254,7 @@ def run_ours(args):
 
   # per-kernel-class CUDA-event timing (separate short pass so the events do not perturb `value`)
   eng.profile(True)
-  prof_steps = min(args.steps, 10)
+  prof_steps = min(args.steps, 50)
   timed(devb, prof_steps, False)
   prof = eng.profile_read()
   eng.profile(False)
