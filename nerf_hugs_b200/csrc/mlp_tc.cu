@@ -48,7 +48,7 @@ struct EncArgs {
 #define HUGS_ENC_ROWS 8
 #endif
 #ifndef HUGS_ENC_SPLIT
-#define HUGS_ENC_SPLIT 8
+#define HUGS_ENC_SPLIT 4
 #endif
 constexpr int kEncRows = HUGS_ENC_ROWS;
 constexpr int kEncSplit = HUGS_ENC_SPLIT;     // threads per sample (each takes a contiguous range of basis directions)
