@@ -478,6 +478,7 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
   }
   cudaStream_t st = (cudaStream_t)stream;
   const int L = d.num_levels, n = n_rays;
+  if ((rc = tc_ensure_training(h))) return rc;
   if ((rc = forward_levels(h, params, rays, n, train_frac, jitter, 0, 0, nullptr, true, st))) return rc;
 
   float* denom = h->scalars;          // [0] loss normaliser

@@ -926,19 +926,9 @@ int tc_create(hugs_handle* h) {
   }
   tc->total_feat_rows = frow; tc->total_save_rows = srow;
   if ((rc = tc_alloc(h, &tc->feat, (size_t)frow * kFeatPad))) return rc;
-  if ((rc = tc_alloc(h, &tc->act, (size_t)srow * kW)) || (rc = tc_alloc(h, &tc->dz, (size_t)srow * kW))) return rc;
-  if ((rc = tc_alloc(h, &tc->gate, (size_t)srow * 4))) return rc;
-  HUGS_CUDA(cudaMemset(tc->gate, 0, (size_t)srow * 4 * sizeof(uint2)));
   for (int l = 0; l < L; ++l) tc->drgb_rows = std::max(tc->drgb_rows, tc->cap[l]);
-  if ((rc = tc_alloc(h, &tc->drgb, (size_t)tc->drgb_rows * kHeadCols))) return rc;
-  // unused columns (head gradients beyond col 3, view-activation columns 128..255) must read as zero
-  HUGS_CUDA(cudaMemset(tc->drgb, 0, (size_t)tc->drgb_rows * kHeadCols * 2));
-  HUGS_CUDA(cudaMemset(tc->act, 0, (size_t)srow * kW * 2));
-  HUGS_CUDA(cudaMemset(tc->dz, 0, (size_t)srow * kW * 2));
   if ((rc = tc_alloc(h, &tc->viewbias, (size_t)d.max_rays * 128))) return rc;
-  if ((rc = make_map(&tc->map_feat, tc->feat, frow, kFeatPad, 128)) ||
-      (rc = make_map(&tc->map_act, tc->act, srow, kW, 128)) || (rc = make_map(&tc->map_dz, tc->dz, srow, kW, 128)))
-    return rc;
+  if ((rc = make_map(&tc->map_feat, tc->feat, frow, kFeatPad, 128))) return rc;
   HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   HUGS_CUDA(cudaFuncSetAttribute(mlp_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
   {
@@ -946,9 +936,33 @@ int tc_create(hugs_handle* h) {
     tc->use_pp = !(e && strcmp(e, "single") == 0);
     tc->use_cg2 = tc->use_pp && !(e && strcmp(e, "pp") == 0);
   }
-  int rc2 = pp_init(h);
-  if (rc2) return rc2;
-  return wgrad_create(h);
+  return pp_init(h);
+}
+
+// Saved activations / dZ / ReLU gates / head gradients (1,056 B per saved row: 10.6 KB per NeRF sample) and the
+// weight-gradient state exist only on handles that train: allocated by the first hugs_loss_and_grad, so a render-only
+// handle with a large max_rays (render_chunk_size) does not reserve tens of GB it never touches.
+int tc_ensure_training(hugs_handle* h) {
+  TcState* tc = h->tc;
+  HUGS_REQUIRE(tc, "tensor-core state missing");
+  if (tc->train_ready) return HUGS_OK;
+  const size_t srow = (size_t)tc->total_save_rows;
+  int rc;
+  if ((rc = tc_alloc(h, &tc->act, srow * kW)) || (rc = tc_alloc(h, &tc->dz, srow * kW)) ||
+      (rc = tc_alloc(h, &tc->gate, srow * 4)) || (rc = tc_alloc(h, &tc->drgb, (size_t)tc->drgb_rows * kHeadCols)))
+    return rc;
+  // unused columns (head gradients beyond col 3, view-activation columns 128..255) must read as zero
+  HUGS_CUDA(cudaMemset(tc->gate, 0, srow * 4 * sizeof(uint2)));
+  HUGS_CUDA(cudaMemset(tc->drgb, 0, (size_t)tc->drgb_rows * kHeadCols * 2));
+  HUGS_CUDA(cudaMemset(tc->act, 0, srow * kW * 2));
+  HUGS_CUDA(cudaMemset(tc->dz, 0, srow * kW * 2));
+  HUGS_CUDA(cudaDeviceSynchronize());      // the caller's stream may be non-blocking w.r.t. the default stream
+  if ((rc = make_map(&tc->map_act, tc->act, (long long)srow, kW, 128)) ||
+      (rc = make_map(&tc->map_dz, tc->dz, (long long)srow, kW, 128)))
+    return rc;
+  if ((rc = wgrad_create(h))) return rc;
+  tc->train_ready = true;
+  return HUGS_OK;
 }
 
 void tc_destroy(hugs_handle* h) {

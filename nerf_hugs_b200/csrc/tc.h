@@ -8,6 +8,8 @@ int tc_create(hugs_handle* h);
 void tc_destroy(hugs_handle* h);
 // fp32 flat params -> packed bf16 operand tensors (+ fp32 bias packs)
 int tc_pack_params(hugs_handle* h, const float* params, cudaStream_t st);
+// allocate the training-only buffers of the handle on first use (saved activations, dZ, gates, weight-gradient state)
+int tc_ensure_training(hugs_handle* h);
 // encode + fused MLP chain for level l; fills h->raw[l]; saves activations when `training`
 int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, bool training, cudaStream_t st);
 // dgrad chain + wgrad for level l from h->d_raw[l]; accumulates into grad (flat fp32, flax layout)

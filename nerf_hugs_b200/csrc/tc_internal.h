@@ -153,6 +153,7 @@ struct TcState {
   std::vector<int> cap, feat_row0, save_row0;   // per level
   int total_feat_rows = 0, total_save_rows = 0;
   int num_sms = 148;
+  bool train_ready = false;          // training buffers + weight-gradient state allocated (tc_ensure_training)
   bool use_pp = true;                // two-tile ping-pong chain kernel (HUGS_CHAIN=single selects the older one)
   bool use_cg2 = true;               // ... on CTA pairs with tcgen05 cta_group::2 (HUGS_CHAIN=pp selects one CTA per unit)
   void* pack_tables = nullptr;

@@ -82,3 +82,25 @@ def test_checkpoint_round_trip_through_the_flax_format(tmp_path):
   a, _ = model.apply(state.params, None, utils.Rays(**rays), 0.5, True)
   b, _ = model2.apply(state2.params, None, utils.Rays(**rays), 0.5, True)
   assert torch.equal(a[-1]['rgb'], b[-1]['rgb'])
+
+
+def test_render_only_handle_does_not_reserve_training_buffers():
+  """Saved activations / dZ / gates (10.6 KB per NeRF sample) are allocated by the first training call only: a render
+  handle sized for a 16384-ray chunk stays small; the same handle can still start training later."""
+  from nerf_hugs_b200.internal import train_utils, utils
+  torch.cuda.synchronize(); torch.cuda.empty_cache()
+  free0, _ = torch.cuda.mem_get_info()
+  config = _config(16384)
+  model, state, render_eval_pfn, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=16384)
+  rays, gt = H.make_rays(256, seed=4)
+  model.apply(state.params, None, utils.Rays(**rays), 0.5, True)
+  torch.cuda.synchronize()
+  free1, _ = torch.cuda.mem_get_info()
+  used_render = free0 - free1
+  assert used_render < 6 * 2 ** 30, used_render          # features (3 GB) + per-sample fp32 buffers, not the 24 GB of saves
+  gen = torch.Generator(device=model.engine.device); gen.manual_seed(0)
+  state, stats, gen = train_pstep(gen, state, utils.Batch(rays=utils.Rays(**rays), rgb=gt), 0.1, None)
+  assert np.isfinite(stats['loss'])
+  free2, _ = torch.cuda.mem_get_info()
+  assert free1 - free2 > 15 * 2 ** 30                    # the training buffers appeared with the first training step
+  model.engine.close()
