@@ -238,3 +238,30 @@ def test_model_forward_and_train_step_smoke():
   assert np.isfinite(float(stats['loss']))
   assert any(float(g.abs().max()) > 0 for n, g in grads.items() if n.startswith('PropMLP_0'))
   assert any(float(g.abs().max()) > 0 for n, g in grads.items() if n.startswith('NerfMLP_0'))
+
+
+def test_adam_update_matches_an_independent_implementation():
+  """optax.adam is not importable here (parity unpinned for it); its published update rule
+  m_hat / (sqrt(v_hat) + eps) with bias correction (train_utils.py:487-512, eps = 1e-6) is the one torch.optim.Adam
+  implements, so the oracle's update is checked against that independent implementation on the oracle's own gradients
+  (gradient clipping switched off so that the raw gradients are what both optimisers see)."""
+  from tests import helpers as H
+  torch.manual_seed(0)
+  ocfg, _ = H.config_pair(n_prop=16, n_nerf=16, max_rays=8)
+  lcfg = O.LossConfig(grad_max_norm=0.0, grad_max_val=0.0)
+  basis = torch.tensor(H.basis_np())
+  params = O.init_params(ocfg, seed=0, bias_scale=0.1)
+  rays, gt = H.make_rays(8, seed=1)
+  names = [n for n, _ in O.tree_leaves(params)]
+  twin = {n: torch.nn.Parameter(v.detach().clone()) for n, v in O.tree_leaves(params)}
+  opt = torch.optim.Adam(list(twin.values()), lr=1.0, betas=(lcfg.adam_beta1, lcfg.adam_beta2), eps=lcfg.adam_eps)
+  state = O.init_opt_state(params)
+  for step in range(3):
+    params, state, stats, raw = O.train_step(ocfg, lcfg, params, state, step, rays, gt, 0.5, basis)
+    for g in opt.param_groups:
+      g['lr'] = stats['lr']
+    for n in names:
+      twin[n].grad = raw[n].detach().clone()
+    opt.step()
+  for n, v in O.tree_leaves(params):
+    np.testing.assert_allclose(v.detach().numpy(), twin[n].detach().numpy(), rtol=2e-6, atol=1e-9, err_msg=n)
