@@ -89,8 +89,11 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
   lr_fn = lambda step: hmath.learning_rate_decay(step, config.lr_init, config.lr_final, config.max_steps,
                                                 config.lr_delay_steps, config.lr_delay_mult)
   dev = eng.device
-  grad = torch.empty(eng.n_params, device=dev)
-  stats_dev = torch.empty(16, device=dev)
+  # the flat gradient and the 16 stats share one buffer: a single all-reduce per step (train_utils.py:457-459 pmean's
+  # both); the 16-float offset keeps the stats 64-byte aligned
+  bucket = torch.zeros(eng.n_params + 16 + (-eng.n_params) % 16, device=dev)
+  grad = bucket[:eng.n_params]
+  stats_dev = bucket[bucket.numel() - 16:]
   norms_dev = torch.empty(9, device=dev)
   L = model.num_levels
   # every step's stats are copied (asynchronously) into a pinned host ring, so a stats object stays valid after later
@@ -109,7 +112,7 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
       jitter = torch.rand(L, n, generator=rng, device=dev)
     model._ensure_packed(state.params)
     eng.loss_and_grad(state.params, rays, rgb[..., :3], float(train_frac), jitter, lcfg, grad, stats_dev)
-    allreduce_sum_([grad, stats_dev])               # pmean(grad), pmean(stats)  (train_utils.py:457-459)
+    allreduce_sum_([bucket])                        # pmean(grad), pmean(stats)  (train_utils.py:457-459), one collective
     a = _lib.AdamCfg()
     a.lr = float(lr_fn(state.step))
     a.beta1, a.beta2, a.eps = config.adam_beta1, config.adam_beta2, config.adam_eps
