@@ -22,6 +22,11 @@
 // traffic (L2 -> shared memory, and shared memory -> tensor core) is halved.  The leader CTA issues all MMAs;
 // barriers the issuer waits on live in the leader and receive the peer's TMA completions / epilogue arrivals
 // through the cluster address space, barriers signalled by the tensor core are multicast to both CTAs.
+// In this mode additionally: a weight stage (one K panel) is fetched once per unit and used by both tiles; layer
+// biases are applied by a K = 16 MMA (ones x [bias_hi, bias_lo]) that initialises the accumulator; the epilogue is
+// one TMEM wait + pack + eight 16-byte stores; the forward stores 64-bit ReLU gate masks which the backward program
+// loads one epilogue ahead; one barrier per tile collects the elected arrivals of all epilogue groups of both CTAs.
+// DESIGN.md ("Tensor-core kernel structure") has the rationale and profiles/r01_ab_experiments.md the measurements.
 #include <algorithm>
 
 #include "tc_device.cuh"
