@@ -82,6 +82,31 @@ def run_hugs(steps, batch=4096):
                     'h2d_bytes_per_step': 0}))
 
 
+def run_config_b(steps, batch=4096):
+  """SURVEY §8d variant B: the repo-default 3-level 64 / 64 / 32 sampling (360.gin geometry, 256-wide MLPs)."""
+  import bench
+  bind = [b for b in bench.gin_bindings(batch) if 'num_levels' not in b and 'num_nerf_samples' not in b]
+  bind += ['Model.num_levels = 3', 'Model.num_nerf_samples = 32']
+  config = configs.load_config([], bind, save_config=False)
+  dev = torch.device('cuda', 0)
+  model, state, _, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=batch, device=dev)
+  rays, rgb = bench.synthetic_batch(batch, seed=5)
+  b = utils.Batch(rays=utils.Rays(**{k: v.to(dev) for k, v in rays.items()}), rgb=rgb.to(dev))
+  gen = torch.Generator(device=dev); gen.manual_seed(1)
+  for _ in range(10):
+    train_pstep(gen, state, b, 0.1, None)
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  for _ in range(steps):
+    _, stats, _ = train_pstep(gen, state, b, 0.1, None)
+  e1.record(); torch.cuda.synchronize()
+  ms = e0.elapsed_time(e1) / steps
+  print(json.dumps({'config': 'Mip-NeRF 360 variant B: 3 levels, 64 / 64 / 32 samples, 256-wide MLPs (SURVEY §8d)',
+                    'metric': 'training rays/s', 'value': batch / ms * 1e3, 'ms_per_step': ms, 'rays_per_gpu': batch,
+                    'n_gpus': 1, 'steps': steps, 'loss': float(stats['loss'])}))
+
+
 def run_render(resolutions=((800, 800), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840))):
   import bench
   config = configs.load_config([], bench.gin_bindings(4096), save_config=False)
@@ -115,3 +140,5 @@ if __name__ == '__main__':
     run_hugs(a.steps)
   if 'render' in a.what:
     run_render()
+  if 'b' in a.what:
+    run_config_b(a.steps)
