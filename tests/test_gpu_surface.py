@@ -97,10 +97,10 @@ def test_render_only_handle_does_not_reserve_training_buffers():
   torch.cuda.synchronize()
   free1, _ = torch.cuda.mem_get_info()
   used_render = free0 - free1
-  assert used_render < 6 * 2 ** 30, used_render          # features (3 GB) + per-sample fp32 buffers, not the 24 GB of saves
+  assert used_render < 8 * 2 ** 30, used_render          # features (3 GB) + per-sample fp32 buffers, not the 27 GB of saves
   gen = torch.Generator(device=model.engine.device); gen.manual_seed(0)
   state, stats, gen = train_pstep(gen, state, utils.Batch(rays=utils.Rays(**rays), rgb=gt), 0.1, None)
   assert np.isfinite(stats['loss'])
   free2, _ = torch.cuda.mem_get_info()
-  assert free1 - free2 > 15 * 2 ** 30                    # the training buffers appeared with the first training step
+  assert free1 - free2 > 12 * 2 ** 30                    # the training buffers appeared with the first training step
   model.engine.close()
