@@ -248,13 +248,9 @@ __global__ void __launch_bounds__(kPpThreads, 1) mlp_pp_kernel(const __grid_cons
       const uint32_t idesc256 = ptx::make_idesc_bf16(kCg2 ? 256 : 128, 256, 0, 0);
       // the issuing thread never reads the data behind these barriers itself (the tensor core does, behind
       // tcgen05.fence::after_thread_sync), so CTA-scope waits suffice also for the peer's arrivals
-#ifdef HUGS_EXP_SLEEPWAIT
+      // (a polling wait with a short suspend hint instead of the hardware-suspended one measured the same and only adds
+      //  shared-memory traffic: profiles/r01_ab_experiments.md)
       auto wait = [](uint32_t bar, uint32_t parity) { ptx::mbar_wait_u32(bar, parity); };
-#else
-      auto wait = [](uint32_t bar, uint32_t parity) {
-        if (kCg2) ptx::mbar_wait_poll_u32(bar, parity); else ptx::mbar_wait_u32(bar, parity);
-      };
-#endif
       auto commit = [](uint32_t bar) { if (kCg2) ptx::mma_commit_mc2_u32(bar); else ptx::mma_commit_u32(bar); };
       int stage = 0; uint32_t phase = 0;
       uint32_t wait_phase = 0;   // bits 0-7 panel_ready, 8-15 feat_ready
