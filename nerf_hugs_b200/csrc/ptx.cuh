@@ -5,10 +5,6 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#ifndef HUGS_POLL_NS
-#define HUGS_POLL_NS 40u
-#endif
-
 namespace hugs {
 namespace ptx {
 
@@ -62,29 +58,6 @@ __device__ __forceinline__ void mbar_wait_u32(uint32_t bar_addr, uint32_t parity
   }
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) { mbar_wait_u32(smem_u32(bar), parity); }
-// Polling wait (short suspend hint): for barriers completed by arrivals / TMA transactions that come from the peer CTA
-// through the cluster network, where a long hardware suspend was measured to wake up late.
-__device__ __forceinline__ void mbar_wait_poll_u32(uint32_t bar_addr, uint32_t parity) {
-  uint32_t spins = 0;
-  long long t0 = 0;
-  for (;;) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(bar_addr), "r"(parity), "r"(HUGS_POLL_NS)
-        : "memory");
-    if (ok) return;
-    if ((++spins & 0xFFFFFu) == 0u) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) mbar_wait_timeout(bar_addr, parity);
-    }
-  }
-}
-
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile(
