@@ -197,3 +197,31 @@ def test_sample_intervals_vs_reference_golden(eng, name, anneal):
   assert (err <= tol + 2e-6).all(), float((err - tol).max())
   assert (err <= 2e-6).mean() > 0.99
   assert (np.diff(out.cpu().numpy(), axis=-1) >= 0).all()
+
+
+def test_sample_intervals_single_interval_known_answer(eng):
+  """The reference's RNG-free known answer (stepfun_test.py:579-586): all mass in one interval -> linspace over it."""
+  t = torch.tensor([[1., 2, 3, 4, 5, 6]])
+  logits = torch.tensor([[0., 0, 100, 0, 0]])
+  u_base, mj = O.sample_u(10, True, None)
+  out, idx = eng.sample_intervals(t, logits, u_base, None, mj, 10, (0., 10.), want_idx=True)
+  np.testing.assert_allclose(out.cpu().numpy()[0], np.linspace(3, 4, 11), atol=1e-5, rtol=1e-5)
+  assert (idx.cpu().numpy() == 2).all()
+
+
+def test_alpha_weights_delta_density_known_answer():
+  """render_test.py:443-463: one interval with a huge density gives one-hot weights (atol 1e-5)."""
+  from nerf_hugs_b200.engine import Engine
+  _, ecfg = H.config_pair(precision='fp32', max_rays=128, opaque=False)
+  e = Engine(ecfg, H.basis_np())
+  rng = np.random.default_rng(0)
+  n, d = 100, 128
+  r = rng.normal(size=(n, d))
+  mask = (r == r.max(-1, keepdims=True)).astype(np.float32)
+  raw_d = torch.tensor(np.where(mask > 0, 1e10, -1e4).astype(np.float32))      # softplus(raw - 1): 1e10 / 0
+  tdist = torch.tensor(np.sort(rng.uniform(0.5, 2.5, (n, d + 1)).astype(np.float32), -1))
+  dirs = torch.tensor(rng.normal(size=(n, 3)).astype(np.float32))
+  out = e.alpha_composite(raw_d, None, tdist, dirs, torch.full((n, 1), 3.0))
+  np.testing.assert_allclose(out['weights'].cpu().numpy(), mask, atol=1e-5, rtol=1e-5)
+  np.testing.assert_allclose(out['acc'].cpu().numpy(), 1.0, atol=1e-5)
+  e.close()
