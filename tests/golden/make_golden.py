@@ -76,6 +76,30 @@ def camera_golden(rng):
            cam_idx=cam_idx, pix_x=px, pix_y=py, origins=o, directions=d, viewdirs=v, radii=r)
 
 
+def nerfacto_golden(rng, ray_utils):
+  """density_to_weight (quirks B2 / B6), render_features, render_depth (B7), pdf_sample of nerfacto/utils/ray_utils.py."""
+  n, S = 48, 64
+  bins = np.sort(rng.uniform(0.5, 6.0, (n, S + 1)).astype(np.float32), -1)
+  dens = (rng.uniform(0, 1, (n, S)).astype(np.float32) ** 3) * 8
+  dens[:3] = 0.0
+  dirs = rng.normal(size=(n, 3)).astype(np.float32)
+  feats = rng.uniform(size=(n, S, 3)).astype(np.float32)
+  bg = rng.uniform(size=(n, 3)).astype(np.float32)
+  out = {'bins': bins, 'dens': dens, 'dirs': dirs, 'feats': feats, 'bg': bg}
+  for opaque in (False, True):
+    w, a, tr = ray_utils.density_to_weight(torch.tensor(dens), torch.tensor(bins), torch.tensor(dirs), opaque)
+    out[f'w_{int(opaque)}'], out[f'a_{int(opaque)}'], out[f't_{int(opaque)}'] = w.numpy(), a.numpy(), tr.numpy()
+    out[f'rgb_{int(opaque)}'] = ray_utils.render_features(w, torch.tensor(feats), torch.tensor(bg), False).numpy()
+    out[f'depth_{int(opaque)}'] = ray_utils.render_depth(w, torch.tensor(bins)).numpy()
+  sb = np.sort(rng.uniform(0, 1, (n, S + 1)).astype(np.float32), -1); sb[:, 0], sb[:, -1] = 0.0, 1.0
+  ww = rng.uniform(0, 1, (n, S)).astype(np.float32) ** 4
+  ww[:2] = 0.0
+  out['pdf_bins'], out['pdf_w'] = sb, ww
+  out['pdf_out'] = ray_utils.pdf_sample(torch.tensor(sb), torch.tensor(ww), 32, False, True).numpy()
+  out['uniform_out'] = ray_utils.uniform_sample(5, 16, False, True, 'cpu').numpy()
+  np.savez(f'{OUT}/nerfacto_ops.npz', **out)
+
+
 def main():
   torch.manual_seed(0)
   rng = np.random.default_rng(0)
@@ -92,6 +116,8 @@ def main():
   ray_utils = load(f'{REF}/nerfacto/utils/ray_utils.py', 'ref_ray_utils')
   loss_utils = load(f'{REF}/nerfacto/utils/loss_utils.py', 'ref_loss_utils')
   cf = load(f'{REF}/nerfacto/models/custom_functions.py', 'ref_custom_functions')
+
+  nerfacto_golden(np.random.default_rng(11), ray_utils)
 
   # --- sample_intervals (deterministic branch == stepfun.sample_intervals(rng=None)) ---
   cases = {}
