@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(kWarps * 32) composite_kernel(CompositeArgs a)
   lt = warp_sum(lt);
   if (lane == 0 && a.out.distance_mean) {
     float dm = expf(lt / fmaxf(kF32Eps, acc));
-    if (dm != dm) dm = INFINITY;
+    if (dm != dm) dm = 0.f;   // jnp.nan_to_num(x, jnp.inf): inf lands in `copy`, NaN -> 0 (render.py:222)
     a.out.distance_mean[ray] = fminf(fmaxf(dm, td[0]), td[S]);
   }
   // weighted percentiles over (t ++ far, w ++ bg_w): cw = [0, min(1, cumsum(w_aug[:-1])), 1]
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(kWarps * 32) composite_kernel(CompositeArgs a)
     int i1 = min(max(lo, 1), n - 1), i0 = i1 - 1;
     auto tq = [&](int k) { return k <= S ? td[k] : a.far[ray]; };
     float dxp = CW[i1] - CW[i0];
-    float f = (fabsf(dxp) <= 1.4e-45f) ? tq(i0) : tq(i0) + ((p - CW[i0]) / dxp) * (tq(i1) - tq(i0));
+    float f = (fabsf(dxp) <= 1.4210855e-14f) ? tq(i0)   /* jnp.interp: np.spacing(finfo(f32).eps) */ : tq(i0) + ((p - CW[i0]) / dxp) * (tq(i1) - tq(i0));
     float* dst = lane == 0 ? a.out.distance_p5 : (lane == 1 ? a.out.distance_median : a.out.distance_p95);
     if (dst) dst[ray] = f;
   }

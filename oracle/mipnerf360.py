@@ -242,7 +242,10 @@ def _interp_1d(x, xp, fp):
   f0, f1 = torch.gather(fp, -1, i0), torch.gather(fp, -1, i1)
   dx = x1 - x0
   # jnp.interp: f = fp[i-1] + (x - xp[i-1]) / dx * df, with dx==0 -> fp[i-1]-ish; clamp ends.
-  w = torch.where(dx.abs() <= torch.finfo(x.dtype).tiny, torch.zeros_like(dx), (x - x0) / torch.where(dx == 0, torch.ones_like(dx), dx))
+  # jax's _interp: dx0 = |dx| <= np.spacing(finfo(dtype).eps)  (1.42e-14 in float32) -> fp[i-1]
+  tiny = float(np.spacing(np.finfo(np.float32 if x.dtype == torch.float32 else np.float64).eps))
+  dx0 = dx.abs() <= tiny
+  w = torch.where(dx0, torch.zeros_like(dx), (x - x0) / torch.where(dx0, torch.ones_like(dx), dx))
   out = f0 + w * (f1 - f0)
   out = torch.where(x < xp[..., :1], fp[..., :1].expand_as(out), out)
   out = torch.where(x > xp[..., -1:], fp[..., -1:].expand_as(out), out)
@@ -413,7 +416,9 @@ def volumetric_rendering(rgbs, weights, tdist, bg_rgbs, t_far, compute_extras):
     rendering['acc'] = acc
     expectation = lambda x: (weights * x).sum(-1) / torch.clamp_min(acc, eps)
     t_mids = 0.5 * (tdist[..., :-1] + tdist[..., 1:])
-    dm = torch.nan_to_num(torch.exp(expectation(torch.log(t_mids))), nan=float('inf'))
+    # `jnp.nan_to_num(x, jnp.inf)` (render.py:222): the second positional parameter of nan_to_num is `copy`, not `nan`,
+    # so NaN -> 0.0 and +inf -> float32 max (pinned by tests/golden/mip360_ops.npz::vr_nan_distance_mean)
+    dm = torch.nan_to_num(torch.exp(expectation(torch.log(t_mids))), nan=0.0)
     rendering['distance_mean'] = torch.minimum(torch.maximum(dm, tdist[..., 0]), tdist[..., -1])
     t_aug = torch.cat([tdist, t_far], -1)
     weights_aug = torch.cat([weights, bg_w], -1)

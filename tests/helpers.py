@@ -47,3 +47,75 @@ def config_pair(num_levels=2, n_prop=64, n_nerf=128, width=256, nerf_depth=8, pr
                       opaque_background=opaque, num_glo_features=glo, num_embeddings=16, precision=precision,
                       max_rays=max_rays)
   return ocfg, ecfg
+
+
+# ----------------------------------------------------------------------------------------------
+# Model-level golden cases: the reference's own Model.__call__ was run on these inputs by
+# tests/golden/make_golden_mipnerf360.py (fixtures: tests/golden/mip360_model.npz).
+# ----------------------------------------------------------------------------------------------
+GOLDEN_MODEL_CASES = {
+    # SURVEY §8d config A geometry (360.gin: contract + reciprocal spacing, opaque background), deterministic sampling
+    'A': dict(n=24, seed=21, near=0.2, far=1e6, levels=2, n_prop=64, n_nerf=128, width=256, nerf_depth=8, prop_depth=4,
+              glo=0, contract=True, raydist='reciprocal', opaque=True, jitter=False, train_frac=0.6, pseed=100),
+    # train-mode sampling (one uniform draw per level and ray), HuGS static masks in the data loss (quirk B1)
+    'A_train': dict(n=24, seed=22, near=0.2, far=1e6, levels=2, n_prop=64, n_nerf=128, width=256, nerf_depth=8,
+                    prop_depth=4, glo=0, contract=True, raydist='reciprocal', opaque=True, jitter=True, train_frac=0.3,
+                    pseed=101, transient='withmask'),
+    # phototourism_*_withmask.gin shape: no contraction, linear spacing, GLO vectors, 3 levels (repo default 64/64/32)
+    'photo': dict(n=20, seed=23, near=1.0, far=2.0, levels=3, n_prop=64, n_nerf=32, width=256, nerf_depth=8,
+                  prop_depth=4, glo=4, contract=False, raydist=None, opaque=False, jitter=True, train_frac=1.0,
+                  pseed=102, transient='withmask'),
+}
+
+
+def golden_params(c, feat=504, basis_n=21):
+  """flax-named parameter tree (NumPy float32) of golden case `c`, regenerated from c['pseed']:
+  he_uniform kernels, small non-zero biases (so the bias path is exercised), N(0, 1/sqrt(g)) GLO rows."""
+  rng = np.random.default_rng(c['pseed'])
+  W, view_in = c['width'], 3 + 6 * 4
+
+  def mlp(depth, rgb, glo):
+    shapes, d = [], feat
+    for i in range(depth):
+      shapes.append((d, W)); d = W
+      if i % 4 == 0 and i > 0:
+        d = W + feat
+    shapes.append((d, 1))
+    if rgb:
+      shapes += [(d, 256), (256 + view_in + glo, 128), (128, 3)]
+    layers = {}
+    for i, (fi, fo) in enumerate(shapes):
+      bound = np.sqrt(6.0 / fi)
+      layers[f'Dense_{i}'] = {'kernel': rng.uniform(-bound, bound, (fi, fo)).astype(np.float32),
+                              'bias': rng.uniform(-0.1, 0.1, (fo,)).astype(np.float32)}
+    return layers
+
+  tree = {'NerfMLP_0': mlp(c['nerf_depth'], True, c['glo']), 'PropMLP_0': mlp(c['prop_depth'], False, 0)}
+  if c['glo'] > 0:
+    tree['GloEmbed_0'] = {'embedding': (rng.normal(size=(16, c['glo'])) / np.sqrt(c['glo'])).astype(np.float32)}
+  return tree
+
+
+def golden_jitter(c):
+  """Unit-uniform draws [levels][n, 1] handed to stepfun.sample in place of jax.random.uniform."""
+  rng = np.random.default_rng(c['pseed'] + 7)
+  return [rng.uniform(0, 1, (c['n'], 1)).astype(np.float32) for _ in range(c['levels'])]
+
+
+def param_checksum(tree):
+  def leaves(t):
+    if isinstance(t, dict):
+      for k in sorted(t):
+        yield from leaves(t[k])
+    else:
+      yield np.asarray(t, np.float64)
+  vs = list(leaves(tree))
+  return [float(sum(v.sum() for v in vs)), float(sum(np.abs(v).sum() for v in vs))]
+
+
+def golden_case_configs(c, precision='fp32'):
+  """(oracle ModelConfig, EngineConfig kwargs) of a golden case."""
+  return config_pair(num_levels=c['levels'], n_prop=c['n_prop'], n_nerf=c['n_nerf'], width=c['width'],
+                     nerf_depth=c['nerf_depth'], prop_depth=c['prop_depth'], precision=precision,
+                     max_rays=max(c['n'], 128), glo=c['glo'], contract=c['contract'], raydist=c['raydist'],
+                     opaque=c['opaque'])
