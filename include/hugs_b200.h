@@ -37,8 +37,11 @@ typedef enum {
 typedef enum { HUGS_RAYDIST_NONE = 0, HUGS_RAYDIST_RECIPROCAL = 1, HUGS_RAYDIST_LOG = 2,
                HUGS_RAYDIST_PIECEWISE = 3 } hugs_raydist_fn;   /* coord.py:63-99 */
 typedef enum { HUGS_RAY_CONE = 0, HUGS_RAY_CYLINDER = 1 } hugs_ray_shape; /* render.py:103-127 */
-typedef enum { HUGS_PRECISION_FP32 = 0,   /* CUDA-core fp32 MLP: parity mode (1e-4 vs oracle) */
-               HUGS_PRECISION_BF16_TC = 1 /* tcgen05 bf16 x bf16 -> fp32: throughput mode     */
+typedef enum { HUGS_PRECISION_FP32 = 0,    /* CUDA-core fp32 MLP (render only): independent cross-check              */
+               HUGS_PRECISION_BF16_TC = 1, /* tcgen05 bf16 x bf16 -> fp32: throughput mode                            */
+               HUGS_PRECISION_TC_SPLIT = 2 /* the SAME tcgen05 kernels with every operand split into bf16 hi + lo
+                                              halves (4 products, fp32 accumulate, fp32 epilogues): forward and
+                                              backward at fp32-level accuracy (render 1e-4, gradients 1e-3)          */
 } hugs_precision;
 typedef enum { HUGS_LOSS_CHARB = 0, HUGS_LOSS_MSE = 1 } hugs_data_loss;  /* train_utils.py:96-103 */
 
@@ -169,6 +172,11 @@ int hugs_ipe_features(const hugs_handle* h, const hugs_rays* rays, const float* 
                       int32_t n_rays, int32_t n_samples, int32_t contract, float* features,
                       void* stream);
 
+/* Test hook: the throughput-mode bf16 IPE encoder on its own ([n*S, 512] bf16, engine column order
+ * f' = (b * degs + k) * 2 + {sin, shifted sin}; columns >= 2*num_basis*degs are zero).  Needs a tensor-core handle. */
+int hugs_debug_encode_bf16(hugs_handle* h, const hugs_rays* rays, const float* tdist, int32_t n_rays,
+                           int32_t n_samples, int32_t contract, void* features_bf16, void* stream);
+
 /* ---- model-level entry points ---- */
 
 /* Model.__call__ with rng=None or caller-provided jitter (models.py:74-330);
@@ -180,7 +188,8 @@ int hugs_forward(hugs_handle* h, const float* params, const hugs_rays* rays, int
 
 /* loss_fn + value_and_grad of train_utils.train_step (train_utils.py:407-455) on this rank's
  * rays.  grad_out: flat fp32 [param_count] (overwritten).  stats_out: fp32[16]:
- * [0] loss, [1] data, [2] interlevel, [3] distortion, [4..4+L) mse per level. */
+ * [0] loss, [1] data, [2] interlevel, [3] distortion, [4..4+L) mse per level (proposal levels: of their
+ * background-only rendering, as the reference reports them). */
 int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* rays,
                        const float* rgb_gt, int32_t n_rays, float train_frac, const float* jitter,
                        const hugs_loss_cfg* loss, float* grad_out, float* stats_out, void* stream);
@@ -189,6 +198,12 @@ int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* ray
  * (already all-reduced) flat gradient.  norms_out (optional) fp32[9]: {grad norm, abs-max, clip multiplier} per module. */
 int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
                    const hugs_adam_cfg* cfg, float* norms_out, void* stream);
+
+/* hugs_adam_step + the per-tensor statistics trees of train_step (train_utils.py:442,461-462,470-473) from the same pass:
+ * tensor_stats_out fp32[5 * n_tensors] (tensor order of hugs_param_layout), per tensor
+ * {sum w^2 before the update, sum g^2, max |g| (averaged, unclipped gradient), sum delta^2, max |delta| (applied update)}. */
+int hugs_adam_step_stats(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
+                         const hugs_adam_cfg* cfg, float* norms_out, float* tensor_stats_out, void* stream);
 
 /* ---- batch assembly on the device (the caller of the path: SURVEY.md §8f item 2) ---- */
 

@@ -87,9 +87,11 @@ SYMBOLS = {
     'hugs_max_dilate_weights': (C.c_int, [_P, _P, _I, _I, _F, _F, _F, _P, _P, _P]),
     'hugs_alpha_composite': (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, C.POINTER(LevelOut), _P]),
     'hugs_ipe_features': (C.c_int, [_P, C.POINTER(Rays), _P, _I, _I, _I, _P, _P]),
+    'hugs_debug_encode_bf16': (C.c_int, [_P, C.POINTER(Rays), _P, _I, _I, _I, _P, _P]),
     'hugs_forward': (C.c_int, [_P, _P, C.POINTER(Rays), _I, _F, _P, _I, _I, C.POINTER(LevelOut), _P]),
     'hugs_loss_and_grad': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _F, _P, C.POINTER(LossCfg), _P, _P, _P]),
     'hugs_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P]),
+    'hugs_adam_step_stats': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P, _P]),
     'hugs_make_ray_batch': (C.c_int, [C.POINTER(CameraSet), _P, _P, _P, _I, C.POINTER(RayBatch), _P]),
     'hugs_launch_count': (C.c_int64, []),
     'hugs_profile_enable': (C.c_int, [_P, _I]),

@@ -21,7 +21,6 @@ SOURCES = [
     ('mlp_tc.cu', []),
     ('mlp_pp.cu', []),
     ('wgrad_tc.cu', []),
-    ('tc_microbench.cu', []),
     ('optim.cu', []),
     ('raygen.cu', []),
 ]

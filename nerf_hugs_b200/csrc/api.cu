@@ -92,7 +92,8 @@ int validate(const hugs_model_desc& d) {
   HUGS_REQUIRE(d.max_rays >= 1, "max_rays must be >= 1");
   HUGS_REQUIRE(d.raydist_fn >= 0 && d.raydist_fn <= 3, "unknown raydist_fn %d", d.raydist_fn);
   HUGS_REQUIRE(d.ray_shape == HUGS_RAY_CONE || d.ray_shape == HUGS_RAY_CYLINDER, "unknown ray_shape");
-  HUGS_REQUIRE(d.precision == HUGS_PRECISION_FP32 || d.precision == HUGS_PRECISION_BF16_TC, "unknown precision");
+  HUGS_REQUIRE(d.precision == HUGS_PRECISION_FP32 || d.precision == HUGS_PRECISION_BF16_TC ||
+               d.precision == HUGS_PRECISION_TC_SPLIT, "unknown precision");
   return HUGS_OK;
 }
 
@@ -207,7 +208,14 @@ HUGS_API int hugs_create(const hugs_model_desc* desc, hugs_handle** out) {
       return fail(rc);
   }
   if ((rc = dev_alloc(h, &h->view_in, n * h->view_in_dim))) return fail(rc);
-  if ((rc = dev_alloc(h, &h->ray_stats, n * 8))) return fail(rc);
+  if ((rc = dev_alloc(h, &h->ray_stats, n * 12))) return fail(rc);
+  {
+    std::vector<int64_t> ends;
+    for (const auto& t : h->tensors) ends.push_back(t.offset + (int64_t)t.rows * t.cols);
+    if ((rc = dev_alloc(h, &h->tensor_ends, ends.size()))) return fail(rc);
+    if (cudaMemcpy(h->tensor_ends, ends.data(), sizeof(int64_t) * ends.size(), cudaMemcpyHostToDevice) != cudaSuccess)
+      return fail(cuda_fail(cudaGetLastError(), "tensor table upload", __FILE__, __LINE__));
+  }
   if ((rc = dev_alloc(h, &h->scalars, 2048))) return fail(rc);
   if (d.precision == HUGS_PRECISION_FP32) {
     const int wmax = std::max({d.nerf_width, d.prop_width, d.bottleneck_width, d.view_width});
@@ -244,7 +252,7 @@ HUGS_API int hugs_param_layout(const hugs_handle* h, hugs_tensor_desc* out, int3
 
 HUGS_API int hugs_params_changed(hugs_handle* h, const float* params, void* stream) {
   HUGS_REQUIRE(h && params, "hugs_params_changed: null argument");
-  if (h->d.precision == HUGS_PRECISION_BF16_TC) return tc_pack_params(h, params, (cudaStream_t)stream);
+  if (h->d.precision != HUGS_PRECISION_FP32) return tc_pack_params(h, params, (cudaStream_t)stream);
   return HUGS_OK;
 }
 
@@ -308,6 +316,14 @@ HUGS_API int hugs_ipe_features(const hugs_handle* h, const hugs_rays* rays, cons
   IpeArgs a{rays->origins, rays->directions, rays->radii, tdist, h->basis, n_rays, n_samples,
             h->d.num_basis, h->d.min_deg_point, h->d.max_deg_point, h->d.ray_shape, contract, features};
   return launch_ipe_features(a, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_debug_encode_bf16(hugs_handle* h, const hugs_rays* rays, const float* tdist, int32_t n_rays,
+                                    int32_t n_samples, int32_t contract, void* features_bf16, void* stream) {
+  HUGS_REQUIRE(h && rays && tdist && features_bf16, "hugs_debug_encode_bf16: null argument");
+  HUGS_REQUIRE(h->d.precision != HUGS_PRECISION_FP32, "hugs_debug_encode_bf16 needs a tensor-core handle");
+  return tc_debug_encode(h, rays, tdist, n_rays, n_samples, contract, static_cast<__nv_bfloat16*>(features_bf16),
+                         (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------ model-level entry points
@@ -413,7 +429,7 @@ int forward_levels(hugs_handle* h, const float* params, const hugs_rays* rays, i
   h->cur_params = params;
   h->cur_embed_idx = rays->embed_idx;
   if ((rc = launch_view_inputs(rays->viewdirs, rays->embed_idx, h->glo_off >= 0 ? params + h->glo_off : nullptr,
-                               n, d.deg_view, d.num_glo_features, zero_glo, h->view_in, st)))
+                               n, d.deg_view, d.num_glo_features, zero_glo, d.num_embeddings, h->view_in, st)))
     return rc;
   for (int l = 0; l < d.num_levels; ++l) {
     const bool is_prop = l < d.num_levels - 1;
@@ -468,8 +484,9 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
   if (rc) return rc;
   HUGS_REQUIRE(n_rays > 0, "hugs_loss_and_grad: empty batch");
   const hugs_model_desc& d = h->d;
-  if (d.precision != HUGS_PRECISION_BF16_TC) {
-    set_error("hugs_loss_and_grad needs HUGS_PRECISION_BF16_TC (the fp32 CUDA-core path is render-only)");
+  if (d.precision == HUGS_PRECISION_FP32) {
+    set_error("hugs_loss_and_grad needs a tensor-core precision mode (HUGS_PRECISION_BF16_TC for throughput, "
+              "HUGS_PRECISION_TC_SPLIT for fp32-level parity); the fp32 CUDA-core path is render-only");
     return HUGS_ERR_UNSUPPORTED;
   }
   if (loss->data_coarse_loss_mult != 0.f) {
@@ -482,7 +499,7 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
   if ((rc = forward_levels(h, params, rays, n, train_frac, jitter, 0, 0, nullptr, true, st))) return rc;
 
   float* denom = h->scalars;          // [0] loss normaliser
-  float* sums = h->scalars + 8;       // [8..] column sums of ray_stats
+  float* sums = h->scalars + 8;       // [8..24) column sums of ray_stats
   ProfScope* ps_loss = new ProfScope(h, HUGS_K_COMPOSITE_LOSS, st);
   struct Guard { ProfScope** p; ~Guard() { delete *p; *p = nullptr; } } guard{&ps_loss};
   if ((rc = launch_lossmult_sum(rays->lossmult, rays->static_mask, loss->use_static_mask,
@@ -506,11 +523,15 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
     a.S = h->samples(L - 1); a.opaque_background = d.opaque_background; a.density_bias = d.density_bias;
     a.scale = loss->interlevel_loss_mult / ((float)n * (float)a.S);
     a.d_raw = h->d_raw[l]; a.ray_stats = h->ray_stats + (size_t)n * (4 + l);
+    a.rgb_gt = rgb_gt; a.lossmult = rays->lossmult; a.static_mask = rays->static_mask; a.loss = *loss;
+    a.bg = d.bg_intensity; a.sq_stats = h->ray_stats + (size_t)n * (8 + l);
     if ((rc = launch_prop_loss_bwd(a, st))) return rc;
   }
   if ((rc = launch_column_sums(h->ray_stats, n, 4, 3, sums, st))) return rc;
-  for (int l = 0; l < L - 1; ++l)
+  for (int l = 0; l < L - 1; ++l) {
     if ((rc = launch_column_sums(h->ray_stats + (size_t)n * (4 + l), n, 1, 1, sums + 4 + l, st))) return rc;
+    if ((rc = launch_column_sums(h->ray_stats + (size_t)n * (8 + l), n, 1, 1, sums + 8 + l, st))) return rc;
+  }
   if ((rc = launch_finalize_stats(h, *loss, n, denom, sums, stats_out, st))) return rc;
   delete ps_loss; ps_loss = nullptr;
 

@@ -309,6 +309,24 @@ __global__ void __launch_bounds__(kWarps * 32) prop_loss_bwd_kernel(PropLossBwdA
     a.d_raw[(size_t)ray * Sp + i] = dden * sigmoid_f(pre);
   }
   if (lane == 0 && a.ray_stats) a.ray_stats[ray] = loss;
+  if (a.sq_stats) {
+    float acc = 0.f;
+    for (int i = lane; i < Sp; i += 32) acc += WT[i];
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      float lm;
+      if (a.loss.use_static_mask) {
+        float m = a.static_mask ? (a.static_mask[ray] >= 0.5f ? 1.f : 0.f) : 1.f;
+        lm = m + (1.f - m) * a.loss.withmask_transient_weight;
+      } else {
+        lm = (a.loss.disable_multiscale_loss || !a.lossmult) ? 1.f : a.lossmult[ray];
+      }
+      const float c = fmaxf(0.f, 1.f - acc) * a.bg;
+      float sq = 0.f;
+      for (int ch = 0; ch < 3; ++ch) { const float r = c - a.rgb_gt[ray * 3 + ch]; sq += lm * (r * r); }
+      a.sq_stats[ray] = sq;
+    }
+  }
 }
 
 __global__ void lossmult_sum_kernel(const float* lossmult, const float* static_mask, int use_mask,
@@ -352,11 +370,14 @@ __global__ void column_sums_kernel(const float* in, int n_rows, int stride, int 
   }
 }
 
+// the opt-in for > 48 KB of dynamic shared memory is a per-device attribute: one flag per device ordinal
 template <class K>
-int set_smem_once(K kernel, bool* flag) {
-  if (!*flag) {
+int set_smem_once(K kernel, bool* flags) {
+  int dev = 0;
+  HUGS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !flags[dev]) {
     HUGS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    *flag = true;
+    if (dev >= 0 && dev < 64) flags[dev] = true;
   }
   return HUGS_OK;
 }
@@ -365,8 +386,8 @@ int set_smem_once(K kernel, bool* flag) {
 
 int launch_composite(const CompositeArgs& a, cudaStream_t stream) {
   HUGS_REQUIRE(a.S >= 2 && a.S <= 256, "composite: samples per ray must be in [2,256], got %d", a.S);
-  static bool f = false;
-  int rc = set_smem_once(composite_kernel, &f);
+  static bool f[64] = {};
+  int rc = set_smem_once(composite_kernel, f);
   if (rc) return rc;
   if (a.n_rays <= 0) return HUGS_OK;
   size_t smem = (size_t)kWarps * (4 * a.S + 8) * sizeof(float);
@@ -377,8 +398,8 @@ int launch_composite(const CompositeArgs& a, cudaStream_t stream) {
 
 int launch_final_loss_bwd(const LossBwdArgs& a, cudaStream_t stream) {
   HUGS_REQUIRE(a.S >= 2 && a.S <= 256, "loss: samples per ray must be in [2,256], got %d", a.S);
-  static bool f = false;
-  int rc = set_smem_once(final_loss_bwd_kernel, &f);
+  static bool f[64] = {};
+  int rc = set_smem_once(final_loss_bwd_kernel, f);
   if (rc) return rc;
   if (a.n_rays <= 0) return HUGS_OK;
   size_t smem = (size_t)kWarps * 8 * a.S * sizeof(float);
@@ -389,8 +410,8 @@ int launch_final_loss_bwd(const LossBwdArgs& a, cudaStream_t stream) {
 
 int launch_prop_loss_bwd(const PropLossBwdArgs& a, cudaStream_t stream) {
   HUGS_REQUIRE(a.S >= 2 && a.S <= 256 && a.Sp >= 2 && a.Sp <= 256, "interlevel: samples per ray must be in [2,256]");
-  static bool f = false;
-  int rc = set_smem_once(prop_loss_bwd_kernel, &f);
+  static bool f[64] = {};
+  int rc = set_smem_once(prop_loss_bwd_kernel, f);
   if (rc) return rc;
   if (a.n_rays <= 0) return HUGS_OK;
   size_t smem = (size_t)kWarps * (7 * a.Sp + 1 + 3 * a.S) * sizeof(float);

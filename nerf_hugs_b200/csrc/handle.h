@@ -48,6 +48,7 @@ struct hugs_handle {
   float* act[3] = {nullptr, nullptr, nullptr};// fp32 path: [n*Smax, max width]
   float* ray_stats = nullptr;                 // [n, 4 + L]
   float* scalars = nullptr;                   // [64] device scalars (denominators, norms, ...)
+  int64_t* tensor_ends = nullptr;             // [tensors.size()] end offset of every parameter tensor (per-tensor statistics)
   std::vector<void*> allocs;
   hugs::TcState* tc = nullptr;
   // ---- optional CUDA-event profiling of kernel classes (hugs_profile_enable / hugs_profile_read) ----

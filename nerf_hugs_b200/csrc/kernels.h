@@ -82,6 +82,13 @@ struct PropLossBwdArgs {
   float scale = 0.f;                   // interlevel_loss_mult / (n_rays * S)
   float* d_raw = nullptr;              // [n, Sp] out
   float* ray_stats = nullptr;          // [n] out: per-ray sum of lossfun_outer
+  // stats['mses'] of a proposal level (train_utils.py:94): its rendering is max(0, 1 - acc) * bg
+  const float* rgb_gt = nullptr;       // [n, 3]
+  const float* lossmult = nullptr;     // [n] or nullptr
+  const float* static_mask = nullptr;  // [n] or nullptr
+  hugs_loss_cfg loss{};
+  float bg = 1.f;
+  float* sq_stats = nullptr;           // [n] out: lossmult-weighted squared error of the level's rendering (optional)
 };
 int launch_prop_loss_bwd(const PropLossBwdArgs& a, cudaStream_t stream);
 

@@ -17,7 +17,7 @@ struct IpeArgs {
 int launch_ipe_features(const IpeArgs& a, cudaStream_t stream);
 
 int launch_view_inputs(const float* viewdirs, const int32_t* embed_idx, const float* glo_table, int n_rays,
-                       int deg_view, int glo, int zero_glo, float* out, cudaStream_t stream);
+                       int deg_view, int glo, int zero_glo, int num_embeddings, float* out, cudaStream_t stream);
 
 struct DenseSeg { const float* x; int k; int ld; int row_div; };
 struct DenseArgs {

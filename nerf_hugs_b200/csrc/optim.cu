@@ -57,20 +57,61 @@ __global__ void grad_norm_final_kernel(const float* partial, float max_norm, flo
   out[m * 3 + 2] = max_norm > 0.f ? fminf(1.f, max_norm / (kF32Eps + sqrtf(c))) : 1.f;
 }
 
+// kStats: additionally accumulates, per parameter tensor, {sum w^2 (before the update), sum g^2, max |g| (the averaged,
+// unclipped gradient), sum delta^2, max |delta| (the applied update)} -> tstats[tensor][5]: the stats['weight_l2s'],
+// ['grad_norms'], ['grad_maxes'], ['opt_update_norms'], ['opt_update_maxes'] trees of train_utils.py:442,461-462,470-473
+// come out of the pass that already touches every parameter.
+template <bool kStats>
 __global__ void __launch_bounds__(256) adam_kernel(float* params, const float* grad, float* mu, float* nu,
                                                    int64_t n, int64_t e0, int64_t e1, const float* norms,
-                                                   hugs_adam_cfg cfg, float bc1, float bc2) {
+                                                   hugs_adam_cfg cfg, float bc1, float bc2,
+                                                   const int64_t* tensor_ends, int n_tensors, float* tstats) {
+  __shared__ int64_t ends[128];
+  if (kStats) {
+    for (int k = threadIdx.x; k < n_tensors; k += 256) ends[k] = tensor_ends[k];
+    __syncthreads();
+  }
   const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  if (i >= n) return;
-  const int m = i < e0 ? 0 : (i < e1 ? 1 : 2);
-  float g = clipv(grad[i] * cfg.grad_scale, cfg.grad_max_val) * norms[m * 3 + 2];
-  if (g != g) g = 0.f;                                  // jnp.nan_to_num
-  else if (isinf(g)) g = g > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
-  float m1 = cfg.beta1 * mu[i] + (1.f - cfg.beta1) * g;
-  float m2 = cfg.beta2 * nu[i] + (1.f - cfg.beta2) * g * g;
-  mu[i] = m1; nu[i] = m2;
-  float mhat = m1 / bc1, vhat = m2 / bc2;
-  params[i] = params[i] - cfg.lr * mhat / (sqrtf(vhat) + cfg.eps);
+  const bool ok = i < n;
+  float w2 = 0.f, g2 = 0.f, ga = 0.f, d2 = 0.f, da = 0.f;
+  if (ok) {
+    const int m = i < e0 ? 0 : (i < e1 ? 1 : 2);
+    const float gs = grad[i] * cfg.grad_scale;
+    float g = clipv(gs, cfg.grad_max_val) * norms[m * 3 + 2];
+    if (g != g) g = 0.f;                                  // jnp.nan_to_num
+    else if (isinf(g)) g = g > 0.f ? 3.4028234663852886e38f : -3.4028234663852886e38f;
+    float m1 = cfg.beta1 * mu[i] + (1.f - cfg.beta1) * g;
+    float m2 = cfg.beta2 * nu[i] + (1.f - cfg.beta2) * g * g;
+    mu[i] = m1; nu[i] = m2;
+    float mhat = m1 / bc1, vhat = m2 / bc2;
+    const float p_old = params[i];
+    const float p_new = p_old - cfg.lr * mhat / (sqrtf(vhat) + cfg.eps);
+    params[i] = p_new;
+    if (kStats) {
+      const float d = p_new - p_old;
+      w2 = p_old * p_old; g2 = gs * gs; ga = fabsf(gs); d2 = d * d; da = fabsf(d);
+    }
+  }
+  if (kStats) {
+    int lo = 0, hi = n_tensors - 1;                        // tensor of element i: first k with i < ends[k]
+    const int64_t key = ok ? i : n - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (key < ends[mid]) hi = mid; else lo = mid + 1; }
+    const int t = lo;
+    const int t0 = __shfl_sync(kFull, t, 0);
+    float* dst = tstats + (size_t)t * 5;
+    if (__all_sync(kFull, t == t0)) {                      // the common case: the warp sits inside one tensor
+      w2 = warp_sum(w2); g2 = warp_sum(g2); d2 = warp_sum(d2); ga = warp_max(ga); da = warp_max(da);
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(dst + 0, w2); atomicAdd(dst + 1, g2); atomicAdd(dst + 3, d2);
+        atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(ga));
+        atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(da));
+      }
+    } else if (ok) {
+      atomicAdd(dst + 0, w2); atomicAdd(dst + 1, g2); atomicAdd(dst + 3, d2);
+      atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(ga));
+      atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(da));
+    }
+  }
 }
 
 __global__ void finalize_stats_kernel(hugs_loss_cfg loss, int n, int L, int S_final, const float* denom,
@@ -87,6 +128,8 @@ __global__ void finalize_stats_kernel(hugs_loss_cfg loss, int n, int L, int S_fi
   for (int i = 0; i < 16; ++i) stats[i] = 0.f;
   stats[0] = data + inter + dist; stats[1] = data; stats[2] = inter; stats[3] = dist;
   stats[4 + L - 1] = mse;
+  // proposal levels render rgb = max(0, 1 - acc) * bg (their MLP has no colour, models.py:469-470): stats['mses'][l]
+  for (int l = 0; l < L - 1; ++l) stats[4 + l] = sums[8 + l] / dn;
 }
 
 }  // namespace
@@ -103,12 +146,12 @@ int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, cons
 
 using namespace hugs;
 
-HUGS_API int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
-                            const hugs_adam_cfg* cfg, float* norms_out, void* stream) {
+namespace {
+int adam_step_impl(hugs_handle* h, float* params, const float* grad, float* mu, float* nu, const hugs_adam_cfg* cfg,
+                   float* norms_out, float* tensor_stats_out, cudaStream_t st) {
   HUGS_REQUIRE(h && params && grad && mu && nu && cfg, "hugs_adam_step: null argument");
   HUGS_REQUIRE(cfg->step >= 0, "hugs_adam_step: step must be >= 0");
   HUGS_REQUIRE(cfg->grad_scale > 0.f, "hugs_adam_step: grad_scale must be > 0 (1 on a single GPU)");
-  cudaStream_t st = (cudaStream_t)stream;
   ProfScope ps(h, HUGS_K_ADAM_PACK, st);
   float* partial = h->scalars + 64;   // see hugs_create: scalars has room for 64 + 3*kRedBlocks*3
   float* norms = h->scalars + 32;
@@ -122,10 +165,32 @@ HUGS_API int hugs_adam_step(hugs_handle* h, float* params, const float* grad, fl
   const double t = (double)cfg->step + 1.0;
   const float bc1 = (float)(1.0 - pow((double)cfg->beta1, t)), bc2 = (float)(1.0 - pow((double)cfg->beta2, t));
   const int64_t n = h->n_params;
-  adam_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
-                                                           h->module_end[1], norms, *cfg, bc1, bc2);
+  const int n_tensors = (int)h->tensors.size();
+  if (tensor_stats_out) {
+    HUGS_REQUIRE(n_tensors <= 128, "too many parameter tensors for the per-tensor statistics");
+    HUGS_CUDA(cudaMemsetAsync(tensor_stats_out, 0, sizeof(float) * 5 * n_tensors, st));
+    adam_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
+                                                                   h->module_end[1], norms, *cfg, bc1, bc2,
+                                                                   h->tensor_ends, n_tensors, tensor_stats_out);
+  } else {
+    adam_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
+                                                                    h->module_end[1], norms, *cfg, bc1, bc2, nullptr,
+                                                                    0, nullptr);
+  }
   HUGS_LAUNCH_CHECK();
   if (norms_out) HUGS_CUDA(cudaMemcpyAsync(norms_out, norms, sizeof(float) * 9, cudaMemcpyDeviceToDevice, st));
-  if (h->d.precision == HUGS_PRECISION_BF16_TC) return tc_pack_params(h, params, st);
+  if (h->d.precision != HUGS_PRECISION_FP32) return tc_pack_params(h, params, st);
   return HUGS_OK;
+}
+}  // namespace
+
+HUGS_API int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
+                            const hugs_adam_cfg* cfg, float* norms_out, void* stream) {
+  return adam_step_impl(h, params, grad, mu, nu, cfg, norms_out, nullptr, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_adam_step_stats(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
+                                  const hugs_adam_cfg* cfg, float* norms_out, float* tensor_stats_out, void* stream) {
+  HUGS_REQUIRE(tensor_stats_out, "hugs_adam_step_stats: tensor_stats_out is required");
+  return adam_step_impl(h, params, grad, mu, nu, cfg, norms_out, tensor_stats_out, (cudaStream_t)stream);
 }

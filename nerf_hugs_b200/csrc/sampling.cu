@@ -207,10 +207,12 @@ int launch_resample(const ResampleArgs& a, cudaStream_t stream) {
   size_t per_warp = (size_t)((np + 1) + np + (3 * np + 1) + 3 * np + (3 * np + 1) + ns) * sizeof(float);
   size_t smem = per_warp * kWarpsPerBlock;
   HUGS_REQUIRE(smem <= 200 * 1024, "resample: %d bins / %d samples per ray exceed shared memory", np, ns);
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_set[64] = {};   // per device ordinal: the shared-memory opt-in is a per-device attribute
+  int dev = 0;
+  HUGS_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
     HUGS_CUDA(cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
   if (a.n_rays <= 0) return HUGS_OK;
   int blocks = (a.n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock;

@@ -1,5 +1,7 @@
 // Tensor-core (tcgen05) MLP path: host interface used by api.cu / optim.cu.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "handle.h"
 
 namespace hugs {
@@ -14,6 +16,10 @@ int tc_ensure_training(hugs_handle* h);
 int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, bool training, cudaStream_t st);
 // dgrad chain + wgrad for level l from h->d_raw[l]; accumulates into grad (flat fp32, flax layout)
 int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, float* grad, cudaStream_t st);
+
+// test hook: the throughput-mode bf16 feature encoder on its own ([n*S, 512] bf16, engine column order)
+int tc_debug_encode(hugs_handle* h, const hugs_rays* rays, const float* tdist, int n_rays, int S, int contract,
+                    __nv_bfloat16* out, cudaStream_t st);
 
 int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, const float* denom, const float* sums,
                           float* stats_out, cudaStream_t st);

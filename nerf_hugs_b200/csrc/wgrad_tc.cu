@@ -12,6 +12,10 @@
 // The remaining tiny reductions (biases = column sums of dZ, the N<=3 head kernels, the per-ray
 // view-direction / GLO inputs of the view layer) run on CUDA cores.
 //
+// Split-precision mode (HUGS_PRECISION_TC_SPLIT): A and dZ are stored as hi + lo bf16 halves (lo `lo_rows` further down in
+// the same tensors); every work item is issued four times (A_hi/A_lo x dZ_hi/dZ_lo) through the unchanged kernel and the
+// four fp32 partial products meet in the gradient buffer.
+//
 // Reference semantics: jax.value_and_grad of train_utils.py:407-455 restricted to the Dense layers of
 // models.py:449-519.
 #include <algorithm>
@@ -49,6 +53,7 @@ struct WgState {
 
 namespace {
 
+constexpr int kMaxWgItems = 4096;
 constexpr int kWgStages = 3;
 constexpr int kWgStageBytes = 65536;       // A0 16K | A1 16K | B 32K
 constexpr int kWgThreads = 192;
@@ -240,41 +245,51 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
 // ---------------------------------------------------------------- CUDA-core reductions (view layer extras)
 // dzv_ray[ray][c] = sum over the ray's samples of dZ_view[s][c]
-__global__ void __launch_bounds__(128) ray_sum_kernel(const __nv_bfloat16* dzv, int n_rays, int S, float* out) {
+__global__ void __launch_bounds__(128) ray_sum_kernel(const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int n_rays,
+                                                      int S, float* out) {
   const int ray = blockIdx.x, c = threadIdx.x;
   if (ray >= n_rays) return;
   float acc = 0.f;
   const __nv_bfloat16* src = dzv + (size_t)ray * S * kW + c;
   for (int s = 0; s < S; ++s) acc += __bfloat162float(src[(size_t)s * kW]);
+  if (dzv_lo) {   // split-precision mode: dZ = hi + lo
+    const __nv_bfloat16* lo = dzv_lo + (size_t)ray * S * kW + c;
+    for (int s = 0; s < S; ++s) acc += __bfloat162float(lo[(size_t)s * kW]);
+  }
   out[(size_t)ray * 128 + c] = acc;
 }
 
 // dW_view[bott + j][c] += sum_ray bf16(view_in[ray][j]) * dzv_ray[ray][c]; block = input row j, thread = c
 __global__ void __launch_bounds__(128) view_extra_wgrad_kernel(const float* view_in, int view_in_dim,
                                                                const float* dzv_ray, int n_rays, long long koff,
-                                                               int bott_w, float* grad) {
+                                                               int bott_w, int exact, float* grad) {
   const int j = blockIdx.x, c = threadIdx.x;
   const int chunk = (n_rays + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * chunk, r1 = min(r0 + chunk, n_rays);
   if (r1 <= r0) return;
   float acc = 0.f;
-  for (int r = r0; r < r1; ++r)
-    acc = fmaf(__bfloat162float(__float2bfloat16(view_in[(size_t)r * view_in_dim + j])), dzv_ray[(size_t)r * 128 + c], acc);
+  for (int r = r0; r < r1; ++r) {
+    float x = view_in[(size_t)r * view_in_dim + j];
+    if (!exact) x = __bfloat162float(__float2bfloat16(x));
+    acc = fmaf(x, dzv_ray[(size_t)r * 128 + c], acc);
+  }
   atomicAdd(grad + koff + (long long)(bott_w + j) * 128 + c, acc);
 }
 
 // GLO embedding rows: d_embed[idx[ray]][g] += sum_c dzv_ray[ray][c] * bf16(W_view[bott + dir_dim + g][c])
 __global__ void glo_grad_kernel(const float* dzv_ray, const int32_t* embed_idx, const float* params,
                                 long long view_koff, int bott_w, int dir_dim, int glo, int n_rays,
-                                long long glo_off, float* grad) {
+                                long long glo_off, int num_embeddings, int exact, float* grad) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_rays * glo) return;
   const int ray = idx / glo, g = idx % glo;
   const float* wrow = params + view_koff + (long long)(bott_w + dir_dim + g) * 128;
   float acc = 0.f;
   for (int c = 0; c < 128; ++c)
-    acc = fmaf(dzv_ray[(size_t)ray * 128 + c], __bfloat162float(__float2bfloat16(wrow[c])), acc);
-  atomicAdd(grad + glo_off + (long long)embed_idx[ray] * glo + g, acc);
+    acc = fmaf(dzv_ray[(size_t)ray * 128 + c], exact ? wrow[c] : __bfloat162float(__float2bfloat16(wrow[c])), acc);
+  const int row = embed_idx[ray];
+  if (row < 0 || row >= num_embeddings) return;     // out-of-range rows never touch memory (hugs_forward reports them)
+  atomicAdd(grad + glo_off + (long long)row * glo + g, acc);
 }
 
 }  // namespace
@@ -285,16 +300,17 @@ int wgrad_create(hugs_handle* h) {
   WgState* w = new WgState();
   tc->wg = w;
   int rc;
-  if ((rc = make_map(&w->map_act64, tc->act, tc->total_save_rows, kW, 64)) ||
-      (rc = make_map(&w->map_dz64, tc->dz, tc->total_save_rows, kW, 64)) ||
-      (rc = make_map(&w->map_feat64, tc->feat, tc->total_feat_rows, kFeatPad, 64)) ||
-      (rc = make_map(&w->map_dh64, tc->drgb, tc->drgb_rows, kHeadCols, 64)))
+  const long long parts = tc->split ? 2 : 1;
+  if ((rc = make_map(&w->map_act64, tc->act, parts * tc->total_save_rows, kW, 64)) ||
+      (rc = make_map(&w->map_dz64, tc->dz, parts * tc->total_save_rows, kW, 64)) ||
+      (rc = make_map(&w->map_feat64, tc->feat, parts * tc->total_feat_rows, kFeatPad, 64)) ||
+      (rc = make_map(&w->map_dh64, tc->drgb, parts * tc->drgb_rows, kHeadCols, 64)))
     return rc;
   const int L = h->d.num_levels;
   w->host.resize(L); w->dev.assign(L, nullptr); w->built_for.assign(L, -1);
   for (int l = 0; l < L; ++l) {
     void* q = nullptr;
-    HUGS_CUDA(cudaMalloc(&q, sizeof(WgItem) * 1024));
+    HUGS_CUDA(cudaMalloc(&q, sizeof(WgItem) * kMaxWgItems));
     h->allocs.push_back(q);
     w->dev[l] = static_cast<WgItem*>(q);
   }
@@ -363,9 +379,8 @@ static void build_items(hugs_handle* h, int level, int n_tiles, std::vector<WgIt
   int used = 0;
   // Several items per CTA even out the differences between items (measured: NerfMLP 1.28 -> 1.17 ms with 3 items per
   // CTA), but every item pays one accumulator flush: only when an item still streams >= ~250 stages.
-  const char* wenv = getenv("HUGS_WG_WAVES");
   const float stages_per_sm = (float)T * total / (float)tc->num_sms;
-  const int waves = wenv ? atoi(wenv) : std::min(4, std::max(1, (int)(stages_per_sm / 250.f)));
+  const int waves = std::min(4, std::max(1, (int)(stages_per_sm / 250.f)));
   const int target = tc->num_sms * std::max(1, waves);
   for (size_t i = 0; i < units.size(); ++i) {
     splits[i] = std::max(1, (int)(target * units[i].cost / total));
@@ -376,12 +391,21 @@ static void build_items(hugs_handle* h, int level, int n_tiles, std::vector<WgIt
     const size_t k = i % units.size();
     if (splits[k] < std::max(1, T / 4)) { ++splits[k]; ++used; }
   }
+  // split-precision mode: (A_hi + A_lo)^T (dZ_hi + dZ_lo) as four items; the bias column sums ride on the A_hi items only,
+  // so that each dZ half is summed exactly once
+  const int n_a = tc->split ? 2 : 1, n_b = tc->split ? 2 : 1;
   for (size_t i = 0; i < units.size(); ++i) {
     for (int k = 0; k < splits[i]; ++k) {
-      WgItem w = units[i].w;
-      w.st0 = (int)((long long)T * k / splits[i]);
-      w.st1 = (int)((long long)T * (k + 1) / splits[i]);
-      if (w.st1 > w.st0) items->push_back(w);
+      for (int pa = 0; pa < n_a; ++pa)
+        for (int pb = 0; pb < n_b; ++pb) {
+          WgItem w = units[i].w;
+          w.st0 = (int)((long long)T * k / splits[i]);
+          w.st1 = (int)((long long)T * (k + 1) / splits[i]);
+          w.a_row0 += pa * (w.a_map ? tc->total_feat_rows : tc->total_save_rows);
+          w.b_row0 += pb * (w.b_map ? tc->drgb_rows : tc->total_save_rows);
+          if (pa > 0) w.bias_mode = 0;
+          if (w.st1 > w.st0) items->push_back(w);
+        }
     }
   }
 }
@@ -399,7 +423,7 @@ int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t s
   const int cap = tc->cap[level], srow = tc->save_row0[level];
   if (w->built_for[level] != n_samples) {
     build_items(h, level, n_tiles, &w->host[level]);
-    HUGS_REQUIRE(w->host[level].size() <= 1024, "wgrad: too many work items");
+    HUGS_REQUIRE(w->host[level].size() <= (size_t)kMaxWgItems, "wgrad: too many work items");
     HUGS_CUDA(cudaMemcpyAsync(w->dev[level], w->host[level].data(), sizeof(WgItem) * w->host[level].size(),
                               cudaMemcpyHostToDevice, st));
     HUGS_CUDA(cudaStreamSynchronize(st));
@@ -419,16 +443,18 @@ int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t s
 
   if (mv.has_rgb) {
     const DenseView& vv = mv.dense[D + 2];
-    ray_sum_kernel<<<n_rays, 128, 0, st>>>(tc->dz + (size_t)(srow + (D + 1) * cap) * kW, n_rays, S, w->dzv_ray);
+    const __nv_bfloat16* dzv = tc->dz + (size_t)(srow + (D + 1) * cap) * kW;
+    ray_sum_kernel<<<n_rays, 128, 0, st>>>(dzv, tc->split ? dzv + (size_t)tc->total_save_rows * kW : nullptr, n_rays, S,
+                                           w->dzv_ray);
     HUGS_LAUNCH_CHECK();
     view_extra_wgrad_kernel<<<dim3(h->view_in_dim, 32), 128, 0, st>>>(h->view_in, h->view_in_dim, w->dzv_ray, n_rays,
-                                                           vv.kernel_off, d.bottleneck_width, grad);
+                                                           vv.kernel_off, d.bottleneck_width, tc->split ? 1 : 0, grad);
     HUGS_LAUNCH_CHECK();
     if (d.num_glo_features > 0) {
       const int tot = n_rays * d.num_glo_features;
       glo_grad_kernel<<<(tot + 127) / 128, 128, 0, st>>>(w->dzv_ray, h->cur_embed_idx, h->cur_params, vv.kernel_off,
                                                          d.bottleneck_width, 3 + 6 * d.deg_view, d.num_glo_features,
-                                                         n_rays, h->glo_off, grad);
+                                                         n_rays, h->glo_off, d.num_embeddings, tc->split ? 1 : 0, grad);
       HUGS_LAUNCH_CHECK();
     }
   }

@@ -18,7 +18,7 @@ from ._lib import lib, check
 
 RAYDIST = {None: 0, 'reciprocal': 1, 'log': 2, 'piecewise': 3}
 RAY_SHAPE = {'cone': 0, 'cylinder': 1}
-PRECISION = {'fp32': 0, 'bf16_tc': 1}
+PRECISION = {'fp32': 0, 'bf16_tc': 1, 'tc_split': 2}
 
 
 @dataclasses.dataclass
@@ -165,6 +165,16 @@ class Engine:
       r.embed_idx = t.data_ptr()
     return r, keep, n
 
+  def check_embed_idx(self, embed_idx):
+    """Raises if a GLO row index is outside [0, num_embeddings) (nn.Embed / jnp.take never touch memory out of range; the
+    kernels clamp, this makes the mistake loud).  Synchronises: call it when a dataset is set up, not per step."""
+    if self.cfg.num_glo_features > 0 and embed_idx is not None:
+      t = torch.as_tensor(embed_idx)
+      lo, hi = int(t.min()), int(t.max())
+      if lo < 0 or hi >= self.cfg.num_embeddings:
+        raise IndexError(f'embed_idx range [{lo}, {hi}] is outside the GLO table of {self.cfg.num_embeddings} rows '
+                         '(Model.num_embeddings)')
+
   # ---- model-level calls --------------------------------------------------------------------
   def forward(self, params: torch.Tensor, rays: Dict[str, torch.Tensor], train_frac: float,
               jitter: Optional[torch.Tensor] = None, compute_extras: bool = True, zero_glo: bool = False,
@@ -219,10 +229,17 @@ class Engine:
     self._keep = keep + [gt, jit]
     return grad, stats
 
-  def adam_step(self, params, grad, mu, nu, adam_cfg: '_lib.AdamCfg', norms_out: Optional[torch.Tensor] = None):
+  def adam_step(self, params, grad, mu, nu, adam_cfg: '_lib.AdamCfg', norms_out: Optional[torch.Tensor] = None,
+                tensor_stats_out: Optional[torch.Tensor] = None):
+    """clip + nan_to_num + Adam; `tensor_stats_out` ([len(layout), 5] fp32) also receives, per parameter tensor,
+    {sum w^2, sum g^2, max |g|, sum delta^2, max |delta|} (hugs_adam_step_stats)."""
     with torch.cuda.device(self.device):
-      check(lib.hugs_adam_step(self._h, _ptr(params), _ptr(grad), _ptr(mu), _ptr(nu), C.byref(adam_cfg),
-                               _ptr(norms_out), self._stream()))
+      if tensor_stats_out is None:
+        check(lib.hugs_adam_step(self._h, _ptr(params), _ptr(grad), _ptr(mu), _ptr(nu), C.byref(adam_cfg),
+                                 _ptr(norms_out), self._stream()))
+      else:
+        check(lib.hugs_adam_step_stats(self._h, _ptr(params), _ptr(grad), _ptr(mu), _ptr(nu), C.byref(adam_cfg),
+                                       _ptr(norms_out), _ptr(tensor_stats_out), self._stream()))
 
   # ---- measurement hooks ----------------------------------------------------------------------
   def profile(self, enable: bool):
@@ -290,6 +307,16 @@ class Engine:
     check(lib.hugs_alpha_composite(self._h, _ptr(raw_density), _ptr(raw_rgb), _ptr(tdist), None, _ptr(directions),
                                    _ptr(far), n, S, int(compute_extras), C.byref(o), self._stream()))
     torch.cuda.synchronize(dev)
+    return out
+
+  def debug_encode_bf16(self, rays, tdist, contract: bool):
+    """The throughput-mode bf16 IPE encoder on its own: [n*S, 512] bf16, engine column order (test hook)."""
+    r, keep, n = self._rays(rays)
+    tdist = _f32(tdist, self.device)
+    S = tdist.shape[-1] - 1
+    out = torch.empty(n * S, 512, device=self.device, dtype=torch.bfloat16)
+    check(lib.hugs_debug_encode_bf16(self._h, C.byref(r), _ptr(tdist), n, S, int(contract), _ptr(out), self._stream()))
+    torch.cuda.synchronize(self.device)
     return out
 
   def ipe_features(self, rays, tdist, contract: bool):

@@ -94,10 +94,13 @@ class Model:
     return self.engine.flatten_params(tree)
 
   def _ensure_packed(self, flat: torch.Tensor):
-    key = (flat.data_ptr(), flat._version)
-    if key != self._packed_version:
+    """Re-derives the packed bf16 operand copies unless `flat` is the very tensor (same object, same version counter)
+    they were derived from.  The tensor is held by a strong reference: a temporary built from a parameter tree can
+    then never be freed and have its address handed to the next, different tree."""
+    ref = self._packed_version
+    if ref is None or ref[0] is not flat or ref[1] != flat._version:
       self.engine.params_changed(flat)
-      self._packed_version = key
+      self._packed_version = (flat, flat._version)
 
   # -- forward ----------------------------------------------------------------------------------
   def apply(self, variables, rng, rays, train_frac, compute_extras, zero_glo=False, zero_tra=False):

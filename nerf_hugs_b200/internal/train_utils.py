@@ -85,6 +85,10 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
   `state` is updated in place and returned (the reference donates it, train_utils.py:483).
   """
   eng = model.engine
+  if getattr(config, 'weight_decay_mults', None):
+    raise NotImplementedError(
+        "Config.weight_decay_mults is set: the 'weight' loss term (train_utils.py:444-447) is not on this path "
+        '(no shipped gin sets it); silently training without it would change the optimisation')
   lcfg = loss_cfg_from(config, is_finetune)
   lr_fn = lambda step: hmath.learning_rate_decay(step, config.lr_init, config.lr_final, config.max_steps,
                                                 config.lr_delay_steps, config.lr_delay_mult)
@@ -95,14 +99,17 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
   grad = bucket[:eng.n_params]
   stats_dev = bucket[bucket.numel() - 16:]
   norms_dev = torch.empty(9, device=dev)
+  n_t = len(eng.layout)
+  tstats_dev = torch.empty(n_t, 5, device=dev)
+  names = [t[0] for t in eng.layout]
   L = model.num_levels
   # every step's stats are copied (asynchronously) into a pinned host ring, so a stats object stays valid after later
   # steps have been launched and reading it waits only for its own step
-  ring = torch.empty(_STATS_RING, 25).pin_memory()
+  ring = torch.empty(_STATS_RING, 25 + 5 * n_t).pin_memory()
   holders = [None] * _STATS_RING
 
   def train_step(rng, state: TrainState, batch: utils.Batch, train_frac, inlier_thresholds=None):
-    del inlier_thresholds   # RobustNeRF only (out of scope)
+    del inlier_thresholds   # read by compute_robustnerf_loss only; transient_type='robustnerf' is refused by models.Model
     rank, world = _world()
     rays = {k: _to_device(v, dev) for k, v in batch.rays.as_dict().items()}
     rgb = _to_device(batch.rgb, dev)
@@ -118,17 +125,18 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
     a.beta1, a.beta2, a.eps = config.adam_beta1, config.adam_beta2, config.adam_eps
     a.grad_max_norm, a.grad_max_val = config.grad_max_norm, config.grad_max_val
     a.step, a.grad_scale = int(state.step), 1.0 / world
-    eng.adam_step(state.params, grad, state.mu, state.nu, a, norms_dev)
-    model._packed_version = (state.params.data_ptr(), state.params._version)   # adam_step re-packs bf16 operands
+    eng.adam_step(state.params, grad, state.mu, state.nu, a, norms_dev, tstats_dev)
+    model._packed_version = (state.params, state.params._version)   # adam_step re-packs the bf16 operands
     slot = state.step % _STATS_RING
     if holders[slot] is not None:
       holders[slot]._fetch()                          # about to reuse the slot: materialise its old owner
     ring[slot, :16].copy_(stats_dev, non_blocking=True)
-    ring[slot, 16:].copy_(norms_dev, non_blocking=True)
+    ring[slot, 16:25].copy_(norms_dev, non_blocking=True)
+    ring[slot, 25:].copy_(tstats_dev.reshape(-1), non_blocking=True)
     ev = torch.cuda.Event()
     ev.record(torch.cuda.current_stream(dev))
     state.step += 1
-    stats = _LazyStats(ring[slot], ev, L, world, a.lr)
+    stats = _LazyStats(ring[slot], ev, L, world, a.lr, names)
     holders[slot] = stats
     return state, stats, rng
 
@@ -138,40 +146,77 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
 _STATS_RING = 64
 
 
+def _summarize(names, values, reduce):
+  """train_utils.summarize_tree(tree, fn, max_depth=3): 'Module', 'Module/Dense_k' and 'Module/Dense_k/kernel' keys."""
+  out = {}
+  for name, v in zip(names, values):
+    parts = name.split('/')
+    for d in range(1, len(parts) + 1):
+      k = '/'.join(parts[:d])
+      out[k] = v if k not in out else reduce(out[k], v)
+  return out
+
+
 class _LazyStats(dict):
   """stats pytree of train_step (train_utils.py:442-476).  The values sit in a pinned host slot filled by an
-  asynchronous copy; the first access waits for that step's event only, so the training loop does not synchronise
-  every step (the reference reads them every print_every)."""
+  asynchronous copy; the first access (of any kind) waits for that step's event only, so the training loop does not
+  synchronise every step (the reference reads them every print_every)."""
 
-  def __init__(self, host_slot, event, L, world, lr):
+  def __init__(self, host_slot, event, L, world, lr, names):
     super().__init__()
     self._h, self._ev, self._L, self._world, self._lr, self._done = host_slot, event, L, world, lr, False
+    self._names = names
 
   def _fetch(self):
     if self._done:
       return
+    self._done = True
     if self._ev is not None:
       self._ev.synchronize()
+    import numpy as np
     s = self._h[:16].numpy() / self._world
-    n = self._h[16:].numpy().copy()
-    mses = s[4:4 + self._L]
-    psnrs = [-10.0 * _pymath.log10(max(float(m), 1e-30)) for m in mses]
+    t = self._h[25:].numpy().reshape(-1, 5).astype(np.float64)
+    mses = np.array(s[4:4 + self._L])
+    psnrs = -10.0 / _pymath.log(10.0) * np.log(np.maximum(mses, 1e-30))      # image.mse_to_psnr
+    add, mx = (lambda a, b: a + b), max
     dict.update(self, {
         'loss': float(s[0]),
         'losses': {'data': float(s[1]), 'interlevel': float(s[2]), 'distortion': float(s[3])},
-        'mses': mses, 'psnrs': psnrs, 'psnr': psnrs[-1], 'lr': self._lr,
-        'grad_norms': {'NerfMLP_0': float(n[0]), 'PropMLP_0': float(n[3]), 'GloEmbed_0': float(n[6])},
-        'grad_maxes': {'NerfMLP_0': float(n[1]), 'PropMLP_0': float(n[4]), 'GloEmbed_0': float(n[7])},
+        'mses': mses, 'psnrs': psnrs, 'psnr': float(psnrs[-1]), 'lr': self._lr,
+        'weight_l2s': _summarize(self._names, t[:, 0], add),                                   # tree_norm_sq
+        'grad_norms': {k: _pymath.sqrt(v) for k, v in _summarize(self._names, t[:, 1], add).items()},
+        'grad_maxes': _summarize(self._names, t[:, 2], mx),
+        'opt_update_norms': {k: _pymath.sqrt(v) for k, v in _summarize(self._names, t[:, 3], add).items()},
+        'opt_update_maxes': _summarize(self._names, t[:, 4], mx),
     })
-    self._done = True
 
   def __getitem__(self, k):
     self._fetch()
     return dict.__getitem__(self, k)
 
+  def __contains__(self, k):
+    self._fetch()
+    return dict.__contains__(self, k)
+
+  def __iter__(self):
+    self._fetch()
+    return dict.__iter__(self)
+
+  def __len__(self):
+    self._fetch()
+    return dict.__len__(self)
+
+  def get(self, k, default=None):
+    self._fetch()
+    return dict.get(self, k, default)
+
   def keys(self):
     self._fetch()
     return dict.keys(self)
+
+  def values(self):
+    self._fetch()
+    return dict.values(self)
 
   def items(self):
     self._fetch()

@@ -30,7 +30,9 @@ and gin are not installable in this environment.  Pinning:
 Numerics: everything runs in `dtype` (float32 to mirror the reference on CPU,
 float64 as the tie-breaking twin).  `quant='bf16'` rounds the *inputs and
 kernels* of every Dense layer to bfloat16 (fp32 accumulate, fp32 bias) which is
-the arithmetic the tensor-core throughput mode of the CUDA path performs.
+the arithmetic the tensor-core throughput mode of the CUDA path performs;
+`quant='bf16_train'` additionally rounds every Dense layer's incoming gradient
+to bfloat16 in the backward pass, which is what that mode's saved dZ tiles do.
 """
 from __future__ import annotations
 
@@ -526,22 +528,48 @@ def init_params(cfg: ModelConfig, seed: int = 0, dtype=torch.float32, bias_scale
 
 
 def _q(x, quant):
-  return x.to(torch.bfloat16).to(x.dtype) if quant == 'bf16' else x
+  return x.to(torch.bfloat16).to(x.dtype) if quant in ('bf16', 'bf16_train') else x
+
+
+class _DenseBf16Train(torch.autograd.Function):
+  """Dense layer as the tensor-core throughput mode trains it: bf16-rounded inputs and kernel in the forward pass
+  (fp32 accumulate, fp32 bias) and, in the backward pass, the incoming gradient dZ rounded to bf16 *before* it is
+  used - the chain kernel keeps dZ as a bf16 tile that feeds the dgrad MMA, the weight-gradient GEMM and the bias
+  column sums alike (csrc/mlp_pp.cu backward epilogues, csrc/wgrad_tc.cu).  The saved activation is the bf16 one."""
+
+  @staticmethod
+  def forward(ctx, x, kernel, bias):
+    xq, kq = _q(x, 'bf16'), _q(kernel, 'bf16')
+    ctx.save_for_backward(xq, kq)
+    return xq @ kq + bias
+
+  @staticmethod
+  def backward(ctx, g):
+    xq, kq = ctx.saved_tensors
+    gq = _q(g, 'bf16')
+    g2 = gq.reshape(-1, gq.shape[-1])
+    return gq @ kq.T, xq.reshape(-1, xq.shape[-1]).T @ g2, g2.sum(0)
 
 
 def _dense(x, layer, quant):
+  if quant == 'bf16_train':
+    return _DenseBf16Train.apply(x, layer['kernel'], layer['bias'])
   return _q(x, quant) @ _q(layer['kernel'], quant) + layer['bias']
 
 
 def mlp_apply(mcfg: MLPConfig, p, means, covs, viewdirs, glo_vec, basis, quant=None,
-              return_features=False):
-  """models.py:405-550 (transient head omitted: out of scope)."""
-  if mcfg.warp_fn == 'contract':
-    means, covs = track_linearize_contract(means, covs)
-  elif mcfg.warp_fn is not None:
-    raise ValueError(mcfg.warp_fn)
-  lifted_means, lifted_vars = lift_and_diagonalize(means, covs, basis)
-  x = integrated_pos_enc(lifted_means, lifted_vars, mcfg.min_deg_point, mcfg.max_deg_point)
+              return_features=False, features=None):
+  """models.py:405-550 (transient head omitted: out of scope).  `features`: test hook, IPE features computed elsewhere
+  (e.g. the CUDA encoder's bf16 features) replace the encoding of (means, covs)."""
+  if features is not None:
+    x = features
+  else:
+    if mcfg.warp_fn == 'contract':
+      means, covs = track_linearize_contract(means, covs)
+    elif mcfg.warp_fn is not None:
+      raise ValueError(mcfg.warp_fn)
+    lifted_means, lifted_vars = lift_and_diagonalize(means, covs, basis)
+    x = integrated_pos_enc(lifted_means, lifted_vars, mcfg.min_deg_point, mcfg.max_deg_point)
   inputs = x
   li = 0
   for i in range(mcfg.net_depth):
@@ -573,7 +601,7 @@ def mlp_apply(mcfg: MLPConfig, p, means, covs, viewdirs, glo_vec, basis, quant=N
 
 def model_apply(cfg: ModelConfig, params, rays: Dict[str, torch.Tensor], train_frac: float,
                 compute_extras: bool, basis: torch.Tensor, jitter: Optional[Sequence[torch.Tensor]] = None,
-                zero_glo: bool = False, quant=None, vis_num_rays: int = 16):
+                zero_glo: bool = False, quant=None, vis_num_rays: int = 16, features=None):
   """models.py:74-330 Model.__call__.
 
   rays: dict with origins, directions, viewdirs [...,3]; radii, near, far [...,1];
@@ -629,7 +657,8 @@ def model_apply(cfg: ModelConfig, params, rays: Dict[str, torch.Tensor], train_f
     p = params['PropMLP_0' if is_prop else 'NerfMLP_0']
     ray_results = mlp_apply(mcfg, p, means, covs,
                             rays['viewdirs'] if cfg.use_viewdirs else None,
-                            None if is_prop else glo_vec, basis, quant=quant)
+                            None if is_prop else glo_vec, basis, quant=quant,
+                            features=None if features is None else features[i_level])
     weights = compute_alpha_weights(ray_results['density'], tdist, rays['directions'],
                                     opaque_background=cfg.opaque_background)[0]
     rendering = volumetric_rendering(ray_results['rgb'], weights, tdist, cfg.bg_intensity,
@@ -725,10 +754,10 @@ def distortion_loss(ray_history, lcfg: LossConfig):
 
 
 def loss_fn(cfg: ModelConfig, lcfg: LossConfig, params, rays, rgb_gt, train_frac, basis,
-            jitter=None, quant=None):
+            jitter=None, quant=None, features=None):
   """train_utils.py:413-448 (transient_type in {None,'withmask'}, no weight decay)."""
   renderings, ray_history = model_apply(cfg, params, rays, train_frac, False, basis,
-                                        jitter=jitter, quant=quant)
+                                        jitter=jitter, quant=quant, features=features)
   losses = {}
   losses['data'], stats = compute_data_loss(rgb_gt, rays, renderings, lcfg,
                                             lcfg.transient_type == 'withmask')
@@ -768,7 +797,7 @@ def clip_gradients(grads, lcfg: LossConfig):
 
 
 def train_step(cfg: ModelConfig, lcfg: LossConfig, params, opt_state, step: int, rays, rgb_gt,
-               train_frac, basis, jitter=None, quant=None):
+               train_frac, basis, jitter=None, quant=None, features=None):
   """train_utils.py:386-477 on one device: value_and_grad -> clip -> nan_to_num -> optax.adam.
 
   params: nested dict of leaf tensors (updated functionally; new dict returned).
@@ -789,7 +818,7 @@ def train_step(cfg: ModelConfig, lcfg: LossConfig, params, opt_state, step: int,
     return tree
 
   p = rebuild(leaves)
-  loss, stats, _, _ = loss_fn(cfg, lcfg, p, rays, rgb_gt, train_frac, basis, jitter, quant)
+  loss, stats, _, _ = loss_fn(cfg, lcfg, p, rays, rgb_gt, train_frac, basis, jitter, quant, features)
   gl = torch.autograd.grad(loss, leaves, allow_unused=True)
   gl = [torch.zeros_like(l) if g is None else g for g, l in zip(gl, leaves)]
   gtree = rebuild(gl)

@@ -31,10 +31,10 @@ def _report(name, d):
 
 
 def _run_pair(precision, quant, n=96, seed=0, num_levels=2, n_prop=64, n_nerf=128, glo=0, contract=True,
-              raydist='reciprocal', jitter=False, near=0.2, far=1e6):
+              raydist='reciprocal', jitter=False, near=0.2, far=1e6, ray_shape='cone'):
   from nerf_hugs_b200.engine import Engine
   ocfg, ecfg = H.config_pair(num_levels=num_levels, n_prop=n_prop, n_nerf=n_nerf, precision=precision,
-                             max_rays=max(n, 128), glo=glo, contract=contract, raydist=raydist)
+                             max_rays=max(n, 128), glo=glo, contract=contract, raydist=raydist, ray_shape=ray_shape)
   basis = H.basis_np()
   params = O.init_params(ocfg, seed=seed, bias_scale=0.1)
   rays, gt = H.make_rays(n, seed=seed + 1, near=near, far=far)
@@ -126,3 +126,19 @@ def test_forward_tc_three_levels_repo_default_sampling():
   stats = {k: _relerr(res[-1][k], rend[-1][k]) for k in ('rgb', 'acc', 'distance_mean')}
   _report('forward_tc_L3', stats)
   assert stats['rgb'] < 1e-2 and stats['acc'] < 1e-2, stats
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tc_split'])
+@pytest.mark.parametrize('raydist,ray_shape,near,far', [('log', 'cone', 0.2, 50.0), ('piecewise', 'cone', 0.0, 1e4),
+                                                         ('reciprocal', 'cylinder', 0.2, 1e6), (None, 'cylinder', 1.0, 3.0)])
+def test_forward_parity_other_ray_warps_and_shapes(precision, raydist, ray_shape, near, far):
+  """coord.construct_ray_warps with fn = jnp.log / 'piecewise' (coord.py:63-99; piecewise allows near = 0) and
+  ray_shape = 'cylinder' (render.py:81-100): 1e-4 parity of both the CUDA-core and the tensor-core split path."""
+  rend, hist, res, eh = _run_pair(precision, None, raydist=raydist, ray_shape=ray_shape, near=near, far=far, n=40)
+  for l in range(2):
+    assert float((eh[l]['sdist'] - hist[l]['sdist']).abs().max()) < 5e-5
+    np.testing.assert_allclose(eh[l]['sdist'].numpy()[:, [0, -1]], hist[l]['sdist'].numpy()[:, [0, -1]], atol=1e-6)
+  stats = {k: _relerr(res[-1][k], rend[-1][k]) for k in ('rgb', 'acc', 'distance_mean', 'distance_median')}
+  _report(f'forward_{precision}_{raydist}_{ray_shape}', stats)
+  for k, e in stats.items():
+    assert e < 1e-4, (k, stats)

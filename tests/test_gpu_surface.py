@@ -104,3 +104,87 @@ def test_render_only_handle_does_not_reserve_training_buffers():
   free2, _ = torch.cuda.mem_get_info()
   assert free1 - free2 > 12 * 2 ** 30                    # the training buffers appeared with the first training step
   model.engine.close()
+
+
+def test_train_pstep_stats_contract():
+  """stats of train_step (train_utils.py:442-476): every key train.py:174-213 histograms, with summarize_tree's three
+  key depths, checked against values recomputed from the parameters / gradient / update themselves."""
+  import math
+  from nerf_hugs_b200 import _lib
+  from nerf_hugs_b200.internal import train_utils, utils
+  config = _config(64, glo=4)
+  model, state, _, train_pstep, lr_fn = train_utils.setup_model(config, rng=0, max_rays=128)
+  eng = model.engine
+  rays, gt = H.make_rays(64, seed=2, glo=True)
+  batch = utils.Batch(rays=utils.Rays(**rays), rgb=gt)
+  p0 = state.params.clone()
+  # the gradient of the very same step (deterministic sampling so that it can be recomputed)
+  config.randomized = False
+  train_pstep = train_utils.create_train_step(model, config)
+  g_ref, _ = eng.loss_and_grad(p0, rays, gt, 0.1, None, train_utils.loss_cfg_from(config))
+  g_ref = g_ref.clone()
+  eng.params_changed(p0)
+  state, stats, _ = train_pstep(None, state, batch, 0.1, None)
+  for k in ('loss', 'losses', 'mses', 'psnrs', 'psnr', 'weight_l2s', 'grad_norms', 'grad_maxes', 'opt_update_norms',
+            'opt_update_maxes'):
+    assert k in stats, k
+  assert len(stats['mses']) == 2 and len(stats['psnrs']) == 2 and np.all(np.isfinite(stats['psnrs']))
+  assert 0.0 < stats['mses'][0] < 2.0                     # proposal level: MSE of its background-only rendering
+  delta = (state.params - p0)
+  for name, off, r, c, _ in eng.layout:
+    sl = slice(off, off + r * c)
+    np.testing.assert_allclose(stats['weight_l2s'][name], float((p0[sl].double() ** 2).sum()), rtol=1e-5)
+    np.testing.assert_allclose(stats['grad_norms'][name], float(g_ref[sl].double().norm()), rtol=1e-3, atol=1e-12)
+    np.testing.assert_allclose(stats['grad_maxes'][name], float(g_ref[sl].abs().max()), rtol=1e-3, atol=1e-12)
+    np.testing.assert_allclose(stats['opt_update_norms'][name], float(delta[sl].double().norm()), rtol=1e-5, atol=1e-12)
+    np.testing.assert_allclose(stats['opt_update_maxes'][name], float(delta[sl].abs().max()), rtol=1e-6, atol=1e-12)
+  # summarize_tree depths: module and layer entries aggregate their tensors
+  mods = {'NerfMLP_0', 'PropMLP_0', 'GloEmbed_0'}
+  assert mods <= set(stats['weight_l2s']) and 'NerfMLP_0/Dense_3' in stats['grad_norms']
+  nerf = [(o, r * c) for n, o, r, c, _ in eng.layout if n.startswith('NerfMLP_0/')]
+  tot = sum(float((p0[o:o + k].double() ** 2).sum()) for o, k in nerf)
+  np.testing.assert_allclose(stats['weight_l2s']['NerfMLP_0'], tot, rtol=1e-5)
+  np.testing.assert_allclose(stats['grad_norms']['NerfMLP_0'],
+                             math.sqrt(sum(float((g_ref[o:o + k].double() ** 2).sum()) for o, k in nerf)), rtol=1e-3)
+  eng.close()
+
+
+def test_weight_decay_mults_is_loud():
+  from nerf_hugs_b200.internal import train_utils
+  config = _config(64)
+  config.weight_decay_mults = {'NerfMLP_0': 0.1}
+  with pytest.raises(NotImplementedError, match='weight_decay_mults'):
+    train_utils.setup_model(config, rng=0, max_rays=128)
+
+
+def test_apply_with_two_parameter_trees_back_to_back():
+  """Model.apply(tree) builds a temporary flat tensor; the packed bf16 operands must follow the tree that
+  is being rendered, also when the allocator hands the next temporary the same address."""
+  from nerf_hugs_b200.internal import train_utils, utils
+  config = _config(64)
+  model, state, _, _, _ = train_utils.setup_model(config, rng=0, max_rays=128)
+  rays, _ = H.make_rays(64, seed=2)
+  r = utils.Rays(**rays)
+  t1, t2 = model.init(1), model.init(2)
+  a1, _ = model.apply(t1, None, r, 0.5, False)
+  a2, _ = model.apply(t2, None, r, 0.5, False)
+  b2, _ = model.apply(model.flat_params(t2), None, r, 0.5, False)
+  b1, _ = model.apply(model.flat_params(t1), None, r, 0.5, False)
+  assert torch.equal(a1[-1]['rgb'], b1[-1]['rgb']) and torch.equal(a2[-1]['rgb'], b2[-1]['rgb'])
+  assert not torch.equal(a1[-1]['rgb'], a2[-1]['rgb'])
+  model.engine.close()
+
+
+def test_embed_idx_out_of_range_is_loud_and_memory_safe():
+  from nerf_hugs_b200.internal import train_utils, utils
+  config = _config(64, glo=4)
+  model, state, _, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=128)
+  rays, gt = H.make_rays(64, seed=2, glo=True)
+  rays['embed_idx'] = rays['embed_idx'] + 100            # table has 16 rows
+  with pytest.raises(IndexError, match='embed_idx'):
+    model.engine.check_embed_idx(rays['embed_idx'])
+  # the kernels clamp / skip: no fault, finite results
+  state, stats, _ = train_pstep(None, state, utils.Batch(rays=utils.Rays(**rays), rgb=gt), 0.1, None)
+  torch.cuda.synchronize()
+  assert np.isfinite(stats['loss']) and torch.isfinite(state.params).all()
+  model.engine.close()

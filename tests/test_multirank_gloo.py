@@ -30,7 +30,9 @@ def _worker(rank, world, port, out_dir):
   stats = torch.tensor([float(rank + 1), 2.0])
   w = train_utils.allreduce_sum_([grad, stats])
   assert w == world
-  st = train_utils._LazyStats(torch.cat([stats, torch.zeros(14 + 9)]), None, 2, w, 1e-3)   # host slot: 16 stats + 9 norms
+  names = ['NerfMLP_0/Dense_0/kernel', 'NerfMLP_0/Dense_0/bias']
+  st = train_utils._LazyStats(torch.cat([stats, torch.zeros(14 + 9 + 5 * len(names))]), None, 2, w, 1e-3, names)   # host slot: 16 stats + 9 norms + 5 per tensor
+  assert 'weight_l2s' in st and set(st['grad_norms']) == {'NerfMLP_0', 'NerfMLP_0/Dense_0', 'NerfMLP_0/Dense_0/kernel', 'NerfMLP_0/Dense_0/bias'}
   np.save(os.path.join(out_dir, f'r{rank}.npy'), np.concatenate([(grad / w).numpy(), [st['loss']]]))
   dist.barrier()
   dist.destroy_process_group()
