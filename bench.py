@@ -31,18 +31,52 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_PROP, N_NERF, WIDTH = 64, 128, 256
+LEVELS, N_PROP, N_NERF, WIDTH, NERF_WIDTH = 2, 64, 128, 256, 256
 FLOPS_PROP_SAMPLE = 651776          # 2*sum(K*N) over the PropMLP(256) Dense layers
-FLOPS_NERF_SAMPLE = 1638400         # NerfMLP(256)
-FLOPS_RAY_FWD = N_PROP * FLOPS_PROP_SAMPLE + N_NERF * FLOPS_NERF_SAMPLE   # 251.4 MFLOP
+
+
+def nerf_sample_flops(w):
+  """2 * sum(K * N) over the NerfMLP Dense layers: 1,638,400 at width 256, 17,344,000 at 1024."""
+  return 2 * (504 * w + 3 * w * w + w * w + (w + 504) * w + 2 * w * w + w + w * 256 + 283 * 128 + 128 * 3)
+
+
+FLOPS_NERF_SAMPLE = nerf_sample_flops(NERF_WIDTH)
+FLOPS_RAY_FWD = (LEVELS - 1) * N_PROP * FLOPS_PROP_SAMPLE + N_NERF * FLOPS_NERF_SAMPLE   # config A: 251.4 MFLOP
 METRIC = 'training rays/s (Mip-NeRF 360, 4096-ray batch, 64+128 samples/ray, 256-wide MLPs)'
 WORKLOAD = ('Mip-NeRF 360 config A (SURVEY §8d): 360.gin geometry, num_levels=2, 64 proposal + 128 NeRF samples/ray, '
             'PropMLP 4x256, NerfMLP 8x256, IPE 504, contract + reciprocal spacing')
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full captures (bytes)
-NCU_DRAM_BYTES = {'chain_fwd_nerf': 1.087201e9 + 2.650518e9, 'chain_bwd_nerf': 0.182906e9 + 2.507198e9,
-                  'wgrad_nerf': 6.827791e9 + 0.006946e9, 'chain_fwd_prop': 0.272877e9 + 0.512431e9,
-                  'wgrad_prop': 1.463295e9 + 0.004237e9}
-NCU_DRAM_SOURCE = 'profiles/r01_ncu_full_train_step_final.json (ncu --set full, one training step, 4096 rays)'
+WORKLOADS = {   # BASELINE config 2 and its variants (SURVEY §8d): levels, proposal samples, NeRF samples, NerfMLP width
+    'A': (2, 64, 128, 256, None),
+    'Aprime': (2, 64, 128, 1024, "variant A' of config A: NerfMLP.net_width = 1024 (every shipped gin), layer-at-a-time path"),
+    'B': (3, 64, 32, 256, 'variant B: the repo-default 3 levels 64 / 64 / 32, NerfMLP 8x256'),
+    '360gin': (3, 64, 32, 1024, 'MipNeRF360/configs/360.gin as shipped: 3 levels 64 / 64 / 32, NerfMLP 8x1024'),
+}
+
+
+def set_workload(name):
+  global LEVELS, N_PROP, N_NERF, NERF_WIDTH, FLOPS_NERF_SAMPLE, FLOPS_RAY_FWD, WORKLOAD
+  LEVELS, N_PROP, N_NERF, NERF_WIDTH, note = WORKLOADS[name]
+  FLOPS_NERF_SAMPLE = nerf_sample_flops(NERF_WIDTH)
+  FLOPS_RAY_FWD = (LEVELS - 1) * N_PROP * FLOPS_PROP_SAMPLE + N_NERF * FLOPS_NERF_SAMPLE
+  if note:
+    WORKLOAD = f'Mip-NeRF 360, {note}; 360.gin geometry (contract + reciprocal spacing), IPE 504, PropMLP 4x256'
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch come from the newest committed `ncu --set full` summary under
+# profiles/ (written by scripts/ncu_summary.py from a capture of THIS workload), never from constants in this file
+NCU_DRAM_FILE = os.path.join(ROOT, 'profiles', 'ncu_dram_bytes.json')
+
+
+def ncu_dram_bytes():
+  try:
+    d = json.load(open(NCU_DRAM_FILE))
+    return d.get('bytes_per_launch', {}), d.get('source')
+  except Exception:
+    return {}, None
+
+
+def workload_config(args, per_gpu, global_batch):
+  """`config` of the JSON line: identical for the CUDA arm and the reference arm (the workload, not the implementation)."""
+  return {'workload': WORKLOAD, 'rays_per_gpu': per_gpu, 'global_batch': global_batch, 'scaling': args.scaling}
 
 
 def synthetic_batch(n_rays, seed, n_cams=100, hw=800, focal=1111.1):
@@ -73,11 +107,11 @@ def gin_bindings(batch_size):
   """Explicit bindings of benchmark config A."""
   return [f'Config.batch_size = {batch_size}', 'Config.near = 0.2', 'Config.far = 1e6', 'Config.patch_size = 1',
           "Config.data_loss_type = 'charb'", 'Config.distortion_loss_mult = 0.01', 'Config.interlevel_loss_mult = 1.0',
-          'Model.raydist_fn = @jnp.reciprocal', 'Model.opaque_background = True', 'Model.num_levels = 2',
+          'Model.raydist_fn = @jnp.reciprocal', 'Model.opaque_background = True', f'Model.num_levels = {LEVELS}',
           f'Model.num_prop_samples = {N_PROP}', f'Model.num_nerf_samples = {N_NERF}',
           'PropMLP.warp_fn = @coord.contract', 'PropMLP.net_depth = 4', f'PropMLP.net_width = {WIDTH}',
           'PropMLP.disable_rgb = True', 'NerfMLP.warp_fn = @coord.contract', 'NerfMLP.net_depth = 8',
-          f'NerfMLP.net_width = {WIDTH}']
+          f'NerfMLP.net_width = {NERF_WIDTH}']
 
 
 class ClockSampler(threading.Thread):
@@ -126,9 +160,9 @@ def cpu_oracle_rate(sample_rays, repeats, threads=None):
   from oracle import mipnerf360 as O
   if threads:
     torch.set_num_threads(threads)
-  ocfg = O.ModelConfig(num_levels=2, num_prop_samples=N_PROP, num_nerf_samples=N_NERF, raydist_fn='reciprocal',
+  ocfg = O.ModelConfig(num_levels=LEVELS, num_prop_samples=N_PROP, num_nerf_samples=N_NERF, raydist_fn='reciprocal',
                        opaque_background=True,
-                       nerf_mlp=O.MLPConfig(net_depth=8, net_width=WIDTH, warp_fn='contract'),
+                       nerf_mlp=O.MLPConfig(net_depth=8, net_width=NERF_WIDTH, warp_fn='contract'),
                        prop_mlp=O.MLPConfig(net_depth=4, net_width=WIDTH, disable_rgb=True, warp_fn='contract'))
   lcfg = O.LossConfig()
   basis = torch.tensor(np.load(os.path.join(ROOT, 'tests', 'golden', 'geopoly_basis.npz'))['icosahedron_2'].T,
@@ -136,7 +170,7 @@ def cpu_oracle_rate(sample_rays, repeats, threads=None):
   params = O.init_params(ocfg, seed=0)
   opt = O.init_opt_state(params)
   rays, rgb = synthetic_batch(sample_rays, seed=123)
-  jit = [torch.rand(sample_rays, 1) for _ in range(2)]
+  jit = [torch.rand(sample_rays, 1) for _ in range(LEVELS)]
   times = []
   for i in range(repeats + 1):
     t0 = time.perf_counter()
@@ -155,20 +189,22 @@ def run_reference(args):
   import torch
   sample = args.ref_rays
   from oracle import mipnerf360 as O  # noqa: F401  (import cost outside the timed region)
-  rate, dt, threads = None, None, None
-  total = args.warmup + args.steps
+  # all host cores, also under torchrun (which exports OMP_NUM_THREADS=1 to every rank)
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  per_gpu = args.rays if args.scaling == 'weak' else args.rays // world
   # one warm-up pass inside cpu_oracle_rate, then `steps` timed repeats (warm-ups beyond 1 add nothing on CPU)
-  rate, dt, threads = cpu_oracle_rate(sample, max(1, args.steps))
+  rate, dt, threads = cpu_oracle_rate(sample, max(1, args.steps), threads=cores)
   line = {
       'impl': 'reference', 'metric': METRIC, 'value': rate, 'unit': 'rays/s', 'n_gpus': args.gpus,
       'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True,
       'scaling': args.scaling, 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-      'config': {'workload': WORKLOAD, 'rays_per_gpu': args.rays, 'global_batch': args.rays,
-                 'sample': f'each step = a bounded sample of {sample} rays of the {args.rays}-ray batch on the host CPU '
-                           f'(torch fp32 port of the reference JAX path; JAX is not installable offline)'},
+      'config': workload_config(args, per_gpu, per_gpu * world),
       'cpu_baseline': {'value': rate, 'unit': 'rays/s', 'cores': threads, 'kind': 'port',
-                       'sample': f'{sample} rays x {args.steps} train steps (fwd+bwd+Adam), torch fp32, '
-                                 f'os.cpu_count()={os.cpu_count()}'},
+                       'sample': f'each step = a bounded sample of {sample} rays of the batch, {args.steps} train '
+                                 f'steps (fwd+bwd+Adam) of the torch fp32 port of the reference JAX path (JAX is not '
+                                 f'installable offline), torch threads = os.cpu_count() = {cores}'},
       'e2e': {'value': rate, 'unit': 'rays/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
       'gpu_launches': 0,
   }
@@ -263,7 +299,8 @@ def run_ours(args):
   if rank == 0:
     peaks = measured_peaks()
     src = f"{peaks['source']} (MEASURED_PEAKS.json)"
-    n_nerf, n_prop = per_gpu * N_NERF, per_gpu * N_PROP
+    n_nerf, n_prop = per_gpu * N_NERF, per_gpu * N_PROP * (LEVELS - 1)
+    wn = NERF_WIDTH
 
     def tensor_line(cls, kernel, flops):
       t = kern_ms.get(cls)
@@ -288,17 +325,29 @@ def run_ours(args):
         tensor_line('chain_fwd_nerf', 'mlp_pp_kernel<train, cta_pair> NerfMLP forward chain (tcgen05 cta_group::2)',
                     n_nerf * FLOPS_NERF_SAMPLE),
         tensor_line('chain_bwd_nerf', 'mlp_pp_kernel<train, cta_pair> NerfMLP dgrad chain',
-                    n_nerf * 2 * (7 * 256 * 256 + 256 * 256 + 256 * 128)),
-        hbm_line('wgrad_nerf', 'wgrad_kernel NerfMLP weight gradients (tcgen05, MN-major operands)', wg_bytes_nerf),
+                    n_nerf * 2 * (7 * wn * wn + wn * 256 + 256 * 128)),
+        (hbm_line('wgrad_nerf', 'wgrad_kernel NerfMLP weight gradients (tcgen05, MN-major operands)', wg_bytes_nerf)
+         if wn == 256 else tensor_line('wgrad_nerf', 'wgrad_kernel NerfMLP weight gradients, one launch per layer',
+                                       n_nerf * FLOPS_NERF_SAMPLE)),
         tensor_line('chain_fwd_prop', 'mlp_pp_kernel<train, cta_pair> PropMLP forward chain', n_prop * FLOPS_PROP_SAMPLE),
         hbm_line('wgrad_prop', 'wgrad_kernel PropMLP weight gradients', wg_bytes_prop),
     ]
+    # the per-ray kernels (HBM / latency bound): algorithmic bytes = what one launch must read and write
+    samp_bytes = per_gpu * ((2 * (N_PROP + 1) * 4 + 8) + ((2 * N_PROP + 1) * 4 + 2 * (N_NERF + 1) * 4 + 8))
+    comp_bytes = per_gpu * (N_PROP * 8 + (N_PROP + 1) * 4 + 12                                   # proposal composite
+                            + N_NERF * 36 + 2 * (N_NERF + 1) * 4 + 28                            # final loss + backward
+                            + N_PROP * 8 + 2 * (N_PROP + 1) * 4 + N_NERF * 4 + (N_NERF + 1) * 4)  # interlevel + backward
+    if LEVELS == 2:
+      lines += [hbm_line('sample', 'resample_kernel x2 (dilate + resample, one warp per ray)', samp_bytes),
+                hbm_line('composite_loss', 'composite_kernel + final_loss_bwd_kernel + prop_loss_bwd_kernel + reductions',
+                         comp_bytes)]
     lines = [l for l in lines if l['ms_per_launch']]
     dom = max(lines, key=lambda l: l['ms_per_launch'])
+    dram, dram_src = ncu_dram_bytes()
     for l in lines:
-      l['traffic'] = NCU_DRAM_BYTES.get(l['class']) if per_gpu == 4096 else None
+      l['traffic'] = dram.get(l['class']) if per_gpu == 4096 else None
     roofline = dict(dom)
-    roofline['traffic_source'] = NCU_DRAM_SOURCE
+    roofline['traffic_source'] = dram_src
     roofline['dominant_by'] = 'largest CUDA-event time per step among the kernel classes'
     roofline['step_tflops_3x_convention'] = 3 * FLOPS_RAY_FWD * per_gpu / (ms / args.steps * 1e-3) / 1e12
     roofline['step_frac_of_tensor_peak'] = roofline['step_tflops_3x_convention'] / peaks['bf16_sustained']
@@ -314,9 +363,11 @@ def run_ours(args):
         'metric': METRIC, 'value': value, 'unit': 'rays/s', 'n_gpus': world, 'steps': args.steps, 'warmup': W,
         'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': args.scaling, 'vs_baseline': None,
         'dtype': 'bf16', 'data': 'synthetic',
-        'config': {'workload': WORKLOAD, 'rays_per_gpu': per_gpu, 'global_batch': global_batch, 'parallelism': f'ray-sharded dp{world}',
-                   'l2_policy': 'per-step working set (>5 GB of saved activations) >> 126 MB L2; 4 distinct batches cycled',
-                   'precision': 'bf16 operands, fp32 accumulate (tcgen05); fp32 sampling/compositing/losses/Adam'},
+        'config': workload_config(args, per_gpu, global_batch),
+        'arm': {'parallelism': f'ray-sharded dp{world}, one process per GPU, NerfMLP gradient all-reduce overlapped with '
+                               f'the proposal backward',
+                'l2_policy': 'per-step working set (>5 GB of saved activations) >> 126 MB L2; 4 distinct batches cycled',
+                'precision': 'bf16 operands, fp32 accumulate (tcgen05); fp32 sampling/compositing/losses/Adam'},
         'e2e': {'value': e2e, 'unit': 'rays/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': 64 + 36,
                 'ms_per_step': ms_e2e / args.steps, 'last_loss': float(last_loss)},
         'gpu_launches': int(launches),
@@ -341,7 +392,9 @@ def main():
   ap.add_argument('--scaling', default='weak', choices=['weak', 'strong'])
   ap.add_argument('--ref-rays', type=int, default=128, help='bounded CPU sample (rays per step)')
   ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--config', default='A', choices=sorted(WORKLOADS), help='A = BASELINE config 2 (default); variants of SURVEY §8d')
   args = ap.parse_args()
+  set_workload(args.config)
   if args.impl == 'reference':
     run_reference(args)
   else:

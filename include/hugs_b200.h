@@ -194,6 +194,16 @@ int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* ray
                        const float* rgb_gt, int32_t n_rays, float train_frac, const float* jitter,
                        const hugs_loss_cfg* loss, float* grad_out, float* stats_out, void* stream);
 
+/* Train-mode sampling randomness without a jitter tensor: when `jitter` is NULL in hugs_loss_and_grad and a non-zero
+ * seed was set, the sampling kernel draws one uniform per (level, ray) from a counter-based hash of (seed, counter)
+ * (the role of `rng, key = random.split(rng)` in train_step, train_utils.py:408; the stream is this library's own —
+ * threefry cannot be reproduced without JAX).  seed == 0 switches it off. */
+int hugs_set_train_rng(hugs_handle* h, uint64_t seed, uint64_t counter);
+/* Multi-GPU overlap: `cuda_event` (a cudaEvent_t, or NULL to clear) is recorded on the call's stream inside
+ * hugs_loss_and_grad as soon as the NerfMLP_0 / GloEmbed_0 part of grad_out is final, i.e. before the proposal levels'
+ * backward pass, so that the all-reduce of that part (jax.lax.pmean, train_utils.py:457-458) can start early. */
+int hugs_set_grad_ready_event(hugs_handle* h, void* cuda_event);
+
 /* clip_gradients + nan_to_num + optax.adam apply (train_utils.py:351-369,464-468) on the
  * (already all-reduced) flat gradient.  norms_out (optional) fp32[9]: {grad norm, abs-max, clip multiplier} per module. */
 int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
@@ -223,6 +233,9 @@ typedef struct {
   const float* fars;           /* packed [pixels], NULL => `far` */
   const int32_t* embed_idxs;   /* [n_cams], NULL => camera index */
   float near, far;
+  const float* distortion;     /* [6] k1 k2 k3 k4 p1 p2 (Dataset.distortion_params, camera_utils.py:460-494), NULL => none */
+  int32_t camtype;             /* 0 perspective, 1 fisheye (camera_utils.ProjectionType) */
+  int32_t reserved_;
 } hugs_camera_set;
 
 /* utils.Rays + Batch.rgb as writable struct-of-arrays device pointers, each [n_rays, C] contiguous. */
@@ -236,7 +249,7 @@ typedef struct {
 } hugs_ray_batch;
 
 /* Dataset._make_ray_batch (datasets.py:446-482) -> camera_utils.cast_ray_batch -> pixels_to_rays
- * (camera_utils.py:503-607,610-669) for perspective cameras without lens distortion / NDC:
+ * (camera_utils.py:503-607,610-669) for perspective and fisheye cameras with optional lens distortion (no NDC):
  * rays, HuGS static mask, near/far and ground-truth colours of pixels (cam_idx[i], pix_y[i], pix_x[i]). */
 int hugs_make_ray_batch(const hugs_camera_set* cams, const int32_t* cam_idx, const int32_t* pix_x,
                         const int32_t* pix_y, int32_t n_rays, const hugs_ray_batch* out, void* stream);

@@ -64,7 +64,8 @@ class LevelOut(C.Structure):
 class CameraSet(C.Structure):
   _fields_ = [(n, C.c_void_p) for n in ('pixtocams', 'camtoworlds', 'heights', 'widths', 'pixel_offset', 'images',
                                         'images_u8', 'static_masks', 'nears', 'fars', 'embed_idxs')] + \
-             [('near', C.c_float), ('far', C.c_float)]
+             [('near', C.c_float), ('far', C.c_float), ('distortion', C.c_void_p), ('camtype', C.c_int32),
+              ('reserved_', C.c_int32)]
 
 
 class RayBatch(C.Structure):
@@ -90,6 +91,8 @@ SYMBOLS = {
     'hugs_debug_encode_bf16': (C.c_int, [_P, C.POINTER(Rays), _P, _I, _I, _I, _P, _P]),
     'hugs_forward': (C.c_int, [_P, _P, C.POINTER(Rays), _I, _F, _P, _I, _I, C.POINTER(LevelOut), _P]),
     'hugs_loss_and_grad': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _F, _P, C.POINTER(LossCfg), _P, _P, _P]),
+    'hugs_set_train_rng': (C.c_int, [_P, C.c_uint64, C.c_uint64]),
+    'hugs_set_grad_ready_event': (C.c_int, [_P, _P]),
     'hugs_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P]),
     'hugs_adam_step_stats': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P, _P]),
     'hugs_make_ray_batch': (C.c_int, [C.POINTER(CameraSet), _P, _P, _P, _I, C.POINTER(RayBatch), _P]),

@@ -21,6 +21,8 @@ SOURCES = [
     ('mlp_tc.cu', []),
     ('mlp_pp.cu', []),
     ('wgrad_tc.cu', []),
+    ('dense_tc.cu', []),
+    ('layered.cu', []),
     ('optim.cu', []),
     ('raygen.cu', []),
 ]

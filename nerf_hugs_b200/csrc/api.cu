@@ -331,7 +331,7 @@ namespace hugs {
 namespace {
 
 int run_level_sampling(hugs_handle* h, int l, const hugs_rays* rays, int n, float train_frac,
-                       const float* jitter, float s_near, float* prod_samples, cudaStream_t st) {
+                       const float* jitter, uint64_t rng_key, float s_near, float* prod_samples, cudaStream_t st) {
   const hugs_model_desc& d = h->d;
   const int S = h->samples(l);
   ResampleArgs a;
@@ -348,7 +348,11 @@ int run_level_sampling(hugs_handle* h, int l, const hugs_rays* rays, int n, floa
   a.anneal = d.anneal_slope > 0 ? (d.anneal_slope * train_frac) / ((d.anneal_slope - 1.f) * train_frac + 1.f) : 1.f;
   a.padding = d.resample_padding;
   if (jitter) { a.u_base = h->u_train[l]; a.jitter = jitter + (size_t)l * n; a.max_jitter = h->max_jitter[l]; }
-  else        { a.u_base = h->u_det[l]; }
+  else if (rng_key) {
+    a.u_base = h->u_train[l]; a.max_jitter = h->max_jitter[l];
+    a.jitter_key = rng_key * 0xD1342543DE82EF95ull + (uint64_t)(l + 1);      // one independent stream per level
+    if (a.jitter_key == 0) a.jitter_key = 1;
+  } else { a.u_base = h->u_det[l]; }
   a.s_out = h->sdist[l]; a.t_out = h->tdist[l];
   a.raydist_fn = d.raydist_fn; a.near = rays->near; a.far = rays->far;
   ProfScope ps(h, HUGS_K_SAMPLE, st);
@@ -422,6 +426,8 @@ float s_near_of(const hugs_model_desc& d, float train_frac) {
 int forward_levels(hugs_handle* h, const float* params, const hugs_rays* rays, int n, float train_frac,
                    const float* jitter, int compute_extras, int zero_glo, const hugs_level_out* out,
                    bool training, cudaStream_t st) {
+  // training without a jitter tensor: draws come from the handle's counter-based stream (hugs_set_train_rng), if any
+  const uint64_t rng_key = (training && !jitter) ? h->train_rng_key : 0;
   const hugs_model_desc& d = h->d;
   int rc;
   const float s_near = s_near_of(d, train_frac);
@@ -434,7 +440,7 @@ int forward_levels(hugs_handle* h, const float* params, const hugs_rays* rays, i
   for (int l = 0; l < d.num_levels; ++l) {
     const bool is_prop = l < d.num_levels - 1;
     const int S = h->samples(l);
-    if ((rc = run_level_sampling(h, l, rays, n, train_frac, jitter, s_near, &prod, st))) return rc;
+    if ((rc = run_level_sampling(h, l, rays, n, train_frac, jitter, rng_key, s_near, &prod, st))) return rc;
     if (d.precision == HUGS_PRECISION_FP32) rc = run_level_mlp_fp32(h, l, params, rays, n, st);
     else rc = tc_mlp_forward(h, l, rays, n, training, st);
     if (rc) return rc;
@@ -536,7 +542,25 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
   delete ps_loss; ps_loss = nullptr;
 
   HUGS_CUDA(cudaMemsetAsync(grad_out, 0, sizeof(float) * h->n_params, st));
-  for (int l = L - 1; l >= 0; --l)
+  for (int l = L - 1; l >= 0; --l) {
     if ((rc = tc_mlp_backward(h, l, rays, n, grad_out, st))) return rc;
+    // NerfMLP_0 and GloEmbed_0 gradients are final here: a caller-provided event lets the all-reduce of that part of the
+    // gradient start while the proposal levels are still in their backward pass
+    if (l == L - 1 && h->grad_ready_event) HUGS_CUDA(cudaEventRecord(h->grad_ready_event, st));
+  }
+  return HUGS_OK;
+}
+
+HUGS_API int hugs_set_train_rng(hugs_handle* h, uint64_t seed, uint64_t counter) {
+  HUGS_REQUIRE(h, "hugs_set_train_rng: null handle");
+  // seed == 0 switches the in-kernel draws off again (deterministic sampling when no jitter tensor is passed)
+  h->train_rng_key = seed == 0 ? 0 : (seed ^ 0xA0761D6478BD642Full) * 0xE7037ED1A0B428DBull + counter * 0x8EBC6AF09C88C6E3ull + 1;
+  if (seed != 0 && h->train_rng_key == 0) h->train_rng_key = 1;
+  return HUGS_OK;
+}
+
+HUGS_API int hugs_set_grad_ready_event(hugs_handle* h, void* cuda_event) {
+  HUGS_REQUIRE(h, "hugs_set_grad_ready_event: null handle");
+  h->grad_ready_event = (cudaEvent_t)cuda_event;
   return HUGS_OK;
 }

@@ -1,0 +1,286 @@
+// Layer-at-a-time tensor-core Dense kernels for MLP widths the chain kernel (mlp_pp.cu) does not hold in shared memory:
+// NerfMLP.net_width = 512 / 1024, i.e. every non-debug gin of the reference (MipNeRF360/configs/360.gin:14-16).
+//
+//   Y[M, N] = epilogue( [A0 | A1][M, K] . W[N, K]^T )          (bf16 x bf16 -> fp32 in TMEM)
+//
+// One persistent CTA pair (cluster of 2, tcgen05 cta_group::2) per SM pair walks output tiles of 256 rows (128 per CTA) x
+// BN <= 256 columns, N fastest so that the pairs working on one row block re-read its A panels from L2.  Per K panel of
+// 64: TMA loads this CTA's 128 A rows and its half of the BN weight rows into a 4-stage ring (completion on the leader's
+// barrier), the leader issues 4 MMAs (M = 256, N = BN, K = 16), two 256-column accumulators alternate so that the
+// epilogue of tile i runs under the MMAs of tile i + 1.  Epilogues: bias + ReLU / linear / per-ray view bias -> bf16 ->
+// swizzled staging panels -> TMA store; fp32 head columns (raw density / raw rgb); backward: ReLU gate from the saved
+// activation (+ the rank-1 density-head term) -> bf16 dZ.
+//
+// Reference semantics: models.py:437-519 (MLP.__call__) and its jax.value_and_grad (train_utils.py:454-455).
+#include <algorithm>
+
+#include "tc_device.cuh"
+#include "dense_tc.h"
+
+namespace hugs {
+namespace {
+
+constexpr int kDStages = 4;
+constexpr int kDStageBytes = 32768;        // A: 128 rows x 64 (16 KB) | B: <= 128 rows x 64 (16 KB)
+constexpr int kDOutPanels = 4;             // staging: this CTA's 128 rows x 256 output columns
+constexpr int kDEpiWarps = 8;
+constexpr int kDThreads = (2 + kDEpiWarps) * 32;
+constexpr int kDSmem = 1024 + kDStages * kDStageBytes + kDOutPanels * kPanelBytes + 256;
+static_assert(kDSmem <= 232448, "shared memory budget");
+
+__global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_constant__ DenseParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* ring = base;
+  uint8_t* stage_out = base + kDStages * kDStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kDOutPanels * kPanelBytes);
+  uint64_t* full = bars; uint64_t* empty = bars + kDStages;
+  uint64_t* acc_full = bars + 2 * kDStages; uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  const uint32_t ring_u32 = ptx::smem_u32(ring);
+  const uint32_t full_u32 = ptx::smem_u32(full), empty_u32 = ptx::smem_u32(empty);
+  const uint32_t accfull_u32 = ptx::smem_u32(acc_full), accempty_u32 = ptx::smem_u32(acc_empty);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.a_map[0]); ptx::prefetch_tmap(&p.b_map); ptx::prefetch_tmap(&p.out_map);
+    for (int i = 0; i < kDStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * kDEpiWarps); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_cg2(tmem_ptr, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const int n_tiles = p.m_tiles * p.n_tiles;
+  const int kp_total = p.a_kp[0] + p.a_kp[1];
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = pair; t < n_tiles; t += n_pairs) {
+        const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+        const int bn = p.tile_bn[nt], n0 = p.tile_n0[nt];
+        const CUtensorMap* bmap = bn == 256 ? &p.b_map : (bn == 128 ? &p.b_map_64 : &p.b_map_8);
+        const uint32_t bytes = 16384u + (uint32_t)(bn / 2) * 128u;
+        const int row = mt * 256 + rank * 128;
+        int kcol_w = p.b_col0;
+        for (int seg = 0; seg < 2; ++seg) {
+          for (int kp = 0; kp < p.a_kp[seg]; ++kp) {
+            ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+            if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
+            const uint32_t bar = ptx::mapa_u32(full_u32 + stage * 8, 0);
+            ptx::tma_load_2d_cg2(ring_u32 + stage * kDStageBytes, &p.a_map[seg], bar, p.a_col0[seg] + kp * 64,
+                                 p.a_row0[seg] + row);
+            ptx::tma_load_2d_cg2(ring_u32 + stage * kDStageBytes + 16384, bmap, bar, kcol_w, p.b_row0 + n0 + rank * (bn / 2));
+            kcol_w += 64;
+            if (++stage == kDStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t ae_phase = 0;     // bit s: parity of the next acc_empty phase of accumulator s
+      int it = 0;
+      for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+        const int nt = t % p.n_tiles;
+        const int bn = p.tile_bn[nt];
+        const uint32_t idesc = ptx::make_idesc_bf16(256, bn, 0, 0);
+        const int as = it & 1;
+        if (it >= 2) {           // the epilogue of the tile that used this accumulator two tiles ago has drained it
+          ptx::mbar_wait_u32(accempty_u32 + as * 8, (ae_phase >> as) & 1u);
+          ae_phase ^= 1u << as;
+          ptx::tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int kp = 0; kp < kp_total; ++kp) {
+          ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+          ptx::tc_fence_after();
+          const uint64_t da = ptx::desc_from(kDescHi, ring_u32 + stage * kDStageBytes);
+          const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kDStageBytes + 16384);
+          ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, kp > 0 ? 1u : 0u);
+          ptx::mma_bf16_ss_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
+          ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
+          ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
+          ptx::mma_commit_mc2_u32(empty_u32 + stage * 8);
+          if (++stage == kDStages) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit_mc2_u32(accfull_u32 + as * 8);
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int ew = warp - 2;
+    const int quarter = ew & 3, half = ew >> 2;
+    const int row = quarter * 32 + lane;                // row inside this CTA's 128-row block == TMEM lane
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool store_leader = ew == 0 && lane == 0;
+    uint32_t af_phase = 0;
+    int it = 0;
+    float v[32];
+    for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
+      const int mt = t / p.n_tiles, nt = t % p.n_tiles;
+      const int bn = p.tile_bn[nt], n0 = p.tile_n0[nt], epi = p.tile_epi[nt];
+      const int as = it & 1;
+      const int grow = mt * 256 + rank * 128 + row;     // row of the GEMM (sample index relative to the level)
+      const bool valid = grow < p.m_rows;
+      ptx::mbar_wait_u32(accfull_u32 + as * 8, (af_phase >> as) & 1u);
+      af_phase ^= 1u << as;
+      ptx::tc_fence_after();
+      const uint32_t acc_addr = lane_addr + (uint32_t)(as * 256);
+      if (epi == DE_HEAD_F32) {
+        // fp32 head columns: raw_out[row * raw_c + raw_chan0 + c] = acc[c] + bias[n0 + c], c < raw_nchan
+        if (half == 0) {
+          uint32_t r4[4];
+          ptx::tmem_ld4(acc_addr, r4);
+          ptx::tmem_ld_wait();
+          if (valid)
+            for (int c = 0; c < p.raw_nchan; ++c)
+              p.raw_out[(size_t)grow * p.raw_c + p.raw_chan0 + c] = __uint_as_float(r4[c]) + p.bias[n0 + c];
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(accempty_u32 + as * 8, 0));
+        continue;
+      }
+      // the previous tile's TMA stores must have read the staging panels before they are rewritten
+      if (store_leader) ptx::tma_wait_group_read<0>();
+      asm volatile("bar.sync 1, %0;" ::"n"(kDEpiWarps * 32) : "memory");
+      const int cols_per_half = bn / 2;                 // 128 | 64
+      for (int c0 = 0; c0 < cols_per_half; c0 += 32) {
+        const int col = half * cols_per_half + c0;      // column inside the tile
+        load_acc32(acc_addr + (uint32_t)col, v);
+        const int n = n0 + col;                         // output column of the GEMM
+        if (epi == DE_RELU || epi == DE_LINEAR) {
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+          for (int c = 0; c < 8; ++c) {
+            const float4 b = __ldg(b4 + c);
+            v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+          }
+        } else if (epi == DE_VIEW) {
+          if (valid) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(grow / p.S) * p.view_ld + n);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 b = __ldg(b4 + c);
+              v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+            }
+          }
+        } else if (epi == DE_BWD_RELU) {
+          if (p.rank1_row) {
+            const float dd = valid ? __bfloat162float(__float2bfloat16(p.rank1_row[(size_t)grow * p.rank1_stride])) : 0.f;
+            const float4* w4 = reinterpret_cast<const float4*>(p.rank1_col + n);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const float4 w = __ldg(w4 + c);
+              v[c * 4 + 0] = fmaf(dd, w.x, v[c * 4 + 0]); v[c * 4 + 1] = fmaf(dd, w.y, v[c * 4 + 1]);
+              v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
+            }
+          }
+          // ReLU gate from the saved (post-ReLU, hence >= 0) bf16 activation; padding rows carry no gradient
+          uint4 mk[4];
+          if (valid) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.mask_act + ((size_t)p.mask_row0 + grow) * p.mask_ld + n);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) mk[c] = __ldg(src + c);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) mk[c] = make_uint4(0u, 0u, 0u, 0u);
+          }
+          apply_mask32(mk, v);
+        } else if (epi == DE_BWD_LINEAR) {
+          if (!valid) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = 0.f;
+          }
+        }
+        uint8_t* panel = stage_out + (col >> 6) * kPanelBytes;
+        const int chunk0 = (col & 63) >> 3;
+        if (epi == DE_RELU || epi == DE_VIEW) store_half32<true>(panel, row, chunk0, v);
+        else store_half32<false>(panel, row, chunk0, v);
+      }
+      // accumulator drained: the MMA issuer may reuse it (tile it + 2)
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(accempty_u32 + as * 8, 0));
+      ptx::fence_proxy_async();
+      asm volatile("bar.sync 1, %0;" ::"n"(kDEpiWarps * 32) : "memory");
+      if (store_leader) {
+        for (int pn = 0; pn < bn / 64; ++pn)
+          ptx::tma_store_2d(&p.out_map, stage_out + pn * kPanelBytes, p.out_col0 + n0 + pn * 64,
+                            p.out_row0 + mt * 256 + rank * 128);
+        ptx::tma_commit_group();
+      }
+    }
+    if (store_leader) ptx::tma_wait_group<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_cg2(tmem_base, 512);
+}
+
+// dZ_view = (d_rgb . W_rgb^T) * [view activation > 0] (bf16), plus the head-gradient rows (d_r, d_g, d_b, d_density)
+// of the head weight-gradient GEMMs.  CUDA cores: K = 3.
+__global__ void __launch_bounds__(128) bwd_start_kernel(const float* d_raw, const __nv_bfloat16* view_act, int view_ld,
+                                                        const float* w_rgb /* [128][3] fp32, bf16-rounded */, int n_samples,
+                                                        int n_rows_pad, __nv_bfloat16* dz_view, int dz_ld,
+                                                        __nv_bfloat16* drgb) {
+  const int s = blockIdx.x, c = threadIdx.x;
+  if (s >= n_rows_pad) return;
+  float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (s < n_samples) dr = reinterpret_cast<const float4*>(d_raw)[s];
+  if (c == 0) {
+    uint4* dst = reinterpret_cast<uint4*>(drgb + (size_t)s * kHeadCols);
+    dst[0] = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
+  }
+  const float d0 = __bfloat162float(__float2bfloat16(dr.y)), d1 = __bfloat162float(__float2bfloat16(dr.z)),
+              d2 = __bfloat162float(__float2bfloat16(dr.w));
+  float g = d0 * w_rgb[c * 3] + d1 * w_rgb[c * 3 + 1] + d2 * w_rgb[c * 3 + 2];
+  const bool on = s < n_samples && __bfloat162float(view_act[(size_t)s * view_ld + c]) > 0.f;
+  dz_view[(size_t)s * dz_ld + c] = __float2bfloat16(on ? g : 0.f);
+}
+
+}  // namespace
+
+int dense_tc_init() {
+  HUGS_CUDA(cudaFuncSetAttribute(dense_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDSmem));
+  return HUGS_OK;
+}
+
+int dense_tc_launch(const DenseParams& p, int num_sms, cudaStream_t st) {
+  const int n_tiles = p.m_tiles * p.n_tiles;
+  if (n_tiles <= 0) return HUGS_OK;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * std::min(n_tiles, num_sms / 2));
+  cfg.blockDim = dim3(kDThreads);
+  cfg.dynamicSmemBytes = kDSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  HUGS_CUDA(cudaLaunchKernelEx(&cfg, dense_tc_kernel, p));
+  ++g_launch_count;
+  return HUGS_OK;
+}
+
+int launch_bwd_start(const float* d_raw, const __nv_bfloat16* view_act, int view_ld, const float* w_rgb, int n_samples,
+                     int n_rows_pad, __nv_bfloat16* dz_view, int dz_ld, __nv_bfloat16* drgb, cudaStream_t st) {
+  if (n_rows_pad <= 0) return HUGS_OK;
+  bwd_start_kernel<<<n_rows_pad, 128, 0, st>>>(d_raw, view_act, view_ld, w_rgb, n_samples, n_rows_pad, dz_view, dz_ld, drgb);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+}  // namespace hugs

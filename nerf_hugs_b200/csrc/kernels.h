@@ -21,6 +21,7 @@ struct ResampleArgs {
   const float* u_base = nullptr;  // [ns]
   const float* jitter = nullptr;  // [n] uniform draws in [0,1) or nullptr
   float max_jitter = 0.f;
+  uint64_t jitter_key = 0;        // != 0 (and jitter == nullptr): one draw per ray from hash(jitter_key, ray) in the kernel
   float* s_out = nullptr;         // [n, ns+1]
   float* t_out = nullptr;         // [n, ns+1] metric distances (optional)
   float* centers_out = nullptr;   // [n, ns] (optional)

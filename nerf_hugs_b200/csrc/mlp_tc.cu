@@ -11,6 +11,7 @@
 #include "encode.cuh"
 #include "ptx.cuh"
 #include "tc_device.cuh"
+#include "dense_tc.h"
 #include "tc_internal.h"
 
 namespace hugs {
@@ -328,10 +329,14 @@ int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, i
 int tc_create(hugs_handle* h) {
   const hugs_model_desc& d = h->d;
   const int ndeg = d.max_deg_point - d.min_deg_point;
-  if (d.nerf_width != kW || (d.num_levels > 1 && d.prop_width != kW) || d.bottleneck_width != kW ||
+  // NerfMLP: 256 wide -> chain kernel; 512 / 768 / 1024 ... -> layer-at-a-time GEMMs.  PropMLP: 256 (every shipped gin).
+  const bool nerf_layered = d.nerf_width != kW;
+  if ((nerf_layered && (d.nerf_width % 256 != 0 || d.nerf_width > 2048 || d.precision == HUGS_PRECISION_TC_SPLIT)) ||
+      (d.num_levels > 1 && d.prop_width != kW) || d.bottleneck_width != kW ||
       d.view_width != 128 || h->feat_dim > kFeatPad || (ndeg % 4) != 0 || ndeg > 16) {
-    set_error("tensor-core path supports net_width 256, bottleneck 256, view width 128 and <= 512 IPE features "
-              "with a degree count divisible by 4 (got widths %d/%d/%d/%d, %d features); use HUGS_PRECISION_FP32",
+    set_error("tensor-core path supports NerfMLP.net_width 256 (chain kernel, both precision modes) or 512 / 768 / 1024 "
+              "(layer-at-a-time kernels, bf16 mode), PropMLP.net_width 256, bottleneck 256, view width 128 and <= 512 IPE "
+              "features with a degree count divisible by 4 (got widths %d/%d/%d/%d, %d features); use HUGS_PRECISION_FP32",
               d.nerf_width, d.prop_width, d.bottleneck_width, d.view_width, h->feat_dim);
     return HUGS_ERR_UNSUPPORTED;
   }
@@ -347,7 +352,7 @@ int tc_create(hugs_handle* h) {
   tc->split = d.precision == HUGS_PRECISION_TC_SPLIT;
   const int parts = tc->split ? 2 : 1;       // hi (+ lo) halves of every bf16 operand tensor, stacked along the rows
   int rc;
-  if ((rc = build_mlp_schedule(h, h->nerf, &tc->nerf))) return rc;
+  if (!nerf_layered && (rc = build_mlp_schedule(h, h->nerf, &tc->nerf))) return rc;
   if (d.num_levels > 1 && (rc = build_mlp_schedule(h, h->prop, &tc->prop))) return rc;
   for (TcMlp* m : {&tc->nerf, &tc->prop}) {
     if (!m->present) continue;
@@ -367,9 +372,9 @@ int tc_create(hugs_handle* h) {
   int frow = 0, srow = 0;
   for (int l = 0; l < L; ++l) {
     const int S = h->samples(l);
-    tc->cap[l] = (int)((((long long)d.max_rays * S + kTileM - 1) / kTileM) * kTileM);
+    tc->cap[l] = (int)((((long long)d.max_rays * S + 255) / 256) * 256);     // whole 256-row GEMM tiles
     tc->feat_row0[l] = frow; frow += tc->cap[l];
-    const int n_saved = (l == L - 1) ? d.nerf_depth + 2 : d.prop_depth;
+    const int n_saved = (l == L - 1) ? (nerf_layered ? 0 : d.nerf_depth + 2) : d.prop_depth;
     tc->save_row0[l] = srow; srow += n_saved * tc->cap[l];
   }
   tc->total_feat_rows = frow; tc->total_save_rows = srow;
@@ -377,6 +382,8 @@ int tc_create(hugs_handle* h) {
   for (int l = 0; l < L; ++l) tc->drgb_rows = std::max(tc->drgb_rows, tc->cap[l]);
   if ((rc = tc_alloc(h, &tc->viewbias, (size_t)d.max_rays * 128))) return rc;
   if ((rc = make_map(&tc->map_feat, tc->feat, (long long)parts * frow, kFeatPad, 128))) return rc;
+  HUGS_CUDA(cudaMemset(tc->feat, 0, (size_t)parts * frow * kFeatPad * 2));
+  if (nerf_layered && (rc = layered_create(h, h->nerf, L - 1, &tc->nerf_layered))) return rc;
   return pp_init(h);
 }
 
@@ -405,12 +412,17 @@ int tc_ensure_training(hugs_handle* h) {
       (rc = make_map(&tc->map_dz, tc->dz, (long long)(parts * srow), kW, 128)))
     return rc;
   if ((rc = wgrad_create(h))) return rc;
+  if (tc->nerf_layered && (rc = layered_ensure_training(h, tc->nerf_layered))) return rc;
   tc->train_ready = true;
   return HUGS_OK;
 }
 
 void tc_destroy(hugs_handle* h) {
-  if (h->tc) { wgrad_destroy(h); delete h->tc; h->tc = nullptr; }
+  if (h->tc) {
+    wgrad_destroy(h);
+    if (h->tc->nerf_layered) layered_destroy(h->tc->nerf_layered);
+    delete h->tc; h->tc = nullptr;
+  }
 }
 
 int tc_pack_params(hugs_handle* h, const float* params, cudaStream_t st) {
@@ -418,6 +430,7 @@ int tc_pack_params(hugs_handle* h, const float* params, cudaStream_t st) {
   HUGS_REQUIRE(tc, "tensor-core state missing");
   PackArgs a;
   int rc;
+  if (tc->nerf_layered && (rc = layered_pack(h, tc->nerf_layered, params, st))) return rc;
   for (int which = 0; which < 2; ++which) {
     const TcMlp& m = which == 0 ? tc->nerf : tc->prop;
     if (!m.present) continue;
@@ -439,7 +452,9 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
   const MlpViews& mv = is_prop ? h->prop : h->nerf;
   const int S = h->samples(level);
   const int n_samples = n_rays * S;
-  const int n_tiles = (n_samples + kTileM - 1) / kTileM;
+  const bool layered = !is_prop && tc->nerf_layered != nullptr;
+  // rows of the feature tensor written (zeros beyond n_samples): whole chain tiles / whole 256-row GEMM tiles
+  const int n_tiles = layered ? 2 * ((n_samples + 255) / 256) : (n_samples + kTileM - 1) / kTileM;
   const int contract = is_prop ? d.prop_contract : d.nerf_contract;
   __nv_bfloat16* feat = tc->feat + (size_t)tc->feat_row0[level] * kFeatPad;
   // 1. bf16 IPE features (own column order) -> feat[level]
@@ -469,14 +484,16 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
                                                                128, n_rays, tc->split ? 1 : 0, tc->viewbias);
     HUGS_LAUNCH_CHECK();
   }
-  // 3. fused chain
+  // 3. fused chain (or one GEMM per layer)
   ProfScope ps(h, is_prop ? HUGS_K_CHAIN_FWD_PROP : HUGS_K_CHAIN_FWD_NERF, st);
+  if (layered) return layered_forward(h, tc->nerf_layered, level, n_rays, training, st);
   return pp_launch(h, level, n_rays, training ? 1 : 0, st);
 }
 
 int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays, float* grad, cudaStream_t st) {
   (void)rays;
   const bool is_prop = level < h->d.num_levels - 1;
+  if (!is_prop && h->tc->nerf_layered) return layered_backward(h, h->tc->nerf_layered, level, n_rays, grad, st);
   {
     ProfScope ps(h, is_prop ? HUGS_K_CHAIN_BWD_PROP : HUGS_K_CHAIN_BWD_NERF, st);
     int rc = pp_launch(h, level, n_rays, 2, st);

@@ -57,24 +57,37 @@ __global__ void grad_norm_final_kernel(const float* partial, float max_norm, flo
   out[m * 3 + 2] = max_norm > 0.f ? fminf(1.f, max_norm / (kF32Eps + sqrtf(c))) : 1.f;
 }
 
+constexpr int kAdamPerThread = 8;            // elements per thread: a block covers 2048 consecutive parameters
+
 // kStats: additionally accumulates, per parameter tensor, {sum w^2 (before the update), sum g^2, max |g| (the averaged,
 // unclipped gradient), sum delta^2, max |delta| (the applied update)} -> tstats[tensor][5]: the stats['weight_l2s'],
 // ['grad_norms'], ['grad_maxes'], ['opt_update_norms'], ['opt_update_maxes'] trees of train_utils.py:442,461-462,470-473
-// come out of the pass that already touches every parameter.
+// come out of the pass that already touches every parameter.  A block that lies inside one tensor (almost all do)
+// reduces in shared memory and issues one set of five atomics.
 template <bool kStats>
 __global__ void __launch_bounds__(256) adam_kernel(float* params, const float* grad, float* mu, float* nu,
                                                    int64_t n, int64_t e0, int64_t e1, const float* norms,
                                                    hugs_adam_cfg cfg, float bc1, float bc2,
                                                    const int64_t* tensor_ends, int n_tensors, float* tstats) {
   __shared__ int64_t ends[128];
+  __shared__ float red[5][8];
   if (kStats) {
     for (int k = threadIdx.x; k < n_tensors; k += 256) ends[k] = tensor_ends[k];
     __syncthreads();
   }
-  const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
-  const bool ok = i < n;
+  const int64_t base = (int64_t)blockIdx.x * (256 * kAdamPerThread);
+  auto tensor_of = [&](int64_t key) {
+    int lo = 0, hi = n_tensors - 1;                        // first k with key < ends[k]
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (key < ends[mid]) hi = mid; else lo = mid + 1; }
+    return lo;
+  };
+  const int64_t last = (base + 256 * kAdamPerThread <= n ? base + 256 * kAdamPerThread : n) - 1;
+  const bool uniform = kStats && tensor_of(base) == tensor_of(last);
   float w2 = 0.f, g2 = 0.f, ga = 0.f, d2 = 0.f, da = 0.f;
-  if (ok) {
+#pragma unroll
+  for (int r = 0; r < kAdamPerThread; ++r) {
+    const int64_t i = base + r * 256 + threadIdx.x;
+    if (i >= n) break;
     const int m = i < e0 ? 0 : (i < e1 ? 1 : 2);
     const float gs = grad[i] * cfg.grad_scale;
     float g = clipv(gs, cfg.grad_max_val) * norms[m * 3 + 2];
@@ -89,27 +102,30 @@ __global__ void __launch_bounds__(256) adam_kernel(float* params, const float* g
     params[i] = p_new;
     if (kStats) {
       const float d = p_new - p_old;
-      w2 = p_old * p_old; g2 = gs * gs; ga = fabsf(gs); d2 = d * d; da = fabsf(d);
+      if (uniform) {
+        w2 += p_old * p_old; g2 += gs * gs; ga = fmaxf(ga, fabsf(gs)); d2 += d * d; da = fmaxf(da, fabsf(d));
+      } else {                                             // a block that straddles tensors (biases): per element
+        float* dst = tstats + (size_t)tensor_of(i) * 5;
+        atomicAdd(dst + 0, p_old * p_old); atomicAdd(dst + 1, gs * gs); atomicAdd(dst + 3, d * d);
+        atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(fabsf(gs)));
+        atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(fabsf(d)));
+      }
     }
   }
-  if (kStats) {
-    int lo = 0, hi = n_tensors - 1;                        // tensor of element i: first k with i < ends[k]
-    const int64_t key = ok ? i : n - 1;
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (key < ends[mid]) hi = mid; else lo = mid + 1; }
-    const int t = lo;
-    const int t0 = __shfl_sync(kFull, t, 0);
-    float* dst = tstats + (size_t)t * 5;
-    if (__all_sync(kFull, t == t0)) {                      // the common case: the warp sits inside one tensor
-      w2 = warp_sum(w2); g2 = warp_sum(g2); d2 = warp_sum(d2); ga = warp_max(ga); da = warp_max(da);
-      if ((threadIdx.x & 31) == 0) {
-        atomicAdd(dst + 0, w2); atomicAdd(dst + 1, g2); atomicAdd(dst + 3, d2);
-        atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(ga));
-        atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(da));
+  if (kStats && uniform) {
+    w2 = warp_sum(w2); g2 = warp_sum(g2); d2 = warp_sum(d2); ga = warp_max(ga); da = warp_max(da);
+    const int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { red[0][w] = w2; red[1][w] = g2; red[2][w] = ga; red[3][w] = d2; red[4][w] = da; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int k = 1; k < 8; ++k) {
+        red[0][0] += red[0][k]; red[1][0] += red[1][k]; red[3][0] += red[3][k];
+        red[2][0] = fmaxf(red[2][0], red[2][k]); red[4][0] = fmaxf(red[4][0], red[4][k]);
       }
-    } else if (ok) {
-      atomicAdd(dst + 0, w2); atomicAdd(dst + 1, g2); atomicAdd(dst + 3, d2);
-      atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(ga));
-      atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(da));
+      float* dst = tstats + (size_t)tensor_of(base) * 5;
+      atomicAdd(dst + 0, red[0][0]); atomicAdd(dst + 1, red[1][0]); atomicAdd(dst + 3, red[3][0]);
+      atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(red[2][0]));
+      atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(red[4][0]));
     }
   }
 }
@@ -169,11 +185,11 @@ int adam_step_impl(hugs_handle* h, float* params, const float* grad, float* mu, 
   if (tensor_stats_out) {
     HUGS_REQUIRE(n_tensors <= 128, "too many parameter tensors for the per-tensor statistics");
     HUGS_CUDA(cudaMemsetAsync(tensor_stats_out, 0, sizeof(float) * 5 * n_tensors, st));
-    adam_kernel<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
+    adam_kernel<true><<<(unsigned)((n + 256 * kAdamPerThread - 1) / (256 * kAdamPerThread)), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
                                                                    h->module_end[1], norms, *cfg, bc1, bc2,
                                                                    h->tensor_ends, n_tensors, tensor_stats_out);
   } else {
-    adam_kernel<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
+    adam_kernel<false><<<(unsigned)((n + 256 * kAdamPerThread - 1) / (256 * kAdamPerThread)), 256, 0, st>>>(params, grad, mu, nu, n, h->module_end[0],
                                                                     h->module_end[1], norms, *cfg, bc1, bc2, nullptr,
                                                                     0, nullptr);
   }

@@ -1,8 +1,10 @@
 // On-device ray generation and per-pixel batch gather.
 //
 // Reference semantics (paths under /root/reference/MipNeRF360/internal):
-//   camera_utils.py:503-607  pixels_to_rays (perspective camera, no lens distortion, no NDC): three rays per pixel
-//                            (centre, +x, +y) through pixtocam, OpenCV -> OpenGL flip, camtoworld rotation;
+//   camera_utils.py:503-607  pixels_to_rays (no NDC): three rays per pixel (centre, +x, +y) through pixtocam,
+//                            optional lens undistortion (:460-494: 10 Newton iterations on the radial k1..k4 /
+//                            tangential p1, p2 model, residual and Jacobian of :409-457), optional fisheye projection
+//                            (:557-568), OpenCV -> OpenGL flip, camtoworld rotation;
 //                            radii = mean distance to the two neighbours * 2 / sqrt(12)
 //   camera_utils.py:655-659  pix_coords = (pixel + 0.5) / (width, height)
 //   datasets.py:446-482      Dataset._make_ray_batch: static_masks[cam][y, x] (the HuGS mask), nears / fars[cam][y, x],
@@ -35,6 +37,11 @@ __global__ void __launch_bounds__(128) make_ray_batch_kernel(RayGenArgs a) {
   for (int k = 0; k < 9; ++k) p[k] = (double)__ldg(P + k);
 #pragma unroll
   for (int k = 0; k < 12; ++k) m[k] = (double)__ldg(M + k);
+  double kd[6] = {0, 0, 0, 0, 0, 0};    // k1 k2 k3 k4 p1 p2
+  if (a.cams.distortion) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) kd[k] = (double)__ldg(a.cams.distortion + k);
+  }
   double dir[3][3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -42,6 +49,34 @@ __global__ void __launch_bounds__(128) make_ray_batch_kernel(RayGenArgs a) {
     double cam[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) cam[k] = p[k * 3] * px + p[k * 3 + 1] * py + p[k * 3 + 2];
+    if (a.cams.distortion) {
+      // _radial_and_tangential_undistort (camera_utils.py:460-494)
+      const double xd = cam[0], yd = cam[1], k1 = kd[0], k2 = kd[1], k3 = kd[2], k4 = kd[3], p1 = kd[4], p2 = kd[5];
+      double ux = xd, uy = yd;
+      for (int it = 0; it < 10; ++it) {
+        const double rr = ux * ux + uy * uy;
+        const double dd = 1.0 + rr * (k1 + rr * (k2 + rr * (k3 + rr * k4)));
+        const double fx = dd * ux + 2 * p1 * ux * uy + p2 * (rr + 2 * ux * ux) - xd;
+        const double fy = dd * uy + 2 * p2 * ux * uy + p1 * (rr + 2 * uy * uy) - yd;
+        const double d_r = (k1 + rr * (2.0 * k2 + rr * (3.0 * k3 + rr * 4.0 * k4)));
+        const double d_x = 2.0 * ux * d_r, d_y = 2.0 * uy * d_r;
+        const double fx_x = dd + d_x * ux + 2.0 * p1 * uy + 6.0 * p2 * ux;
+        const double fx_y = d_y * ux + 2.0 * p1 * ux + 2.0 * p2 * uy;
+        const double fy_x = d_x * uy + 2.0 * p2 * uy + 2.0 * p1 * ux;
+        const double fy_y = dd + d_y * uy + 2.0 * p2 * ux + 6.0 * p1 * uy;
+        const double den = fy_x * fx_y - fx_x * fy_y;
+        const double sx = fabs(den) > 1e-9 ? (fx * fy_y - fy * fx_y) / den : 0.0;
+        const double sy = fabs(den) > 1e-9 ? (fy * fx_x - fx * fy_x) / den : 0.0;
+        ux += sx; uy += sy;
+      }
+      cam[0] = ux; cam[1] = uy; cam[2] = 1.0;
+    }
+    if (a.cams.camtype == 1) {   // ProjectionType.FISHEYE (camera_utils.py:557-568)
+      double theta = sqrt(cam[0] * cam[0] + cam[1] * cam[1]);
+      theta = fmin(3.141592653589793, theta);
+      const double sot = sin(theta) / theta;
+      cam[0] *= sot; cam[1] *= sot; cam[2] = cos(theta);
+    }
     cam[1] = -cam[1]; cam[2] = -cam[2];
 #pragma unroll
     for (int k = 0; k < 3; ++k) dir[r][k] = m[k * 4] * cam[0] + m[k * 4 + 1] * cam[1] + m[k * 4 + 2] * cam[2];
@@ -100,6 +135,7 @@ HUGS_API int hugs_make_ray_batch(const hugs_camera_set* cams, const int32_t* cam
   HUGS_REQUIRE(out->origins && out->directions && out->viewdirs && out->radii && out->near && out->far &&
                out->lossmult && out->static_mask && out->embed_idx, "null ray output");
   HUGS_REQUIRE(!out->rgb || cams->images || cams->images_u8, "rgb requested but the camera set holds no images");
+  HUGS_REQUIRE(cams->camtype == 0 || cams->camtype == 1, "camtype must be 0 (perspective) or 1 (fisheye), got %d", cams->camtype);
   if (n_rays == 0) return HUGS_OK;
   RayGenArgs a{*cams, cam_idx, pix_x, pix_y, n_rays, *out};
   make_ray_batch_kernel<<<(n_rays + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);

@@ -53,6 +53,16 @@ __device__ __forceinline__ float s_to_t(int fn, float s, float near, float far) 
   }
 }
 
+// One uniform draw in [0, 1) per (key, ray): splitmix64 finaliser, top 24 bits (the reference draws jax.random.uniform per
+// level and ray, stepfun.py:206-209; threefry is not reproducible without JAX, so the stream is this library's own).
+__device__ __forceinline__ float jitter_draw(uint64_t key, int ray) {
+  uint64_t z = key + 0x9E3779B97F4A7C15ull * (uint64_t)(ray + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z = z ^ (z >> 31);
+  return (float)(z >> 40) * (1.0f / 16777216.0f);
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) resample_kernel(ResampleArgs a) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -162,9 +172,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) resample_kernel(ResampleA
       __syncwarp();
     }
     // ---- sorted_interp -------------------------------------------------------------------
-    const float jit = a.jitter ? a.jitter[ray] * a.max_jitter : 0.f;
+    const bool jittered = a.jitter != nullptr || a.jitter_key != 0;
+    const float jit = a.jitter ? a.jitter[ray] * a.max_jitter
+                               : (a.jitter_key ? jitter_draw(a.jitter_key, ray) * a.max_jitter : 0.f);
     for (int j = lane; j < ns; j += 32) {
-      float u = a.u_in ? a.u_in[(size_t)ray * ns + j] : (a.jitter ? a.u_base[j] + jit : a.u_base[j]);
+      float u = a.u_in ? a.u_in[(size_t)ray * ns + j] : (jittered ? a.u_base[j] + jit : a.u_base[j]);
       // i0 = max{k : u >= cw_k} (0 if none); i1 = min{k : u < cw_k} (nb if none)
       int cnt = count_before<false>([&](int k) { return CW[k]; }, nb + 1, u);  // #{cw_k <= u}
       int i0 = max(cnt - 1, 0), i1 = min(cnt, nb);

@@ -102,9 +102,11 @@ struct TcMlp {
 };
 
 struct WgState;
+struct LayeredMlp;
 
 struct TcState {
   TcMlp nerf, prop;
+  LayeredMlp* nerf_layered = nullptr;   // NerfMLP.net_width != 256: layer-at-a-time path (layered.cu) instead of the chain
   WgState* wg = nullptr;
   bool split = false;                // HUGS_PRECISION_TC_SPLIT: every bf16 operand tensor holds a hi and a lo half
   __nv_bfloat16* feat = nullptr;     // per level region [cap_l, 512]
@@ -137,6 +139,32 @@ int pp_init(hugs_handle* h);
 int pp_launch(hugs_handle* h, int level, int n_rays, int direction, cudaStream_t st);
 
 // wgrad_tc.cu
+struct WgItem {
+  int a_map;        // index into WgParams::maps of the A tensor (saved activations, features, ...)
+  int a_row0;       // first row of this level in the A tensor
+  int a_col0;       // first A column of the 256-wide superblock
+  int b_row0;       // first row of the dZ slot
+  int b_col0;       // first dZ column of this item (layer-at-a-time path: 256-column blocks of a wider dZ)
+  int n;            // dZ columns (256 | 128 | 64)
+  int st0, st1;     // [st0, st1) 64-sample stages
+  int out;          // kernel columns
+  long long koff;   // kernel offset in the flat gradient
+  int in_base;      // kernel row of A column a_col0 (feature mode: first feature row)
+  int feat_mode;    // 1: A columns are features in engine order -> permute rows on flush
+  int b_map;        // index into WgParams::maps of the B tensor (dZ, head gradients, ...)
+  int flush_mode;   // 0: kernel tile; 1: density head (column 3 -> [in,1]); 2: rgb head (columns 0..2 -> [in,3])
+  int bias_mode;    // 0: none; 1: all n columns -> boff + c; 2: column 3 -> boff; 3: columns 0..2 -> boff + c
+  long long boff;   // bias offset in the flat gradient
+};
+
+struct WgUnit { WgItem w; float cost; int group; };
+constexpr int kWgMaxMaps = 12;
+void wgrad_plan(const std::vector<WgUnit>& units, int T, int num_sms, std::vector<WgItem>* items);
+int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgItem* dev_items, int n_items, float* grad,
+                 cudaStream_t st);
+// view-layer extras shared by the chain and the layered path: dW rows of the direction / GLO inputs, GLO embedding rows
+int wgrad_view_extras(hugs_handle* h, const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int dz_ld, int n_rays, int S,
+                      float* grad, cudaStream_t st);
 int wgrad_create(hugs_handle* h);
 void wgrad_destroy(hugs_handle* h);
 int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t st);

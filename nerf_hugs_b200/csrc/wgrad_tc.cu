@@ -26,22 +26,7 @@
 
 namespace hugs {
 
-struct WgItem {
-  int a_map;        // 0: saved activations, 1: features
-  int a_row0;       // first row of this level in the A tensor
-  int a_col0;       // first A column of the 256-wide superblock
-  int b_row0;       // first row of the dZ slot
-  int n;            // dZ columns (256 | 128)
-  int st0, st1;     // [st0, st1) 64-sample stages
-  int out;          // kernel columns
-  long long koff;   // kernel offset in the flat gradient
-  int in_base;      // kernel row of A column a_col0 (feature mode: first feature row)
-  int feat_mode;    // 1: A columns are features in engine order -> permute rows on flush
-  int b_map;        // 0: dZ tensor, 1: head-gradient tensor (kHeadCols wide)
-  int flush_mode;   // 0: kernel tile; 1: density head (column 3 -> [in,1]); 2: rgb head (columns 0..2 -> [in,3])
-  int bias_mode;    // 0: none; 1: all n columns -> boff + c; 2: column 3 -> boff; 3: columns 0..2 -> boff + c
-  long long boff;   // bias offset in the flat gradient
-};
+enum { WG_MAP_ACT = 0, WG_MAP_FEAT = 1, WG_MAP_DZ = 2, WG_MAP_DH = 3 };   // chain path; the layered path adds its own
 
 struct WgState {
   CUtensorMap map_act64, map_feat64, map_dz64, map_dh64;
@@ -61,7 +46,7 @@ constexpr int kWgScratchFloats = 4 * 32 * 33;   // per epilogue warp: 32 x 32 ac
 constexpr int kWgSmem = 1024 + kWgStages * kWgStageBytes + 256 + kWgScratchFloats * 4;
 
 struct alignas(64) WgParams {
-  CUtensorMap map_act64, map_feat64, map_dz64, map_dh64;
+  CUtensorMap maps[kWgMaxMaps];
   const WgItem* items;
   int n_items, nb, ndeg, feat_dim;
   float* grad;
@@ -79,8 +64,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   float* scratch = reinterpret_cast<float*>(base + kWgStages * kWgStageBytes + 256);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 4 && lane == 0) {
-    ptx::prefetch_tmap(&p.map_act64); ptx::prefetch_tmap(&p.map_feat64); ptx::prefetch_tmap(&p.map_dz64);
-    ptx::prefetch_tmap(&p.map_dh64);
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.maps[i]);
     // a stage is released by the MMA commit and by the four epilogue warps (bias column sums read B)
     for (int i = 0; i < kWgStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 5); }
     ptx::mbar_init(acc_full, 1); ptx::mbar_init(acc_empty, 128);
@@ -97,7 +81,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       int stage = 0; uint32_t phase = 0;
       for (int it = blockIdx.x; it < p.n_items; it += gridDim.x) {
         const WgItem w = p.items[it];
-        const CUtensorMap* amap = w.a_map ? &p.map_feat64 : &p.map_act64;
+        const CUtensorMap* amap = &p.maps[w.a_map];
         const int nb_atoms = w.n >> 6;
         for (int st = w.st0; st < w.st1; ++st) {
           ptx::mbar_wait(&empty[stage], phase ^ 1);
@@ -105,9 +89,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
           ptx::mbar_expect_tx(&full[stage], (4 + nb_atoms) * 8192);
           for (int a = 0; a < 4; ++a)
             ptx::tma_load_2d(s + a * 8192, amap, &full[stage], w.a_col0 + a * 64, w.a_row0 + st * 64);
-          const CUtensorMap* bmap = w.b_map ? &p.map_dh64 : &p.map_dz64;
+          const CUtensorMap* bmap = &p.maps[w.b_map];
           for (int a = 0; a < nb_atoms; ++a)
-            ptx::tma_load_2d(s + 32768 + a * 8192, bmap, &full[stage], a * 64, w.b_row0 + st * 64);
+            ptx::tma_load_2d(s + 32768 + a * 8192, bmap, &full[stage], w.b_col0 + a * 64, w.b_row0 + st * 64);
           if (++stage == kWgStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -178,7 +162,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
       }
       if (sum_cols && w.st1 > w.st0) {
         const int c = 2 * t;
-        if (w.bias_mode == 1) { atomicAdd(p.grad + w.boff + c, s0); atomicAdd(p.grad + w.boff + c + 1, s1); }
+        if (w.bias_mode == 1) { atomicAdd(p.grad + w.boff + w.b_col0 + c, s0); atomicAdd(p.grad + w.boff + w.b_col0 + c + 1, s1); }
         else if (w.bias_mode == 2) { if (c == 2) atomicAdd(p.grad + w.boff, s1); }
         else if (w.bias_mode == 3) {
           if (c == 0) { atomicAdd(p.grad + w.boff, s0); atomicAdd(p.grad + w.boff + 1, s1); }
@@ -212,11 +196,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 #pragma unroll
               for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = __uint_as_float(r[j]);
               __syncwarp();
-              const bool col_ok = c + lane < w.out;
+              const bool col_ok = w.b_col0 + c + lane < w.out;
 #pragma unroll 4
               for (int rr = 0; rr < 32; ++rr) {
                 const int kr = __shfl_sync(0xffffffffu, krow, rr);
-                if (kr >= 0 && col_ok) atomicAdd(p.grad + w.koff + (long long)kr * w.out + c + lane, sc[rr * 33 + lane]);
+                if (kr >= 0 && col_ok)
+                  atomicAdd(p.grad + w.koff + (long long)kr * w.out + w.b_col0 + c + lane, sc[rr * 33 + lane]);
               }
               __syncwarp();
             }
@@ -245,16 +230,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 
 // ---------------------------------------------------------------- CUDA-core reductions (view layer extras)
 // dzv_ray[ray][c] = sum over the ray's samples of dZ_view[s][c]
-__global__ void __launch_bounds__(128) ray_sum_kernel(const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int n_rays,
-                                                      int S, float* out) {
+__global__ void __launch_bounds__(128) ray_sum_kernel(const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int ld,
+                                                      int n_rays, int S, float* out) {
   const int ray = blockIdx.x, c = threadIdx.x;
   if (ray >= n_rays) return;
   float acc = 0.f;
-  const __nv_bfloat16* src = dzv + (size_t)ray * S * kW + c;
-  for (int s = 0; s < S; ++s) acc += __bfloat162float(src[(size_t)s * kW]);
+  const __nv_bfloat16* src = dzv + (size_t)ray * S * ld + c;
+  for (int s = 0; s < S; ++s) acc += __bfloat162float(src[(size_t)s * ld]);
   if (dzv_lo) {   // split-precision mode: dZ = hi + lo
-    const __nv_bfloat16* lo = dzv_lo + (size_t)ray * S * kW + c;
-    for (int s = 0; s < S; ++s) acc += __bfloat162float(lo[(size_t)s * kW]);
+    const __nv_bfloat16* lo = dzv_lo + (size_t)ray * S * ld + c;
+    for (int s = 0; s < S; ++s) acc += __bfloat162float(lo[(size_t)s * ld]);
   }
   out[(size_t)ray * 128 + c] = acc;
 }
@@ -334,80 +319,125 @@ static void build_items(hugs_handle* h, int level, int n_tiles, std::vector<WgIt
   const int D = mv.depth;
   const int cap = tc->cap[level], srow = tc->save_row0[level], frow = tc->feat_row0[level];
   const int T = n_tiles * 2;   // 64-sample stages
-  struct Unit { WgItem w; float cost; };
-  std::vector<Unit> units;
+  // Units that stream a common operand (the IPE features against dZ of layer 0 and of the skip layer; the last trunk
+  // activation against the bottleneck and the density-head gradients) form a *group*: they are cut into the same sample
+  // ranges and queued next to each other, so that neighbouring CTAs stream the shared rows at the same time and the
+  // second reader hits L2 instead of HBM (the kernel is HBM-bound; this removes up to 20 % of its DRAM reads).
+  std::vector<WgUnit> units;
+  int next_group = 16;
+  constexpr int kGroupFeat = 1, kGroupLast = 2;
   auto add = [&](int a_map, int a_row0, int a_col0, int b_slot, int n, const DenseView& v, int in_base, int feat_mode,
-                 bool first_of_layer) {
+                 bool first_of_layer, int group) {
     WgItem w{};
-    w.a_map = a_map; w.a_row0 = a_row0; w.a_col0 = a_col0; w.b_row0 = srow + b_slot * cap; w.n = n;
+    w.a_map = a_map ? WG_MAP_FEAT : WG_MAP_ACT; w.a_row0 = a_row0; w.a_col0 = a_col0; w.b_map = WG_MAP_DZ;
+    w.b_row0 = srow + b_slot * cap; w.n = n;
     w.out = v.out; w.koff = v.kernel_off; w.in_base = in_base; w.feat_mode = feat_mode;
     w.bias_mode = first_of_layer ? 1 : 0; w.boff = v.bias_off;
-    units.push_back({w, (512.f + 2.f * n) / 1024.f});   // the kernel is HBM-bound: cost = bytes streamed per sample
+    // the kernel is HBM-bound: cost = bytes streamed per sample
+    units.push_back({w, (512.f + 2.f * n) / 1024.f, group > 0 ? group : next_group++});
   };
   bool cat = false;
   for (int l = 0; l < D; ++l) {
     const DenseView& v = mv.dense[l];
     if (l == 0) {
-      for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, 0, 256, v, 0, 1, sb == 0);
+      for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, 0, 256, v, 0, 1, sb == 0, kGroupFeat);
     } else {
-      add(0, srow + (l - 1) * cap, 0, l, 256, v, 0, 0, true);
-      if (cat) for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, l, 256, v, kW, 1, false);
+      add(0, srow + (l - 1) * cap, 0, l, 256, v, 0, 0, true, cat ? kGroupFeat : 0);
+      if (cat) for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, l, 256, v, kW, 1, false, kGroupFeat);
     }
     cat = (l % d.skip_layer == 0 && l > 0);
   }
   if (mv.has_rgb) {
-    add(0, srow + (D - 1) * cap, 0, D, 256, mv.dense[D + 1], 0, 0, true);        // bottleneck
-    add(0, srow + D * cap, 0, D + 1, 128, mv.dense[D + 2], 0, 0, true);          // view layer (bottleneck rows)
+    add(0, srow + (D - 1) * cap, 0, D, 256, mv.dense[D + 1], 0, 0, true, kGroupLast);     // bottleneck
+    add(0, srow + D * cap, 0, D + 1, 128, mv.dense[D + 2], 0, 0, true, 0);               // view layer (bottleneck rows)
   }
   {  // density head: A = last trunk activation, B = head gradients (column 3)
     WgItem w{};
-    w.a_map = 0; w.a_row0 = srow + (D - 1) * cap; w.a_col0 = 0; w.b_map = 1; w.b_row0 = 0; w.n = kHeadCols;
+    w.a_map = WG_MAP_ACT; w.a_row0 = srow + (D - 1) * cap; w.a_col0 = 0; w.b_map = WG_MAP_DH; w.b_row0 = 0; w.n = kHeadCols;
     w.out = 1; w.koff = mv.dense[D].kernel_off; w.flush_mode = 1; w.bias_mode = 2; w.boff = mv.dense[D].bias_off;
-    units.push_back({w, (512.f + 2.f * kHeadCols) / 1024.f});
+    units.push_back({w, (512.f + 2.f * kHeadCols) / 1024.f, kGroupLast});
   }
   if (mv.has_rgb) {  // rgb head: A = view activation (columns 128..255 are zero), B = head gradients (columns 0..2)
     WgItem w{};
-    w.a_map = 0; w.a_row0 = srow + (D + 1) * cap; w.a_col0 = 0; w.b_map = 1; w.b_row0 = 0; w.n = kHeadCols;
+    w.a_map = WG_MAP_ACT; w.a_row0 = srow + (D + 1) * cap; w.a_col0 = 0; w.b_map = WG_MAP_DH; w.b_row0 = 0; w.n = kHeadCols;
     w.out = 3; w.koff = mv.dense[D + 3].kernel_off; w.flush_mode = 2; w.bias_mode = 3; w.boff = mv.dense[D + 3].bias_off;
-    units.push_back({w, (512.f + 2.f * kHeadCols) / 1024.f});
+    units.push_back({w, (512.f + 2.f * kHeadCols) / 1024.f, next_group++});
   }
-  float total = 0.f;
-  for (auto& u : units) total += u.cost;
-  items->clear();
-  // one wave of CTAs: splits proportional to cost (at least 1, at most one split per 4 stages)
-  std::vector<int> splits(units.size());
-  int used = 0;
-  // Several items per CTA even out the differences between items (measured: NerfMLP 1.28 -> 1.17 ms with 3 items per
-  // CTA), but every item pays one accumulator flush: only when an item still streams >= ~250 stages.
-  const float stages_per_sm = (float)T * total / (float)tc->num_sms;
-  const int waves = std::min(4, std::max(1, (int)(stages_per_sm / 250.f)));
-  const int target = tc->num_sms * std::max(1, waves);
-  for (size_t i = 0; i < units.size(); ++i) {
-    splits[i] = std::max(1, (int)(target * units[i].cost / total));
-    splits[i] = std::min(splits[i], std::max(1, T / 4));
-    used += splits[i];
-  }
-  for (size_t i = 0; used < target && i < units.size() * 4; ++i) {   // hand out the remainder round-robin
-    const size_t k = i % units.size();
-    if (splits[k] < std::max(1, T / 4)) { ++splits[k]; ++used; }
-  }
+  std::vector<WgItem> planned;
+  wgrad_plan(units, T, tc->num_sms, &planned);
   // split-precision mode: (A_hi + A_lo)^T (dZ_hi + dZ_lo) as four items; the bias column sums ride on the A_hi items only,
   // so that each dZ half is summed exactly once
   const int n_a = tc->split ? 2 : 1, n_b = tc->split ? 2 : 1;
-  for (size_t i = 0; i < units.size(); ++i) {
-    for (int k = 0; k < splits[i]; ++k) {
-      for (int pa = 0; pa < n_a; ++pa)
-        for (int pb = 0; pb < n_b; ++pb) {
-          WgItem w = units[i].w;
-          w.st0 = (int)((long long)T * k / splits[i]);
-          w.st1 = (int)((long long)T * (k + 1) / splits[i]);
-          w.a_row0 += pa * (w.a_map ? tc->total_feat_rows : tc->total_save_rows);
-          w.b_row0 += pb * (w.b_map ? tc->drgb_rows : tc->total_save_rows);
-          if (pa > 0) w.bias_mode = 0;
-          if (w.st1 > w.st0) items->push_back(w);
-        }
-    }
+  items->clear();
+  for (const WgItem& base : planned)
+    for (int pa = 0; pa < n_a; ++pa)
+      for (int pb = 0; pb < n_b; ++pb) {
+        WgItem w = base;
+        w.a_row0 += pa * (w.a_map == WG_MAP_FEAT ? tc->total_feat_rows : tc->total_save_rows);
+        w.b_row0 += pb * (w.b_map == WG_MAP_DH ? tc->drgb_rows : tc->total_save_rows);
+        if (pa > 0) w.bias_mode = 0;
+        items->push_back(w);
+      }
+}
+
+// Cuts the units of one weight-gradient launch into work items (sample ranges).  Units of a *group* stream a common
+// operand: they are cut into the same sample ranges and queued next to each other, so that neighbouring CTAs stream the
+// shared rows at the same time and the second reader hits L2 instead of HBM.  T = number of 64-sample stages.
+void wgrad_plan(const std::vector<WgUnit>& units, int T, int num_sms, std::vector<WgItem>* items) {
+  float total = 0.f;
+  for (auto& u : units) total += u.cost;
+  items->clear();
+  std::vector<int> group_ids;   // in first-appearance order
+  for (auto& u : units)
+    if (std::find(group_ids.begin(), group_ids.end(), u.group) == group_ids.end()) group_ids.push_back(u.group);
+  // Several items per CTA even out the differences between items (measured: NerfMLP 1.28 -> 1.17 ms with 3 items per
+  // CTA), but every item pays one accumulator flush: only when an item still streams >= ~250 stages.
+  const float stages_per_sm = (float)T * total / (float)num_sms;
+  const int waves = std::min(4, std::max(1, (int)(stages_per_sm / 250.f)));
+  const int target = num_sms * std::max(1, waves);
+  // sample ranges per group: proportional to the mean cost of its units (at least 1, at most one range per 4 stages)
+  const int max_splits = std::max(1, T / 4);
+  std::vector<int> splits(group_ids.size()), members(group_ids.size(), 0);
+  std::vector<float> gcost(group_ids.size(), 0.f);
+  for (auto& u : units) {
+    const size_t g = std::find(group_ids.begin(), group_ids.end(), u.group) - group_ids.begin();
+    ++members[g]; gcost[g] += u.cost;
   }
+  int used = 0;
+  for (size_t g = 0; g < group_ids.size(); ++g) {
+    splits[g] = std::max(1, (int)(target * gcost[g] / total / members[g]));
+    splits[g] = std::min(splits[g], max_splits);
+    used += splits[g] * members[g];
+  }
+  for (size_t i = 0; i < group_ids.size() * 4; ++i) {   // hand out the remainder round-robin
+    const size_t g = i % group_ids.size();
+    if (used + members[g] <= target && splits[g] < max_splits) { ++splits[g]; used += members[g]; }
+  }
+  for (size_t g = 0; g < group_ids.size(); ++g)
+    for (int k = 0; k < splits[g]; ++k)
+      for (auto& u : units) {
+        if (u.group != group_ids[g]) continue;
+        WgItem w = u.w;
+        w.st0 = (int)((long long)T * k / splits[g]);
+        w.st1 = (int)((long long)T * (k + 1) / splits[g]);
+        if (w.st1 > w.st0) items->push_back(w);
+      }
+}
+
+// One launch of the weight-gradient kernel over `n_items` device-resident work items.
+int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgItem* dev_items, int n_items, float* grad,
+                 cudaStream_t st) {
+  if (n_items <= 0) return HUGS_OK;
+  HUGS_REQUIRE(n_maps <= kWgMaxMaps, "wgrad: too many tensor maps");
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n_maps; ++i) p.maps[i] = maps[i];
+  for (int i = n_maps; i < kWgMaxMaps; ++i) p.maps[i] = maps[0];
+  p.items = dev_items; p.n_items = n_items;
+  p.nb = h->d.num_basis; p.ndeg = h->d.max_deg_point - h->d.min_deg_point; p.feat_dim = h->feat_dim; p.grad = grad;
+  wgrad_kernel<<<std::min(n_items, h->tc->num_sms), kWgThreads, kWgSmem, st>>>(p);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
 }
 
 int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t st) {
@@ -419,7 +449,6 @@ int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t s
   const int D = mv.depth, S = h->samples(level);
   const int n_samples = n_rays * S;
   const int n_tiles = (n_samples + kTileM - 1) / kTileM;
-  const int n_rows = n_tiles * kTileM;
   const int cap = tc->cap[level], srow = tc->save_row0[level];
   if (w->built_for[level] != n_samples) {
     build_items(h, level, n_tiles, &w->host[level]);
@@ -429,34 +458,40 @@ int wgrad_run(hugs_handle* h, int level, int n_rays, float* grad, cudaStream_t s
     HUGS_CUDA(cudaStreamSynchronize(st));
     w->built_for[level] = n_samples;
   }
-  WgParams p;
-  memset(&p, 0, sizeof(p));
-  p.map_act64 = w->map_act64; p.map_feat64 = w->map_feat64; p.map_dz64 = w->map_dz64; p.map_dh64 = w->map_dh64;
-  p.items = w->dev[level]; p.n_items = (int)w->host[level].size();
-  p.nb = d.num_basis; p.ndeg = d.max_deg_point - d.min_deg_point; p.feat_dim = h->feat_dim; p.grad = grad;
   {
     ProfScope ps(h, is_prop ? HUGS_K_WGRAD_PROP : HUGS_K_WGRAD_NERF, st);
-    wgrad_kernel<<<std::min(p.n_items, tc->num_sms), kWgThreads, kWgSmem, st>>>(p);
-    HUGS_LAUNCH_CHECK();
+    const CUtensorMap maps[4] = {w->map_act64, w->map_feat64, w->map_dz64, w->map_dh64};
+    int rc = wgrad_launch(h, maps, 4, w->dev[level], (int)w->host[level].size(), grad, st);
+    if (rc) return rc;
   }
   ProfScope ps_red(h, HUGS_K_REDUCTIONS, st);
-
   if (mv.has_rgb) {
-    const DenseView& vv = mv.dense[D + 2];
     const __nv_bfloat16* dzv = tc->dz + (size_t)(srow + (D + 1) * cap) * kW;
-    ray_sum_kernel<<<n_rays, 128, 0, st>>>(dzv, tc->split ? dzv + (size_t)tc->total_save_rows * kW : nullptr, n_rays, S,
-                                           w->dzv_ray);
+    return wgrad_view_extras(h, dzv, tc->split ? dzv + (size_t)tc->total_save_rows * kW : nullptr, kW, n_rays, S, grad, st);
+  }
+  return HUGS_OK;
+}
+
+// view layer: weight rows of the per-ray inputs (direction encoding, GLO vector) and the GLO embedding rows, from the
+// per-ray sums of dZ_view (rows of `dz_ld` bf16 elements, 128 valid columns)
+int wgrad_view_extras(hugs_handle* h, const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int dz_ld, int n_rays, int S,
+                      float* grad, cudaStream_t st) {
+  TcState* tc = h->tc;
+  WgState* w = tc->wg;
+  const hugs_model_desc& d = h->d;
+  const DenseView& vv = h->nerf.dense[h->nerf.depth + 2];
+  const int exact = tc->split ? 1 : 0;
+  ray_sum_kernel<<<n_rays, 128, 0, st>>>(dzv, dzv_lo, dz_ld, n_rays, S, w->dzv_ray);
+  HUGS_LAUNCH_CHECK();
+  view_extra_wgrad_kernel<<<dim3(h->view_in_dim, 32), 128, 0, st>>>(h->view_in, h->view_in_dim, w->dzv_ray, n_rays,
+                                                                    vv.kernel_off, d.bottleneck_width, exact, grad);
+  HUGS_LAUNCH_CHECK();
+  if (d.num_glo_features > 0) {
+    const int tot = n_rays * d.num_glo_features;
+    glo_grad_kernel<<<(tot + 127) / 128, 128, 0, st>>>(w->dzv_ray, h->cur_embed_idx, h->cur_params, vv.kernel_off,
+                                                       d.bottleneck_width, 3 + 6 * d.deg_view, d.num_glo_features, n_rays,
+                                                       h->glo_off, d.num_embeddings, exact, grad);
     HUGS_LAUNCH_CHECK();
-    view_extra_wgrad_kernel<<<dim3(h->view_in_dim, 32), 128, 0, st>>>(h->view_in, h->view_in_dim, w->dzv_ray, n_rays,
-                                                           vv.kernel_off, d.bottleneck_width, tc->split ? 1 : 0, grad);
-    HUGS_LAUNCH_CHECK();
-    if (d.num_glo_features > 0) {
-      const int tot = n_rays * d.num_glo_features;
-      glo_grad_kernel<<<(tot + 127) / 128, 128, 0, st>>>(w->dzv_ray, h->cur_embed_idx, h->cur_params, vv.kernel_off,
-                                                         d.bottleneck_width, 3 + 6 * d.deg_view, d.num_glo_features,
-                                                         n_rays, h->glo_off, d.num_embeddings, tc->split ? 1 : 0, grad);
-      HUGS_LAUNCH_CHECK();
-    }
   }
   return HUGS_OK;
 }

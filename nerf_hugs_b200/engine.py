@@ -229,6 +229,15 @@ class Engine:
     self._keep = keep + [gt, jit]
     return grad, stats
 
+  def set_train_rng(self, seed: int, counter: int):
+    """In-kernel jitter draws for loss_and_grad(jitter=None): seed 0 switches them off (deterministic sampling)."""
+    check(lib.hugs_set_train_rng(self._h, int(seed) & (2 ** 64 - 1), int(counter) & (2 ** 64 - 1)))
+
+  def set_grad_ready_event(self, event: Optional[torch.cuda.Event]):
+    """`event` is recorded inside loss_and_grad once the NerfMLP_0 / GloEmbed_0 gradients are final."""
+    self._grad_event = event            # keep it alive
+    check(lib.hugs_set_grad_ready_event(self._h, None if event is None else C.c_void_p(event.cuda_event)))
+
   def adam_step(self, params, grad, mu, nu, adam_cfg: '_lib.AdamCfg', norms_out: Optional[torch.Tensor] = None,
                 tensor_stats_out: Optional[torch.Tensor] = None):
     """clip + nan_to_num + Adam; `tensor_stats_out` ([len(layout), 5] fp32) also receives, per parameter tensor,

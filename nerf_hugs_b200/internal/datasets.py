@@ -5,7 +5,8 @@ The reference builds every training batch on the host (NumPy gathers + pixels_to
 cameras live in HBM once, and a batch is produced by one kernel (`hugs_make_ray_batch`) from integer
 (camera, x, y) draws made on the device — same fields, shapes and value semantics as `Dataset._make_ray_batch`.
 
-Out of scope (raise NotImplementedError): lens distortion, fisheye cameras, NDC, spherical render paths.
+Lens distortion (`Dataset.distortion_params`, one set per dataset as in the reference) and fisheye cameras are handled in
+the kernel; NDC and the spherical render paths are out of scope (NotImplementedError).
 """
 import ctypes as C
 from typing import Optional, Sequence
@@ -35,10 +36,11 @@ class DeviceDataset:
                static_masks: Optional[Sequence] = None, nears: Optional[Sequence] = None,
                fars: Optional[Sequence] = None, embed_idxs=None, near: float = 0.2, far: float = 1e6,
                distortion_params=None, camtype: str = 'perspective', device=None):
-    if distortion_params is not None and any(d is not None for d in np.atleast_1d(distortion_params)):
-      raise NotImplementedError('lens distortion (camera_utils._radial_and_tangential_undistort) is not supported on the device path')
-    if camtype != 'perspective':
+    if camtype not in ('perspective', 'fisheye'):
       raise NotImplementedError(f'camera type {camtype!r} is not supported on the device path')
+    if distortion_params is not None and not isinstance(distortion_params, dict):
+      raise NotImplementedError('distortion_params must be one dict of k1..k4, p1, p2 for the whole dataset (as '
+                                'datasets.Dataset.distortion_params); per-camera lists are not supported')
     if not torch.cuda.is_available():
       raise RuntimeError('DeviceDataset needs a CUDA device (the product path has no CPU fallback)')
     dev = torch.device('cuda', torch.cuda.current_device()) if device is None else torch.device(device)
@@ -81,6 +83,14 @@ class DeviceDataset:
     cs.static_masks, cs.nears, cs.fars = _ptr(self.static_masks), _ptr(self.nears), _ptr(self.fars)
     cs.embed_idxs = _ptr(self.embed_idxs)
     cs.near, cs.far = self.near, self.far
+    self.distortion = None
+    if distortion_params is not None:
+      unknown = set(distortion_params) - {'k1', 'k2', 'k3', 'k4', 'p1', 'p2'}
+      if unknown:
+        raise ValueError(f'unknown distortion parameters {sorted(unknown)}')
+      self.distortion = f32([distortion_params.get(k, 0.0) for k in ('k1', 'k2', 'k3', 'k4', 'p1', 'p2')])
+    cs.distortion = _ptr(self.distortion)
+    cs.camtype = {'perspective': 0, 'fisheye': 1}[camtype]
     self._cs = cs
 
   # datasets.py:446-482

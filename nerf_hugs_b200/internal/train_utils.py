@@ -76,12 +76,23 @@ def _to_device(x, device):
   return x.to(device, non_blocking=True)
 
 
+def _rng_seed(rng):
+  """Seed of the per-step sampling randomness: a torch.Generator, an int, or None."""
+  if rng is None:
+    return 0
+  if isinstance(rng, torch.Generator):
+    return int(rng.initial_seed()) or 1
+  return int(rng) or 1
+
+
 def create_train_step(model: models.Model, config, is_finetune: bool = False):
   """train_utils.create_train_step (train_utils.py:372-484).
 
   train_pstep(rng, state, batch, train_frac, inlier_thresholds) -> (state, stats, rng)
-    rng:   torch.Generator on the model's device (or None when config.randomized is False)
-    batch: utils.Batch of this rank's rays (host or device tensors; host tensors are copied here)
+    rng:   a torch.Generator / int seed (or None when sampling should be deterministic); together with the step count it
+           keys the counter-based jitter stream of the sampling kernel (hugs_set_train_rng): no RNG kernel per step
+    batch: utils.Batch of this rank's rays (host or device tensors; host tensors are staged on a copy stream, so the
+           transfer of batch i overlaps the GPU work of step i - 1)
   `state` is updated in place and returned (the reference donates it, train_utils.py:483).
   """
   eng = model.engine
@@ -93,8 +104,8 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
   lr_fn = lambda step: hmath.learning_rate_decay(step, config.lr_init, config.lr_final, config.max_steps,
                                                 config.lr_delay_steps, config.lr_delay_mult)
   dev = eng.device
-  # the flat gradient and the 16 stats share one buffer: a single all-reduce per step (train_utils.py:457-459 pmean's
-  # both); the 16-float offset keeps the stats 64-byte aligned
+  # the flat gradient and the 16 stats share one buffer (train_utils.py:457-459 pmean's both); the 16-float offset keeps
+  # the stats 64-byte aligned
   bucket = torch.zeros(eng.n_params + 16 + (-eng.n_params) % 16, device=dev)
   grad = bucket[:eng.n_params]
   stats_dev = bucket[bucket.numel() - 16:]
@@ -103,23 +114,69 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
   tstats_dev = torch.empty(n_t, 5, device=dev)
   names = [t[0] for t in eng.layout]
   L = model.num_levels
+  # flat layout: [NerfMLP_0 | PropMLP_0 | GloEmbed_0]; the NerfMLP_0 part is final before the proposal levels' backward
+  nerf_end = max([off + r * c for _, off, r, c, mod in eng.layout if mod == 0], default=0)
   # every step's stats are copied (asynchronously) into a pinned host ring, so a stats object stays valid after later
   # steps have been launched and reading it waits only for its own step
   ring = torch.empty(_STATS_RING, 25 + 5 * n_t).pin_memory()
   holders = [None] * _STATS_RING
+  ov = {'side': None, 'event': None, 'copy': None, 'slots': [None] * _STAGE_SLOTS, 'i': 0}
+
+  def stage(batch):
+    """(rays dict, rgb, slot): host tensors are copied to rotating device buffers on a copy stream; a batch that already
+    lives on the device passes through (slot None)."""
+    items = dict(batch.rays.as_dict())
+    items['rgb'] = batch.rgb
+    items = {k: (v if (v is None or torch.is_tensor(v)) else torch.as_tensor(v)) for k, v in items.items()}
+    if all(v is None or v.device == dev for v in items.values()):
+      return {k: v for k, v in items.items() if k != 'rgb'}, items['rgb'], None
+    if ov['copy'] is None:
+      ov['copy'] = torch.cuda.Stream(dev)
+    slot = ov['i'] % _STAGE_SLOTS
+    ov['i'] += 1
+    bufs, free_ev = ov['slots'][slot] or ({}, None)
+    with torch.cuda.stream(ov['copy']):
+      if free_ev is not None:
+        ov['copy'].wait_event(free_ev)        # the step that last read this slot has finished
+      for k, v in items.items():
+        if v is None:
+          bufs[k] = None
+          continue
+        buf = bufs.get(k)
+        if buf is None or buf.shape != v.shape or buf.dtype != v.dtype:
+          buf = torch.empty(v.shape, dtype=v.dtype, device=dev)
+        buf.copy_(v, non_blocking=True)
+        bufs[k] = buf
+      done = torch.cuda.Event()
+      done.record(ov['copy'])
+    torch.cuda.current_stream(dev).wait_event(done)
+    ov['slots'][slot] = [bufs, None]
+    return {k: v for k, v in bufs.items() if k != 'rgb'}, bufs['rgb'], slot
 
   def train_step(rng, state: TrainState, batch: utils.Batch, train_frac, inlier_thresholds=None):
     del inlier_thresholds   # read by compute_robustnerf_loss only; transient_type='robustnerf' is refused by models.Model
     rank, world = _world()
-    rays = {k: _to_device(v, dev) for k, v in batch.rays.as_dict().items()}
-    rgb = _to_device(batch.rgb, dev)
-    n = rays['origins'].reshape(-1, 3).shape[0]
-    jitter = None
-    if config.randomized and rng is not None:
-      jitter = torch.rand(L, n, generator=rng, device=dev)
+    rays, rgb, slot_in = stage(batch)
+    eng.set_train_rng(_rng_seed(rng) if config.randomized else 0, state.step)
     model._ensure_packed(state.params)
-    eng.loss_and_grad(state.params, rays, rgb[..., :3], float(train_frac), jitter, lcfg, grad, stats_dev)
-    allreduce_sum_([bucket])                        # pmean(grad), pmean(stats)  (train_utils.py:457-459), one collective
+    if world > 1 and ov['event'] is None:
+      ov['side'] = torch.cuda.Stream(dev)
+      ov['event'] = torch.cuda.Event()
+      ov['event'].record(torch.cuda.current_stream(dev))          # materialises the cudaEvent_t
+      eng.set_grad_ready_event(ov['event'])
+    eng.loss_and_grad(state.params, rays, rgb[..., :3], float(train_frac), None, lcfg, grad, stats_dev)
+    if slot_in is not None:                                       # the staging slot is free once this step has read it
+      ev = torch.cuda.Event()
+      ev.record(torch.cuda.current_stream(dev))
+      ov['slots'][slot_in][1] = ev
+    if world > 1:
+      # pmean(grad), pmean(stats) (train_utils.py:457-459) as two collectives on one communicator: the NerfMLP_0 part
+      # (87 % of the floats) starts as soon as it is final, under the proposal levels' backward pass; the rest follows
+      with torch.cuda.stream(ov['side']):
+        ov['side'].wait_event(ov['event'])
+        early = dist.all_reduce(bucket[:nerf_end], op=dist.ReduceOp.SUM, async_op=True)
+      dist.all_reduce(bucket[nerf_end:], op=dist.ReduceOp.SUM)
+      early.wait()
     a = _lib.AdamCfg()
     a.lr = float(lr_fn(state.step))
     a.beta1, a.beta2, a.eps = config.adam_beta1, config.adam_beta2, config.adam_eps
@@ -143,6 +200,7 @@ def create_train_step(model: models.Model, config, is_finetune: bool = False):
   return train_step
 
 
+_STAGE_SLOTS = 3
 _STATS_RING = 64
 
 

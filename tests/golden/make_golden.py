@@ -72,8 +72,17 @@ def camera_golden(rng):
   px = (rng.uniform(size=n) * hw[cam_idx, 1]).astype(np.int64)
   py = (rng.uniform(size=n) * hw[cam_idx, 0]).astype(np.int64)
   o, d, v, r = cu.pixels_to_rays(px, py, pixtocams[cam_idx], camtoworlds[cam_idx], xnp=np)
-  np.savez(f'{OUT}/camera.npz', heights=hw[:, 0], widths=hw[:, 1], pixtocams=pixtocams, camtoworlds=camtoworlds,
-           cam_idx=cam_idx, pix_x=px, pix_y=py, origins=o, directions=d, viewdirs=v, radii=r)
+  out = dict(heights=hw[:, 0], widths=hw[:, 1], pixtocams=pixtocams, camtoworlds=camtoworlds,
+             cam_idx=cam_idx, pix_x=px, pix_y=py, origins=o, directions=d, viewdirs=v, radii=r)
+  # lens distortion (10 Newton iterations, camera_utils.py:460-494) and fisheye projection (:557-568)
+  dist = dict(k1=0.12, k2=-0.05, k3=0.01, k4=-0.002, p1=0.003, p2=-0.002)
+  out['dist_params'] = np.array([dist[k] for k in ('k1', 'k2', 'k3', 'k4', 'p1', 'p2')], np.float32)
+  dist = {k: float(np.float32(v)) for k, v in dist.items()}
+  for tag, kw in (('dist', dict(distortion_params=dist)), ('fish', dict(camtype=cu.ProjectionType.FISHEYE)),
+                  ('distfish', dict(distortion_params=dist, camtype=cu.ProjectionType.FISHEYE))):
+    o2, d2, v2, r2 = cu.pixels_to_rays(px, py, pixtocams[cam_idx], camtoworlds[cam_idx], xnp=np, **kw)
+    out.update({f'{tag}_directions': d2, f'{tag}_viewdirs': v2, f'{tag}_radii': r2})
+  np.savez(f'{OUT}/camera.npz', **out)
 
 
 def nerfacto_golden(rng, ray_utils):

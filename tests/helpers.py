@@ -34,17 +34,18 @@ def make_rays(n, seed=0, near=0.2, far=1e6, scene_radius=1.0, glo=False, n_embed
 
 
 def config_pair(num_levels=2, n_prop=64, n_nerf=128, width=256, nerf_depth=8, prop_depth=4, precision='fp32',
-                max_rays=256, glo=0, contract=True, raydist='reciprocal', opaque=True, max_deg=12, ray_shape='cone'):
+                max_rays=256, glo=0, contract=True, raydist='reciprocal', opaque=True, max_deg=12, ray_shape='cone',
+                nerf_width=None):
   from nerf_hugs_b200.engine import EngineConfig
   warp = 'contract' if contract else None
   ocfg = O.ModelConfig(num_levels=num_levels, num_prop_samples=n_prop, num_nerf_samples=n_nerf,
                        raydist_fn=raydist, opaque_background=opaque, num_glo_features=glo, num_embeddings=16,
                        ray_shape=ray_shape,
-                       nerf_mlp=O.MLPConfig(net_depth=nerf_depth, net_width=width, warp_fn=warp, max_deg_point=max_deg),
+                       nerf_mlp=O.MLPConfig(net_depth=nerf_depth, net_width=nerf_width or width, warp_fn=warp, max_deg_point=max_deg),
                        prop_mlp=O.MLPConfig(net_depth=prop_depth, net_width=width, disable_rgb=True, warp_fn=warp,
                                             max_deg_point=max_deg))
   ecfg = EngineConfig(num_levels=num_levels, num_prop_samples=n_prop, num_nerf_samples=n_nerf,
-                      nerf_depth=nerf_depth, nerf_width=width, prop_depth=prop_depth, prop_width=width,
+                      nerf_depth=nerf_depth, nerf_width=nerf_width or width, prop_depth=prop_depth, prop_width=width,
                       raydist_fn=raydist, nerf_contract=contract, prop_contract=contract,
                       opaque_background=opaque, num_glo_features=glo, num_embeddings=16, precision=precision,
                       max_rays=max_rays, max_deg_point=max_deg, ray_shape=ray_shape)

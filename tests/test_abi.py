@@ -33,7 +33,7 @@ def test_struct_sizes_match_header():
   assert ctypes.sizeof(_lib.Rays) == 72
   assert ctypes.sizeof(_lib.LossCfg) == 36
   assert ctypes.sizeof(_lib.AdamCfg) == 32
-  assert ctypes.sizeof(_lib.CameraSet) == 96
+  assert ctypes.sizeof(_lib.CameraSet) == 112
   assert ctypes.sizeof(_lib.RayBatch) == 96
 
 

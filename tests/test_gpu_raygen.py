@@ -75,11 +75,26 @@ def test_generate_ray_batch_and_patch_sampling():
   assert len(np.unique(ci)) <= 2 and (ci[0] == ci[0, 0, 0]).all()
 
 
+@pytest.mark.parametrize('tag', ['dist', 'fish', 'distfish'])
+def test_lens_distortion_and_fisheye_vs_reference_golden(tag):
+  """Newton lens undistortion (camera_utils.py:460-494) and the fisheye projection (:557-568) in the ray-generation
+  kernel, against outputs of the reference's own pixels_to_rays."""
+  from nerf_hugs_b200.internal.datasets import DeviceDataset
+  ds = _dataset()
+  dist = dict(zip(('k1', 'k2', 'k3', 'k4', 'p1', 'p2'), [float(v) for v in G['dist_params']]))
+  dd = DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'],
+                     distortion_params=dist if 'dist' in tag else None, camtype='fisheye' if 'fish' in tag else 'perspective')
+  b = dd.make_ray_batch(torch.tensor(G['pix_x']), torch.tensor(G['pix_y']), torch.tensor(G['cam_idx']), want_rgb=False)
+  got = {k: v.cpu().numpy() for k, v in b.rays.as_dict().items()}
+  for k in ('directions', 'viewdirs', 'radii'):
+    np.testing.assert_allclose(got[k], G[f'{tag}_{k}'].astype(np.float32), rtol=3e-7, atol=1e-9, err_msg=k)
+
+
 def test_unsupported_camera_models_are_loud():
   from nerf_hugs_b200.internal.datasets import DeviceDataset
   ds = _dataset()
   with pytest.raises(NotImplementedError):
-    DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], camtype='fisheye')
+    DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], camtype='pano')
   with pytest.raises(NotImplementedError):
     DeviceDataset(ds['pixtocams'], ds['camtoworlds'], ds['heights'], ds['widths'], distortion_params=[{'k1': 0.1}])
 

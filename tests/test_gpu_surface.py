@@ -121,9 +121,10 @@ def test_train_pstep_stats_contract():
   # the gradient of the very same step (deterministic sampling so that it can be recomputed)
   config.randomized = False
   train_pstep = train_utils.create_train_step(model, config)
+  eng.params_changed(p0)
+  eng.set_train_rng(0, 0)
   g_ref, _ = eng.loss_and_grad(p0, rays, gt, 0.1, None, train_utils.loss_cfg_from(config))
   g_ref = g_ref.clone()
-  eng.params_changed(p0)
   state, stats, _ = train_pstep(None, state, batch, 0.1, None)
   for k in ('loss', 'losses', 'mses', 'psnrs', 'psnr', 'weight_l2s', 'grad_norms', 'grad_maxes', 'opt_update_norms',
             'opt_update_maxes'):
