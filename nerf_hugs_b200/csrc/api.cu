@@ -505,7 +505,6 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
   if ((rc = forward_levels(h, params, rays, n, train_frac, jitter, 0, 0, nullptr, true, st))) return rc;
 
   float* denom = h->scalars;          // [0] loss normaliser
-  float* sums = h->scalars + 8;       // [8..24) column sums of ray_stats
   ProfScope* ps_loss = new ProfScope(h, HUGS_K_COMPOSITE_LOSS, st);
   struct Guard { ProfScope** p; ~Guard() { delete *p; *p = nullptr; } } guard{&ps_loss};
   if ((rc = launch_lossmult_sum(rays->lossmult, rays->static_mask, loss->use_static_mask,
@@ -533,12 +532,7 @@ HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_
     a.bg = d.bg_intensity; a.sq_stats = h->ray_stats + (size_t)n * (8 + l);
     if ((rc = launch_prop_loss_bwd(a, st))) return rc;
   }
-  if ((rc = launch_column_sums(h->ray_stats, n, 4, 3, sums, st))) return rc;
-  for (int l = 0; l < L - 1; ++l) {
-    if ((rc = launch_column_sums(h->ray_stats + (size_t)n * (4 + l), n, 1, 1, sums + 4 + l, st))) return rc;
-    if ((rc = launch_column_sums(h->ray_stats + (size_t)n * (8 + l), n, 1, 1, sums + 8 + l, st))) return rc;
-  }
-  if ((rc = launch_finalize_stats(h, *loss, n, denom, sums, stats_out, st))) return rc;
+  if ((rc = launch_finalize_stats(h, *loss, n, denom, h->ray_stats, stats_out, st))) return rc;
   delete ps_loss; ps_loss = nullptr;
 
   HUGS_CUDA(cudaMemsetAsync(grad_out, 0, sizeof(float) * h->n_params, st));

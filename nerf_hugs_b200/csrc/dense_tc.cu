@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
   } else {
     // =============================== epilogue warps ===============================
     const int ew = warp - 2;
-    const int quarter = ew & 3, half = ew >> 2;
+    // a warp may only touch the TMEM lanes [32 * (warp % 4), +32): the lane quarter follows the hardware warp id
+    const int quarter = warp & 3, half = ew >> 2;
     const int row = quarter * 32 + lane;                // row inside this CTA's 128-row block == TMEM lane
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
     const bool store_leader = ew == 0 && lane == 0;

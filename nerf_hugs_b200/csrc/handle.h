@@ -61,7 +61,6 @@ struct hugs_handle {
     cudaEvent_t e; cudaEventCreate(&e); return e;
   }
 
-  long long* dbg_counters = nullptr;          // development instrumentation (hugs_debug_counters)
   uint64_t train_rng_key = 0;                 // hugs_set_train_rng: in-kernel jitter draws when no jitter tensor is passed
   cudaEvent_t grad_ready_event = nullptr;     // hugs_set_grad_ready_event: recorded after the NeRF level's backward
   const float* cur_params = nullptr;          // parameters of the call in flight

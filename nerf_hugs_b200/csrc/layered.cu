@@ -355,7 +355,9 @@ void build_wgrad(hugs_handle* h, LayeredMlp* m, int level, int n_samples) {
   for (int ab = 0; ab < W / 256; ++ab)
     units.push_back(unit(LW_ACT, (D - 1) * cap, ab * 256, LW_DZB, 0, 256, mv.dense[D + 1], ab * 256, 0, ab == 0 ? 1 : 0, 0));
   flush(units);
-  // launches 2..: trunk layers D-1 .. 0; dZ_l lives in dz[(D - 1 - l) & 1]
+  // launches 2..: trunk layers D-1 .. 0; dZ_l lives in dz[(D - 1 - l) & 1].  All (A block, dZ block) units of a layer form
+  // one group: the 16 (24 with the skip features) items of a sample range are queued next to each other, so every A
+  // and dZ block is streamed from HBM once and read by its other three consumers out of L2
   for (int l = D - 1; l >= 0; --l) {
     const int bmap = ((D - 1 - l) & 1) ? LW_DZ1 : LW_DZ0;
     const bool cat_in = l > 0 && ((l - 1) % m->skip == 0 && (l - 1) > 0);
@@ -363,11 +365,11 @@ void build_wgrad(hugs_handle* h, LayeredMlp* m, int level, int n_samples) {
       if (l > 0)
         for (int ab = 0; ab < W / 256; ++ab)
           units.push_back(unit(LW_ACT, (l - 1) * cap, ab * 256, bmap, bb * 256, 256, mv.dense[l], ab * 256, 0,
-                               ab == 0 ? 1 : 0, ab));
+                               ab == 0 ? 1 : 0, 0));
       if (l == 0 || cat_in)
         for (int sb = 0; sb < kFeatPad / 256; ++sb)
           units.push_back(unit(LW_FEAT, tc->feat_row0[level], sb * 256, bmap, bb * 256, 256, mv.dense[l], l == 0 ? 0 : W, 1,
-                               (l == 0 && sb == 0) ? 1 : 0, 50 + sb));
+                               (l == 0 && sb == 0) ? 1 : 0, 0));
     }
     flush(units);
   }

@@ -104,11 +104,19 @@ __global__ void __launch_bounds__(256) adam_kernel(float* params, const float* g
       const float d = p_new - p_old;
       if (uniform) {
         w2 += p_old * p_old; g2 += gs * gs; ga = fmaxf(ga, fabsf(gs)); d2 += d * d; da = fmaxf(da, fabsf(d));
-      } else {                                             // a block that straddles tensors (biases): per element
-        float* dst = tstats + (size_t)tensor_of(i) * 5;
-        atomicAdd(dst + 0, p_old * p_old); atomicAdd(dst + 1, gs * gs); atomicAdd(dst + 3, d * d);
-        atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(fabsf(gs)));
-        atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(fabsf(d)));
+      } else {                                             // a block that straddles tensors (biases): per warp / lane
+        const unsigned act = __activemask();
+        const int t = tensor_of(i);
+        const int t0 = __shfl_sync(act, t, __ffs(act) - 1);
+        float a0 = p_old * p_old, a1 = gs * gs, a2 = fabsf(gs), a3 = d * d, a4 = fabsf(d);
+        float* dst = tstats + (size_t)t * 5;
+        if (act == kFull && __all_sync(kFull, t == t0)) {
+          a0 = warp_sum(a0); a1 = warp_sum(a1); a3 = warp_sum(a3); a2 = warp_max(a2); a4 = warp_max(a4);
+          if ((threadIdx.x & 31) != 0) continue;
+        }
+        atomicAdd(dst + 0, a0); atomicAdd(dst + 1, a1); atomicAdd(dst + 3, a3);
+        atomicMax(reinterpret_cast<int*>(dst + 2), __float_as_int(a2));
+        atomicMax(reinterpret_cast<int*>(dst + 4), __float_as_int(a4));
       }
     }
   }
@@ -130,8 +138,33 @@ __global__ void __launch_bounds__(256) adam_kernel(float* params, const float* g
   }
 }
 
-__global__ void finalize_stats_kernel(hugs_loss_cfg loss, int n, int L, int S_final, const float* denom,
-                                      const float* sums, float* stats) {
+// One block: the per-ray loss partials (ray_stats: [n, 4] of the final level, then one [n] column per proposal level
+// for the interlevel term and one for the level's squared error) are summed column by column in a fixed order, then
+// the scalars of stats_out are formed (train_utils.py:93-111, 228-248): deterministic, one launch.
+__global__ void __launch_bounds__(1024) reduce_finalize_stats_kernel(hugs_loss_cfg loss, int n, int L, int S_final,
+                                                                    const float* denom, const float* ray_stats,
+                                                                    float* stats) {
+  __shared__ float red[32];
+  __shared__ float sums[16];
+  // column c: c < 3 -> ray_stats[r * 4 + c]; 4 + l -> interlevel of level l; 8 + l -> squared error of level l
+  for (int c = 0; c < 12; ++c) {
+    const bool final_col = c < 3;
+    const int l = c >= 8 ? c - 8 : c - 4;
+    if (!final_col && (c == 3 || l < 0 || l >= L - 1)) { if (threadIdx.x == 0) sums[c] = 0.f; continue; }
+    const float* src = final_col ? ray_stats + c : ray_stats + (size_t)n * c;
+    const int stride = final_col ? 4 : 1;
+    float s = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += src[(size_t)i * stride];
+    s = warp_sum(s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      float v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+      v = warp_sum(v);
+      if (threadIdx.x == 0) sums[c] = v;
+    }
+    __syncthreads();
+  }
   if (threadIdx.x != 0) return;
   const float dn = fmaxf(denom[0], kF32Eps);
   const float data = loss.data_loss_mult * sums[0] / dn;
@@ -150,10 +183,10 @@ __global__ void finalize_stats_kernel(hugs_loss_cfg loss, int n, int L, int S_fi
 
 }  // namespace
 
-int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, const float* denom, const float* sums,
+int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, const float* denom, const float* ray_stats,
                           float* stats_out, cudaStream_t st) {
-  finalize_stats_kernel<<<1, 32, 0, st>>>(loss, n, h->d.num_levels, h->samples(h->d.num_levels - 1), denom, sums,
-                                          stats_out);
+  reduce_finalize_stats_kernel<<<1, 1024, 0, st>>>(loss, n, h->d.num_levels, h->samples(h->d.num_levels - 1), denom,
+                                                   ray_stats, stats_out);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
 }

@@ -21,7 +21,7 @@ int tc_mlp_backward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays
 int tc_debug_encode(hugs_handle* h, const hugs_rays* rays, const float* tdist, int n_rays, int S, int contract,
                     __nv_bfloat16* out, cudaStream_t st);
 
-int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, const float* denom, const float* sums,
+int launch_finalize_stats(hugs_handle* h, const hugs_loss_cfg& loss, int n, const float* denom, const float* ray_stats,
                           float* stats_out, cudaStream_t st);
 
 }  // namespace hugs

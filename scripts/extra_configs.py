@@ -1,4 +1,6 @@
-"""Measurements of the BASELINE.json parity configs that are not the bench line (one GPU; JSON lines on stdout):
+"""Measurements of the BASELINE.json parity configs that are not the bench line (JSON lines on stdout; one GPU, or N GPUs
+of one box under `python -m torch.distributed.run --nproc-per-node N scripts/extra_configs.py ...`: rays shard over the
+ranks, times are the maximum over ranks, rank 0 prints):
 
   config 3  Mip-NeRF 360 with HuGS static masks, Phototourism-shape synthetic scene
             (phototourism_1024_withmask.gin shape: no warp_fn / raydist_fn, per-pixel near/far, patch 16, 48 GLO
@@ -18,8 +20,46 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
 
+import torch.distributed as dist
+
 from nerf_hugs_b200.internal import configs, models, train_utils, utils
 from nerf_hugs_b200.internal.datasets import DeviceDataset
+
+RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (('RANK', '0'), ('WORLD_SIZE', '1'), ('LOCAL_RANK', '0')))
+
+
+def device():
+  torch.cuda.set_device(LOCAL)
+  dev = torch.device('cuda', LOCAL)
+  if WORLD > 1 and not dist.is_initialized():
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    dist.init_process_group('nccl', device_id=dev)
+  return dev
+
+
+def timed(fn, steps, dev):
+  """ms per step: barrier + synchronize on both sides, CUDA events, maximum over ranks."""
+  if WORLD > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  e0.record()
+  out = None
+  for _ in range(steps):
+    out = fn()
+  e1.record()
+  if WORLD > 1:
+    dist.barrier()
+  torch.cuda.synchronize()
+  ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+  if WORLD > 1:
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+  return float(ms.item()), out
+
+
+def emit(d):
+  if RANK == 0:
+    print(json.dumps(d), flush=True)
 
 
 def sphere_cameras(rng, n_cams, hw):
@@ -56,10 +96,10 @@ def run_hugs(steps, batch=4096):
           'PropMLP.net_depth = 4', 'PropMLP.net_width = 256', 'PropMLP.disable_rgb = True', 'NerfMLP.net_depth = 8',
           'NerfMLP.net_width = 256']
   config = configs.load_config([], bind, save_config=False)
-  dev = torch.device('cuda', 0)
+  dev = device()
   model, state, _, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=batch, device=dev)
   dd = hugs_dataset()
-  gen = torch.Generator(device=dev); gen.manual_seed(1)
+  gen = torch.Generator(device=dev); gen.manual_seed(1 + RANK)
 
   def step():
     b = dd.next_train_batch(gen, batch, config.patch_size, config.patch_dilation, config.image_num_per_batch)
@@ -67,19 +107,14 @@ def run_hugs(steps, batch=4096):
 
   for _ in range(10):
     step()
-  torch.cuda.synchronize()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  e0.record()
-  for _ in range(steps):
-    _, stats, _ = step()
-  e1.record(); torch.cuda.synchronize()
-  ms = e0.elapsed_time(e1) / steps
+  ms, out = timed(step, steps, dev)
+  stats = out[1]
   b = dd.next_train_batch(gen, batch, config.patch_size, config.patch_dilation, config.image_num_per_batch)
-  print(json.dumps({'config': 'Mip-NeRF 360 + HuGS static masks (Phototourism-shape synthetic, patch 16, GLO 48, no warp / '
-                              'raydist), device-side batch assembly', 'metric': 'training rays/s', 'value': batch / ms * 1e3,
-                    'ms_per_step': ms, 'rays_per_gpu': batch, 'n_gpus': 1, 'steps': steps,
-                    'loss': float(stats['loss']), 'static_fraction': float(b.rays.static_mask.mean()),
-                    'h2d_bytes_per_step': 0}))
+  emit({'config': 'BASELINE config 3: Mip-NeRF 360 + HuGS static masks (Phototourism-shape synthetic, patch 16, GLO 48, no '
+                  'warp / raydist), device-side batch assembly, rays sharded over the GPUs (weak scaling)',
+        'metric': 'training rays/s', 'value': WORLD * batch / ms * 1e3, 'ms_per_step': ms, 'rays_per_gpu': batch,
+        'n_gpus': WORLD, 'steps': steps, 'loss': float(stats['loss']),
+        'static_fraction': float(b.rays.static_mask.mean()), 'h2d_bytes_per_step': 0})
 
 
 def run_config_b(steps, batch=4096):
@@ -88,47 +123,40 @@ def run_config_b(steps, batch=4096):
   bind = [b for b in bench.gin_bindings(batch) if 'num_levels' not in b and 'num_nerf_samples' not in b]
   bind += ['Model.num_levels = 3', 'Model.num_nerf_samples = 32']
   config = configs.load_config([], bind, save_config=False)
-  dev = torch.device('cuda', 0)
+  dev = device()
   model, state, _, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=batch, device=dev)
-  rays, rgb = bench.synthetic_batch(batch, seed=5)
+  rays, rgb = bench.synthetic_batch(batch, seed=5 + RANK)
   b = utils.Batch(rays=utils.Rays(**{k: v.to(dev) for k, v in rays.items()}), rgb=rgb.to(dev))
   gen = torch.Generator(device=dev); gen.manual_seed(1)
   for _ in range(10):
     train_pstep(gen, state, b, 0.1, None)
-  torch.cuda.synchronize()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  e0.record()
-  for _ in range(steps):
-    _, stats, _ = train_pstep(gen, state, b, 0.1, None)
-  e1.record(); torch.cuda.synchronize()
-  ms = e0.elapsed_time(e1) / steps
-  print(json.dumps({'config': 'Mip-NeRF 360 variant B: 3 levels, 64 / 64 / 32 samples, 256-wide MLPs (SURVEY §8d)',
-                    'metric': 'training rays/s', 'value': batch / ms * 1e3, 'ms_per_step': ms, 'rays_per_gpu': batch,
-                    'n_gpus': 1, 'steps': steps, 'loss': float(stats['loss'])}))
+  ms, out = timed(lambda: train_pstep(gen, state, b, 0.1, None), steps, dev)
+  emit({'config': 'Mip-NeRF 360 variant B: 3 levels, 64 / 64 / 32 samples, 256-wide MLPs (SURVEY §8d)',
+        'metric': 'training rays/s', 'value': WORLD * batch / ms * 1e3, 'ms_per_step': ms, 'rays_per_gpu': batch,
+        'n_gpus': WORLD, 'steps': steps, 'loss': float(out[1]['loss'])})
 
 
 def run_render(resolutions=((800, 800), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840))):
   import bench
   config = configs.load_config([], bench.gin_bindings(4096), save_config=False)
-  config.render_chunk_size = 65536
-  dev = torch.device('cuda', 0)
-  model, state, render_eval_pfn, _, _ = train_utils.setup_model(config, rng=0, max_rays=config.render_chunk_size, device=dev)
+  config.render_chunk_size = 65536 * WORLD          # every rank renders 65536 rays of a chunk
+  dev = device()
+  model, state, render_eval_pfn, _, _ = train_utils.setup_model(config, rng=0, max_rays=65536, device=dev)
   rng = np.random.default_rng(0)
   for h, w in resolutions:
     p2c, c2w = sphere_cameras(rng, 1, np.array([[h, w]]))
     dd = DeviceDataset(p2c, c2w, [h], [w], near=0.2, far=1e6)
     rays = dd.generate_ray_batch(0).rays
     fn = lambda _, chunk: render_eval_pfn(state.params, 1.0, None, chunk)
-    out = models.render_image(fn, rays, None, config, verbose=False)       # warm-up
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    out = models.render_image(fn, rays, None, config, verbose=False)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    render = lambda: models.render_image(fn, rays, None, config, verbose=False, world_size=WORLD)
+    render()                                                                # warm-up
+    ms, out = timed(render, 1, dev)
+    dt = ms * 1e-3
     assert tuple(out['rgb'].shape) == (h, w, 3) and torch.isfinite(out['rgb']).all()
-    print(json.dumps({'config': f'full-frame render {w}x{h} (config A weights, compute_extras, chunk {config.render_chunk_size})',
-                      'metric': 'render rays/s', 'value': h * w / dt, 'frame_s': dt, 'n_gpus': 1,
-                      'outputs': sorted(k for k in out if not k.startswith('ray_'))}))
+    emit({'config': f'BASELINE config 5: full-frame render {w}x{h} (config A weights, compute_extras, 65536 rays per GPU '
+                    f'and chunk, rows striped over the GPUs, all-gather per chunk)',
+          'metric': 'render rays/s', 'value': h * w / dt, 'frame_s': dt, 'n_gpus': WORLD,
+          'outputs': sorted(k for k in out if not k.startswith('ray_'))})
 
 
 if __name__ == '__main__':
@@ -142,3 +170,6 @@ if __name__ == '__main__':
     run_render()
   if 'b' in a.what:
     run_config_b(a.steps)
+  if WORLD > 1:
+    dist.barrier()
+    dist.destroy_process_group()

@@ -42,6 +42,12 @@ def main():
   header, units, data = rows[0], rows[1], rows[2:]
   col = {h: i for i, h in enumerate(header)}
   kernels, dram = [], {}
+  # the capture may start anywhere inside a step (e.g. view_extra_wgrad_kernel also matches the regex "wgrad_kernel"):
+  # find the rotation of the launch order whose chain / wgrad pattern fits the captured names
+  names = ['wgrad' if 'wgrad_kernel' in r[col['Kernel Name']] else 'chain' for r in data]
+  expect = ['wgrad' if c.startswith('wgrad') else 'chain' for c in ORDER]
+  rot = next((k for k in range(len(ORDER)) if len(data) == len(ORDER) and
+              all(names[i] == expect[(i + k) % len(ORDER)] for i in range(len(ORDER)))), None)
   for i, r in enumerate(data):
     k = {}
     for name in KEEP:
@@ -51,9 +57,9 @@ def main():
     total = to_bytes(r[col['dram__bytes_read.sum']], units[col['dram__bytes_read.sum']]) + \
         to_bytes(r[col['dram__bytes_write.sum']], units[col['dram__bytes_write.sum']])
     k['dram_bytes_total'] = total
-    if i < len(ORDER) and len(data) == len(ORDER):
-      k['class'] = ORDER[i]
-      dram[ORDER[i]] = total
+    if rot is not None:
+      k['class'] = ORDER[(i + rot) % len(ORDER)]
+      dram[k['class']] = total
     kernels.append(k)
   note = (f'ncu --set full --clock-control none of the six MLP kernels of one training step (config A, 4096 rays, '
           f'scripts/profile_fwd.py train), capture {os.path.basename(rep)}. Cold-cache serialised replay: compare shares '
