@@ -223,7 +223,18 @@ def run_ours(args):
   dev = torch.device('cuda', local)
   if world > 1:
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-    dist.init_process_group('nccl', device_id=dev)
+    # NCCL announces its version on stdout when the first communicator is created: keep stdout for the one JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+      dist.init_process_group('nccl', device_id=dev)
+      dist.all_reduce(torch.zeros(1, device=dev))
+      torch.cuda.synchronize()
+    finally:
+      sys.stdout.flush()
+      os.dup2(saved_stdout, 1)
+      os.close(saved_stdout)
   from nerf_hugs_b200.internal import configs, train_utils, utils
   from nerf_hugs_b200.engine import Engine
 

@@ -20,15 +20,36 @@ bind = ['Config.batch_size = 512', 'Config.near = 0.2', 'Config.far = 1e6', 'Con
         'Model.num_prop_samples = 64', 'Model.num_nerf_samples = 128', 'PropMLP.warp_fn = @coord.contract',
         'PropMLP.net_depth = 4', 'PropMLP.disable_rgb = True', 'NerfMLP.warp_fn = @coord.contract', 'NerfMLP.net_width = 256']
 config = configs.load_config([], bind, save_config=False)
-model, state, render_eval_pfn, train_pstep, _ = train_utils.setup_model(config, rng=0, max_rays=1024, device=dev)
+model, state, render_eval_pfn, train_pstep, lr_fn = train_utils.setup_model(config, rng=0, max_rays=1024, device=dev)
 
 # training: every rank takes its slice of one global batch; parameters must stay replicated
 rays, gt = H.make_rays(512, seed=1)
 mine = utils.Batch(rays=utils.Rays(**{k: utils.rank_slice(v, rank, world) for k, v in rays.items()}),
                    rgb=utils.rank_slice(gt, rank, world))
 gen = torch.Generator(device=dev); gen.manual_seed(100 + rank)
-for _ in range(2):
+# the update train_pstep must produce in its first step: pmean of the per-rank gradients (train_utils.py:457-458), then
+# clip + Adam - computed here with ONE plain all-reduce, against train_pstep's two overlapped collectives
+from nerf_hugs_b200 import _lib
+eng = model.engine
+p0 = state.params.clone()
+eng.params_changed(p0)
+eng.set_train_rng(train_utils._rng_seed(gen), 0)
+g, _ = eng.loss_and_grad(p0, {k: v.to(dev) for k, v in mine.rays.as_dict().items()}, mine.rgb.to(dev), 0.1, None,
+                         train_utils.loss_cfg_from(config))
+g = g.clone()
+dist.all_reduce(g)
+a = _lib.AdamCfg()
+a.lr, a.beta1, a.beta2, a.eps = float(lr_fn(0)), config.adam_beta1, config.adam_beta2, config.adam_eps
+a.grad_max_norm, a.grad_max_val, a.step, a.grad_scale = config.grad_max_norm, config.grad_max_val, 0, 1.0 / world
+p_expect, mu, nu = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+eng.adam_step(p_expect, g, mu, nu, a)
+eng.params_changed(state.params)
+for i in range(2):
   state, stats, gen = train_pstep(gen, state, mine, 0.1, None)
+  if i == 0:
+    d_exp, d_got = (p_expect - p0), (state.params - p0)
+    rel = float((d_exp - d_got).norm() / d_exp.norm())
+    assert rel < 1e-3, f'overlapped all-reduce changed the update: {rel}'      # fp32 atomics reorder the reductions
 ref = state.params.clone()
 dist.broadcast(ref, 0)
 assert torch.equal(ref, state.params), 'replicas diverged'
