@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define HUGS_ABI_VERSION 1
+#define HUGS_ABI_VERSION 2
 
 typedef enum {
   HUGS_OK = 0,
@@ -44,6 +44,11 @@ typedef enum { HUGS_PRECISION_FP32 = 0,    /* CUDA-core fp32 MLP (render only): 
                                               backward at fp32-level accuracy (render 1e-4, gradients 1e-3)          */
 } hugs_precision;
 typedef enum { HUGS_LOSS_CHARB = 0, HUGS_LOSS_MSE = 1 } hugs_data_loss;  /* train_utils.py:96-103 */
+/* Input encoding of the MLPs.  HUGS_ENC_IPE: integrated positional encoding of contracted conical-frustum Gaussians
+ * (MipNeRF360/internal/coord.py:102-133).  HUGS_ENC_POINT_PE: the torch twin's pos_enc(x, min_deg, max_deg,
+ * append_identity=True) of the interval midpoint o + d * (t0 + t1) / 2, optionally contracted by
+ * spatial_distortion_norm2 (nerfacto/models/custom_functions.py:15-21,55-63; nerfacto/models/nerf.py:299-300,788-794). */
+typedef enum { HUGS_ENC_IPE = 0, HUGS_ENC_POINT_PE = 1 } hugs_encoding;
 
 /* Model description == the gin-bound fields of models.Model / NerfMLP / PropMLP
  * (MipNeRF360/internal/models.py:47-71, :360-391) the hot path reads. */
@@ -74,6 +79,8 @@ typedef struct {
   float   density_bias, rgb_premultiplier, rgb_bias, rgb_padding;
   int32_t precision;           /* hugs_precision */
   int32_t max_rays;            /* workspace is sized for this many rays per call */
+  int32_t encoding;            /* hugs_encoding (0 = IPE: every Mip-NeRF 360 config) */
+  int32_t reserved_[3];
 } hugs_model_desc;
 
 /* utils.Rays (MipNeRF360/internal/utils.py:44-57) as struct-of-arrays device pointers,
@@ -214,6 +221,86 @@ int hugs_adam_step(hugs_handle* h, float* params, const float* grad, float* mu, 
  * {sum w^2 before the update, sum g^2, max |g| (averaged, unclipped gradient), sum delta^2, max |delta| (applied update)}. */
 int hugs_adam_step_stats(hugs_handle* h, float* params, const float* grad, float* mu, float* nu,
                          const hugs_adam_cfg* cfg, float* norms_out, float* tensor_stats_out, void* stream);
+
+/* ---- the torch twins: nerfacto/{train,eval}.py call surface (SURVEY.md §8(a) last row, §8(b) last row) ----
+ *
+ * nerfacto/models/nerf.py::Model.forward_rays is, per field ('coarse', 'fine'): sample_intervals under no_grad ->
+ * s_to_t -> field MLP on point encodings -> density_to_weight -> render_features / render_depth.  The host mirror
+ * (nerf_hugs_b200/nerfacto/models/nerf.py) strings the operators below together and exposes them to torch autograd;
+ * one hugs_handle (num_levels = 1, encoding = HUGS_ENC_POINT_PE) per field carries the MLP. */
+
+/* MLP.forward of one field on caller-provided interval fenceposts (nerf.py:299-318,788-860 == the NerfMLP of
+ * MipNeRF360/internal/models.py:405-550 with a point encoding): raw_out [n, S, 4] = pre-activation density and rgb.
+ * Uses the handle's last (NeRF) level; n_samples <= num_nerf_samples.  rays: origins, directions, viewdirs
+ * (+ embed_idx with appearance embeddings; radii with HUGS_ENC_IPE).  training != 0 saves what hugs_field_backward needs. */
+int hugs_field_forward(hugs_handle* h, const float* params, const hugs_rays* rays, const float* tdist,
+                       int32_t n_rays, int32_t n_samples, int32_t training, int32_t zero_glo, float* raw_out,
+                       void* stream);
+/* loss.backward() through the field of the preceding hugs_field_forward(training = 1): d_raw [n, S, 4] ->
+ * grad_out (flat fp32 [param_count], flax layout, overwritten). */
+int hugs_field_backward(hugs_handle* h, const float* params, const hugs_rays* rays, int32_t n_rays,
+                        int32_t n_samples, const float* d_raw, float* grad_out, void* stream);
+
+/* utils/ray_utils.py:113-223 sample + sample_intervals (torch.searchsorted(side='right') + gather; quirk B5: a ray
+ * whose bins all have zero width gets uniform logits).  u = u_base[j] + jitter[ray * jitter_stride + j * (stride > 1)]
+ * * max_jitter; jitter NULL = deterministic.  spacing_fn (hugs_raydist_fn: NONE = 'uniform', RECIPROCAL, PIECEWISE) with
+ * near / far [n] turns the new fenceposts into euclidean ones (nerf.py:221-226) when t_out != NULL. */
+int hugs_nf_sample_intervals(const float* bins, const float* weights, const float* u_base, const float* jitter,
+                             int32_t jitter_stride, float max_jitter, float anneal, float padding, int32_t n_rays,
+                             int32_t n_bins, int32_t n_samples, float dom_lo, float dom_hi, int32_t spacing_fn,
+                             const float* near, const float* far, float* bins_out, float* t_out, void* stream);
+/* nerf.py:287-295: fenceposts around the sorted union of the centres of two fencepost sets. */
+int hugs_nf_merge_bins(const float* bins_a, int32_t n_a, const float* bins_b, int32_t n_b, int32_t n_rays,
+                       float dom_lo, float dom_hi, int32_t spacing_fn, const float* near, const float* far,
+                       float* bins_out, float* t_out, void* stream);
+
+typedef enum { HUGS_DENSITY_SOFTPLUS = 0, HUGS_DENSITY_TRUNC_EXP = 1, HUGS_DENSITY_RELU = 2 } hugs_density_act;
+typedef struct {
+  int32_t opaque_background;
+  int32_t density_activation;    /* hugs_density_act (nerf.py:682-691, nerfacto.py:702-710) */
+  float   density_bias;
+  float   rgb_premultiplier, rgb_bias, rgb_padding;   /* nerf.py:696-698,832 */
+  int32_t reserved_[2];
+} hugs_nf_render_cfg;
+
+/* utils/ray_utils.py:226-249 density_to_weight (quirk B2: deltas from the FIRST fencepost; B6: nan_to_num),
+ * :295-312 render_features (per-ray background colour), :336-346 render_depth before its clip.
+ * raw [n, S, C]: C = 4 (density, r, g, b pre-activation) or C = 1 (density only: rgb_out must be NULL).
+ * steps_max: device scalar, atomically raised to max over rays of the last interval midpoint (caller zeroes it);
+ * hugs_nf_clip_depth applies the batch-wide clip of quirk B7. */
+int hugs_nf_composite(const hugs_nf_render_cfg* cfg, const float* raw, int32_t raw_channels, const float* tdist,
+                      const float* directions, const float* bg_rgb, int32_t n_rays, int32_t n_samples,
+                      float* weights_out, float* rgb_out, float* depth_out, float* acc_out, float* steps_max,
+                      void* stream);
+int hugs_nf_clip_depth(float* depth, const float* steps_max, int32_t n_rays, void* stream);
+/* Backward of hugs_nf_composite (+ the clip): upstream gradients d_weights [n,S], d_rgb [n,3], d_depth [n], d_acc [n]
+ * (each may be NULL) -> d_raw [n, S, C]. */
+int hugs_nf_composite_bwd(const hugs_nf_render_cfg* cfg, const float* raw, int32_t raw_channels, const float* tdist,
+                          const float* directions, const float* bg_rgb, int32_t n_rays, int32_t n_samples,
+                          const float* d_weights, const float* d_rgb, const float* d_depth, const float* d_acc,
+                          const float* steps_max, float* d_raw, void* stream);
+
+/* nerf.py:404-461 / nerfacto.py:428-490 compute_data_loss / compute_withmask_loss of one rendering:
+ * e = (pred - gt)^2, l = e (HUGS_LOSS_MSE) or sqrt(e + padding^2) (HUGS_LOSS_CHARB), lossmult m per ray (static_mask >= 0.5
+ * ? 1 : transient_weight; NULL mask: 1) broadcast over the channels BEFORE the sums (no quirk B1 on the torch side).
+ * sums_out fp32[3] (zeroed here) = {sum m*l, sum m*e, sum m (x channels)}; dl_out [n,3] = m * dl/dpred for the backward. */
+int hugs_nf_rgb_loss(const float* pred, const float* gt, const float* static_mask, float transient_weight,
+                     int32_t loss_type, float charb_padding, int32_t n_rays, float* sums_out, float* dl_out, void* stream);
+/* d_pred = upstream[0] * scale / max(sums[2], eps) * dl   (upstream: device scalar dL/dloss) */
+int hugs_nf_rgb_loss_bwd(const float* dl, const float* sums, const float* upstream, float scale, int32_t n_rays,
+                         float* d_pred, void* stream);
+
+/* torch parameters <-> the flat flax-layout buffer of a handle: one table-driven copy instead of one per tensor.
+ * table (DEVICE pointer) of n entries; direction 0: flat[flat_off + i*cols + j] = transpose ? ptr[j*rows + i]
+ * : ptr[i*cols + j]; direction 1: the reverse (flat -> tensors).  nn.Linear.weight is [out, in] (transpose = 1 against
+ * the [in, out] kernel of hugs_param_layout). */
+typedef struct {
+  float*  ptr;
+  int64_t flat_off;
+  int32_t rows, cols;            /* shape of the FLAT (flax) view */
+  int32_t transpose, reserved_;
+} hugs_tensor_copy;
+int hugs_params_copy(const hugs_tensor_copy* table, int32_t n, float* flat, int32_t direction, void* stream);
 
 /* ---- batch assembly on the device (the caller of the path: SURVEY.md §8f item 2) ---- */
 

@@ -30,7 +30,7 @@ class ModelDesc(C.Structure):
       ('resample_padding', C.c_float), ('near_anneal_rate', C.c_float), ('near_anneal_init', C.c_float),
       ('num_glo_features', C.c_int32), ('num_embeddings', C.c_int32),
       ('density_bias', C.c_float), ('rgb_premultiplier', C.c_float), ('rgb_bias', C.c_float), ('rgb_padding', C.c_float),
-      ('precision', C.c_int32), ('max_rays', C.c_int32),
+      ('precision', C.c_int32), ('max_rays', C.c_int32), ('encoding', C.c_int32), ('reserved_', C.c_int32 * 3),
   ]
 
 
@@ -68,6 +68,17 @@ class CameraSet(C.Structure):
               ('reserved_', C.c_int32)]
 
 
+class NfRenderCfg(C.Structure):
+  _fields_ = [('opaque_background', C.c_int32), ('density_activation', C.c_int32), ('density_bias', C.c_float),
+              ('rgb_premultiplier', C.c_float), ('rgb_bias', C.c_float), ('rgb_padding', C.c_float),
+              ('reserved_', C.c_int32 * 2)]
+
+
+class TensorCopy(C.Structure):
+  _fields_ = [('ptr', C.c_void_p), ('flat_off', C.c_int64), ('rows', C.c_int32), ('cols', C.c_int32),
+              ('transpose', C.c_int32), ('reserved_', C.c_int32)]
+
+
 class RayBatch(C.Structure):
   _fields_ = [(n, C.c_void_p) for n in ('origins', 'directions', 'viewdirs', 'radii', 'near', 'far', 'lossmult',
                                         'static_mask', 'embed_idx', 'cam_idx', 'pix_coords', 'rgb')]
@@ -96,6 +107,16 @@ SYMBOLS = {
     'hugs_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P]),
     'hugs_adam_step_stats': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P, _P]),
     'hugs_make_ray_batch': (C.c_int, [C.POINTER(CameraSet), _P, _P, _P, _I, C.POINTER(RayBatch), _P]),
+    'hugs_field_forward': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _I, _I, _I, _P, _P]),
+    'hugs_field_backward': (C.c_int, [_P, _P, C.POINTER(Rays), _I, _I, _P, _P, _P]),
+    'hugs_nf_sample_intervals': (C.c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P]),
+    'hugs_nf_merge_bins': (C.c_int, [_P, _I, _P, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P]),
+    'hugs_nf_composite': (C.c_int, [C.POINTER(NfRenderCfg), _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P]),
+    'hugs_nf_clip_depth': (C.c_int, [_P, _P, _I, _P]),
+    'hugs_nf_composite_bwd': (C.c_int, [C.POINTER(NfRenderCfg), _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
+    'hugs_nf_rgb_loss': (C.c_int, [_P, _P, _P, _F, _I, _F, _I, _P, _P, _P]),
+    'hugs_nf_rgb_loss_bwd': (C.c_int, [_P, _P, _P, _F, _I, _P, _P]),
+    'hugs_params_copy': (C.c_int, [_P, _I, _P, _I, _P]),
     'hugs_launch_count': (C.c_int64, []),
     'hugs_profile_enable': (C.c_int, [_P, _I]),
     'hugs_profile_read': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

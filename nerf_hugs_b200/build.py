@@ -17,6 +17,7 @@ SOURCES = [
     ('api.cu', []),
     ('sampling.cu', ['-fmad=false']),
     ('composite.cu', ['-fmad=false']),
+    ('nerfacto_ops.cu', ['-fmad=false']),
     ('mlp_simt.cu', ['-fmad=false']),
     ('mlp_tc.cu', []),
     ('mlp_pp.cu', []),

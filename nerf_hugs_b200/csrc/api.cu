@@ -82,7 +82,9 @@ int validate(const hugs_model_desc& d) {
   HUGS_REQUIRE(d.num_levels == 1 || (d.num_prop_samples >= 2 && d.num_prop_samples <= 256),
                "num_prop_samples must be in [2,256]");
   HUGS_REQUIRE(d.num_basis >= 1 && d.num_basis <= 32, "num_basis must be in [1,32]");
-  HUGS_REQUIRE(d.max_deg_point > d.min_deg_point && d.max_deg_point - d.min_deg_point <= 16, "bad IPE degrees");
+  HUGS_REQUIRE(d.encoding == HUGS_ENC_IPE || d.encoding == HUGS_ENC_POINT_PE, "unknown encoding %d", d.encoding);
+  HUGS_REQUIRE(d.max_deg_point > d.min_deg_point && d.max_deg_point - d.min_deg_point <= (d.encoding == HUGS_ENC_IPE ? 16 : 40),
+               "bad positional-encoding degrees");
   HUGS_REQUIRE(d.nerf_depth >= 1 && d.prop_depth >= 1 && d.nerf_width >= 1 && d.prop_width >= 1, "bad MLP shape");
   HUGS_REQUIRE(d.skip_layer >= 1, "skip_layer must be >= 1");
   HUGS_REQUIRE(d.deg_view >= 0 && d.deg_view <= 8, "deg_view must be in [0,8]");
@@ -164,7 +166,15 @@ HUGS_API int hugs_create(const hugs_model_desc* desc, hugs_handle** out) {
   rc = HUGS_OK;
   auto fail = [&](int code) { hugs_destroy(h); return code; };
   if (cudaGetDevice(&h->device) != cudaSuccess) return fail(HUGS_ERR_CUDA);
-  h->feat_dim = 2 * d.num_basis * (d.max_deg_point - d.min_deg_point);
+  if (d.encoding == HUGS_ENC_POINT_PE) {
+    h->feat_dim = 3 + 6 * (d.max_deg_point - d.min_deg_point);    // pos_enc(..., append_identity=True)
+    h->perm_nb = 0;
+  } else {
+    h->feat_dim = 2 * d.num_basis * (d.max_deg_point - d.min_deg_point);
+    h->perm_nb = d.num_basis;
+  }
+  h->feat_panels = (h->feat_dim + 63) / 64;
+  h->max_nerf_samples = d.num_nerf_samples;
   h->view_in_dim = 3 + 6 * d.deg_view + d.num_glo_features;
 
   int64_t off = 0;
@@ -313,6 +323,11 @@ HUGS_API int hugs_alpha_composite(const hugs_handle* h, const float* raw_density
 HUGS_API int hugs_ipe_features(const hugs_handle* h, const hugs_rays* rays, const float* tdist, int32_t n_rays,
                                int32_t n_samples, int32_t contract, float* features, void* stream) {
   HUGS_REQUIRE(h && rays && tdist && features, "hugs_ipe_features: null argument");
+  if (h->d.encoding == HUGS_ENC_POINT_PE) {
+    PointPeArgs pa{rays->origins, rays->directions, tdist, n_rays, n_samples, h->d.min_deg_point,
+                   h->d.max_deg_point - h->d.min_deg_point, contract, features, nullptr, nullptr, 0, 0, 0};
+    return launch_point_pe(pa, (cudaStream_t)stream);
+  }
   IpeArgs a{rays->origins, rays->directions, rays->radii, tdist, h->basis, n_rays, n_samples,
             h->d.num_basis, h->d.min_deg_point, h->d.max_deg_point, h->d.ray_shape, contract, features};
   return launch_ipe_features(a, (cudaStream_t)stream);
@@ -367,9 +382,16 @@ int run_level_mlp_fp32(hugs_handle* h, int l, const float* params, const hugs_ra
   const int S = h->samples(l);
   const int M = n * S;
   ProfScope ps(h, HUGS_K_MLP_FP32, st);
-  IpeArgs ia{rays->origins, rays->directions, rays->radii, h->tdist[l], h->basis, n, S, d.num_basis,
-             d.min_deg_point, d.max_deg_point, d.ray_shape, is_prop ? d.prop_contract : d.nerf_contract, h->feat};
-  int rc = launch_ipe_features(ia, st);
+  int rc;
+  if (d.encoding == HUGS_ENC_POINT_PE) {
+    PointPeArgs pa{rays->origins, rays->directions, h->tdist[l], n, S, d.min_deg_point, d.max_deg_point - d.min_deg_point,
+                   is_prop ? d.prop_contract : d.nerf_contract, h->feat, nullptr, nullptr, 0, 0, 0};
+    rc = launch_point_pe(pa, st);
+  } else {
+    IpeArgs ia{rays->origins, rays->directions, rays->radii, h->tdist[l], h->basis, n, S, d.num_basis,
+               d.min_deg_point, d.max_deg_point, d.ray_shape, is_prop ? d.prop_contract : d.nerf_contract, h->feat};
+    rc = launch_ipe_features(ia, st);
+  }
   if (rc) return rc;
   const float* x = h->feat;
   int xk = h->feat_dim;
@@ -409,9 +431,10 @@ int run_level_mlp_fp32(hugs_handle* h, int l, const float* params, const hugs_ra
   return HUGS_OK;
 }
 
-int check_rays(const hugs_handle* h, const hugs_rays* rays, int n) {
-  HUGS_REQUIRE(rays && rays->origins && rays->directions && rays->viewdirs && rays->radii && rays->near && rays->far,
-               "rays: origins/directions/viewdirs/radii/near/far are required");
+int check_rays(const hugs_handle* h, const hugs_rays* rays, int n, bool field_only = false) {
+  HUGS_REQUIRE(rays && rays->origins && rays->directions && rays->viewdirs, "rays: origins/directions/viewdirs are required");
+  HUGS_REQUIRE(field_only || (rays->near && rays->far), "rays: near/far are required");
+  HUGS_REQUIRE(h->d.encoding == HUGS_ENC_POINT_PE || rays->radii, "rays: radii are required by the integrated encoding");
   HUGS_REQUIRE(n >= 0 && n <= h->d.max_rays, "n_rays %d exceeds max_rays %d of this handle", n, h->d.max_rays);
   HUGS_REQUIRE(h->d.num_glo_features == 0 || rays->embed_idx, "rays: embed_idx is required with GLO features");
   return HUGS_OK;
@@ -557,4 +580,152 @@ HUGS_API int hugs_set_grad_ready_event(hugs_handle* h, void* cuda_event) {
   HUGS_REQUIRE(h, "hugs_set_grad_ready_event: null handle");
   h->grad_ready_event = (cudaEvent_t)cuda_event;
   return HUGS_OK;
+}
+
+// ------------------------------------------------------------------ torch twins (nerfacto/)
+
+namespace hugs {
+namespace {
+// Runs `fn` with the last level of the handle re-pointed at caller buffers and sized for n_samples.
+template <class F>
+int with_field_buffers(hugs_handle* h, int n_samples, const float* tdist, float* raw, const float* d_raw, F fn) {
+  const int l = h->d.num_levels - 1;
+  float* keep_t = h->tdist[l]; float* keep_r = h->raw[l]; float* keep_d = h->d_raw[l];
+  const int keep_s = h->d.num_nerf_samples;
+  if (tdist) h->tdist[l] = const_cast<float*>(tdist);
+  if (raw) h->raw[l] = raw;
+  if (d_raw) h->d_raw[l] = const_cast<float*>(d_raw);
+  h->d.num_nerf_samples = n_samples;
+  const int rc = fn(l);
+  h->tdist[l] = keep_t; h->raw[l] = keep_r; h->d_raw[l] = keep_d; h->d.num_nerf_samples = keep_s;
+  return rc;
+}
+}  // namespace
+}  // namespace hugs
+
+HUGS_API int hugs_field_forward(hugs_handle* h, const float* params, const hugs_rays* rays, const float* tdist,
+                                int32_t n_rays, int32_t n_samples, int32_t training, int32_t zero_glo, float* raw_out,
+                                void* stream) {
+  HUGS_REQUIRE(h && params && tdist && raw_out, "hugs_field_forward: null argument");
+  int rc = check_rays(h, rays, n_rays, true);
+  if (rc) return rc;
+  HUGS_REQUIRE(n_samples >= 2 && n_samples <= h->max_nerf_samples, "hugs_field_forward: n_samples %d outside [2, %d]",
+               n_samples, h->max_nerf_samples);
+  if (n_rays == 0) return HUGS_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const hugs_model_desc& d = h->d;
+  if (training) {
+    if (d.precision == HUGS_PRECISION_FP32) {
+      set_error("hugs_field_forward(training) needs a tensor-core precision mode; the fp32 CUDA-core path is render-only");
+      return HUGS_ERR_UNSUPPORTED;
+    }
+    if ((rc = tc_ensure_training(h))) return rc;
+  }
+  h->cur_params = params;
+  h->cur_embed_idx = rays->embed_idx;
+  if ((rc = launch_view_inputs(rays->viewdirs, rays->embed_idx, h->glo_off >= 0 ? params + h->glo_off : nullptr, n_rays,
+                               d.deg_view, d.num_glo_features, zero_glo, d.num_embeddings, h->view_in, st)))
+    return rc;
+  return with_field_buffers(h, n_samples, tdist, raw_out, nullptr, [&](int l) {
+    if (d.precision == HUGS_PRECISION_FP32) return run_level_mlp_fp32(h, l, params, rays, n_rays, st);
+    return tc_mlp_forward(h, l, rays, n_rays, training != 0, st);
+  });
+}
+
+HUGS_API int hugs_field_backward(hugs_handle* h, const float* params, const hugs_rays* rays, int32_t n_rays,
+                                 int32_t n_samples, const float* d_raw, float* grad_out, void* stream) {
+  HUGS_REQUIRE(h && params && d_raw && grad_out, "hugs_field_backward: null argument");
+  int rc = check_rays(h, rays, n_rays, true);
+  if (rc) return rc;
+  HUGS_REQUIRE(h->d.precision != HUGS_PRECISION_FP32 && h->tc, "hugs_field_backward needs a tensor-core precision mode");
+  HUGS_REQUIRE(n_samples >= 2 && n_samples <= h->max_nerf_samples, "hugs_field_backward: n_samples %d outside [2, %d]",
+               n_samples, h->max_nerf_samples);
+  HUGS_REQUIRE(n_rays > 0, "hugs_field_backward: empty batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  h->cur_params = params;
+  h->cur_embed_idx = rays->embed_idx;
+  HUGS_CUDA(cudaMemsetAsync(grad_out, 0, sizeof(float) * h->n_params, st));
+  return with_field_buffers(h, n_samples, nullptr, nullptr, d_raw,
+                            [&](int l) { return tc_mlp_backward(h, l, rays, n_rays, grad_out, st); });
+}
+
+HUGS_API int hugs_nf_sample_intervals(const float* bins, const float* weights, const float* u_base, const float* jitter,
+                                      int32_t jitter_stride, float max_jitter, float anneal, float padding, int32_t n_rays,
+                                      int32_t n_bins, int32_t n_samples, float dom_lo, float dom_hi, int32_t spacing_fn,
+                                      const float* near, const float* far, float* bins_out, float* t_out, void* stream) {
+  HUGS_REQUIRE(n_samples > 1, "num_samples must be > 1, is %d.", n_samples);
+  HUGS_REQUIRE(n_bins >= 1 && n_rays >= 0, "hugs_nf_sample_intervals: bad sizes");
+  if (n_rays == 0) return HUGS_OK;
+  HUGS_REQUIRE(bins && weights && u_base && bins_out, "hugs_nf_sample_intervals: null argument");
+  HUGS_REQUIRE(!t_out || (near && far), "hugs_nf_sample_intervals: near / far are required with t_out");
+  HUGS_REQUIRE(!jitter || jitter_stride == 1 || jitter_stride == n_samples, "hugs_nf_sample_intervals: jitter_stride must be 1 or n_samples");
+  ResampleArgs a;
+  a.t_in = bins; a.w_in = weights; a.n_rays = n_rays; a.np = n_bins; a.ns = n_samples; a.dom_lo = dom_lo; a.dom_hi = dom_hi;
+  a.anneal = anneal; a.padding = padding; a.u_base = u_base; a.jitter = jitter; a.jitter_stride = jitter ? jitter_stride : 1;
+  a.max_jitter = max_jitter; a.torch_twin = 1; a.s_out = bins_out; a.t_out = t_out; a.raydist_fn = spacing_fn;
+  a.near = near; a.far = far;
+  return launch_resample(a, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_merge_bins(const float* bins_a, int32_t n_a, const float* bins_b, int32_t n_b, int32_t n_rays,
+                                float dom_lo, float dom_hi, int32_t spacing_fn, const float* near, const float* far,
+                                float* bins_out, float* t_out, void* stream) {
+  HUGS_REQUIRE(bins_a && bins_b && bins_out, "hugs_nf_merge_bins: null argument");
+  HUGS_REQUIRE(!t_out || (near && far), "hugs_nf_merge_bins: near / far are required with t_out");
+  NfMergeArgs a;
+  a.bins_a = bins_a; a.na = n_a; a.bins_b = bins_b; a.nb = n_b; a.n_rays = n_rays; a.dom_lo = dom_lo; a.dom_hi = dom_hi;
+  a.spacing_fn = spacing_fn; a.near = near; a.far = far; a.bins_out = bins_out; a.t_out = t_out;
+  return launch_nf_merge(a, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_composite(const hugs_nf_render_cfg* cfg, const float* raw, int32_t raw_channels, const float* tdist,
+                               const float* directions, const float* bg_rgb, int32_t n_rays, int32_t n_samples,
+                               float* weights_out, float* rgb_out, float* depth_out, float* acc_out, float* steps_max,
+                               void* stream) {
+  HUGS_REQUIRE(cfg && raw && tdist && directions, "hugs_nf_composite: null argument");
+  HUGS_REQUIRE(raw_channels == 4 || !rgb_out, "hugs_nf_composite: rgb needs raw_channels == 4");
+  NfCompositeArgs a;
+  a.cfg = *cfg; a.raw = raw; a.C = raw_channels; a.tdist = tdist; a.directions = directions; a.bg_rgb = bg_rgb;
+  a.n_rays = n_rays; a.S = n_samples; a.weights = weights_out; a.rgb = rgb_out; a.depth = depth_out; a.acc = acc_out;
+  a.steps_max = steps_max;
+  return launch_nf_composite(a, false, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_clip_depth(float* depth, const float* steps_max, int32_t n_rays, void* stream) {
+  HUGS_REQUIRE(depth && steps_max, "hugs_nf_clip_depth: null argument");
+  return launch_nf_clip_depth(depth, steps_max, n_rays, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_composite_bwd(const hugs_nf_render_cfg* cfg, const float* raw, int32_t raw_channels,
+                                   const float* tdist, const float* directions, const float* bg_rgb, int32_t n_rays,
+                                   int32_t n_samples, const float* d_weights, const float* d_rgb, const float* d_depth,
+                                   const float* d_acc, const float* steps_max, float* d_raw, void* stream) {
+  HUGS_REQUIRE(cfg && raw && tdist && directions && d_raw, "hugs_nf_composite_bwd: null argument");
+  HUGS_REQUIRE(!d_depth || steps_max, "hugs_nf_composite_bwd: steps_max is required with d_depth");
+  NfCompositeArgs a;
+  a.cfg = *cfg; a.raw = raw; a.C = raw_channels; a.tdist = tdist; a.directions = directions; a.bg_rgb = bg_rgb;
+  a.n_rays = n_rays; a.S = n_samples; a.d_weights = d_weights; a.d_rgb = raw_channels == 4 ? d_rgb : nullptr;
+  a.d_depth = d_depth; a.d_acc = d_acc; a.steps_max_in = steps_max; a.d_raw = d_raw;
+  return launch_nf_composite(a, true, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_params_copy(const hugs_tensor_copy* table, int32_t n, float* flat, int32_t direction, void* stream) {
+  HUGS_REQUIRE(table && flat && n >= 0, "hugs_params_copy: null argument");
+  HUGS_REQUIRE(direction == 0 || direction == 1, "hugs_params_copy: direction must be 0 (tensors -> flat) or 1");
+  return launch_params_copy(table, n, flat, direction, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_rgb_loss(const float* pred, const float* gt, const float* static_mask, float transient_weight,
+                              int32_t loss_type, float charb_padding, int32_t n_rays, float* sums_out, float* dl_out,
+                              void* stream) {
+  HUGS_REQUIRE(pred && gt && sums_out && dl_out, "hugs_nf_rgb_loss: null argument");
+  HUGS_REQUIRE(loss_type == HUGS_LOSS_MSE || loss_type == HUGS_LOSS_CHARB, "hugs_nf_rgb_loss: unknown loss type %d", loss_type);
+  return launch_nf_rgb_loss(pred, gt, static_mask, transient_weight, loss_type, charb_padding, n_rays, sums_out, dl_out,
+                            (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_rgb_loss_bwd(const float* dl, const float* sums, const float* upstream, float scale, int32_t n_rays,
+                                  float* d_pred, void* stream) {
+  HUGS_REQUIRE(dl && sums && upstream && d_pred, "hugs_nf_rgb_loss_bwd: null argument");
+  return launch_nf_rgb_loss_bwd(dl, sums, upstream, scale, n_rays, d_pred, (cudaStream_t)stream);
 }

@@ -28,7 +28,10 @@ struct TcState;                   // tensor-core path state (mlp_tc.cu)
 struct hugs_handle {
   hugs_model_desc d{};
   int device = 0;
-  int feat_dim = 0;               // 2 * num_basis * (max_deg - min_deg)
+  int feat_dim = 0;               // IPE: 2 * num_basis * (max_deg - min_deg); point PE: 3 + 6 * (max_deg - min_deg)
+  int feat_panels = 0;            // 64-column K panels that carry features (tensor-core path)
+  int perm_nb = 0;                // basis count of the engine's feature-column permutation (0: reference order, point PE)
+  int max_nerf_samples = 0;       // d.num_nerf_samples at creation (hugs_field_forward may run fewer)
   int view_in_dim = 0;            // 3 + 6*deg_view + glo
   int64_t n_params = 0;
   int64_t glo_off = -1;

@@ -1,5 +1,6 @@
 // Internal launch interfaces between the translation units of libhugs_b200.so.
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,6 +23,8 @@ struct ResampleArgs {
   const float* jitter = nullptr;  // [n] uniform draws in [0,1) or nullptr
   float max_jitter = 0.f;
   uint64_t jitter_key = 0;        // != 0 (and jitter == nullptr): one draw per ray from hash(jitter_key, ray) in the kernel
+  int jitter_stride = 1;          // floats per ray in `jitter`: 1 = one draw per ray, ns = one per sample (torch twin)
+  int torch_twin = 0;             // utils/ray_utils.py:143-144 (quirk B5): a ray whose logits are all -inf gets uniform logits
   float* s_out = nullptr;         // [n, ns+1]
   float* t_out = nullptr;         // [n, ns+1] metric distances (optional)
   float* centers_out = nullptr;   // [n, ns] (optional)
@@ -92,6 +95,52 @@ struct PropLossBwdArgs {
   float* sq_stats = nullptr;           // [n] out: lossmult-weighted squared error of the level's rendering (optional)
 };
 int launch_prop_loss_bwd(const PropLossBwdArgs& a, cudaStream_t stream);
+
+// ---------------------------------------------------------------- nerfacto_ops.cu (torch twins)
+struct NfMergeArgs {
+  const float* bins_a = nullptr; int na = 0;   // [n, na+1]
+  const float* bins_b = nullptr; int nb = 0;   // [n, nb+1]
+  int n_rays = 0;
+  float dom_lo = 0.f, dom_hi = 1.f;
+  int spacing_fn = 0;
+  const float* near = nullptr; const float* far = nullptr;
+  float* bins_out = nullptr;                   // [n, na+nb+1]
+  float* t_out = nullptr;                      // optional
+};
+int launch_nf_merge(const NfMergeArgs& a, cudaStream_t stream);
+
+struct NfCompositeArgs {
+  hugs_nf_render_cfg cfg{};
+  const float* raw = nullptr; int C = 4;       // [n, S, C]
+  const float* tdist = nullptr;                // [n, S+1] euclidean fenceposts
+  const float* directions = nullptr;           // [n, 3]
+  const float* bg_rgb = nullptr;               // [n, 3] or nullptr
+  int n_rays = 0, S = 0;
+  // forward outputs (each optional)
+  float* weights = nullptr; float* rgb = nullptr; float* depth = nullptr; float* acc = nullptr; float* steps_max = nullptr;
+  // backward inputs (each optional) / output
+  const float* d_weights = nullptr; const float* d_rgb = nullptr; const float* d_depth = nullptr; const float* d_acc = nullptr;
+  const float* steps_max_in = nullptr;
+  float* d_raw = nullptr;
+};
+int launch_nf_composite(const NfCompositeArgs& a, bool backward, cudaStream_t stream);
+int launch_nf_clip_depth(float* depth, const float* steps_max, int n, cudaStream_t stream);
+int launch_nf_rgb_loss(const float* pred, const float* gt, const float* mask, float transient_w, int loss_type,
+                       float padding, int n, float* sums, float* dl, cudaStream_t stream);
+int launch_nf_rgb_loss_bwd(const float* dl, const float* sums, const float* upstream, float scale, int n, float* d_pred,
+                           cudaStream_t stream);
+int launch_params_copy(const hugs_tensor_copy* table, int n, float* flat, int direction, cudaStream_t stream);
+
+// pos_enc of interval midpoints (custom_functions.py:55-63): fp32 features [n*S, 3 + 6*ndeg] in the reference's column order,
+// and / or bf16 rows of `ld` columns (hi, optional residual lo; columns beyond the features zero up to `zero_cols`)
+struct PointPeArgs {
+  const float* origins; const float* directions; const float* tdist;
+  int n_rays, S, min_deg, ndeg, contract;
+  float* features;                             // fp32 [n*S, feat_dim] or nullptr
+  __nv_bfloat16* hi; __nv_bfloat16* lo;        // bf16 [rows_pad, ld] or nullptr
+  int ld, zero_cols, rows_pad;
+};
+int launch_point_pe(const PointPeArgs& a, cudaStream_t stream);
 
 // sums `n` floats (optionally thresholded at 0.5 like the static mask) into out[0]
 int launch_lossmult_sum(const float* lossmult, const float* static_mask, int use_mask, float transient_w,

@@ -194,7 +194,7 @@ int layered_pack(hugs_handle* h, LayeredMlp* m, const float* params, cudaStream_
     else if (li == D + 2) { e.rows = 128; e.x_in = 256; e.feat_in = 0; e.b_in = 256; }   // view layer (bottleneck rows)
     else { e.rows = 16; e.x_in = 128; e.feat_in = 0; }                                    // rgb head
   }
-  a.kmax = m->kmax; a.W = W; a.nb = h->d.num_basis; a.ndeg = h->d.max_deg_point - h->d.min_deg_point;
+  a.kmax = m->kmax; a.W = W; a.nb = h->perm_nb; a.ndeg = h->d.max_deg_point - h->d.min_deg_point;
   a.feat_dim = h->feat_dim; a.rows_f = m->rows_f; a.rows_b = m->rows_b; a.tab_floats = m->tab_floats;
   a.w_dens_off = m->w_dens_off; a.w_rgb_off = m->w_rgb_off; a.dens_in = W; a.rgb_in = 128;
   a.dens_koff = mv.dense[D].kernel_off; a.rgb_koff = mv.dense[D + 3].kernel_off;

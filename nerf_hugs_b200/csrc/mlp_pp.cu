@@ -716,6 +716,8 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
     return s;
   };
   // ---- forward ----
+  // features enter in segments of <= 4 K panels: 8 panels for the 504 IPE columns, 2 for a 93-column point encoding
+  const int feat_parts = (h->feat_panels + 3) / 4;
   bool cat = false;
   for (int i = 0; i < D; ++i) {
     const auto& P = m->pack[i];
@@ -725,11 +727,12 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
       if (last) { s.head = 1; if (!mv.has_rgb) s.no_signal = 1; }
     };
     if (i == 0) {
-      for (int part = 0; part < kFeatPad / 256; ++part) {
+      for (int part = 0; part < feat_parts; ++part) {
         PpSeg s = base_seg();
+        s.kps = std::min(4, h->feat_panels - 4 * part);
         s.a_feat = 1; s.feat_col0 = part * 256; s.w_row = P.row0; s.w_col0 = part * 256; s.accumulate = part > 0;
         if (part == 0) s.bias_idx = i;
-        if (part == kFeatPad / 256 - 1) finish(s);
+        if (part == feat_parts - 1) finish(s);
         m->pp_fwd.push_back(s);
       }
     } else {
@@ -738,10 +741,11 @@ int pp_build(hugs_handle* h, const MlpViews& mv, TcMlp* m) {
       if (!cat) finish(s);
       m->pp_fwd.push_back(s);
       if (cat) {
-        for (int part = 0; part < kFeatPad / 256; ++part) {
+        for (int part = 0; part < feat_parts; ++part) {
           PpSeg f = base_seg();
+          f.kps = std::min(4, h->feat_panels - 4 * part);
           f.a_feat = 1; f.feat_col0 = part * 256; f.w_row = P.row0; f.w_col0 = kW + part * 256; f.accumulate = 1;
-          if (part == kFeatPad / 256 - 1) finish(f);
+          if (part == feat_parts - 1) finish(f);
           m->pp_fwd.push_back(f);
         }
       }

@@ -305,7 +305,7 @@ int fill_pack_args(hugs_handle* h, const MlpViews& mv, const TcMlp& m, const flo
   HUGS_REQUIRE(m.pack.size() <= 16, "too many layers to pack");
   for (size_t i = 0; i < m.pack.size(); ++i) a->layers[i] = m.pack[i];
   a->n_layers = (int)m.pack.size(); a->rows_f = m.rows_f; a->rows_b = m.rows_b;
-  a->nb = h->d.num_basis; a->ndeg = h->d.max_deg_point - h->d.min_deg_point; a->feat_dim = h->feat_dim;
+  a->nb = h->perm_nb; a->ndeg = h->d.max_deg_point - h->d.min_deg_point; a->feat_dim = h->feat_dim;
   a->bias_floats = m.bias_floats; a->params = params; a->wt = m.wt; a->wn = m.wn; a->bias = m.bias;
   a->w_dens_off = m.w_dens_off; a->w_rgb_off = m.w_rgb_off;
   a->dens_koff = mv.dense[mv.depth].kernel_off; a->dens_in = mv.dense[mv.depth].in;
@@ -331,9 +331,14 @@ int tc_create(hugs_handle* h) {
   const int ndeg = d.max_deg_point - d.min_deg_point;
   // NerfMLP: 256 wide -> chain kernel; 512 / 768 / 1024 ... -> layer-at-a-time GEMMs.  PropMLP: 256 (every shipped gin).
   const bool nerf_layered = d.nerf_width != kW;
+  const bool pe = d.encoding == HUGS_ENC_POINT_PE;
+  if (pe && nerf_layered) {
+    set_error("point positional encoding is supported with net_width 256 on the tensor-core path (got %d)", d.nerf_width);
+    return HUGS_ERR_UNSUPPORTED;
+  }
   if ((nerf_layered && (d.nerf_width % 256 != 0 || d.nerf_width > 2048 || d.precision == HUGS_PRECISION_TC_SPLIT)) ||
       (d.num_levels > 1 && d.prop_width != kW) || d.bottleneck_width != kW ||
-      d.view_width != 128 || h->feat_dim > kFeatPad || (ndeg % 4) != 0 || ndeg > 16) {
+      d.view_width != 128 || h->feat_dim > kFeatPad || (!pe && ((ndeg % 4) != 0 || ndeg > 16))) {
     set_error("tensor-core path supports NerfMLP.net_width 256 (chain kernel, both precision modes) or 512 / 768 / 1024 "
               "(layer-at-a-time kernels, bf16 mode), PropMLP.net_width 256, bottleneck 256, view width 128 and <= 512 IPE "
               "features with a degree count divisible by 4 (got widths %d/%d/%d/%d, %d features); use HUGS_PRECISION_FP32",
@@ -460,7 +465,15 @@ int tc_mlp_forward(hugs_handle* h, int level, const hugs_rays* rays, int n_rays,
   // 1. bf16 IPE features (own column order) -> feat[level]
   {
     ProfScope ps(h, HUGS_K_ENCODE, st);
-    if (tc->split) {
+    if (d.encoding == HUGS_ENC_POINT_PE) {
+      // pos_enc of the interval midpoints in the reference's arithmetic and column order, bf16 (+ residual half)
+      PointPeArgs pa{rays->origins, rays->directions, h->tdist[level], n_rays, S, d.min_deg_point,
+                     d.max_deg_point - d.min_deg_point, contract, nullptr, feat,
+                     tc->split ? feat + (size_t)tc->total_feat_rows * kFeatPad : nullptr, kFeatPad, h->feat_panels * 64,
+                     n_tiles * kTileM};
+      int rc = launch_point_pe(pa, st);
+      if (rc) return rc;
+    } else if (tc->split) {
       // exact reference arithmetic (safe_sin quirk B12 included), split into hi / lo halves
       EncSplitArgs ea{rays->origins, rays->directions, rays->radii, h->tdist[level], h->basis, n_samples,
                       n_tiles * kTileM, S, d.num_basis, d.min_deg_point, d.max_deg_point - d.min_deg_point,

@@ -11,6 +11,7 @@
 //   coord.py:63-99     s_to_t
 #include "common.cuh"
 #include "kernels.h"
+#include "spacing.cuh"
 
 namespace hugs {
 
@@ -29,28 +30,6 @@ __device__ __forceinline__ int count_before(F f, int n, float v) {
     if (before) lo = mid + 1; else hi = mid;
   }
   return lo;
-}
-
-__device__ __forceinline__ float s_to_t(int fn, float s, float near, float far) {
-  // coord.py:96-98: fn_inv(s * s_far + (1 - s) * s_near)
-  switch (fn) {
-    case HUGS_RAYDIST_RECIPROCAL: {
-      float sn = 1.0f / near, sf = 1.0f / far;
-      return 1.0f / (s * sf + (1.0f - s) * sn);
-    }
-    case HUGS_RAYDIST_LOG: {
-      float sn = logf(near), sf = logf(far);
-      return expf(s * sf + (1.0f - s) * sn);
-    }
-    case HUGS_RAYDIST_PIECEWISE: {
-      float sn = near < 1.f ? .5f * near : 1.f - .5f / near;
-      float sf = far < 1.f ? .5f * far : 1.f - .5f / far;
-      float x = s * sf + (1.0f - s) * sn;
-      return x < .5f ? 2.f * x : .5f / (1.f - x);
-    }
-    default:
-      return s * far + (1.0f - s) * near;
-  }
 }
 
 // One uniform draw in [0, 1) per (key, ray): splitmix64 finaliser, top 24 bits (the reference draws jax.random.uniform per
@@ -153,6 +132,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) resample_kernel(ResampleA
         mx = fmaxf(mx, l);
       }
       mx = warp_max(mx);
+      if (a.torch_twin && mx == -INFINITY) {   // quirk B5 (ray_utils.py:143-144): weights_logit[all -inf rows] = 1
+        for (int i = lane; i < nb; i += 32) CW[i + 1] = 1.0f;
+        mx = 1.0f;
+      }
       float part = 0.f;
       for (int i = lane; i < nb; i += 32) {
         float e = expf(CW[i + 1] - mx);
@@ -173,10 +156,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) resample_kernel(ResampleA
     }
     // ---- sorted_interp -------------------------------------------------------------------
     const bool jittered = a.jitter != nullptr || a.jitter_key != 0;
-    const float jit = a.jitter ? a.jitter[ray] * a.max_jitter
+    const float jit = a.jitter ? a.jitter[(size_t)ray * a.jitter_stride] * a.max_jitter
                                : (a.jitter_key ? jitter_draw(a.jitter_key, ray) * a.max_jitter : 0.f);
     for (int j = lane; j < ns; j += 32) {
-      float u = a.u_in ? a.u_in[(size_t)ray * ns + j] : (jittered ? a.u_base[j] + jit : a.u_base[j]);
+      float u;
+      if (a.u_in) u = a.u_in[(size_t)ray * ns + j];
+      else if (a.jitter && a.jitter_stride > 1) u = a.u_base[j] + a.jitter[(size_t)ray * a.jitter_stride + j] * a.max_jitter;
+      else u = jittered ? a.u_base[j] + jit : a.u_base[j];
       // i0 = max{k : u >= cw_k} (0 if none); i1 = min{k : u < cw_k} (nb if none)
       int cnt = count_before<false>([&](int k) { return CW[k]; }, nb + 1, u);  // #{cw_k <= u}
       int i0 = max(cnt - 1, 0), i1 = min(cnt, nb);

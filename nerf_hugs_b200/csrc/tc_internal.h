@@ -128,7 +128,9 @@ struct TcState {
 int make_map(CUtensorMap* m, const void* base, long long rows, long long cols, int box_rows);
 
 // reference feature column of my column f' = (b*ndeg + k)*2 + s   ->   s*(nb*ndeg) + k*nb + b
+// (nb <= 0: the engine keeps the reference's order, point positional encoding)
 __host__ __device__ inline int ref_feature_col(int fp, int nb, int ndeg) {
+  if (nb <= 0) return fp;
   int s = fp & 1, bk = fp >> 1, b = bk / ndeg, k = bk % ndeg;
   return s * (nb * ndeg) + k * nb + b;
 }

@@ -337,13 +337,14 @@ static void build_items(hugs_handle* h, int level, int n_tiles, std::vector<WgIt
     units.push_back({w, (512.f + 2.f * n) / 1024.f, group > 0 ? group : next_group++});
   };
   bool cat = false;
+  const int n_feat_sb = (h->feat_panels + 3) / 4;    // 256-column superblocks of the feature tensor that carry features
   for (int l = 0; l < D; ++l) {
     const DenseView& v = mv.dense[l];
     if (l == 0) {
-      for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, 0, 256, v, 0, 1, sb == 0, kGroupFeat);
+      for (int sb = 0; sb < n_feat_sb; ++sb) add(1, frow, sb * 256, 0, 256, v, 0, 1, sb == 0, kGroupFeat);
     } else {
       add(0, srow + (l - 1) * cap, 0, l, 256, v, 0, 0, true, cat ? kGroupFeat : 0);
-      if (cat) for (int sb = 0; sb < kFeatPad / 256; ++sb) add(1, frow, sb * 256, l, 256, v, kW, 1, false, kGroupFeat);
+      if (cat) for (int sb = 0; sb < n_feat_sb; ++sb) add(1, frow, sb * 256, l, 256, v, kW, 1, false, kGroupFeat);
     }
     cat = (l % d.skip_layer == 0 && l > 0);
   }
@@ -434,7 +435,7 @@ int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgIt
   for (int i = 0; i < n_maps; ++i) p.maps[i] = maps[i];
   for (int i = n_maps; i < kWgMaxMaps; ++i) p.maps[i] = maps[0];
   p.items = dev_items; p.n_items = n_items;
-  p.nb = h->d.num_basis; p.ndeg = h->d.max_deg_point - h->d.min_deg_point; p.feat_dim = h->feat_dim; p.grad = grad;
+  p.nb = h->perm_nb; p.ndeg = h->d.max_deg_point - h->d.min_deg_point; p.feat_dim = h->feat_dim; p.grad = grad;
   wgrad_kernel<<<std::min(n_items, h->tc->num_sms), kWgThreads, kWgSmem, st>>>(p);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;

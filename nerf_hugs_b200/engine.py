@@ -19,6 +19,7 @@ from ._lib import lib, check
 RAYDIST = {None: 0, 'reciprocal': 1, 'log': 2, 'piecewise': 3}
 RAY_SHAPE = {'cone': 0, 'cylinder': 1}
 PRECISION = {'fp32': 0, 'bf16_tc': 1, 'tc_split': 2}
+ENCODING = {'ipe': 0, 'point_pe': 1}
 
 
 @dataclasses.dataclass
@@ -57,6 +58,7 @@ class EngineConfig:
   rgb_padding: float = 0.001
   precision: str = 'bf16_tc'
   max_rays: int = 4096
+  encoding: str = 'ipe'           # 'point_pe': the torch twin's pos_enc of interval midpoints (nerfacto/models/nerf.py)
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -95,6 +97,7 @@ class Engine:
     d.opaque_background = int(cfg.opaque_background)
     d.near_anneal_rate = -1.0 if cfg.near_anneal_rate is None else cfg.near_anneal_rate
     d.precision = PRECISION[cfg.precision]
+    d.encoding = ENCODING[cfg.encoding]
     self._h = C.c_void_p()
     with torch.cuda.device(self.device):
       check(lib.hugs_create(C.byref(d), C.byref(self._h)))
@@ -250,6 +253,29 @@ class Engine:
         check(lib.hugs_adam_step_stats(self._h, _ptr(params), _ptr(grad), _ptr(mu), _ptr(nu), C.byref(adam_cfg),
                                        _ptr(norms_out), _ptr(tensor_stats_out), self._stream()))
 
+  # ---- one field on caller-provided fenceposts (the torch twins, nerfacto/models/nerf.py:299-318) ------------
+  def field_forward(self, params, rays, tdist, training: bool, zero_glo: bool = False, raw_out=None):
+    """MLP.forward on the midpoints of `tdist` [n, S+1]: raw [n, S, 4] (pre-activation density, rgb)."""
+    r, keep, n = self._rays(rays)
+    tdist = _f32(tdist, self.device)
+    S = tdist.shape[-1] - 1
+    raw = torch.empty(n, S, 4, device=self.device) if raw_out is None else raw_out
+    with torch.cuda.device(self.device):
+      check(lib.hugs_field_forward(self._h, _ptr(params), C.byref(r), _ptr(tdist), n, S, int(training), int(zero_glo),
+                                   _ptr(raw), self._stream()))
+    self._keep = keep + [tdist]
+    return raw
+
+  def field_backward(self, params, rays, n_samples: int, d_raw, grad_out=None):
+    r, keep, n = self._rays(rays)
+    d_raw = _f32(d_raw, self.device)
+    grad = torch.empty(self.n_params, device=self.device) if grad_out is None else grad_out
+    with torch.cuda.device(self.device):
+      check(lib.hugs_field_backward(self._h, _ptr(params), C.byref(r), n, int(n_samples), _ptr(d_raw), _ptr(grad),
+                                    self._stream()))
+    self._keep = keep + [d_raw]
+    return grad
+
   # ---- measurement hooks ----------------------------------------------------------------------
   def profile(self, enable: bool):
     check(lib.hugs_profile_enable(self._h, int(enable)))
@@ -332,7 +358,8 @@ class Engine:
     r, keep, n = self._rays(rays)
     tdist = _f32(tdist, self.device)
     S = tdist.shape[-1] - 1
-    fd = 2 * self.num_basis * (self.cfg.max_deg_point - self.cfg.min_deg_point)
+    ndeg = self.cfg.max_deg_point - self.cfg.min_deg_point
+    fd = 3 + 6 * ndeg if self.cfg.encoding == 'point_pe' else 2 * self.num_basis * ndeg
     out = torch.empty(n * S, fd, device=self.device)
     check(lib.hugs_ipe_features(self._h, C.byref(r), _ptr(tdist), n, S, int(contract), _ptr(out), self._stream()))
     torch.cuda.synchronize(self.device)

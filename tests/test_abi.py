@@ -21,13 +21,13 @@ def test_library_exports_every_declared_symbol():
   for name in declared:
     assert hasattr(_lib.lib, name), f'{name} declared in hugs_b200.h but not exported'
     assert name in _lib.SYMBOLS, f'{name} has no ctypes binding'
-  assert _lib.lib.hugs_abi_version() == 1
+  assert _lib.lib.hugs_abi_version() == 2
 
 
 def test_struct_sizes_match_header():
   from nerf_hugs_b200 import _lib
   # sizeof() of the C structs, printed by a g++ build of include/hugs_b200.h
-  assert ctypes.sizeof(_lib.ModelDesc) == 520
+  assert ctypes.sizeof(_lib.ModelDesc) == 536
   assert ctypes.sizeof(_lib.TensorDesc) == 88
   assert ctypes.sizeof(_lib.LevelOut) == 80
   assert ctypes.sizeof(_lib.Rays) == 72
@@ -35,6 +35,8 @@ def test_struct_sizes_match_header():
   assert ctypes.sizeof(_lib.AdamCfg) == 32
   assert ctypes.sizeof(_lib.CameraSet) == 112
   assert ctypes.sizeof(_lib.RayBatch) == 96
+  assert ctypes.sizeof(_lib.NfRenderCfg) == 32
+  assert ctypes.sizeof(_lib.TensorCopy) == 32
 
 
 def test_create_validates_and_fails_loudly_without_gpu():
