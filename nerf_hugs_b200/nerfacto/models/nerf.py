@@ -179,6 +179,8 @@ class Model(nn.Module):
     self._render_cfg = ops.render_cfg(c.opaque_background, c.density_activation, c.density_bias, c.rgb_premultiplier,
                                       c.rgb_bias, c.rgb_padding)
     self.jitter_override = None     # test hook: {field_type: draws} used in place of torch.rand (ray_utils.py:151-152)
+    self.last_bins = None           # test hook: set to {} to record the euclidean fenceposts of every field evaluation
+    self.bins_override = None       # test hook: {field_type: euclidean fenceposts} evaluated instead of the sampled ones
 
   # ---- the reference's surface ------------------------------------------------------------------------------------
   def get_params_dict(self) -> Dict[str, List[Parameter]]:
@@ -252,6 +254,10 @@ class Model(nn.Module):
       else:
         bins_, _ = ops.sample_intervals(spacing_bins, weights, 1., 0., ns, perturb, c.use_single_jitter, domain, jitter=jit)
         spacing_bins, euclidean_bins = ops.merge_bins(spacing_bins, bins_, domain, fn, near, far)
+      if self.bins_override is not None and field_type in self.bins_override:
+        euclidean_bins = self.bins_override[field_type].to(dev).float().contiguous()
+      if self.last_bins is not None:
+        self.last_bins.setdefault(field_type, []).append(euclidean_bins)
       fe = self._field_engine(field_type, n, dev)
       params = list(fe.params)
       if emb is not None:

@@ -67,6 +67,12 @@ CASES = {
                              num_coarse_nerf_samples_per_ray=32, num_fine_nerf_samples_per_ray=48,
                              proposal_initial_sampler='reciprocal', rgb_loss_type='charb', use_single_jitter=True),
                   n_rays=96, contraction=True, perturb=True, train=True, seed=1),
+    # config 1's model at a 4096-ray batch (the size at which the gradient bar of 1e-3 is meaningful for a ReLU network: see
+    # DESIGN.md "What bounds a gradient comparison"); compact record: batch regenerated from its seed, no per-sample arrays
+    'cfg1_4096': dict(model=dict(net_width=256, max_deg_point=15, use_appearance_embedding=False, eval_embedding='original',
+                                 opaque_background=True, num_coarse_nerf_samples_per_ray=64, num_fine_nerf_samples_per_ray=64,
+                                 proposal_initial_sampler='uniform', rgb_loss_type='mse', use_single_jitter=True),
+                      n_rays=4096, contraction=False, perturb=True, train=True, seed=3, compact=True),
     # evaluation path: deterministic sampling, average embedding, chunked
     'eval': dict(model=dict(net_width=256, max_deg_point=12, use_appearance_embedding=True, appearance_embedding_dim=8,
                             num_embedding=30, eval_embedding='average', opaque_background=True,
@@ -101,8 +107,12 @@ def main():
     out[f'{name}/weights_checksum'] = np.array([float(sum(v.double().abs().sum() for v in sd.values())),
                                                 float(sum(v.numel() for v in sd.values()))])
     batch = make_batch(case['n_rays'], case['seed'])
-    for k, v in batch.items():
-      out[f'{name}/batch/{k}'] = v.numpy()
+    compact = case.get('compact', False)
+    if compact:
+      out[f'{name}/batch_checksum'] = np.array(float(sum(v.double().abs().sum() for v in batch.values())))
+    else:
+      for k, v in batch.items():
+        out[f'{name}/batch/{k}'] = v.numpy()
     draws = []
 
     def rand_spy(*a, **k):
@@ -111,6 +121,16 @@ def main():
       return r
     model.train(case['train'])
     torch.rand = rand_spy
+    # the fenceposts and weights of every field evaluation (one per field and chunk), to separate sampling parity from
+    # field / compositing parity in the tests
+    levels = []
+    real_d2w = ref_nerf.density_to_weight
+
+    def d2w_spy(densities, euclidean_bins, directions, opaque_background=False):
+      res = real_d2w(densities, euclidean_bins, directions, opaque_background)
+      levels.append((euclidean_bins.detach().clone(), res[0].detach().clone()))
+      return res
+    ref_nerf.density_to_weight = d2w_spy
     try:
       if case['train']:
         outputs = model(batch=batch, curr_step=1, perturb=case['perturb'])
@@ -119,6 +139,11 @@ def main():
           outputs = model(batch=batch, curr_step=1, perturb=case['perturb'], chunk_size=32)
     finally:
       torch.rand = real_rand
+      ref_nerf.density_to_weight = real_d2w
+    n_chunks = len(levels) // 2
+    for f, ft in enumerate(() if compact else ('coarse', 'fine')):
+      out[f'{name}/bins/{ft}'] = torch.cat([levels[2 * c + f][0] for c in range(n_chunks)]).numpy()
+      out[f'{name}/weights/{ft}'] = torch.cat([levels[2 * c + f][1] for c in range(n_chunks)]).numpy()
     for i, dr in enumerate(draws):
       out[f'{name}/jitter/{i}'] = dr.numpy()
     out[f'{name}/n_jitter'] = np.array(len(draws))

@@ -17,6 +17,10 @@ CASES = {
                              num_coarse_nerf_samples_per_ray=32, num_fine_nerf_samples_per_ray=48,
                              proposal_initial_sampler='reciprocal', rgb_loss_type='charb', use_single_jitter=True),
                   n_rays=96, contraction=True, perturb=True, train=True, seed=1),
+    'cfg1_4096': dict(model=dict(net_width=256, max_deg_point=15, use_appearance_embedding=False, eval_embedding='original',
+                                 opaque_background=True, num_coarse_nerf_samples_per_ray=64, num_fine_nerf_samples_per_ray=64,
+                                 proposal_initial_sampler='uniform', rgb_loss_type='mse', use_single_jitter=True),
+                      n_rays=4096, contraction=False, perturb=True, train=True, seed=3, compact=True),
     'eval': dict(model=dict(net_width=256, max_deg_point=12, use_appearance_embedding=True, appearance_embedding_dim=8,
                             num_embedding=30, eval_embedding='average', opaque_background=True,
                             num_coarse_nerf_samples_per_ray=16, num_fine_nerf_samples_per_ray=24,
@@ -52,7 +56,34 @@ def build(name, precision=None, device=None):
   return case, model, crit
 
 
+def make_batch(n_rays, seed):
+  """== make_batch of tests/golden/make_golden_nerfacto_nerf.py (BASELINE config 1 geometry)."""
+  g = torch.Generator().manual_seed(seed)
+  H = W = 64
+  focal = 70.
+  pix = torch.randint(0, H * W, (n_rays,), generator=g)
+  py, px = (pix // W).float(), (pix % W).float()
+  dirs = torch.stack([(px + 0.5 - W / 2) / focal, -(py + 0.5 - H / 2) / focal, -torch.ones(n_rays)], -1)
+  origin = torch.tensor([0., 0., 4.]).expand(n_rays, 3).contiguous()
+  viewdir = dirs / dirs.norm(dim=-1, keepdim=True)
+  return {
+      'coord': torch.stack([px / W, py / H], -1),
+      'origin': origin, 'direction': dirs.contiguous(), 'viewdir': viewdir.contiguous(),
+      'bg_rgb': torch.rand(n_rays, 3, generator=g),
+      'embed_idx': torch.randint(0, 30, (n_rays, 1), generator=g).int(),
+      'near': torch.full((n_rays, 1), 2.0), 'far': torch.full((n_rays, 1), 6.0),
+      'rgb': torch.rand(n_rays, 3, generator=g),
+      'static_mask': (torch.rand(n_rays, 1, generator=g) < 0.8).float(),
+  }
+
+
 def load_batch(gold, name, device=None):
+  if CASES[name].get('compact'):
+    batch = make_batch(CASES[name]['n_rays'], CASES[name]['seed'])
+    got = float(sum(v.double().abs().sum() for v in batch.values()))
+    want = float(gold[f'{name}/batch_checksum'])
+    assert abs(got - want) <= 1e-9 * abs(want), 'the seeded batch differs from the one the reference was run on'
+    return {k: (v.to(device) if device is not None else v) for k, v in batch.items()}
   batch = {}
   for k in gold.files:
     if k.startswith(f'{name}/batch/'):
