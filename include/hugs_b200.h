@@ -290,17 +290,72 @@ int hugs_nf_rgb_loss(const float* pred, const float* gt, const float* static_mas
 int hugs_nf_rgb_loss_bwd(const float* dl, const float* sums, const float* upstream, float scale, int32_t n_rays,
                          float* d_pred, void* stream);
 
+/* utils/loss_utils.py:66-84 distortion_loss on the final level: sum_out[0] = sum over rays of lossfun_distortion(c, w)
+ * (the caller divides by n_rays: torch.mean), grad_out [n, S] = d lossfun_distortion / d w per ray. */
+int hugs_nf_distortion_loss(const float* spacing_bins, const float* weights, int32_t n_rays, int32_t n_samples,
+                            float* sum_out, float* grad_out, void* stream);
+/* utils/loss_utils.py:7-63 interlevel_loss term of ONE proposal level: sum_out[0] = sum of lossfun_outer(c, w, cp, wp) over
+ * rays and final-level samples (the caller divides by n_rays * n_samples), grad_out [n, n_prop] = d sum / d wp. */
+int hugs_nf_interlevel_loss(const float* spacing_bins, const float* weights, int32_t n_samples, const float* prop_bins,
+                            const float* prop_weights, int32_t n_prop, int32_t n_rays, float* sum_out, float* grad_out,
+                            void* stream);
+/* dst[i] = src[i] * upstream[0] * mult (upstream: device scalar): the chain rule of the two losses above. */
+int hugs_nf_scale(const float* src, const float* upstream, float mult, int64_t n, float* dst, void* stream);
+
 /* torch parameters <-> the flat flax-layout buffer of a handle: one table-driven copy instead of one per tensor.
- * table (DEVICE pointer) of n entries; direction 0: flat[flat_off + i*cols + j] = transpose ? ptr[j*rows + i]
- * : ptr[i*cols + j]; direction 1: the reverse (flat -> tensors).  nn.Linear.weight is [out, in] (transpose = 1 against
+ * table (DEVICE pointer) of n entries; direction 0: flat[flat_off + i*cols + j] = transpose ? ptr[j*ld + i]
+ * : ptr[i*ld + j] (ld defaults to rows resp. cols); direction 1: the reverse (flat -> tensors).  nn.Linear.weight is [out, in] (transpose = 1 against
  * the [in, out] kernel of hugs_param_layout). */
 typedef struct {
   float*  ptr;
   int64_t flat_off;
   int32_t rows, cols;            /* shape of the FLAT (flax) view */
-  int32_t transpose, reserved_;
+  int32_t transpose;
+  int32_t ld;                    /* elements between consecutive rows of the tensor behind `ptr` (0: dense) */
 } hugs_tensor_copy;
 int hugs_params_copy(const hugs_tensor_copy* table, int32_t n, float* flat, int32_t direction, void* stream);
+
+/* ---- hash-grid fields of the nerfacto twin (nerfacto/models/nerfacto.py:643-1008) ----
+ *
+ * tcnn.Encoding('HashGrid') / ('SphericalHarmonics', degree 4) are a third-party dependency that is not under the reference
+ * tree (tiny-cuda-nn, unpinned git HEAD): nerf_hugs_b200/csrc/hashfield.cu restates its published algorithm; `grid` below has
+ * tcnn's parameter layout (levels back to back, features innermost), so a reference state_dict's `params` tensor is used
+ * in place.  geo_feat_dim == 0: HashMLPDensityField (grid -> 64 -> raw density, fused CUDA-core kernel, raw_out [n, S]);
+ * geo_feat_dim == 64: NerfactoField (grid -> 256 -> [density | 64]; [SH4 | geometry | appearance] -> 256 -> 256 -> rgb, tcgen05
+ * GEMMs, raw_out [n, S, 4]).  Samples whose normalised position leaves [0, 1]^3 are evaluated at 0 and get raw density -inf
+ * (density * selector, nerfacto.py:822-836). */
+typedef struct {
+  int32_t n_levels, features_per_level, log2_hashmap_size, base_res;
+  float   per_level_scale;
+  int32_t hidden_dim, geo_feat_dim, hidden_dim_color;
+  int32_t appearance_dim, num_embeddings;
+  float   bound;               /* positions are mapped by (x + bound) / (2 bound) ... */
+  int32_t contract;            /* ... or, with scene contraction, (spatial_distortion_norm2(x) + 2) / 4 */
+  int32_t max_samples;         /* n_rays * n_samples the workspace is sized for */
+  int32_t max_rays;
+  int32_t reserved_[2];
+} hugs_hashfield_desc;
+typedef struct hugs_hashfield hugs_hashfield;
+
+int hugs_hashfield_create(const hugs_hashfield_desc* desc, hugs_hashfield** out);
+int hugs_hashfield_destroy(hugs_hashfield* h);
+int64_t hugs_hashfield_grid_floats(const hugs_hashfield* h);   /* == tcnn Encoding.params.numel() */
+int64_t hugs_hashfield_mlp_floats(const hugs_hashfield* h);    /* flat fp32 MLP buffer ([in, out] kernels, hugs_hashfield_layout) */
+int hugs_hashfield_layout(const hugs_hashfield* h, hugs_tensor_desc* out, int32_t capacity, int32_t* count);
+int hugs_hashfield_level_info(const hugs_hashfield* h, int32_t level, float* scale, uint32_t* resolution, uint32_t* offset,
+                              uint32_t* entries);
+/* Re-derive the packed bf16 operands after the caller wrote the flat MLP buffer (NerfactoField only). */
+int hugs_hashfield_params_changed(hugs_hashfield* h, const float* mlp, void* stream);
+/* Operator-level hook: the hash encoding alone, fp32 features [n * S, n_levels * 2] of the interval midpoints. */
+int hugs_hashfield_encode(hugs_hashfield* h, const float* grid, const hugs_rays* rays, const float* tdist, int32_t n_rays,
+                          int32_t n_samples, float* features, void* stream);
+/* field(positions, viewdirs, embedded_appearance, None) of nerfacto.py:838-875 / :991-1008 on the interval midpoints. */
+int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const float* mlp, const hugs_rays* rays, const float* tdist,
+                           int32_t n_rays, int32_t n_samples, int32_t training, int32_t zero_app, float* raw_out, void* stream);
+/* Its backward: d_raw -> grid_grad (ACCUMULATED: the caller zeroes it) and mlp_grad (overwritten). */
+int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const float* mlp, const hugs_rays* rays, const float* tdist,
+                            int32_t n_rays, int32_t n_samples, const float* d_raw, float* grid_grad, float* mlp_grad,
+                            void* stream);
 
 /* ---- batch assembly on the device (the caller of the path: SURVEY.md §8f item 2) ---- */
 

@@ -76,7 +76,15 @@ class NfRenderCfg(C.Structure):
 
 class TensorCopy(C.Structure):
   _fields_ = [('ptr', C.c_void_p), ('flat_off', C.c_int64), ('rows', C.c_int32), ('cols', C.c_int32),
-              ('transpose', C.c_int32), ('reserved_', C.c_int32)]
+              ('transpose', C.c_int32), ('ld', C.c_int32)]
+
+
+class HashFieldDesc(C.Structure):
+  _fields_ = [('n_levels', C.c_int32), ('features_per_level', C.c_int32), ('log2_hashmap_size', C.c_int32),
+              ('base_res', C.c_int32), ('per_level_scale', C.c_float), ('hidden_dim', C.c_int32),
+              ('geo_feat_dim', C.c_int32), ('hidden_dim_color', C.c_int32), ('appearance_dim', C.c_int32),
+              ('num_embeddings', C.c_int32), ('bound', C.c_float), ('contract', C.c_int32), ('max_samples', C.c_int32),
+              ('max_rays', C.c_int32), ('reserved_', C.c_int32 * 2)]
 
 
 class RayBatch(C.Structure):
@@ -116,6 +124,20 @@ SYMBOLS = {
     'hugs_nf_composite_bwd': (C.c_int, [C.POINTER(NfRenderCfg), _P, _I, _P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _P, _P]),
     'hugs_nf_rgb_loss': (C.c_int, [_P, _P, _P, _F, _I, _F, _I, _P, _P, _P]),
     'hugs_nf_rgb_loss_bwd': (C.c_int, [_P, _P, _P, _F, _I, _P, _P]),
+    'hugs_hashfield_create': (C.c_int, [C.POINTER(HashFieldDesc), C.POINTER(_P)]),
+    'hugs_hashfield_destroy': (C.c_int, [_P]),
+    'hugs_hashfield_grid_floats': (C.c_int64, [_P]),
+    'hugs_hashfield_mlp_floats': (C.c_int64, [_P]),
+    'hugs_hashfield_layout': (C.c_int, [_P, C.POINTER(TensorDesc), _I, C.POINTER(_I)]),
+    'hugs_hashfield_level_info': (C.c_int, [_P, _I, C.POINTER(C.c_float), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                                            C.POINTER(C.c_uint32)]),
+    'hugs_hashfield_params_changed': (C.c_int, [_P, _P, _P]),
+    'hugs_hashfield_encode': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _I, _P, _P]),
+    'hugs_hashfield_forward': (C.c_int, [_P, _P, _P, C.POINTER(Rays), _P, _I, _I, _I, _I, _P, _P]),
+    'hugs_hashfield_backward': (C.c_int, [_P, _P, _P, C.POINTER(Rays), _P, _I, _I, _P, _P, _P, _P]),
+    'hugs_nf_distortion_loss': (C.c_int, [_P, _P, _I, _I, _P, _P, _P]),
+    'hugs_nf_interlevel_loss': (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
+    'hugs_nf_scale': (C.c_int, [_P, _P, _F, C.c_int64, _P, _P]),
     'hugs_params_copy': (C.c_int, [_P, _I, _P, _I, _P]),
     'hugs_launch_count': (C.c_int64, []),
     'hugs_profile_enable': (C.c_int, [_P, _I]),

@@ -729,3 +729,22 @@ HUGS_API int hugs_nf_rgb_loss_bwd(const float* dl, const float* sums, const floa
   HUGS_REQUIRE(dl && sums && upstream && d_pred, "hugs_nf_rgb_loss_bwd: null argument");
   return launch_nf_rgb_loss_bwd(dl, sums, upstream, scale, n_rays, d_pred, (cudaStream_t)stream);
 }
+
+HUGS_API int hugs_nf_distortion_loss(const float* spacing_bins, const float* weights, int32_t n_rays, int32_t n_samples,
+                                     float* sum_out, float* grad_out, void* stream) {
+  HUGS_REQUIRE(spacing_bins && weights && sum_out && grad_out, "hugs_nf_distortion_loss: null argument");
+  return launch_nf_distortion(spacing_bins, weights, n_rays, n_samples, sum_out, grad_out, (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_interlevel_loss(const float* spacing_bins, const float* weights, int32_t n_samples, const float* prop_bins,
+                                     const float* prop_weights, int32_t n_prop, int32_t n_rays, float* sum_out,
+                                     float* grad_out, void* stream) {
+  HUGS_REQUIRE(spacing_bins && weights && prop_bins && prop_weights && sum_out && grad_out, "hugs_nf_interlevel_loss: null argument");
+  return launch_nf_interlevel(spacing_bins, weights, n_samples, prop_bins, prop_weights, n_prop, n_rays, sum_out, grad_out,
+                              (cudaStream_t)stream);
+}
+
+HUGS_API int hugs_nf_scale(const float* src, const float* upstream, float mult, int64_t n, float* dst, void* stream) {
+  HUGS_REQUIRE(src && upstream && dst, "hugs_nf_scale: null argument");
+  return launch_nf_scale(src, upstream, mult, n, dst, (cudaStream_t)stream);
+}

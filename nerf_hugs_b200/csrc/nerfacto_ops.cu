@@ -238,13 +238,97 @@ __global__ void nf_rgb_loss_bwd_kernel(const float* dl, const float* sums, const
   d_pred[i] = upstream[0] * scale / fmaxf(sums[2], kF32Eps) * dl[i];
 }
 
+// ------------------------------------------------------------------------------------------ proposal losses
+// utils/loss_utils.py:48-84.  One warp per ray; value per ray summed into out[0]; gradients w.r.t. the weights written
+// unscaled (the mean's 1 / count and the upstream gradient are applied by nf_scale_kernel in the autograd backward).
+struct NfLossArgs {
+  const float* c; const float* w; int S;        // final level: spacing fenceposts [n, S+1], weights [n, S]
+  const float* cp; const float* wp; int Sp;     // proposal level (interlevel only)
+  int n_rays;
+  float* out;                                   // [1] sum over rays and samples
+  float* grad;                                  // distortion: [n, S] dL/dw; interlevel: [n, Sp] dL/dwp
+};
+
+// lossfun_distortion (loss_utils.py:66-77) in O(S): the interval midpoints are sorted, so
+// sum_ij w_i w_j |u_i - u_j| = 2 sum_i w_i (u_i W_<i - WU_<i) with exclusive prefix sums
+__global__ void __launch_bounds__(kWarps * 32) nf_distortion_kernel(NfLossArgs a) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kWarps + warp;
+  if (ray >= a.n_rays) return;
+  const int S = a.S;
+  float* PW = smem + warp * 2 * S; float* PWU = PW + S;
+  const float* c = a.c + (size_t)ray * (S + 1);
+  const float* w = a.w + (size_t)ray * S;
+  for (int i = lane; i < S; i += 32) { const float u = (c[i + 1] + c[i]) / 2.f; PW[i] = w[i]; PWU[i] = w[i] * u; }
+  __syncwarp();
+  warp_cumsum_inplace(PW, S, lane);
+  warp_cumsum_inplace(PWU, S, lane);
+  const float wtot = PW[S - 1], wutot = PWU[S - 1];
+  float loss = 0.f;
+  for (int i = lane; i < S; i += 32) {
+    const float wi = w[i], u = (c[i + 1] + c[i]) / 2.f, dl = c[i + 1] - c[i];
+    const float wlt = PW[i] - wi, wult = PWU[i] - wi * u, wgt = wtot - PW[i], wugt = wutot - PWU[i];
+    loss += 2.f * wi * (u * wlt - wult) + wi * wi * dl / 3.f;
+    a.grad[(size_t)ray * S + i] = 2.f * (u * (wlt - wgt) - wult + wugt) + (2.f / 3.f) * wi * dl;
+  }
+  loss = warp_sum(loss);
+  if (lane == 0) atomicAdd(a.out, loss);
+}
+
+// lossfun_outer / outer (loss_utils.py:7-45): w_outer_i = sum of wp over [idx_lo_i, idx_hi_i] with
+// idx_lo = clamp(searchsorted(cp[:-1], c_i, right) - 1, 0, Sp - 1), idx_hi = clamp(searchsorted(cp[1:], c_{i+1}, right), 0, Sp - 1)
+__global__ void __launch_bounds__(kWarps * 32) nf_interlevel_kernel(NfLossArgs a) {
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ray = blockIdx.x * kWarps + warp;
+  if (ray >= a.n_rays) return;
+  const int S = a.S, Sp = a.Sp;
+  float* CY = smem + warp * (2 * Sp + 2);      // [Sp+1] = [0, cumsum(wp)]
+  float* D = CY + Sp + 1;                       // [Sp+1] difference array of the gradient
+  const float* c = a.c + (size_t)ray * (S + 1);
+  const float* w = a.w + (size_t)ray * S;
+  const float* cp = a.cp + (size_t)ray * (Sp + 1);
+  const float* wp = a.wp + (size_t)ray * Sp;
+  for (int j = lane; j < Sp; j += 32) { CY[j + 1] = wp[j]; D[j] = 0.f; }
+  if (lane == 0) { CY[0] = 0.f; D[Sp] = 0.f; }
+  __syncwarp();
+  warp_cumsum_inplace(CY + 1, Sp, lane);
+  float loss = 0.f;
+  for (int i = lane; i < S; i += 32) {
+    const float v0 = c[i], v1 = c[i + 1];
+    int lo = 0, hi = Sp;                       // #{k < Sp : cp[k] <= v0}
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (cp[m] <= v0) lo = m + 1; else hi = m; }
+    const int ilo = min(max(lo - 1, 0), Sp - 1);
+    lo = 0; hi = Sp;                           // #{k < Sp : cp[k + 1] <= v1}
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (cp[m + 1] <= v1) lo = m + 1; else hi = m; }
+    const int ihi = min(max(lo, 0), Sp - 1);
+    const float wo = CY[ihi + 1] - CY[ilo];
+    const float wi = w[i];
+    const float e = fmaxf(wi - wo, 0.f);
+    loss += e * e / (wi + 1.0e-7f);
+    const float hgrad = -2.f * e / (wi + 1.0e-7f);
+    if (hgrad != 0.f && ihi >= ilo) { atomicAdd(&D[ilo], hgrad); atomicAdd(&D[ihi + 1], -hgrad); }
+  }
+  loss = warp_sum(loss);
+  __syncwarp();
+  warp_cumsum_inplace(D, Sp, lane);
+  for (int j = lane; j < Sp; j += 32) a.grad[(size_t)ray * Sp + j] = D[j];
+  if (lane == 0) atomicAdd(a.out, loss);
+}
+
+__global__ void nf_scale_kernel(const float* src, const float* upstream, float mult, long long n, float* dst) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * (upstream[0] * mult);
+}
+
 // ------------------------------------------------------------------------------------------ parameter copies
 __global__ void params_copy_kernel(const hugs_tensor_copy* table, float* flat, int direction) {
   const hugs_tensor_copy t = table[blockIdx.y];
   const long long n = (long long)t.rows * t.cols;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / t.cols), j = (int)(e % t.cols);
-    const long long q = t.transpose ? (long long)j * t.rows + i : e;
+    const long long q = t.transpose ? (long long)j * (t.ld > 0 ? t.ld : t.rows) + i : (long long)i * (t.ld > 0 ? t.ld : t.cols) + j;
     if (direction == 0) flat[t.flat_off + e] = t.ptr[q];
     else t.ptr[q] = flat[t.flat_off + e];
   }
@@ -374,6 +458,40 @@ int launch_nf_rgb_loss_bwd(const float* dl, const float* sums, const float* upst
                            cudaStream_t stream) {
   if (n <= 0) return HUGS_OK;
   nf_rgb_loss_bwd_kernel<<<(n * 3 + 255) / 256, 256, 0, stream>>>(dl, sums, upstream, scale, n, d_pred);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+int launch_nf_distortion(const float* c, const float* w, int n_rays, int S, float* out, float* grad, cudaStream_t stream) {
+  HUGS_REQUIRE(S >= 1 && S <= 4096, "nf_distortion: bad sample count %d", S);
+  static bool f[64] = {};
+  int rc = opt_in_smem(nf_distortion_kernel, f, 160 * 1024);
+  if (rc) return rc;
+  HUGS_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  if (n_rays <= 0) return HUGS_OK;
+  NfLossArgs a{c, w, S, nullptr, nullptr, 0, n_rays, out, grad};
+  nf_distortion_kernel<<<(n_rays + kWarps - 1) / kWarps, kWarps * 32, (size_t)kWarps * 2 * S * sizeof(float), stream>>>(a);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+int launch_nf_interlevel(const float* c, const float* w, int S, const float* cp, const float* wp, int Sp, int n_rays,
+                         float* out, float* grad, cudaStream_t stream) {
+  HUGS_REQUIRE(S >= 1 && Sp >= 1 && Sp <= 4096, "nf_interlevel: bad sample counts %d / %d", S, Sp);
+  static bool f[64] = {};
+  int rc = opt_in_smem(nf_interlevel_kernel, f, 160 * 1024);
+  if (rc) return rc;
+  HUGS_CUDA(cudaMemsetAsync(out, 0, sizeof(float), stream));
+  if (n_rays <= 0) return HUGS_OK;
+  NfLossArgs a{c, w, S, cp, wp, Sp, n_rays, out, grad};
+  nf_interlevel_kernel<<<(n_rays + kWarps - 1) / kWarps, kWarps * 32, (size_t)kWarps * (2 * Sp + 2) * sizeof(float), stream>>>(a);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+int launch_nf_scale(const float* src, const float* upstream, float mult, long long n, float* dst, cudaStream_t stream) {
+  if (n <= 0) return HUGS_OK;
+  nf_scale_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(src, upstream, mult, n, dst);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
 }

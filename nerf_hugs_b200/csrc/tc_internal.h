@@ -157,6 +157,8 @@ struct WgItem {
   int flush_mode;   // 0: kernel tile; 1: density head (column 3 -> [in,1]); 2: rgb head (columns 0..2 -> [in,3])
   int bias_mode;    // 0: none; 1: all n columns -> boff + c; 2: column 3 -> boff; 3: columns 0..2 -> boff + c
   long long boff;   // bias offset in the flat gradient
+  int in_rows;      // > 0: only A columns [a_col0, a_col0 + in_rows) are kernel rows (narrow inputs inside a 256-wide superblock)
+  int head_rows;    // flush_mode 2: kernel rows of the rgb head (0: 128, the view layer's width)
 };
 
 struct WgUnit { WgItem w; float cost; int group; };
@@ -164,6 +166,10 @@ constexpr int kWgMaxMaps = 12;
 void wgrad_plan(const std::vector<WgUnit>& units, int T, int num_sms, std::vector<WgItem>* items);
 int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgItem* dev_items, int n_items, float* grad,
                  cudaStream_t st);
+// the same launch without a model handle (hash-grid fields): feature-permutation parameters passed explicitly
+int wgrad_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
+                     const WgItem* dev_items, int n_items, float* grad, cudaStream_t st);
+int wgrad_kernel_init();
 // view-layer extras shared by the chain and the layered path: dW rows of the direction / GLO inputs, GLO embedding rows
 int wgrad_view_extras(hugs_handle* h, const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int dz_ld, int n_rays, int S,
                       float* grad, cudaStream_t st);

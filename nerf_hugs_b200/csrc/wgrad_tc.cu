@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
               const int fp = w.a_col0 + m;
               krow = fp < p.feat_dim ? w.in_base + ref_feature_col(fp, p.nb, p.ndeg) : -1;
             } else {
-              krow = w.in_base + m;
+              krow = (w.in_rows > 0 && m >= w.in_rows) ? -1 : w.in_base + m;
             }
             // thread = accumulator row, but the gradient rows are `out` floats apart: transpose each 32 x 32 block
             // through shared memory so that one warp instruction adds 32 consecutive floats of one row (one 128-byte
@@ -211,7 +211,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
             ptx::tmem_ld_wait();
             if (w.flush_mode == 1) {
               atomicAdd(p.grad + w.koff + m, __uint_as_float(r4[3]));
-            } else if (m < 128) {
+            } else if (m < (w.head_rows > 0 ? w.head_rows : 128)) {
               atomicAdd(p.grad + w.koff + m * 3 + 0, __uint_as_float(r4[0]));
               atomicAdd(p.grad + w.koff + m * 3 + 1, __uint_as_float(r4[1]));
               atomicAdd(p.grad + w.koff + m * 3 + 2, __uint_as_float(r4[2]));
@@ -428,6 +428,17 @@ void wgrad_plan(const std::vector<WgUnit>& units, int T, int num_sms, std::vecto
 // One launch of the weight-gradient kernel over `n_items` device-resident work items.
 int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgItem* dev_items, int n_items, float* grad,
                  cudaStream_t st) {
+  return wgrad_launch_raw(h->tc->num_sms, h->perm_nb, h->d.max_deg_point - h->d.min_deg_point, h->feat_dim, maps, n_maps,
+                          dev_items, n_items, grad, st);
+}
+
+int wgrad_kernel_init() {
+  HUGS_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+  return HUGS_OK;
+}
+
+int wgrad_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
+                     const WgItem* dev_items, int n_items, float* grad, cudaStream_t st) {
   if (n_items <= 0) return HUGS_OK;
   HUGS_REQUIRE(n_maps <= kWgMaxMaps, "wgrad: too many tensor maps");
   WgParams p;
@@ -435,8 +446,8 @@ int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgIt
   for (int i = 0; i < n_maps; ++i) p.maps[i] = maps[i];
   for (int i = n_maps; i < kWgMaxMaps; ++i) p.maps[i] = maps[0];
   p.items = dev_items; p.n_items = n_items;
-  p.nb = h->perm_nb; p.ndeg = h->d.max_deg_point - h->d.min_deg_point; p.feat_dim = h->feat_dim; p.grad = grad;
-  wgrad_kernel<<<std::min(n_items, h->tc->num_sms), kWgThreads, kWgSmem, st>>>(p);
+  p.nb = perm_nb; p.ndeg = ndeg; p.feat_dim = feat_dim; p.grad = grad;
+  wgrad_kernel<<<std::min(n_items, num_sms), kWgThreads, kWgSmem, st>>>(p);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
 }

@@ -283,3 +283,229 @@ def rgb_loss(pred, gt, static_mask, transient_weight, loss_type, padding, mult):
   """-> (loss, mse): loss carries the gradient, mse is detached."""
   out = _RgbLoss.apply(pred, gt, static_mask, transient_weight, loss_type, padding, mult)
   return out[0], out[1].detach()
+
+
+# ------------------------------------------------------------------------------------------------ hash-grid fields
+class HashFieldEngine:
+  """One hash-grid field (nerfacto.py:643-1008) behind hugs_hashfield_*: the handle, the table-driven copies between the
+  torch parameters and the flat [in, out] MLP buffer.  The hash table itself (`params` of the encoder, tcnn layout) is used
+  in place, never copied."""
+
+  def __init__(self, desc: '_lib.HashFieldDesc', device, grid_param: torch.nn.Parameter,
+               entries: Sequence[Tuple[str, torch.Tensor, int, int, int]]):
+    """entries: (flat tensor name, torch tensor, element offset into it, transpose, ld) in any order."""
+    if not torch.cuda.is_available():
+      raise RuntimeError('nerf_hugs_b200 needs a CUDA device (sm_100a); there is no CPU fallback')
+    self.device = torch.device(device)
+    self.desc = desc
+    self._h = C.c_void_p()
+    with torch.cuda.device(self.device):
+      check(lib.hugs_hashfield_create(C.byref(desc), C.byref(self._h)))
+    self.grid_floats = int(lib.hugs_hashfield_grid_floats(self._h))
+    self.mlp_floats = int(lib.hugs_hashfield_mlp_floats(self._h))
+    cnt = C.c_int32()
+    check(lib.hugs_hashfield_layout(self._h, None, 0, C.byref(cnt)))
+    arr = (_lib.TensorDesc * cnt.value)()
+    check(lib.hugs_hashfield_layout(self._h, arr, cnt.value, C.byref(cnt)))
+    self.layout = {t.name.decode(): (int(t.offset), int(t.rows), int(t.cols)) for t in arr}
+    assert grid_param.numel() == self.grid_floats, (grid_param.numel(), self.grid_floats)
+    self.grid_param = grid_param
+    self.entries = list(entries)
+    self.is_density_only = desc.geo_feat_dim == 0
+    self.flat = torch.zeros(self.mlp_floats, device=self.device)
+    self.gflat = torch.zeros(self.mlp_floats, device=self.device)
+    self._table_key = self._table = self._version_key = None
+
+  def close(self):
+    if self._h:
+      lib.hugs_hashfield_destroy(self._h)
+      self._h = C.c_void_p()
+
+  def __del__(self):
+    try:
+      self.close()
+    except Exception:
+      pass
+
+  def level_info(self, level):
+    s, r, o, e = C.c_float(), C.c_uint32(), C.c_uint32(), C.c_uint32()
+    check(lib.hugs_hashfield_level_info(self._h, level, C.byref(s), C.byref(r), C.byref(o), C.byref(e)))
+    return float(s.value), int(r.value), int(o.value), int(e.value)
+
+  def _make_table(self, tensors):
+    """one hugs_tensor_copy per entry; `tensors[i]` stands for the torch tensor of entry i"""
+    arr = (_lib.TensorCopy * len(self.entries))()
+    for e, (name, _, off, tr, ld), t in zip(arr, self.entries, tensors):
+      foff, rows, cols = self.layout[name.split('#')[0]]
+      if '#' in name:      # "tensor#row0:rows": a block of rows of the flat tensor
+        r0, nr = (int(v) for v in name.split('#')[1].split(':'))
+        foff, rows = foff + r0 * cols, nr
+      e.ptr, e.flat_off, e.rows, e.cols, e.transpose, e.ld = t.data_ptr() + 4 * off, foff, rows, cols, tr, ld
+    return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
+
+  def sync_params(self, force: bool = False, override: Optional[Dict[int, torch.Tensor]] = None):
+    tensors = [e[1] for e in self.entries]
+    if override:
+      tensors = [override.get(id(t), t) for t in tensors]
+    for t in tensors + [self.grid_param]:
+      if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()):
+        raise RuntimeError('field parameters must be contiguous fp32 CUDA tensors (model.to(device) first)')
+    key = tuple(t.data_ptr() for t in tensors)
+    if key != self._table_key:
+      self._table, self._table_key, self._version_key = self._make_table(tensors), key, None
+    vkey = tuple(t._version for t in tensors)
+    if force or override:
+      self._version_key = None
+    if vkey != self._version_key:
+      with torch.cuda.device(self.device):
+        check(lib.hugs_params_copy(_ptr(self._table), len(tensors), _ptr(self.flat), 0, _stream(self.device)))
+        check(lib.hugs_hashfield_params_changed(self._h, _ptr(self.flat), _stream(self.device)))
+      self._version_key = vkey
+
+  def _rays(self, rays):
+    r = _lib.Rays()
+    keep = []
+    n = rays['origins'].shape[0]
+    for k in ('origins', 'directions', 'viewdirs'):
+      if rays.get(k) is not None:
+        t = _f32c(rays[k]).reshape(n, 3)
+        keep.append(t); setattr(r, k, t.data_ptr())
+    if rays.get('embed_idx') is not None:
+      t = rays['embed_idx'].detach().to(torch.int32).contiguous().reshape(n)
+      keep.append(t); r.embed_idx = t.data_ptr()
+    return r, keep, n
+
+  def encode(self, rays, tdist):
+    r, keep, n = self._rays(rays)
+    tdist = _f32c(tdist)
+    S = tdist.shape[1] - 1
+    out = torch.empty(n * S, 2 * self.desc.n_levels, device=self.device)
+    with torch.cuda.device(self.device):
+      check(lib.hugs_hashfield_encode(self._h, _ptr(self.grid_param.detach()), C.byref(r), _ptr(tdist), n, S, _ptr(out),
+                                      _stream(self.device)))
+    return out
+
+  def forward(self, rays, tdist, training: bool, zero_app: bool = False):
+    r, keep, n = self._rays(rays)
+    S = tdist.shape[1] - 1
+    raw = torch.empty((n, S, 1 if self.is_density_only else 4), device=self.device)
+    with torch.cuda.device(self.device):
+      check(lib.hugs_hashfield_forward(self._h, _ptr(self.grid_param.detach()), _ptr(self.flat), C.byref(r), _ptr(tdist), n, S,
+                                       int(training), int(zero_app), _ptr(raw), _stream(self.device)))
+    self._keep = keep
+    return raw
+
+  def backward(self, rays, tdist, d_raw):
+    r, keep, n = self._rays(rays)
+    S = tdist.shape[1] - 1
+    grid_grad = torch.zeros(self.grid_floats, device=self.device)
+    with torch.cuda.device(self.device):
+      check(lib.hugs_hashfield_backward(self._h, _ptr(self.grid_param.detach()), _ptr(self.flat), C.byref(r), _ptr(tdist), n, S,
+                                        _ptr(d_raw), _ptr(grid_grad), _ptr(self.gflat), _stream(self.device)))
+    self._keep = keep
+    return grid_grad
+
+  def export_grads(self, shapes: Sequence[torch.Size]) -> List[torch.Tensor]:
+    """flat MLP gradient -> one tensor per DISTINCT torch parameter of self.entries (several entries may address blocks of
+    one parameter)."""
+    distinct, seen = [], {}
+    for _, t, _, _, _ in self.entries:
+      if id(t) not in seen:
+        seen[id(t)] = len(distinct); distinct.append(t)
+    sizes = [t.numel() for t in distinct]
+    buf = torch.zeros(sum(sizes), device=self.device)
+    outs, o = [], 0
+    for t, sz in zip(distinct, sizes):
+      outs.append(buf[o:o + sz].view(t.shape)); o += sz
+    table = self._make_table([outs[seen[id(t)]] for _, t, _, _, _ in self.entries])
+    with torch.cuda.device(self.device):
+      check(lib.hugs_params_copy(_ptr(table), len(self.entries), _ptr(self.gflat), 1, _stream(self.device)))
+    self._keep_table = table
+    return distinct, outs
+
+
+class _RenderHashField(torch.autograd.Function):
+  """One level of nerfacto's Model.forward_rays (nerfacto.py:329-371): hash-grid field -> density_to_weight ->
+  render_features / render_depth.  Differentiable inputs: the hash table and the field's MLP parameters."""
+
+  @staticmethod
+  def forward(ctx, field: HashFieldEngine, rays, tdist, bg_rgb, cfg, training: bool, zero_app: bool, override, grid, *params):
+    field.sync_params(force=training, override=override)
+    raw = field.forward(rays, tdist, training, zero_app)
+    dirs = _f32c(rays['directions'])
+    bg = None if (bg_rgb is None or field.is_density_only) else _f32c(bg_rgb)
+    weights, rgb, depth, acc, steps_max = composite_forward(cfg, raw, tdist, dirs, bg)
+    ctx.field, ctx.rays, ctx.cfg = field, rays, cfg
+    ctx.param_ids = [id(p) for p in params]
+    ctx.save_for_backward(raw, tdist, dirs, bg, steps_max)
+    ctx.set_materialize_grads(False)
+    if rgb is None:
+      return depth, acc, weights
+    return rgb, depth, acc, weights
+
+  @staticmethod
+  def backward(ctx, *grads):
+    raw, tdist, dirs, bg, steps_max = ctx.saved_tensors
+    field = ctx.field
+    if raw.shape[2] == 1:
+      d_depth, d_acc, d_weights = grads
+      d_rgb = None
+    else:
+      d_rgb, d_depth, d_acc, d_weights = grads
+    d_raw = composite_backward(ctx.cfg, raw, tdist, dirs, bg, steps_max, d_weights, d_rgb, d_depth, d_acc)
+    grid_grad = field.backward(ctx.rays, tdist, d_raw)
+    distinct, outs = field.export_grads(None)
+    by_id = {id(t): g for t, g in zip(distinct, outs)}
+    return (None,) * 8 + (grid_grad,) + tuple(by_id.get(i) for i in ctx.param_ids)
+
+
+def render_hash_field(field: HashFieldEngine, rays, tdist, bg_rgb, cfg, training, zero_app, grid, params, override=None):
+  return _RenderHashField.apply(field, rays, tdist, bg_rgb, cfg, training, zero_app, override, grid, *params)
+
+
+class _ScaledLoss(torch.autograd.Function):
+  """value = sum / count of a per-ray loss kernel; backward = upstream / count * stored gradient (hugs_nf_scale)."""
+
+  @staticmethod
+  def forward(ctx, w_for_grad, total, grad, count):
+    ctx.save_for_backward(grad)
+    ctx.count = float(count)
+    return total[0] / count
+
+  @staticmethod
+  def backward(ctx, up):
+    (grad,) = ctx.saved_tensors
+    dev = grad.device
+    out = torch.empty_like(grad)
+    upc = _f32c(up).reshape(1)
+    with torch.cuda.device(dev):
+      check(lib.hugs_nf_scale(_ptr(grad), _ptr(upc), 1.0 / ctx.count, grad.numel(), _ptr(out), _stream(dev)))
+    return out, None, None, None
+
+
+def distortion_loss(weights_list, spacing_bins_list):
+  """loss_utils.distortion_loss (loss_utils.py:80-84): mean over rays of lossfun_distortion on the final level."""
+  c, w = _f32c(spacing_bins_list[-1]), weights_list[-1]
+  wc = _f32c(w)
+  n, S = wc.shape
+  dev = wc.device
+  total, grad = torch.empty(1, device=dev), torch.empty(n, S, device=dev)
+  with torch.cuda.device(dev):
+    check(lib.hugs_nf_distortion_loss(_ptr(c), _ptr(wc), n, S, _ptr(total), _ptr(grad), _stream(dev)))
+  return _ScaledLoss.apply(w, total, grad, n)
+
+
+def interlevel_loss(weights_list, spacing_bins_list):
+  """loss_utils.interlevel_loss (loss_utils.py:48-63): the final level's (detached) histogram bounds every proposal one."""
+  c, w = _f32c(spacing_bins_list[-1]), _f32c(weights_list[-1])
+  n, S = w.shape
+  dev = w.device
+  loss = 0.0
+  for cp, wp in zip(spacing_bins_list[:-1], weights_list[:-1]):
+    cpc, wpc = _f32c(cp), _f32c(wp)
+    Sp = wpc.shape[1]
+    total, grad = torch.empty(1, device=dev), torch.empty(n, Sp, device=dev)
+    with torch.cuda.device(dev):
+      check(lib.hugs_nf_interlevel_loss(_ptr(c), _ptr(w), S, _ptr(cpc), _ptr(wpc), Sp, n, _ptr(total), _ptr(grad), _stream(dev)))
+    loss = loss + _ScaledLoss.apply(wp, total, grad, n * S)
+  return loss

@@ -90,3 +90,61 @@ def load_batch(gold, name, device=None):
       t = torch.from_numpy(gold[k])
       batch[k.split('/')[-1]] = t.to(device) if device is not None else t
   return batch
+
+
+# ------------------------------------------------------------------------------------------------ nerfacto (hash grid)
+GOLDEN_HASH = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'nerfacto_hash.npz')
+PROP_ARGS = [
+    {'base_res': 16, 'hidden_dim': 64, 'log2_hashmap_size': 12, 'features_per_level': 2, 'num_levels': 5, 'max_res': 64},
+    {'base_res': 16, 'hidden_dim': 64, 'log2_hashmap_size': 13, 'features_per_level': 2, 'num_levels': 7, 'max_res': 128},
+]
+FIELD = dict(hidden_dim=256, geo_feat_dim=64, hidden_dim_color=256, base_res=16, max_res=512, log2_hashmap_size=15,
+             features_per_level=2, enable_tcnn_mlp=False, num_levels=16)
+GRID_GAIN = 3000.0
+
+# must equal CASES of tests/golden/make_golden_nerfacto.py
+HASH_CASES = {
+    'withmask': dict(model=dict(**FIELD, transient_type='withmask', use_appearance_embedding=True, use_transient_embedding=False,
+                                appearance_embedding_dim=48, num_embedding=30, eval_embedding='original', opaque_background=True,
+                                num_nerf_samples_per_ray=16, num_proposal_samples_per_ray=(32, 24), num_proposal_iterations=2,
+                                proposal_net_args_list=PROP_ARGS, proposal_initial_sampler='uniform',
+                                proposal_histogram_padding=0.005, proposal_weights_anneal_max_num_iters=10000,
+                                rgb_loss_type='charb', distortion_loss_mult=0.001),
+                     n_rays=128, bound=2.0, contraction=False, perturb=True, train=True, step=40, seed=5),
+    'contract': dict(model=dict(**FIELD, transient_type=None, use_appearance_embedding=False, opaque_background=False,
+                                density_activation='softplus', num_nerf_samples_per_ray=24,
+                                num_proposal_samples_per_ray=(40, 28), num_proposal_iterations=2, use_same_proposal_network=True,
+                                proposal_net_args_list=PROP_ARGS[:1], proposal_initial_sampler='piecewise',
+                                rgb_loss_type='mse', use_single_jitter=False),
+                     n_rays=96, bound=2.0, contraction=True, perturb=True, train=True, step=2000, seed=6),
+    'eval': dict(model=dict(**FIELD, transient_type='withmask', use_appearance_embedding=True, appearance_embedding_dim=8,
+                            num_embedding=30, eval_embedding='average', opaque_background=True, num_nerf_samples_per_ray=16,
+                            num_proposal_samples_per_ray=(32,), num_proposal_iterations=1, proposal_net_args_list=PROP_ARGS[1:],
+                            proposal_initial_sampler='uniform'),
+                 n_rays=80, bound=2.0, contraction=False, perturb=False, train=False, step=500, seed=7),
+}
+
+
+def build_hash(name, device=None):
+  from nerf_hugs_b200.nerfacto.models import criterion_dict, model_config_dict, model_dict
+  case = HASH_CASES[name]
+  torch.manual_seed(4321 + case['seed'])
+  cfg = model_config_dict['nerfacto'](**case['model'])
+  model = model_dict['nerfacto'](cfg, case['bound'], False, case['contraction'])
+  crit = criterion_dict['nerfacto'](model)
+  with torch.no_grad():
+    for pname, p in model.named_parameters():
+      if pname.endswith('mlp_base.0.params'):
+        p.mul_(GRID_GAIN)
+  if device is not None:
+    model = model.to(device)
+  return case, model, crit
+
+
+def load_hash_batch(gold, name, device=None):
+  batch = {}
+  for k in gold.files:
+    if k.startswith(f'{name}/batch/'):
+      t = torch.from_numpy(gold[k])
+      batch[k.split('/')[-1]] = t.to(device) if device is not None else t
+  return batch

@@ -121,3 +121,58 @@ def test_split_merge_tensor_data():
   assert len(parts) == 3 and parts[2]['a'].shape[0] == 2 and parts[0]['b'][0].shape == (4, 2)
   back = merge_tensor_data(parts)
   assert torch.equal(back['a'], d['a']) and torch.equal(back['b'][1], d['b'][1])
+
+
+# ------------------------------------------------------------------------------------------------ nerfacto (hash grid)
+@pytest.fixture(scope='module')
+def gold_hash():
+  return np.load(H.GOLDEN_HASH)
+
+
+@pytest.mark.parametrize('name', list(H.HASH_CASES))
+def test_nerfacto_state_dict_equals_the_reference(gold_hash, name):
+  # same module tree (buffers, `mlp_base.0.params`, `direction_encoder.params`, Linear indices), same seed -> same values
+  case, model, _ = H.build_hash(name)
+  sd = model.state_dict()
+  assert sorted(sd.keys()) == list(gold_hash[f'{name}/state_keys'])
+  want = gold_hash[f'{name}/weights_checksum']
+  assert sum(v.numel() for v in sd.values()) == int(want[1])
+  got = float(sum(v.double().abs().sum() for v in sd.values()))
+  assert abs(got - want[0]) <= 1e-9 * abs(want[0])
+
+
+def test_nerfacto_param_groups_and_loud_failures():
+  from nerf_hugs_b200.nerfacto.models import model_config_dict, model_dict
+  case, model, _ = H.build_hash('withmask')
+  assert set(model.get_params_dict()) == {'field', 'proposal', 'appearance_embedding'}      # nerfacto.py:250-264
+  C, M = model_config_dict['nerfacto'], model_dict['nerfacto']
+  base = dict(H.HASH_CASES['contract']['model'])
+  with pytest.raises(NotImplementedError):
+    M(C(**{**base, 'enable_tcnn_mlp': True}), 2.0, True, False)
+  with pytest.raises(NotImplementedError):
+    M(C(**{**base, 'hidden_dim': 64}), 2.0, False, False)
+  with pytest.raises(NotImplementedError):
+    M(C(**{**base, 'transient_type': 'robustnerf'}), 2.0, False, False)
+  with pytest.raises(AssertionError):
+    M(C(**base), 1.0, False, True)       # nerfacto.py:133: contraction needs bound == 2
+
+
+def test_nerfacto_no_cpu_path(gold_hash):
+  case, model, _ = H.build_hash('eval')
+  model.eval()
+  with pytest.raises(RuntimeError, match='CUDA'):
+    model(batch=H.load_hash_batch(gold_hash, 'eval'), curr_step=1, perturb=False, chunk_size=32)
+
+
+def test_hashgrid_oracle_level_table():
+  # the restated tcnn geometry: phototourism_nerfacto_withmask.yml's 16 levels, 2^21 entries, base 16 -> 8192
+  from oracle import hashgrid as hg
+  growth = np.exp((np.log(8192) - np.log(16)) / 15)
+  levels, total = hg.level_table(16, 16, growth, 21)
+  assert levels[0][1] == 16 and levels[-1][1] == 8192
+  assert levels[0][3] == 4096 and all(cnt % 8 == 0 for _, _, _, cnt in levels)
+  assert total * 2 == 47857600
+  # dense levels index without hashing: corner (x, y, z) -> x + y * res + z * res^2
+  x, y, z = torch.tensor([3]), torch.tensor([5]), torch.tensor([7])
+  assert int(hg.grid_index(x, y, z, 16, 4096)) == 3 + 5 * 16 + 7 * 256
+  assert int(hg.grid_index(x, y, z, 8192, 1 << 21)) == ((3 * 1) ^ ((5 * 2654435761) & 0xFFFFFFFF) ^ ((7 * 805459861) & 0xFFFFFFFF)) % (1 << 21)
