@@ -63,7 +63,8 @@ def hashgrid_encode(x, params, levels, features_per_level=2):
   table = params.view(-1, F)
   outs = []
   for scale, res, off, cnt in levels:
-    pos = torch.addcmul(torch.full_like(x, 0.5), x, torch.tensor(float(scale), dtype=x.dtype))   # fma(scale, x, 0.5)
+    # fmaf(scale, x, 0.5): one rounding (the product of two float32 numbers is exact in float64)
+    pos = (x.double() * float(scale) + 0.5).to(x.dtype)
     cell = torch.floor(pos)
     w = pos - cell
     c = cell.to(torch.int64)
