@@ -117,15 +117,43 @@ __device__ __forceinline__ void encode_sample(const HashGridCfg& g, const float2
   }
 }
 
-// d_features of one sample -> grid gradient (trilinear weights transposed)
-__device__ __forceinline__ void scatter_sample(const HashGridCfg& g, float2* grid_grad, const float x[3], const float* df) {
+// d_features of one sample -> grid gradient (trilinear weights transposed).  MUST be called by all 32 lanes of a warp
+// (`live` = this lane has a sample): consecutive lanes are consecutive samples of a ray, so on the coarse levels whole
+// runs of lanes hit the same table entry; those runs are summed with a segmented shuffle reduction and only the head of
+// a run issues the atomic (the level-0 table has 4096 entries for millions of samples: without this the atomics of one
+// warp serialise on a handful of addresses).
+constexpr int kAggregateRes = 512;     // levels up to this resolution aggregate; finer ones rarely share an entry
+__device__ __forceinline__ void scatter_sample(const HashGridCfg& g, float2* grid_grad, const float x[3], const float* df,
+                                               bool live) {
+  const int lane = threadIdx.x & 31;
   for (int l = 0; l < g.L; ++l) {
-    const float a = df[2 * l], b = df[2 * l + 1];
-    if (a == 0.f && b == 0.f) continue;
+    const float a = live ? df[2 * l] : 0.f, b = live ? df[2 * l + 1] : 0.f;
+    const bool aggregate = g.res[l] <= (uint32_t)kAggregateRes;
+    if (!aggregate && a == 0.f && b == 0.f) continue;
     Corner c;
     level_corners(g, l, x, c);
+    if (!aggregate) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) atomicAdd(grid_grad + c.idx[k], make_float2(c.w[k] * a, c.w[k] * b));
+      for (int k = 0; k < 8; ++k) atomicAdd(grid_grad + c.idx[k], make_float2(c.w[k] * a, c.w[k] * b));
+      continue;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const uint32_t key = live ? c.idx[k] : (0xFFFFFF00u + (uint32_t)lane);      // idle lanes never join a run
+      float va = c.w[k] * a, vb = c.w[k] * b;
+      const uint32_t prev = __shfl_up_sync(kFull, key, 1);
+      const bool head = lane == 0 || prev != key;
+      // run id = number of run heads at or below this lane: equal ids <=> same contiguous run (equal keys further apart
+      // belong to different runs and issue their own atomics)
+      const uint32_t rid = __popc(__ballot_sync(kFull, head) & (0xFFFFFFFFu >> (31 - lane)));
+#pragma unroll
+      for (int dlt = 1; dlt < 32; dlt <<= 1) {
+        const uint32_t ro = __shfl_down_sync(kFull, rid, dlt);
+        const float ao = __shfl_down_sync(kFull, va, dlt), bo = __shfl_down_sync(kFull, vb, dlt);
+        if (lane + dlt < 32 && ro == rid) { va += ao; vb += bo; }
+      }
+      if (head && live && (va != 0.f || vb != 0.f)) atomicAdd(grid_grad + key, make_float2(va, vb));
+    }
   }
 }
 
@@ -170,19 +198,23 @@ struct ScatterArgs {
 
 __global__ void __launch_bounds__(128) hash_scatter_kernel(ScatterArgs a) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
-  if (s >= a.r.n_rays * a.r.S) return;
-  float x[3];
-  sample_unit_pos(a.r, a.g, s, x);
+  const bool live = s < a.r.n_rays * a.r.S;
+  float x[3] = {0.f, 0.f, 0.f};
   float df[32];
-  const uint4* src = reinterpret_cast<const uint4*>(a.d_feats + (size_t)s * a.ld);
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const uint4 v = __ldg(src + q);
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+  for (int i = 0; i < 32; ++i) df[i] = 0.f;
+  if (live) {
+    sample_unit_pos(a.r, a.g, s, x);
+    const uint4* src = reinterpret_cast<const uint4*>(a.d_feats + (size_t)s * a.ld);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { df[q * 8 + 2 * j] = __uint_as_float(w[j] << 16); df[q * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+    for (int q = 0; q < 4; ++q) {
+      const uint4 v = __ldg(src + q);
+      const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { df[q * 8 + 2 * j] = __uint_as_float(w[j] << 16); df[q * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+    }
   }
-  scatter_sample(a.g, a.grid_grad, x, df);
+  scatter_sample(a.g, a.grid_grad, x, df, live);
 }
 
 // ---------------------------------------------------------------------------------------------------- fused density field
@@ -274,7 +306,7 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
       for (int i = 0; i < kMaxIn; ++i) { if (i >= in) break; df[i] = fmaf(W1[i * kPropHidden + j], dz, df[i]); }
     }
     __syncthreads();
-    if (dr != 0.f) scatter_sample(a.g, a.grid_grad, x, df);
+    scatter_sample(a.g, a.grid_grad, x, df, dr != 0.f);
     // dW1[i][j] += sum_t f[t][i] * dZ[t][j]: output o = i * 64 + j (a warp: one i, 32 consecutive j)
     for (int q = 0, o = threadIdx.x; o < n_out; o += 128, ++q) {
       const int i = o / kPropHidden, j = o % kPropHidden;
@@ -345,25 +377,39 @@ __global__ void ray_bias_kernel(const float* inp, int in_dim, const float* W, in
   rb[idx] = acc + bias[c];
 }
 
-// dZ_head1 = (d_rgb . W_rgb^T) * [head activation > 0] (bf16) + the head-gradient rows (d_r, d_g, d_b, d_density)
-__global__ void __launch_bounds__(kH) field_bwd_start_kernel(const float* d_raw, const __nv_bfloat16* hact, const float* w_rgb,
-                                                             const uint8_t* inside, int n_samples, int n_rows_pad,
-                                                             __nv_bfloat16* dz, __nv_bfloat16* dh, float* d_dens) {
-  const int s = blockIdx.x, c = threadIdx.x;
+// dZ_head1 = (d_rgb . W_rgb^T) * [head activation > 0] (bf16) + the head-gradient rows (d_r, d_g, d_b, d_density).
+// Block = 8 samples x 32 lanes, a lane owns 8 consecutive columns (one 16-byte load / store).
+__global__ void __launch_bounds__(256) field_bwd_start_kernel(const float* d_raw, const __nv_bfloat16* hact, const float* w_rgb,
+                                                              const uint8_t* inside, int n_samples, int n_rows_pad,
+                                                              __nv_bfloat16* dz, __nv_bfloat16* dh, float* d_dens) {
+  __shared__ float wsm[kH * 3];
+  for (int i = threadIdx.x; i < kH * 3; i += blockDim.x) wsm[i] = w_rgb[i];
+  __syncthreads();
+  const int s = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (s >= n_rows_pad) return;
   float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (s < n_samples) dr = reinterpret_cast<const float4*>(d_raw)[s];
+  if (s < n_samples) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + s);
   if (s < n_samples && !inside[s]) dr.x = 0.f;            // density * selector: no density gradient out of range
-  if (c == 0) {
+  if (lane == 0) {
     reinterpret_cast<uint4*>(dh + (size_t)s * kHeadCols)[0] =
         make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
     d_dens[s] = dr.x;
   }
   const float d0 = __bfloat162float(__float2bfloat16(dr.y)), d1 = __bfloat162float(__float2bfloat16(dr.z)),
               d2 = __bfloat162float(__float2bfloat16(dr.w));
-  const float g = d0 * w_rgb[c * 3] + d1 * w_rgb[c * 3 + 1] + d2 * w_rgb[c * 3 + 2];
-  const bool on = s < n_samples && __bfloat162float(hact[(size_t)s * kH + c]) > 0.f;
-  dz[(size_t)s * kH + c] = __float2bfloat16(on ? g : 0.f);
+  uint4 hv = make_uint4(0u, 0u, 0u, 0u);
+  if (s < n_samples) hv = __ldg(reinterpret_cast<const uint4*>(hact + (size_t)s * kH) + lane);
+  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c0 = lane * 8 + 2 * j;
+    const float g0 = d0 * wsm[c0 * 3] + d1 * wsm[c0 * 3 + 1] + d2 * wsm[c0 * 3 + 2];
+    const float g1 = d0 * wsm[c0 * 3 + 3] + d1 * wsm[c0 * 3 + 4] + d2 * wsm[c0 * 3 + 5];
+    // the saved activation is post-ReLU (>= 0): a non-zero bf16 pattern means the gate is open
+    o[j] = ptx::pack_bf16x2((hw[j] & 0xFFFFu) ? g0 : 0.f, (hw[j] >> 16) ? g1 : 0.f);
+  }
+  reinterpret_cast<uint4*>(dz + (size_t)s * kH)[lane] = make_uint4(o[0], o[1], o[2], o[3]);
 }
 
 __global__ void inside_mask_kernel(FieldRays r, HashGridCfg g, uint8_t* inside, float* raw, int C) {
@@ -397,18 +443,24 @@ __global__ void __launch_bounds__(kH) ray_input_wgrad_kernel(const float* inp, i
   if (r1 > r0) atomicAdd(dW + (size_t)(row0 + j) * kH + c, acc);
 }
 
-// d embedding[row][g] += sum_c bf16(W[(row0 + g) * 256 + c]) * dzsum[ray][c]
-__global__ void app_embed_grad_kernel(const float* dzsum, const int32_t* embed_idx, const float* W, int row0, int app,
-                                      int n_rays, int num_emb, float* d_emb) {
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= n_rays * app) return;
-  const int ray = idx / app, g = idx % app;
-  const float* wrow = W + (size_t)(row0 + g) * kH;
-  float acc = 0.f;
-  for (int c = 0; c < kH; ++c) acc = fmaf(dzsum[(size_t)ray * kH + c], __bfloat162float(__float2bfloat16(wrow[c])), acc);
+// d embedding[row][g] += sum_c bf16(W[(row0 + g) * 256 + c]) * dzsum[ray][c]: one warp per ray, lanes over c (coalesced)
+__global__ void __launch_bounds__(256) app_embed_grad_kernel(const float* dzsum, const int32_t* embed_idx, const float* W,
+                                                             int row0, int app, int n_rays, int num_emb, float* d_emb) {
+  const int ray = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (ray >= n_rays) return;
+  float z[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) z[q] = dzsum[(size_t)ray * kH + q * 32 + lane];
   const int row = embed_idx[ray];
-  if (row < 0 || row >= num_emb) return;
-  atomicAdd(d_emb + (size_t)row * app + g, acc);
+  const bool ok = row >= 0 && row < num_emb;
+  for (int g = 0; g < app; ++g) {
+    const float* wrow = W + (size_t)(row0 + g) * kH;
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc = fmaf(z[q], __bfloat162float(__float2bfloat16(__ldg(wrow + q * 32 + lane))), acc);
+    acc = warp_sum(acc);
+    if (lane == 0 && ok) atomicAdd(d_emb + (size_t)row * app + g, acc);
+  }
 }
 
 // bf16 operand packs of the main field.  Source kernels are flax-style [in, out_stride]; a forward block holds element
@@ -877,7 +929,7 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
     return wgrad_launch_raw(h->num_sms, 0, 1, 1 << 30, h->map64, HF_MAPS, h->items_dev + L.first, L.second, mlp_grad, st);
   };
   // start: dZ_head1 from d_rgb, head-gradient rows, masked density gradient
-  field_bwd_start_kernel<<<rows_pad, kH, 0, st>>>(d_raw, h->buf[HF_H1], h->tab + 928, h->inside, M, rows_pad, h->buf[HF_DZH1],
+  field_bwd_start_kernel<<<(rows_pad + 7) / 8, 256, 0, st>>>(d_raw, h->buf[HF_H1], h->tab + 928, h->inside, M, rows_pad, h->buf[HF_DZH1],
                                                   h->buf[HF_DH], h->d_dens);
   HUGS_LAUNCH_CHECK();
   if ((rc = wgrad())) return rc;
@@ -895,7 +947,7 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   ray_input_wgrad_kernel<<<dim3(kSH + app, 32), kH, 0, st>>>(h->ray_in, kSH + app, h->dzsum, n_rays, kG, mlp_grad + h->o_head0_k);
   HUGS_LAUNCH_CHECK();
   if (app > 0) {
-    app_embed_grad_kernel<<<(n_rays * app + 127) / 128, 128, 0, st>>>(h->dzsum, rays->embed_idx, mlp + h->o_head0_k, kG + kSH, app,
+    app_embed_grad_kernel<<<(n_rays + 7) / 8, 256, 0, st>>>(h->dzsum, rays->embed_idx, mlp + h->o_head0_k, kG + kSH, app,
                                                                       n_rays, h->d.num_embeddings, mlp_grad + h->o_emb);
     HUGS_LAUNCH_CHECK();
   }

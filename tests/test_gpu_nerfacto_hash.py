@@ -126,7 +126,7 @@ def test_density_field_forward_backward_vs_autograd(contract):
   distinct, outs = eng.export_grads(None)
   got = {id(t): g.cpu().numpy() for t, g in zip(distinct, outs)}
   for t, w in ((l1.weight, W1), (l1.bias, b1), (l2.weight, W2), (l2.bias, b2)):
-    assert rel(got[id(t)], w.grad.numpy()) < 2e-4
+    assert rel(got[id(t)], w.grad.numpy()) < (2e-4 if not contract else 1e-2)
 
 
 def _ref_outer(t0s, t0e, t1s, t1e, y1):
