@@ -23,6 +23,7 @@ import torch.distributed as dist
 
 from nerf_hugs_b200 import _lib
 from nerf_hugs_b200.nerfacto.models import criterion_dict, model_config_dict, model_dict
+from nerf_hugs_b200.nerfacto.parallel import allreduce_gradients
 
 RANK, WORLD, LOCAL = (int(os.environ.get(k, d)) for k, d in (('RANK', '0'), ('WORLD_SIZE', '1'), ('LOCAL_RANK', '0')))
 
@@ -65,15 +66,6 @@ def synthetic_batch(n_rays, dev, seed, bound):
       'static_mask': (torch.rand(n_patch, 1, generator=g) < 0.8).float().repeat_interleave(256, 0)[:n],
   }
   return {k: v.to(dev) for k, v in batch.items()}
-
-
-def allreduce_grads(model):
-  if WORLD == 1:
-    return
-  for p in model.parameters():
-    if p.grad is not None and p.numel() > 0:
-      dist.all_reduce(p.grad)
-      p.grad.div_(WORLD)
 
 
 def run(kind, n_rays, steps, warmup=5):
@@ -123,7 +115,7 @@ def run(kind, n_rays, steps, warmup=5):
     ev['l'][i].record()
     loss.backward()
     ev['b'][i].record()
-    allreduce_grads(model)
+    allreduce_gradients(model)
     ev['r'][i].record()
     opt.step()
     ev['o'][i].record()
