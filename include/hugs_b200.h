@@ -313,7 +313,9 @@ typedef struct {
   int32_t transpose;
   int32_t ld;                    /* elements between consecutive rows of the tensor behind `ptr` (0: dense) */
 } hugs_tensor_copy;
-int hugs_params_copy(const hugs_tensor_copy* table, int32_t n, float* flat, int32_t direction, void* stream);
+int hugs_params_copy(const hugs_tensor_copy* table, int32_t n, float* flat, int32_t direction, float* tensor_base,
+                     void* stream);   /* tensor_base != NULL: every `ptr` of the table is a BYTE OFFSET from it (a constant table
+                                         for buffers that move, e.g. a fresh gradient buffer per backward pass) */
 
 /* ---- hash-grid fields of the nerfacto twin (nerfacto/models/nerfacto.py:643-1008) ----
  *

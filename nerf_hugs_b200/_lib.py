@@ -138,7 +138,7 @@ SYMBOLS = {
     'hugs_nf_distortion_loss': (C.c_int, [_P, _P, _I, _I, _P, _P, _P]),
     'hugs_nf_interlevel_loss': (C.c_int, [_P, _P, _I, _P, _P, _I, _I, _P, _P, _P]),
     'hugs_nf_scale': (C.c_int, [_P, _P, _F, C.c_int64, _P, _P]),
-    'hugs_params_copy': (C.c_int, [_P, _I, _P, _I, _P]),
+    'hugs_params_copy': (C.c_int, [_P, _I, _P, _I, _P, _P]),
     'hugs_launch_count': (C.c_int64, []),
     'hugs_profile_enable': (C.c_int, [_P, _I]),
     'hugs_profile_read': (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int32)]),

@@ -709,10 +709,11 @@ HUGS_API int hugs_nf_composite_bwd(const hugs_nf_render_cfg* cfg, const float* r
   return launch_nf_composite(a, true, (cudaStream_t)stream);
 }
 
-HUGS_API int hugs_params_copy(const hugs_tensor_copy* table, int32_t n, float* flat, int32_t direction, void* stream) {
+HUGS_API int hugs_params_copy(const hugs_tensor_copy* table, int32_t n, float* flat, int32_t direction, float* tensor_base,
+                              void* stream) {
   HUGS_REQUIRE(table && flat && n >= 0, "hugs_params_copy: null argument");
   HUGS_REQUIRE(direction == 0 || direction == 1, "hugs_params_copy: direction must be 0 (tensors -> flat) or 1");
-  return launch_params_copy(table, n, flat, direction, (cudaStream_t)stream);
+  return launch_params_copy(table, n, flat, direction, tensor_base, (cudaStream_t)stream);
 }
 
 HUGS_API int hugs_nf_rgb_loss(const float* pred, const float* gt, const float* static_mask, float transient_weight,

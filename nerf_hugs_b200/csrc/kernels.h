@@ -133,7 +133,7 @@ int launch_nf_distortion(const float* c, const float* w, int n_rays, int S, floa
 int launch_nf_interlevel(const float* c, const float* w, int S, const float* cp, const float* wp, int Sp, int n_rays,
                          float* out, float* grad, cudaStream_t stream);
 int launch_nf_scale(const float* src, const float* upstream, float mult, long long n, float* dst, cudaStream_t stream);
-int launch_params_copy(const hugs_tensor_copy* table, int n, float* flat, int direction, cudaStream_t stream);
+int launch_params_copy(const hugs_tensor_copy* table, int n, float* flat, int direction, float* base, cudaStream_t stream);
 
 // pos_enc of interval midpoints (custom_functions.py:55-63): fp32 features [n*S, 3 + 6*ndeg] in the reference's column order,
 // and / or bf16 rows of `ld` columns (hi, optional residual lo; columns beyond the features zero up to `zero_cols`)

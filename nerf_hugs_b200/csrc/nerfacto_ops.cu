@@ -323,8 +323,9 @@ __global__ void nf_scale_kernel(const float* src, const float* upstream, float m
 }
 
 // ------------------------------------------------------------------------------------------ parameter copies
-__global__ void params_copy_kernel(const hugs_tensor_copy* table, float* flat, int direction) {
-  const hugs_tensor_copy t = table[blockIdx.y];
+__global__ void params_copy_kernel(const hugs_tensor_copy* table, float* flat, int direction, float* base) {
+  hugs_tensor_copy t = table[blockIdx.y];
+  if (base) t.ptr = reinterpret_cast<float*>(reinterpret_cast<char*>(base) + reinterpret_cast<size_t>(t.ptr));
   const long long n = (long long)t.rows * t.cols;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
     const int i = (int)(e / t.cols), j = (int)(e % t.cols);
@@ -496,9 +497,9 @@ int launch_nf_scale(const float* src, const float* upstream, float mult, long lo
   return HUGS_OK;
 }
 
-int launch_params_copy(const hugs_tensor_copy* table, int n, float* flat, int direction, cudaStream_t stream) {
+int launch_params_copy(const hugs_tensor_copy* table, int n, float* flat, int direction, float* base, cudaStream_t stream) {
   if (n <= 0) return HUGS_OK;
-  params_copy_kernel<<<dim3(32, n), 256, 0, stream>>>(table, flat, direction);
+  params_copy_kernel<<<dim3(32, n), 256, 0, stream>>>(table, flat, direction, base);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
 }

@@ -143,3 +143,135 @@ class DeviceDataset:
     h, w = int(self.heights_np[cam_idx]), int(self.widths_np[cam_idx])
     ys, xs = torch.meshgrid(torch.arange(h, device=self.device), torch.arange(w, device=self.device), indexing='ij')
     return self.make_ray_batch(xs, ys, torch.full_like(xs, cam_idx))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# datasets.load_dataset / datasets.Dataset: the iterator the scripts consume (datasets.py:45-77, 259-443)
+# ------------------------------------------------------------------------------------------------------------------
+class Dataset:
+  """Iterator protocol of `datasets.Dataset` (datasets.py:259-443) over a DeviceDataset.
+
+  The reference fills a `queue.Queue(3)` from a daemon thread that assembles batches with NumPy (`:393-407`); here a batch is
+  one kernel launch on the device, so `__next__` produces it on demand - same `utils.Batch`, same `size`, `peek`,
+  `generate_ray_batch`.  Training batches are this rank's share (`batch_size // world_size` rays: the reference shards with
+  `utils.shard`, utils.py:117-120); test examples are whole images in order.
+
+  Subclasses implement `_load_renderings(config)` exactly as in the reference: set `images` (list of [H, W, 3]),
+  `camtoworlds`, `pixtocams`, `heights`, `widths` and optionally `static_masks`, `nears`, `fars`, `embed_idxs`,
+  `distortion_params`, `camtype`.  Reading COLMAP / Blender / Phototourism files is out of this package's scope (SURVEY.md
+  §2.1): `from_reference(ds)` adopts the arrays of a dataset object loaded by the reference's own loaders instead.
+  """
+
+  def __init__(self, split, is_training, sample_from_half_image, batch_size, patch_size, patch_dilation, image_num_per_batch,
+               data_dir, config, rank=0, world_size=1, seed=20221019):
+    self.split, self.is_training = split, bool(is_training)
+    self.sample_from_half_image = sample_from_half_image
+    self._world = max(1, int(world_size))
+    self._batch_size = batch_size // self._world
+    self._patch_size, self._patch_dilation = max(patch_size, 1), patch_dilation
+    self._image_num_per_batch = max(1, image_num_per_batch // self._world) if image_num_per_batch >= self._world else 1
+    self.data_dir, self.config = data_dir, config
+    self.near, self.far = config.near, config.far
+    self.static_masks = self.nears = self.fars = self.embed_idxs = self.distortion_params = None
+    self.camtype = 'perspective'
+    self._load_renderings(config)
+    self._n_examples = len(self.camtoworlds)
+    self.device_dataset = DeviceDataset(
+        self.pixtocams, self.camtoworlds, self.heights, self.widths, images=self.images, static_masks=self.static_masks,
+        nears=self.nears, fars=self.fars, embed_idxs=self.embed_idxs, near=self.near, far=self.far,
+        distortion_params=self.distortion_params, camtype=self.camtype)
+    self._gen = torch.Generator(device=self.device_dataset.device)
+    self._gen.manual_seed(seed + rank)
+    self._test_idx = 0
+    self._peeked = None
+
+  def _load_renderings(self, config):
+    raise NotImplementedError
+
+  @classmethod
+  def from_reference(cls, ds, is_training, sample_from_half_image, batch_size, patch_size, patch_dilation,
+                     image_num_per_batch, config, **kw):
+    """Adopt the arrays of a `datasets.Dataset` loaded by the reference's own loaders (attributes of datasets.py:310-383)."""
+    class _Adopted(cls):
+      def _load_renderings(self, config):
+        for k in ('images', 'camtoworlds', 'pixtocams', 'static_masks', 'nears', 'fars', 'embed_idxs', 'distortion_params'):
+          setattr(self, k, getattr(ds, k, None))
+        n = len(ds.camtoworlds)
+        hs, ws = getattr(ds, 'heights', None), getattr(ds, 'widths', None)
+        self.heights = hs if hs is not None else [ds.height] * n
+        self.widths = ws if ws is not None else [ds.width] * n
+    return _Adopted(ds.split, is_training, sample_from_half_image, batch_size, patch_size, patch_dilation,
+                    image_num_per_batch, getattr(ds, 'data_dir', None), config, **kw)
+
+  def __iter__(self):
+    return self
+
+  def _make(self):
+    if self.is_training:
+      return self.device_dataset.next_train_batch(self._gen, self._batch_size, self._patch_size, self._patch_dilation,
+                                                  self._image_num_per_batch, self.sample_from_half_image)
+    idx = self._test_idx
+    self._test_idx = (self._test_idx + 1) % self._n_examples
+    return self.device_dataset.generate_ray_batch(idx)
+
+  def __next__(self):
+    if self._peeked is not None:
+      b, self._peeked = self._peeked, None
+      return b
+    return self._make()
+
+  def peek(self):
+    if self._peeked is None:
+      self._peeked = self._make()
+    return self._peeked
+
+  @property
+  def size(self):
+    return self._n_examples
+
+  def generate_ray_batch(self, cam_idx: int) -> utils.Batch:
+    return self.device_dataset.generate_ray_batch(cam_idx)
+
+
+class Synthetic(Dataset):
+  """The synthetic scene of the measurement configs: cameras on a unit sphere looking at the origin, uniform
+  random images; with `config.transient_type == 'withmask'` also 32 x 32-block Bernoulli(0.8) HuGS static masks and per-image
+  near / far (config 3's Phototourism shape).  `Config.dataset_loader = 'synthetic'`."""
+
+  n_cams, hw = 16, (200, 200)
+
+  def _load_renderings(self, config):
+    rng = np.random.default_rng(0 if self.split == 'train' else 1)
+    n, (h, w) = self.n_cams, self.hw
+    pos = rng.normal(size=(n, 3)); pos /= np.linalg.norm(pos, axis=-1, keepdims=True)
+    fwd = -pos
+    right = np.cross(fwd, np.array([0., 0., 1.])); right /= np.linalg.norm(right, axis=-1, keepdims=True) + 1e-9
+    up = np.cross(right, fwd)
+    self.camtoworlds = np.stack([right, up, -fwd, pos], -1).astype(np.float32)
+    focal = 1111.1 / 800. * w
+    self.pixtocams = np.linalg.inv(np.array([[focal, 0, w / 2.], [0, focal, h / 2.], [0, 0, 1.]])).astype(np.float32)
+    self.heights, self.widths = [h] * n, [w] * n
+    self.images = [rng.uniform(size=(h, w, 3)).astype(np.float32) for _ in range(n)]
+    if getattr(config, 'transient_type', None) == 'withmask':
+      blocks = lambda: (rng.uniform(size=((h + 31) // 32, (w + 31) // 32)) < 0.8).astype(np.float32)
+      self.static_masks = [np.kron(blocks(), np.ones((32, 32), np.float32))[:h, :w, None] for _ in range(n)]
+    self.embed_idxs = np.arange(n)
+
+
+_LOADERS = {'synthetic': Synthetic}
+_REFERENCE_LOADERS = ('blender', 'llff', 'tat_nerfpp', 'tat_fvs', 'dtu', 'kubric', 'phototourism', 'distractor')
+
+
+def load_dataset(split, is_training, sample_from_half_image, batch_size, patch_size, patch_dilation, image_num_per_batch,
+                 train_dir, config, **kw):
+  """datasets.load_dataset (datasets.py:45-77): the same nine arguments, dispatched on `config.dataset_loader`."""
+  name = config.dataset_loader
+  if name in _REFERENCE_LOADERS:
+    raise NotImplementedError(
+        f"dataset_loader={name!r}: reading {name} files from disk (images, COLMAP / json poses, HuGS mask files) is outside this "
+        "package's scope (SURVEY.md §2.1).  Load the split with the reference's own datasets.load_dataset and hand it over: "
+        "nerf_hugs_b200.internal.datasets.Dataset.from_reference(ds, sample_from_half_image=..., batch_size=..., ...)")
+  if name not in _LOADERS:
+    raise KeyError(name)
+  return _LOADERS[name](split, is_training, sample_from_half_image, batch_size, patch_size, patch_dilation,
+                        image_num_per_batch, train_dir, config, **kw)

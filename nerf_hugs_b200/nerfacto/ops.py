@@ -175,10 +175,11 @@ class FieldEngine:
     self._gtable_key = None
     self._gtable = None
 
-  def _make_table(self, tensors):
-    arr = (_lib.TensorCopy * len(tensors))()
-    for e, t, (off, rows, cols, tr) in zip(arr, tensors, self.spec):
-      e.ptr, e.flat_off, e.rows, e.cols, e.transpose = t.data_ptr(), off, rows, cols, tr
+  def _make_table(self, ptrs):
+    """one hugs_tensor_copy per parameter; `ptrs` are addresses (import) or byte offsets into a gradient buffer (export)"""
+    arr = (_lib.TensorCopy * len(ptrs))()
+    for e, ptr, (off, rows, cols, tr) in zip(arr, ptrs, self.spec):
+      e.ptr, e.flat_off, e.rows, e.cols, e.transpose = ptr, off, rows, cols, tr
     host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
     return host.to(self.device)
 
@@ -191,27 +192,27 @@ class FieldEngine:
         raise RuntimeError('field parameters must be contiguous fp32 CUDA tensors (model.to(device) first)')
     key = tuple(t.data_ptr() for t in tensors)
     if key != self._table_key:
-      self._table, self._table_key, self._version_key = self._make_table(tensors), key, None
+      self._table, self._table_key, self._version_key = self._make_table(key), key, None
     vkey = tuple(t._version for t in tensors)
     if force or any(t is not p for t, p in zip(tensors, self.params)):
       self._version_key = None
     if vkey != self._version_key:
       with torch.cuda.device(self.device):
-        check(lib.hugs_params_copy(_ptr(self._table), len(tensors), _ptr(self.flat), 0, _stream(self.device)))
+        check(lib.hugs_params_copy(_ptr(self._table), len(tensors), _ptr(self.flat), 0, None, _stream(self.device)))
       self.engine.params_changed(self.flat)
       self._version_key = vkey
 
   def export_grads(self) -> List[torch.Tensor]:
     """flat flax-layout gradient -> one tensor per parameter in torch layout (views of one buffer)."""
     sizes = [rows * cols for _, rows, cols, _ in self.spec]
-    buf = torch.empty(sum(sizes), device=self.device)
+    buf = torch.empty(sum(sizes), device=self.device)       # a fresh buffer per backward pass: autograd may keep it as .grad
     outs, o = [], 0
     for p, sz in zip(self.params, sizes):
       outs.append(buf[o:o + sz].view(p.shape)); o += sz
-    table = self._make_table(outs)
+    if self._gtable is None:                                # constant: byte offsets into `buf` (no per-step host -> device copy)
+      self._gtable = self._make_table([4 * int(sum(sizes[:i])) for i in range(len(sizes))])
     with torch.cuda.device(self.device):
-      check(lib.hugs_params_copy(_ptr(table), len(outs), _ptr(self.gflat), 1, _stream(self.device)))
-    self._keep_table = table
+      check(lib.hugs_params_copy(_ptr(self._gtable), len(outs), _ptr(self.gflat), 1, _ptr(buf), _stream(self.device)))
     return outs
 
 
@@ -314,7 +315,7 @@ class HashFieldEngine:
     self.is_density_only = desc.geo_feat_dim == 0
     self.flat = torch.zeros(self.mlp_floats, device=self.device)
     self.gflat = torch.zeros(self.mlp_floats, device=self.device)
-    self._table_key = self._table = self._version_key = None
+    self._table_key = self._table = self._version_key = self._gtable = None
 
   def close(self):
     if self._h:
@@ -332,15 +333,15 @@ class HashFieldEngine:
     check(lib.hugs_hashfield_level_info(self._h, level, C.byref(s), C.byref(r), C.byref(o), C.byref(e)))
     return float(s.value), int(r.value), int(o.value), int(e.value)
 
-  def _make_table(self, tensors):
-    """one hugs_tensor_copy per entry; `tensors[i]` stands for the torch tensor of entry i"""
+  def _make_table(self, ptrs):
+    """one hugs_tensor_copy per entry; ptrs[i] = address (or byte offset into a gradient buffer) of entry i's torch tensor"""
     arr = (_lib.TensorCopy * len(self.entries))()
-    for e, (name, _, off, tr, ld), t in zip(arr, self.entries, tensors):
+    for e, (name, _, off, tr, ld), ptr in zip(arr, self.entries, ptrs):
       foff, rows, cols = self.layout[name.split('#')[0]]
       if '#' in name:      # "tensor#row0:rows": a block of rows of the flat tensor
         r0, nr = (int(v) for v in name.split('#')[1].split(':'))
         foff, rows = foff + r0 * cols, nr
-      e.ptr, e.flat_off, e.rows, e.cols, e.transpose, e.ld = t.data_ptr() + 4 * off, foff, rows, cols, tr, ld
+      e.ptr, e.flat_off, e.rows, e.cols, e.transpose, e.ld = ptr + 4 * off, foff, rows, cols, tr, ld
     return torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8).to(self.device)
 
   def sync_params(self, force: bool = False, override: Optional[Dict[int, torch.Tensor]] = None):
@@ -352,13 +353,13 @@ class HashFieldEngine:
         raise RuntimeError('field parameters must be contiguous fp32 CUDA tensors (model.to(device) first)')
     key = tuple(t.data_ptr() for t in tensors)
     if key != self._table_key:
-      self._table, self._table_key, self._version_key = self._make_table(tensors), key, None
+      self._table, self._table_key, self._version_key = self._make_table(key), key, None
     vkey = tuple(t._version for t in tensors)
     if force or override:
       self._version_key = None
     if vkey != self._version_key:
       with torch.cuda.device(self.device):
-        check(lib.hugs_params_copy(_ptr(self._table), len(tensors), _ptr(self.flat), 0, _stream(self.device)))
+        check(lib.hugs_params_copy(_ptr(self._table), len(tensors), _ptr(self.flat), 0, None, _stream(self.device)))
         check(lib.hugs_hashfield_params_changed(self._h, _ptr(self.flat), _stream(self.device)))
       self._version_key = vkey
 
@@ -413,14 +414,15 @@ class HashFieldEngine:
       if id(t) not in seen:
         seen[id(t)] = len(distinct); distinct.append(t)
     sizes = [t.numel() for t in distinct]
-    buf = torch.zeros(sum(sizes), device=self.device)
+    buf = torch.empty(sum(sizes), device=self.device)       # a fresh buffer per backward pass (the entries cover every element)
     outs, o = [], 0
     for t, sz in zip(distinct, sizes):
       outs.append(buf[o:o + sz].view(t.shape)); o += sz
-    table = self._make_table([outs[seen[id(t)]] for _, t, _, _, _ in self.entries])
+    if self._gtable is None:                                # constant: byte offsets into `buf`
+      starts = [4 * int(sum(sizes[:i])) for i in range(len(sizes))]
+      self._gtable = self._make_table([starts[seen[id(t)]] for _, t, _, _, _ in self.entries])
     with torch.cuda.device(self.device):
-      check(lib.hugs_params_copy(_ptr(table), len(self.entries), _ptr(self.gflat), 1, _stream(self.device)))
-    self._keep_table = table
+      check(lib.hugs_params_copy(_ptr(self._gtable), len(self.entries), _ptr(self.gflat), 1, _ptr(buf), _stream(self.device)))
     return distinct, outs
 
 

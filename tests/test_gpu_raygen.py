@@ -127,3 +127,30 @@ def test_device_batches_drive_the_training_step():
   # updated parameters agree to rounding only
   assert stats[0][:2] == stats[1][:2], stats
   assert abs(stats[0][2] - stats[1][2]) <= 1e-6 * abs(stats[0][2]) + 1e-6, stats
+
+
+def test_load_dataset_iterator_protocol():
+  # datasets.load_dataset + Dataset.__iter__/__next__/peek/size/generate_ray_batch (datasets.py:45-77, 393-443)
+  from nerf_hugs_b200.internal import configs, datasets
+  bind = ["Config.dataset_loader = 'synthetic'", "Config.transient_type = 'withmask'", 'Config.near = 0.5', 'Config.far = 3.0']
+  config = configs.load_config([], bind, save_config=False)
+  ds = datasets.load_dataset('train', True, False, 1024, 16, 1, 2, None, config)
+  assert ds.size == 16
+  first = ds.peek()
+  b = next(iter(ds))
+  assert b is first
+  assert tuple(b.rgb.shape) == (4, 16, 16, 3) and tuple(b.rays.origins.shape) == (4, 16, 16, 3)     # [patches, 16, 16, C]
+  m = b.rays.static_mask
+  assert torch.all((m == 0) | (m == 1)) and 0.3 < float(m.mean()) <= 1.0
+  assert torch.allclose(b.rays.near, torch.full_like(b.rays.near, 0.5))
+  b2 = next(ds)
+  assert not torch.equal(b2.rays.pix_coords, b.rays.pix_coords)
+  # two ranks of a 2-GPU job draw different, half-sized batches (utils.shard, utils.py:117-120)
+  r0 = datasets.load_dataset('train', True, False, 1024, 16, 1, 2, None, config, rank=0, world_size=2)
+  r1 = datasets.load_dataset('train', True, False, 1024, 16, 1, 2, None, config, rank=1, world_size=2)
+  a0, a1 = next(r0), next(r1)
+  assert a0.rgb.shape[0] == 2 and not torch.equal(a0.rays.pix_coords, a1.rays.pix_coords)
+  test = datasets.load_dataset('test', False, False, 1024, 16, 1, 2, None, config)
+  img = next(test)
+  assert tuple(img.rgb.shape) == (200, 200, 3) and int(img.rays.cam_idx.max()) == 0
+  assert int(next(test).rays.cam_idx.max()) == 1

@@ -124,3 +124,14 @@ def test_learning_rate_decay_matches_oracle():
     a = hmath.learning_rate_decay(step, 2e-3, 2e-5, 250000, 512, 0.01)
     b = O.learning_rate_decay(step, 2e-3, 2e-5, 250000, 512, 0.01)
     assert abs(a - b) <= 1e-15
+
+
+def test_load_dataset_dispatch_is_loud_for_disk_loaders():
+  # datasets.load_dataset (datasets.py:45-77): same arguments; file readers are out of scope and say so
+  from nerf_hugs_b200.internal import configs, datasets
+  config = configs.load_config([], ["Config.dataset_loader = 'phototourism'"], save_config=False)
+  with pytest.raises(NotImplementedError, match='from_reference'):
+    datasets.load_dataset('train', True, False, 4096, 16, 1, 16, '/tmp/x', config)
+  config = configs.load_config([], ["Config.dataset_loader = 'nope'"], save_config=False)
+  with pytest.raises(KeyError):
+    datasets.load_dataset('train', True, False, 4096, 16, 1, 16, '/tmp/x', config)
