@@ -102,18 +102,20 @@ __device__ __forceinline__ void level_corners(const HashGridCfg& g, int l, const
 // features of one sample, level-major: out[l * 2 + f]   (F == 2)
 template <int kMaxL>
 __device__ __forceinline__ void encode_sample(const HashGridCfg& g, const float2* __restrict__ grid, const float x[3], float* out) {
-#pragma unroll 2
+  constexpr int kUnroll = kMaxL <= 16 ? kMaxL : 2;    // few levels: fully unrolled, `out` stays in registers
+#pragma unroll kUnroll
   for (int l = 0; l < kMaxL; ++l) {
-    if (l >= g.L) break;
-    Corner c;
-    level_corners(g, l, x, c);
-    float2 v[8];
+    if (l < g.L) {
+      Corner c;
+      level_corners(g, l, x, c);
+      float2 v[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) v[k] = __ldg(grid + c.idx[k]);
-    float a = 0.f, b = 0.f;
+      for (int k = 0; k < 8; ++k) v[k] = __ldg(grid + c.idx[k]);
+      float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { a = fmaf(c.w[k], v[k].x, a); b = fmaf(c.w[k], v[k].y, b); }
-    out[2 * l] = a; out[2 * l + 1] = b;
+      for (int k = 0; k < 8; ++k) { a = fmaf(c.w[k], v[k].x, a); b = fmaf(c.w[k], v[k].y, b); }
+      out[2 * l] = a; out[2 * l + 1] = b;
+    }
   }
 }
 
@@ -125,10 +127,14 @@ __device__ __forceinline__ void encode_sample(const HashGridCfg& g, const float2
 // Measured on config 4 (profiles/r02_nerfacto.md): no aggregation 15.9 ms backward, levels up to resolution 64 only 15.5 ms,
 // up to 512 8.7 ms, every level 8.7 ms - runs of equal entries are common well beyond the coarsest levels.
 constexpr int kAggregateRes = 512;
+template <int kMaxL>
 __device__ __forceinline__ void scatter_sample(const HashGridCfg& g, float2* grid_grad, const float x[3], const float* df,
                                                bool live) {
   const int lane = threadIdx.x & 31;
-  for (int l = 0; l < g.L; ++l) {
+  constexpr int kUnroll = kMaxL <= 16 ? kMaxL : 1;
+#pragma unroll kUnroll
+  for (int l = 0; l < kMaxL; ++l) {
+    if (l >= g.L) continue;
     const float a = live ? df[2 * l] : 0.f, b = live ? df[2 * l + 1] : 0.f;
     const bool aggregate = g.res[l] <= (uint32_t)kAggregateRes;
     if (!aggregate && a == 0.f && b == 0.f) continue;
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(128) hash_scatter_kernel(ScatterArgs a) {
       for (int j = 0; j < 4; ++j) { df[q * 8 + 2 * j] = __uint_as_float(w[j] << 16); df[q * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
     }
   }
-  scatter_sample(a.g, a.grid_grad, x, df, live);
+  scatter_sample<16>(a.g, a.grid_grad, x, df, live);
 }
 
 // ---------------------------------------------------------------------------------------------------- fused density field
@@ -240,10 +246,13 @@ inline size_t prop_smem_bytes(int in, bool backward) {
   return fl * sizeof(float);
 }
 
-template <bool kBackward>
+// kIn > 0: the input width (2 x levels: 10 and 14 in the shipped configs) is a compile-time constant, so the feature /
+// gradient vectors live in registers and every loop unrolls; kIn == 0 is the generic version (runtime width, local arrays).
+template <bool kBackward, int kIn>
 __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
   extern __shared__ float sm[];
-  const int in = a.g.in_dim, ldf = prop_ldf(in);
+  constexpr int kCap = kIn > 0 ? kIn : kMaxIn;
+  const int in = kIn > 0 ? kIn : a.g.in_dim, ldf = prop_ldf(in);
   float* W1 = sm;                      // [in][64]
   float* b1 = W1 + in * kPropHidden;   // [64]
   float* w2 = b1 + kPropHidden;        // [64]
@@ -257,28 +266,29 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
   const int n = a.r.n_rays * a.r.S;
   const int n_out = in * kPropHidden;
   // backward: per-thread partial sums of dW1 (outputs o = threadIdx.x + 128 q), db1 / dw2 (one column each), db2
-  float acc_w[kPropAcc];
+  constexpr int kAcc = (kCap * kPropHidden + 127) / 128;
+  float acc_w[kAcc];
   float acc_col = 0.f, acc_b2 = 0.f;
 #pragma unroll
-  for (int q = 0; q < kPropAcc; ++q) acc_w[q] = 0.f;
+  for (int q = 0; q < kAcc; ++q) acc_w[q] = 0.f;
   for (int base = blockIdx.x * 128; base < n; base += gridDim.x * 128) {
     const int s = base + threadIdx.x;
     const bool live = s < n;
-    float f[kMaxIn];
+    float f[kCap];
     float x[3] = {0.f, 0.f, 0.f};
     bool inside = false;
 #pragma unroll
-    for (int i = 0; i < kMaxIn; ++i) f[i] = 0.f;
+    for (int i = 0; i < kCap; ++i) f[i] = 0.f;
     if (live) {
       inside = sample_unit_pos(a.r, a.g, s, x);
-      encode_sample<24>(a.g, a.grid, x, f);
+      encode_sample<kCap / 2>(a.g, a.grid, x, f);
     }
     float h[kPropHidden];
 #pragma unroll
     for (int j = 0; j < kPropHidden; ++j) h[j] = b1[j];
-#pragma unroll 2
-    for (int i = 0; i < kMaxIn; ++i) {
-      if (i >= in) break;
+#pragma unroll
+    for (int i = 0; i < kCap; ++i) {
+      if (kIn == 0 && i >= in) break;
       const float fi = f[i];
 #pragma unroll
       for (int j = 0; j < kPropHidden; ++j) h[j] = fmaf(fi, W1[i * kPropHidden + j], h[j]);
@@ -292,35 +302,40 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
     }
     // ---- backward: dZ = d_raw * w2 * [h > 0]; the selector zeroes the density gradient of out-of-range samples ----
     const float dr = (live && inside) ? a.d_raw[s] : 0.f;
-    float df[kMaxIn];
+    float df[kCap];
 #pragma unroll
-    for (int i = 0; i < kMaxIn; ++i) df[i] = 0.f;
+    for (int i = 0; i < kCap; ++i) df[i] = 0.f;
     __syncthreads();                    // the previous chunk's staging has been consumed
-#pragma unroll 2
-    for (int i = 0; i < kMaxIn; ++i) { if (i >= in) break; stF[threadIdx.x * ldf + i] = f[i]; }
+#pragma unroll
+    for (int i = 0; i < kCap; ++i) { if (kIn == 0 && i >= in) break; stF[threadIdx.x * ldf + i] = f[i]; }
 #pragma unroll
     for (int j = 0; j < kPropHidden; ++j) {
       const float hj = h[j];
       const float dz = hj > 0.f ? dr * w2[j] : 0.f;
       stZ[threadIdx.x * 65 + j] = dz;
       stH[threadIdx.x * 65 + j] = dr * fmaxf(hj, 0.f);
-#pragma unroll 2
-      for (int i = 0; i < kMaxIn; ++i) { if (i >= in) break; df[i] = fmaf(W1[i * kPropHidden + j], dz, df[i]); }
+#pragma unroll
+      for (int i = 0; i < kCap; ++i) { if (kIn == 0 && i >= in) break; df[i] = fmaf(W1[i * kPropHidden + j], dz, df[i]); }
     }
     __syncthreads();
-    scatter_sample(a.g, a.grid_grad, x, df, dr != 0.f);
+    scatter_sample<kCap / 2>(a.g, a.grid_grad, x, df, dr != 0.f);
     // dW1[i][j] += sum_t f[t][i] * dZ[t][j]: output o = i * 64 + j (a warp: one i, 32 consecutive j)
-    for (int q = 0, o = threadIdx.x; o < n_out; o += 128, ++q) {
-      const int i = o / kPropHidden, j = o % kPropHidden;
-      float sacc = 0.f;
+#pragma unroll
+    for (int q = 0; q < kAcc; ++q) {
+      const int o = threadIdx.x + 128 * q;
+      if (o < n_out) {
+        const int i = o / kPropHidden, j = o % kPropHidden;
+        float sacc = 0.f;
 #pragma unroll 8
-      for (int t = 0; t < 128; ++t) sacc = fmaf(stF[t * ldf + i], stZ[t * 65 + j], sacc);
-      acc_w[q] += sacc;
+        for (int t = 0; t < 128; ++t) sacc = fmaf(stF[t * ldf + i], stZ[t * 65 + j], sacc);
+        acc_w[q] += sacc;
+      }
     }
     {  // threads 0..63: db1[j] = sum_t dZ[t][j]; threads 64..127: dw2[j] = sum_t d_raw[t] relu(h[t][j])
       const float* src = threadIdx.x < kPropHidden ? stZ : stH;
       const int j = threadIdx.x & (kPropHidden - 1);
       float sacc = 0.f;
+#pragma unroll 8
       for (int t = 0; t < 128; ++t) sacc += src[t * 65 + j];
       acc_col += sacc;
     }
@@ -328,11 +343,25 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
     if ((threadIdx.x & 31) == 0) acc_b2 += pb;
   }
   if (kBackward) {
-    for (int q = 0, o = threadIdx.x; o < n_out; o += 128, ++q) atomicAdd(a.mlp_grad + o, acc_w[q]);
+#pragma unroll
+    for (int q = 0; q < kAcc; ++q) {
+      const int o = threadIdx.x + 128 * q;
+      if (o < n_out) atomicAdd(a.mlp_grad + o, acc_w[q]);
+    }
     const int j = threadIdx.x & (kPropHidden - 1);
     atomicAdd(a.mlp_grad + n_out + (threadIdx.x < kPropHidden ? 0 : kPropHidden) + j, acc_col);
     if ((threadIdx.x & 31) == 0) atomicAdd(a.mlp_grad + n_out + 2 * kPropHidden, acc_b2);
   }
+}
+
+template <bool kBackward>
+int launch_prop_field(const PropArgs& a, int blocks, cudaStream_t st) {
+  const size_t smem = prop_smem_bytes(a.g.in_dim, kBackward);
+  if (a.g.in_dim == 10) prop_field_kernel<kBackward, 10><<<blocks, 128, smem, st>>>(a);
+  else if (a.g.in_dim == 14) prop_field_kernel<kBackward, 14><<<blocks, 128, smem, st>>>(a);
+  else prop_field_kernel<kBackward, 0><<<blocks, 128, smem, st>>>(a);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------- main-field helpers
@@ -742,9 +771,13 @@ HUGS_API int hugs_hashfield_create(const hugs_hashfield_desc* desc, hugs_hashfie
       return fail(rc);
     if ((rc = dense_tc_init())) return fail(rc);
   }
-  if (cudaFuncSetAttribute(prop_field_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(prop_field_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024) != cudaSuccess)
-    return fail(cuda_fail(cudaGetLastError(), "hash field smem opt-in", __FILE__, __LINE__));
+  {
+    cudaError_t e = cudaSuccess;
+    auto opt = [&](auto kernel) { if (e == cudaSuccess) e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); };
+    opt(prop_field_kernel<false, 10>); opt(prop_field_kernel<false, 14>); opt(prop_field_kernel<false, 0>);
+    opt(prop_field_kernel<true, 10>); opt(prop_field_kernel<true, 14>); opt(prop_field_kernel<true, 0>);
+    if (e != cudaSuccess) return fail(cuda_fail(e, "hash field smem opt-in", __FILE__, __LINE__));
+  }
   if (cudaDeviceSynchronize() != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "hugs_hashfield_create sync", __FILE__, __LINE__));
   *out = h;
   return HUGS_OK;
@@ -834,10 +867,7 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
   const FieldRays fr = field_rays(rays, tdist, n_rays, n_samples);
   if (h->is_prop) {
     PropArgs a{fr, h->g, reinterpret_cast<const float2*>(grid), mlp, raw_out, nullptr, nullptr, nullptr};
-    const int grid_dim = std::min((M + 127) / 128, h->num_sms * 8);
-    prop_field_kernel<false><<<grid_dim, 128, prop_smem_bytes(h->g.in_dim, false), st>>>(a);
-    HUGS_LAUNCH_CHECK();
-    return HUGS_OK;
+    return launch_prop_field<false>(a, std::min((M + 127) / 128, h->num_sms * 8), st);
   }
   HUGS_REQUIRE(n_rays <= h->max_rays, "nerfacto field: %d rays exceed the per-ray workspace (%d)", n_rays, h->max_rays);
   if (training && (rc = hf_ensure_training(h))) return rc;
@@ -910,10 +940,7 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   HUGS_CUDA(cudaMemsetAsync(mlp_grad, 0, sizeof(float) * h->mlp_floats, st));
   if (h->is_prop) {
     PropArgs a{fr, h->g, reinterpret_cast<const float2*>(grid), mlp, nullptr, d_raw, reinterpret_cast<float2*>(grid_grad), mlp_grad};
-    const int grid_dim = std::min((M + 127) / 128, h->num_sms * 2);
-    prop_field_kernel<true><<<grid_dim, 128, prop_smem_bytes(h->g.in_dim, true), st>>>(a);
-    HUGS_LAUNCH_CHECK();
-    return HUGS_OK;
+    return launch_prop_field<true>(a, std::min((M + 127) / 128, h->num_sms * 2), st);
   }
   HUGS_REQUIRE(h->train_ready, "nerfacto field: backward without a training forward");
   const int rows_pad = ((M + 255) / 256) * 256;

@@ -156,11 +156,12 @@ if __name__ == '__main__':
   ap.add_argument('what', nargs='*', default=['nerf', 'nerfacto'])
   ap.add_argument('--steps', type=int, default=30)
   ap.add_argument('--rays', type=int, default=0)
+  ap.add_argument('--warmup', type=int, default=5)
   a = ap.parse_args()
   if 'nerf' in a.what:
-    run('nerf', a.rays or 4096 * WORLD, a.steps)
+    run('nerf', a.rays or 4096 * WORLD, a.steps, a.warmup)
   if 'nerfacto' in a.what:
-    run('nerfacto', a.rays or 16384 * WORLD, a.steps)
+    run('nerfacto', a.rays or 16384 * WORLD, a.steps, a.warmup)
   if WORLD > 1:
     dist.barrier()
     dist.destroy_process_group()
