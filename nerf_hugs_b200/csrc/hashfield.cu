@@ -242,7 +242,7 @@ constexpr int kPropAcc = (kMaxIn * kPropHidden + 127) / 128;
 __host__ __device__ inline int prop_ldf(int in) { return in | 1; }     // odd row stride: conflict-free staging
 inline size_t prop_smem_bytes(int in, bool backward) {
   size_t fl = (size_t)in * kPropHidden + 2 * kPropHidden + 4;
-  if (backward) fl += 128 * (size_t)prop_ldf(in) + 2 * 128 * 65;
+  if (backward) fl += 128 * (size_t)prop_ldf(in) + 128 * 65;
   return fl * sizeof(float);
 }
 
@@ -259,16 +259,17 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
   float* b2 = w2 + kPropHidden;        // [1] (+3 pad)
   float* stF = b2 + 4;                 // backward staging: [128][ldf] features
   float* stZ = stF + 128 * ldf;        //                   [128][65] dZ of the hidden layer
-  float* stH = stZ + 128 * 65;         //                   [128][65] d_raw * relu(h)
   const int n_w = in * kPropHidden + 2 * kPropHidden + 1;
   for (int i = threadIdx.x; i < n_w; i += blockDim.x) sm[i] = a.mlp[i];
   __syncthreads();
   const int n = a.r.n_rays * a.r.S;
   const int n_out = in * kPropHidden;
-  // backward: per-thread partial sums of dW1 (outputs o = threadIdx.x + 128 q), db1 / dw2 (one column each), db2
+  // backward: per-thread partial sums of dW1 (outputs o = threadIdx.x + 128 q), db1 (threads 0..63: one column each),
+  // dw2 (lane l of every warp: columns l and l + 32 of the warp's samples), db2
   constexpr int kAcc = (kCap * kPropHidden + 127) / 128;
   float acc_w[kAcc];
-  float acc_col = 0.f, acc_b2 = 0.f;
+  float acc_col = 0.f, acc_b2 = 0.f, acc_w2a = 0.f, acc_w2b = 0.f;
+  const int lane_id = threadIdx.x & 31;
 #pragma unroll
   for (int q = 0; q < kAcc; ++q) acc_w[q] = 0.f;
   for (int base = blockIdx.x * 128; base < n; base += gridDim.x * 128) {
@@ -313,7 +314,9 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
       const float hj = h[j];
       const float dz = hj > 0.f ? dr * w2[j] : 0.f;
       stZ[threadIdx.x * 65 + j] = dz;
-      stH[threadIdx.x * 65 + j] = dr * fmaxf(hj, 0.f);
+      // dw2[j] += sum over the warp's samples of d_raw * relu(h_j): butterfly sum, kept by lane j % 32
+      const float hs = warp_sum(dr * fmaxf(hj, 0.f));
+      if (lane_id == (j & 31)) { if (j < 32) acc_w2a += hs; else acc_w2b += hs; }
 #pragma unroll
       for (int i = 0; i < kCap; ++i) { if (kIn == 0 && i >= in) break; df[i] = fmaf(W1[i * kPropHidden + j], dz, df[i]); }
     }
@@ -331,12 +334,10 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
         acc_w[q] += sacc;
       }
     }
-    {  // threads 0..63: db1[j] = sum_t dZ[t][j]; threads 64..127: dw2[j] = sum_t d_raw[t] relu(h[t][j])
-      const float* src = threadIdx.x < kPropHidden ? stZ : stH;
-      const int j = threadIdx.x & (kPropHidden - 1);
+    if (threadIdx.x < kPropHidden) {   // db1[j] = sum_t dZ[t][j]
       float sacc = 0.f;
 #pragma unroll 8
-      for (int t = 0; t < 128; ++t) sacc += src[t * 65 + j];
+      for (int t = 0; t < 128; ++t) sacc += stZ[t * 65 + threadIdx.x];
       acc_col += sacc;
     }
     const float pb = warp_sum(dr);
@@ -348,9 +349,10 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
       const int o = threadIdx.x + 128 * q;
       if (o < n_out) atomicAdd(a.mlp_grad + o, acc_w[q]);
     }
-    const int j = threadIdx.x & (kPropHidden - 1);
-    atomicAdd(a.mlp_grad + n_out + (threadIdx.x < kPropHidden ? 0 : kPropHidden) + j, acc_col);
-    if ((threadIdx.x & 31) == 0) atomicAdd(a.mlp_grad + n_out + 2 * kPropHidden, acc_b2);
+    if (threadIdx.x < kPropHidden) atomicAdd(a.mlp_grad + n_out + threadIdx.x, acc_col);
+    atomicAdd(a.mlp_grad + n_out + kPropHidden + lane_id, acc_w2a);
+    atomicAdd(a.mlp_grad + n_out + kPropHidden + 32 + lane_id, acc_w2b);
+    if (lane_id == 0) atomicAdd(a.mlp_grad + n_out + 2 * kPropHidden, acc_b2);
   }
 }
 
@@ -940,7 +942,7 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   HUGS_CUDA(cudaMemsetAsync(mlp_grad, 0, sizeof(float) * h->mlp_floats, st));
   if (h->is_prop) {
     PropArgs a{fr, h->g, reinterpret_cast<const float2*>(grid), mlp, nullptr, d_raw, reinterpret_cast<float2*>(grid_grad), mlp_grad};
-    return launch_prop_field<true>(a, std::min((M + 127) / 128, h->num_sms * 2), st);
+    return launch_prop_field<true>(a, std::min((M + 127) / 128, h->num_sms * 3), st);
   }
   HUGS_REQUIRE(h->train_ready, "nerfacto field: backward without a training forward");
   const int rows_pad = ((M + 255) / 256) * 256;
