@@ -20,20 +20,40 @@
 namespace hugs {
 namespace {
 
-constexpr int kDStages = 4;
+constexpr int kDStages = 4;                // ring depth; 3 in the split-precision mode (the staging area doubles)
 constexpr int kDStageBytes = 32768;        // A: 128 rows x 64 (16 KB) | B: <= 128 rows x 64 (16 KB)
-constexpr int kDOutPanels = 4;             // staging: this CTA's 128 rows x 256 output columns
+constexpr int kDOutPanels = 4;             // staging: this CTA's 128 rows x 256 output columns (x 2: hi and lo, split mode)
 constexpr int kDEpiWarps = 8;
 constexpr int kDThreads = (2 + kDEpiWarps) * 32;
-constexpr int kDSmem = 1024 + kDStages * kDStageBytes + kDOutPanels * kPanelBytes + 256;
-static_assert(kDSmem <= 232448, "shared memory budget");
+constexpr int kDSmem = 1024 + 3 * kDStageBytes + 2 * kDOutPanels * kPanelBytes + 256;      // >= the 4-stage / 4-panel layout
+static_assert(kDSmem <= 232448 && kDSmem >= 1024 + kDStages * kDStageBytes + kDOutPanels * kPanelBytes + 256,
+              "shared memory budget");
+
+// 32 fp32 values of one row -> bf16 hi words into `hi_panel`, residual words into `lo_panel` (chunks chunk0 .. chunk0 + 3)
+__device__ __forceinline__ void store_split_half32(uint8_t* hi_panel, uint8_t* lo_panel, int row, int chunk0, const float (&v)[32]) {
+  uint4* ph = reinterpret_cast<uint4*>(hi_panel + row * 128);
+  uint4* pl = reinterpret_cast<uint4*>(lo_panel + row * 128);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float a = v[c * 8 + 2 * j], b = v[c * 8 + 2 * j + 1];
+      h[j] = ptx::pack_bf16x2(a, b);
+      l[j] = ptx::pack_bf16x2(a - __uint_as_float(h[j] << 16), b - __uint_as_float(h[j] & 0xFFFF0000u));
+    }
+    ph[swz_chunk(row, chunk0 + c)] = make_uint4(h[0], h[1], h[2], h[3]);
+    pl[swz_chunk(row, chunk0 + c)] = make_uint4(l[0], l[1], l[2], l[3]);
+  }
+}
 
 __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_constant__ DenseParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int n_stages = p.split ? 3 : kDStages;
   uint8_t* ring = base;
-  uint8_t* stage_out = base + kDStages * kDStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + kDOutPanels * kPanelBytes);
+  uint8_t* stage_out = base + n_stages * kDStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_out + (p.split ? 2 : 1) * kDOutPanels * kPanelBytes);
   uint64_t* full = bars; uint64_t* empty = bars + kDStages;
   uint64_t* acc_full = bars + 2 * kDStages; uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
@@ -57,7 +77,8 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const int n_tiles = p.m_tiles * p.n_tiles;
-  const int kp_total = p.a_kp[0] + p.a_kp[1];
+  int kp_total = 0;
+  for (int seg = 0; seg < p.n_seg; ++seg) kp_total += p.a_kp[seg];
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
@@ -69,17 +90,16 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
         const CUtensorMap* bmap = bn == 256 ? &p.b_map : (bn == 128 ? &p.b_map_64 : &p.b_map_8);
         const uint32_t bytes = 16384u + (uint32_t)(bn / 2) * 128u;
         const int row = mt * 256 + rank * 128;
-        int kcol_w = p.b_col0;
-        for (int seg = 0; seg < 2; ++seg) {
+        for (int seg = 0; seg < p.n_seg; ++seg) {
           for (int kp = 0; kp < p.a_kp[seg]; ++kp) {
             ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
             if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
             const uint32_t bar = ptx::mapa_u32(full_u32 + stage * 8, 0);
             ptx::tma_load_2d_cg2(ring_u32 + stage * kDStageBytes, &p.a_map[seg], bar, p.a_col0[seg] + kp * 64,
                                  p.a_row0[seg] + row);
-            ptx::tma_load_2d_cg2(ring_u32 + stage * kDStageBytes + 16384, bmap, bar, kcol_w, p.b_row0 + n0 + rank * (bn / 2));
-            kcol_w += 64;
-            if (++stage == kDStages) { stage = 0; phase ^= 1; }
+            ptx::tma_load_2d_cg2(ring_u32 + stage * kDStageBytes + 16384, bmap, bar, p.w_col0[seg] + kp * 64,
+                                 p.b_row0 + p.w_row_off[seg] + n0 + rank * (bn / 2));
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -112,7 +132,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
           ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
           ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
           ptx::mma_commit_mc2_u32(empty_u32 + stage * 8);
-          if (++stage == kDStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         ptx::mma_commit_mc2_u32(accfull_u32 + as * 8);
       }
@@ -179,7 +199,8 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
           }
         } else if (epi == DE_BWD_RELU) {
           if (p.rank1_row) {
-            const float dd = valid ? __bfloat162float(__float2bfloat16(p.rank1_row[(size_t)grow * p.rank1_stride])) : 0.f;
+            float dd = valid ? p.rank1_row[(size_t)grow * p.rank1_stride] : 0.f;
+            if (!p.exact_rank1) dd = __bfloat162float(__float2bfloat16(dd));
             const float4* w4 = reinterpret_cast<const float4*>(p.rank1_col + n);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
@@ -207,7 +228,13 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
         }
         uint8_t* panel = stage_out + (col >> 6) * kPanelBytes;
         const int chunk0 = (col & 63) >> 3;
-        if (epi == DE_RELU || epi == DE_VIEW) store_half32<true>(panel, row, chunk0, v);
+        if (p.split) {
+          if (epi == DE_RELU || epi == DE_VIEW) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) v[c] = fmaxf(v[c], 0.f);
+          }
+          store_split_half32(panel, panel + kDOutPanels * kPanelBytes, row, chunk0, v);
+        } else if (epi == DE_RELU || epi == DE_VIEW) store_half32<true>(panel, row, chunk0, v);
         else store_half32<false>(panel, row, chunk0, v);
       }
       // accumulator drained: the MMA issuer may reuse it (tile it + 2)
@@ -217,9 +244,13 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
       ptx::fence_proxy_async();
       asm volatile("bar.sync 1, %0;" ::"n"(kDEpiWarps * 32) : "memory");
       if (store_leader) {
-        for (int pn = 0; pn < bn / 64; ++pn)
+        for (int pn = 0; pn < bn / 64; ++pn) {
           ptx::tma_store_2d(&p.out_map, stage_out + pn * kPanelBytes, p.out_col0 + n0 + pn * 64,
                             p.out_row0 + mt * 256 + rank * 128);
+          if (p.split)
+            ptx::tma_store_2d(&p.out_map, stage_out + (kDOutPanels + pn) * kPanelBytes, p.out_col0 + n0 + pn * 64,
+                              p.out_row0 + p.out_lo_row_off + mt * 256 + rank * 128);
+        }
         ptx::tma_commit_group();
       }
     }
@@ -236,20 +267,32 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
 __global__ void __launch_bounds__(128) bwd_start_kernel(const float* d_raw, const __nv_bfloat16* view_act, int view_ld,
                                                         const float* w_rgb /* [128][3] fp32, bf16-rounded */, int n_samples,
                                                         int n_rows_pad, __nv_bfloat16* dz_view, int dz_ld,
-                                                        __nv_bfloat16* drgb) {
+                                                        __nv_bfloat16* drgb, __nv_bfloat16* dz_view_lo,
+                                                        __nv_bfloat16* drgb_lo) {
   const int s = blockIdx.x, c = threadIdx.x;
   if (s >= n_rows_pad) return;
+  const bool split = dz_view_lo != nullptr;
   float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s < n_samples) dr = reinterpret_cast<const float4*>(d_raw)[s];
   if (c == 0) {
-    uint4* dst = reinterpret_cast<uint4*>(drgb + (size_t)s * kHeadCols);
-    dst[0] = make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
+    const uint32_t h01 = ptx::pack_bf16x2(dr.y, dr.z), h23 = ptx::pack_bf16x2(dr.w, dr.x);
+    reinterpret_cast<uint4*>(drgb + (size_t)s * kHeadCols)[0] = make_uint4(h01, h23, 0u, 0u);
+    if (split) {
+      const uint32_t l01 = ptx::pack_bf16x2(dr.y - __uint_as_float(h01 << 16), dr.z - __uint_as_float(h01 & 0xFFFF0000u));
+      const uint32_t l23 = ptx::pack_bf16x2(dr.w - __uint_as_float(h23 << 16), dr.x - __uint_as_float(h23 & 0xFFFF0000u));
+      reinterpret_cast<uint4*>(drgb_lo + (size_t)s * kHeadCols)[0] = make_uint4(l01, l23, 0u, 0u);
+    }
   }
-  const float d0 = __bfloat162float(__float2bfloat16(dr.y)), d1 = __bfloat162float(__float2bfloat16(dr.z)),
-              d2 = __bfloat162float(__float2bfloat16(dr.w));
+  float d0 = dr.y, d1 = dr.z, d2 = dr.w;
+  if (!split) {   // bf16-round the head gradient once so that dgrad (here) and wgrad (tensor cores) agree
+    d0 = __bfloat162float(__float2bfloat16(d0)); d1 = __bfloat162float(__float2bfloat16(d1)); d2 = __bfloat162float(__float2bfloat16(d2));
+  }
   float g = d0 * w_rgb[c * 3] + d1 * w_rgb[c * 3 + 1] + d2 * w_rgb[c * 3 + 2];
   const bool on = s < n_samples && __bfloat162float(view_act[(size_t)s * view_ld + c]) > 0.f;
-  dz_view[(size_t)s * dz_ld + c] = __float2bfloat16(on ? g : 0.f);
+  if (!on) g = 0.f;
+  const __nv_bfloat16 hi = __float2bfloat16(g);
+  dz_view[(size_t)s * dz_ld + c] = hi;
+  if (split) dz_view_lo[(size_t)s * dz_ld + c] = __float2bfloat16(g - __bfloat162float(hi));
 }
 
 }  // namespace
@@ -259,7 +302,14 @@ int dense_tc_init() {
   return HUGS_OK;
 }
 
-int dense_tc_launch(const DenseParams& p, int num_sms, cudaStream_t st) {
+int dense_tc_launch(const DenseParams& p_in, int num_sms, cudaStream_t st) {
+  DenseParams p = p_in;
+  if (p.n_seg == 0) {     // the two-segment form: weight columns run on from b_col0
+    p.n_seg = 2;
+    p.w_col0[0] = p.b_col0; p.w_col0[1] = p.b_col0 + 64 * p.a_kp[0];
+    p.w_row_off[0] = p.w_row_off[1] = 0;
+  }
+  HUGS_REQUIRE(p.n_seg >= 1 && p.n_seg <= kDMaxSegs, "dense_tc: bad segment count %d", p.n_seg);
   const int n_tiles = p.m_tiles * p.n_tiles;
   if (n_tiles <= 0) return HUGS_OK;
   cudaLaunchConfig_t cfg{};
@@ -277,9 +327,11 @@ int dense_tc_launch(const DenseParams& p, int num_sms, cudaStream_t st) {
 }
 
 int launch_bwd_start(const float* d_raw, const __nv_bfloat16* view_act, int view_ld, const float* w_rgb, int n_samples,
-                     int n_rows_pad, __nv_bfloat16* dz_view, int dz_ld, __nv_bfloat16* drgb, cudaStream_t st) {
+                     int n_rows_pad, __nv_bfloat16* dz_view, int dz_ld, __nv_bfloat16* drgb, __nv_bfloat16* dz_view_lo,
+                     __nv_bfloat16* drgb_lo, cudaStream_t st) {
   if (n_rows_pad <= 0) return HUGS_OK;
-  bwd_start_kernel<<<n_rows_pad, 128, 0, st>>>(d_raw, view_act, view_ld, w_rgb, n_samples, n_rows_pad, dz_view, dz_ld, drgb);
+  bwd_start_kernel<<<n_rows_pad, 128, 0, st>>>(d_raw, view_act, view_ld, w_rgb, n_samples, n_rows_pad, dz_view, dz_ld, drgb,
+                                               dz_view_lo, drgb_lo);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
 }

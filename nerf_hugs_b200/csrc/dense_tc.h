@@ -14,16 +14,23 @@ enum DenseEpi : int {
 };
 
 constexpr int kMaxNTiles = 8;
+constexpr int kDMaxSegs = 6;   // A segments of one GEMM (K concatenation): [x | features] x {hi.hi, lo.hi, hi.lo} in the split mode
 
 struct alignas(64) DenseParams {
-  CUtensorMap a_map[2];        // A segments: bf16 [rows, cols], box 128 rows x 64 cols
+  CUtensorMap a_map[kDMaxSegs];// A segments: bf16 [rows, cols], box 128 rows x 64 cols
   CUtensorMap b_map;           // weights, K-major rows = GEMM output columns: box 128 rows x 64 (BN = 256)
   CUtensorMap b_map_64;        // box 64 rows (BN = 128)
   CUtensorMap b_map_8;         // box 8 rows  (BN = 16)
   CUtensorMap out_map;         // bf16 output [rows, cols], box 128 x 64
-  int a_kp[2];                 // K panels (64 columns) of each A segment
-  int a_row0[2], a_col0[2];
+  int n_seg;                   // 0: the two-segment form (a_kp[0], a_kp[1], weight columns contiguous from b_col0)
+  int a_kp[kDMaxSegs];         // K panels (64 columns) of each A segment
+  int a_row0[kDMaxSegs], a_col0[kDMaxSegs];
+  int w_col0[kDMaxSegs];       // first weight K column of the segment (n_seg > 0)
+  int w_row_off[kDMaxSegs];    // added to the weight row of the segment (the lo half of a split pack)
   int b_row0, b_col0;          // first weight row / K column of this GEMM inside the weight tensor
+  // split-precision mode (HUGS_PRECISION_TC_SPLIT): bf16 outputs are written as hi + residual lo, the lo half
+  // `out_lo_row_off` rows further down in the output tensor; the ring is one stage shorter to make room for its panels
+  int split, out_lo_row_off, exact_rank1;
   int m_tiles, n_tiles, m_rows;
   int tile_n0[kMaxNTiles], tile_bn[kMaxNTiles], tile_epi[kMaxNTiles];
   int S;                       // samples per ray (DE_VIEW)
@@ -37,8 +44,10 @@ struct alignas(64) DenseParams {
 
 int dense_tc_init();
 int dense_tc_launch(const DenseParams& p, int num_sms, cudaStream_t st);
+// lo pointers != nullptr: split-precision mode (unrounded head gradients, hi + lo outputs)
 int launch_bwd_start(const float* d_raw, const __nv_bfloat16* view_act, int view_ld, const float* w_rgb, int n_samples,
-                     int n_rows_pad, __nv_bfloat16* dz_view, int dz_ld, __nv_bfloat16* drgb, cudaStream_t st);
+                     int n_rows_pad, __nv_bfloat16* dz_view, int dz_ld, __nv_bfloat16* drgb, __nv_bfloat16* dz_view_lo,
+                     __nv_bfloat16* drgb_lo, cudaStream_t st);
 
 // layered.cu: per-MLP state of the layer-at-a-time path
 struct LayeredMlp;

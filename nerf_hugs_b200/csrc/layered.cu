@@ -17,6 +17,8 @@ enum { LW_ACT = 0, LW_FEAT = 1, LW_DZ0 = 2, LW_DZ1 = 3, LW_BOTT = 4, LW_VACT = 5
 
 struct LayeredMlp {
   int W = 0, D = 0, level = 0, cap = 0, skip = 4;
+  bool split = false;             // HUGS_PRECISION_TC_SPLIT: every bf16 tensor holds a hi half and, `lo_*` rows further down, a lo half
+  int parts = 1;
   int rows_f = 0, rows_b = 0, kmax = 0, tab_floats = 0;
   std::vector<int> row_f, row_b, bias_off;        // per dense index (flax order: trunk..., density, bottleneck, view, rgb)
   int heads_row_f = 0, heads_bias_off = 0, w_dens_off = 0, w_rgb_off = 0;
@@ -67,11 +69,18 @@ struct LPackArgs {
   const float* params;
   __nv_bfloat16 *wt, *wn;
   float* tab;
+  int part;         // 0: bf16(w) (+ tables); 1: bf16(w - bf16(w)) into the lo half of wt / wn (split-precision mode)
+  int exact_heads;  // split-precision mode: the fp32 head-weight tables are not rounded to bf16
 };
+
+__device__ __forceinline__ __nv_bfloat16 lpack_part(float v, int part) {
+  const __nv_bfloat16 hi = __float2bfloat16(v);
+  return part == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
+}
 
 __global__ void layered_pack_kernel(LPackArgs a) {
   const long long nf = (long long)a.rows_f * a.kmax, nbk = (long long)a.rows_b * a.W;
-  const long long total = nf + nbk + a.tab_floats;
+  const long long total = a.part == 0 ? nf + nbk + a.tab_floats : nf + nbk;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     if (i < nf) {
       const int r = (int)(i / a.kmax), k = (int)(i % a.kmax);
@@ -90,7 +99,7 @@ __global__ void layered_pack_kernel(LPackArgs a) {
         if (in >= 0) v = a.params[L.koff + (long long)in * L.out_stride + n];
         break;
       }
-      a.wt[i] = __float2bfloat16(v);
+      a.wt[i + a.part * nf] = lpack_part(v, a.part);
     } else if (i < nf + nbk) {
       const long long q = i - nf;
       const int r = (int)(q / a.W), c = (int)(q % a.W);
@@ -101,7 +110,7 @@ __global__ void layered_pack_kernel(LPackArgs a) {
         if (c < L.b_out) v = a.params[L.koff + (long long)(r - L.brow0) * L.out_stride + c];
         break;
       }
-      a.wn[q] = __float2bfloat16(v);
+      a.wn[q + a.part * nbk] = lpack_part(v, a.part);
     } else {
       const int q = (int)(i - nf - nbk);
       float v = 0.f;
@@ -109,10 +118,14 @@ __global__ void layered_pack_kernel(LPackArgs a) {
         const LPackEntry& L = a.e[l];
         if (q >= L.bias_off && q < L.bias_off + L.out) { v = a.params[L.boff + (q - L.bias_off)]; break; }
       }
-      if (q >= a.w_dens_off && q < a.w_dens_off + a.dens_in)
-        v = __bfloat162float(__float2bfloat16(a.params[a.dens_koff + (q - a.w_dens_off)]));
-      if (q >= a.w_rgb_off && q < a.w_rgb_off + a.rgb_in * 3)
-        v = __bfloat162float(__float2bfloat16(a.params[a.rgb_koff + (q - a.w_rgb_off)]));
+      if (q >= a.w_dens_off && q < a.w_dens_off + a.dens_in) {
+        v = a.params[a.dens_koff + (q - a.w_dens_off)];
+        if (!a.exact_heads) v = __bfloat162float(__float2bfloat16(v));
+      }
+      if (q >= a.w_rgb_off && q < a.w_rgb_off + a.rgb_in * 3) {
+        v = a.params[a.rgb_koff + (q - a.w_rgb_off)];
+        if (!a.exact_heads) v = __bfloat162float(__float2bfloat16(v));
+      }
       a.tab[q] = v;
     }
   }
@@ -130,6 +143,8 @@ int layered_create(hugs_handle* h, const MlpViews& mv, int level, LayeredMlp** o
   LayeredMlp* m = new LayeredMlp();
   *out = m;
   m->W = mv.width; m->D = mv.depth; m->level = level; m->cap = tc->cap[level]; m->skip = d.skip_layer;
+  m->split = tc->split; m->parts = tc->split ? 2 : 1;
+  const size_t parts = (size_t)m->parts;
   m->kmax = m->W + kFeatPad;
   const int D = m->D, W = m->W;
   const int nd = (int)mv.dense.size();
@@ -153,19 +168,21 @@ int layered_create(hugs_handle* h, const MlpViews& mv, int level, LayeredMlp** o
   m->w_rgb_off = bo; bo += 128 * 3 + 16;
   m->rows_f = ((rf + 127) / 128) * 128; m->rows_b = rb; m->tab_floats = bo;
   int rc;
-  if ((rc = lalloc(h, &m->wt, (size_t)m->rows_f * m->kmax)) || (rc = lalloc(h, &m->wn, (size_t)m->rows_b * W)) ||
+  if ((rc = lalloc(h, &m->wt, parts * m->rows_f * m->kmax)) || (rc = lalloc(h, &m->wn, parts * m->rows_b * W)) ||
       (rc = lalloc(h, &m->tab, (size_t)m->tab_floats)))
     return rc;
-  if ((rc = make_map(&m->map_wt128, m->wt, m->rows_f, m->kmax, 128)) || (rc = make_map(&m->map_wt64, m->wt, m->rows_f, m->kmax, 64)) ||
-      (rc = make_map(&m->map_wt8, m->wt, m->rows_f, m->kmax, 8)) || (rc = make_map(&m->map_wn128, m->wn, m->rows_b, W, 128)))
+  const long long pf = (long long)parts * m->rows_f, pb = (long long)parts * m->rows_b;
+  if ((rc = make_map(&m->map_wt128, m->wt, pf, m->kmax, 128)) || (rc = make_map(&m->map_wt64, m->wt, pf, m->kmax, 64)) ||
+      (rc = make_map(&m->map_wt8, m->wt, pf, m->kmax, 8)) || (rc = make_map(&m->map_wn128, m->wn, pb, W, 128)))
     return rc;
-  // inference buffers: two ping-pong activation slots, bottleneck, view activation
+  // inference buffers: two ping-pong activation slots, bottleneck, view activation (hi half, then the lo half)
   m->act_slots = 2;
-  if ((rc = lalloc(h, &m->act, (size_t)m->act_slots * m->cap * W)) || (rc = lalloc(h, &m->bott, (size_t)m->cap * 256)) ||
-      (rc = lalloc(h, &m->vact, (size_t)m->cap * 128)))
+  if ((rc = lalloc(h, &m->act, parts * m->act_slots * m->cap * W)) || (rc = lalloc(h, &m->bott, parts * m->cap * 256)) ||
+      (rc = lalloc(h, &m->vact, parts * m->cap * 128)))
     return rc;
-  if ((rc = make_map(&m->map_act, m->act, (long long)m->act_slots * m->cap, W, 128)) ||
-      (rc = make_map(&m->map_bott, m->bott, m->cap, 256, 128)) || (rc = make_map(&m->map_vact, m->vact, m->cap, 128, 128)))
+  if ((rc = make_map(&m->map_act, m->act, (long long)parts * m->act_slots * m->cap, W, 128)) ||
+      (rc = make_map(&m->map_bott, m->bott, (long long)parts * m->cap, 256, 128)) ||
+      (rc = make_map(&m->map_vact, m->vact, (long long)parts * m->cap, 128, 128)))
     return rc;
   return dense_tc_init();
 }
@@ -199,8 +216,12 @@ int layered_pack(hugs_handle* h, LayeredMlp* m, const float* params, cudaStream_
   a.w_dens_off = m->w_dens_off; a.w_rgb_off = m->w_rgb_off; a.dens_in = W; a.rgb_in = 128;
   a.dens_koff = mv.dense[D].kernel_off; a.rgb_koff = mv.dense[D + 3].kernel_off;
   a.params = params; a.wt = m->wt; a.wn = m->wn; a.tab = m->tab;
-  layered_pack_kernel<<<1024, 256, 0, st>>>(a);
-  HUGS_LAUNCH_CHECK();
+  a.exact_heads = m->split ? 1 : 0;
+  for (int part = 0; part < m->parts; ++part) {
+    a.part = part;
+    layered_pack_kernel<<<1024, 256, 0, st>>>(a);
+    HUGS_LAUNCH_CHECK();
+  }
   return HUGS_OK;
 }
 
@@ -208,27 +229,29 @@ int layered_ensure_training(hugs_handle* h, LayeredMlp* m) {
   if (m->train_ready) return HUGS_OK;
   TcState* tc = h->tc;
   const int W = m->W, D = m->D;
+  const size_t parts = (size_t)m->parts;
+  const long long pc = (long long)parts * m->cap;
   int rc;
   // every trunk activation is kept for the backward pass
   m->act_slots = D;
-  if ((rc = lalloc(h, &m->act, (size_t)m->act_slots * m->cap * W))) return rc;
-  if ((rc = make_map(&m->map_act, m->act, (long long)m->act_slots * m->cap, W, 128))) return rc;
+  if ((rc = lalloc(h, &m->act, parts * m->act_slots * m->cap * W))) return rc;
+  if ((rc = make_map(&m->map_act, m->act, (long long)parts * m->act_slots * m->cap, W, 128))) return rc;
   for (int i = 0; i < 2; ++i) {
-    if ((rc = lalloc(h, &m->dz[i], (size_t)m->cap * W))) return rc;
-    if ((rc = make_map(&m->map_dz[i], m->dz[i], m->cap, W, 128))) return rc;
+    if ((rc = lalloc(h, &m->dz[i], parts * m->cap * W))) return rc;
+    if ((rc = make_map(&m->map_dz[i], m->dz[i], pc, W, 128))) return rc;
   }
-  if ((rc = lalloc(h, &m->dz_bott, (size_t)m->cap * 256)) || (rc = lalloc(h, &m->dz_view, (size_t)m->cap * 128)) ||
-      (rc = lalloc(h, &m->drgb, (size_t)m->cap * kHeadCols)) || (rc = lalloc(h, &m->items_dev, 4096)))
+  if ((rc = lalloc(h, &m->dz_bott, parts * m->cap * 256)) || (rc = lalloc(h, &m->dz_view, parts * m->cap * 128)) ||
+      (rc = lalloc(h, &m->drgb, parts * m->cap * kHeadCols)) || (rc = lalloc(h, &m->items_dev, 4096 * 4)))
     return rc;
-  if ((rc = make_map(&m->map_dzb, m->dz_bott, m->cap, 256, 128)) || (rc = make_map(&m->map_dzv, m->dz_view, m->cap, 128, 128)))
+  if ((rc = make_map(&m->map_dzb, m->dz_bott, pc, 256, 128)) || (rc = make_map(&m->map_dzv, m->dz_view, pc, 128, 128)))
     return rc;
   // 64-sample boxes for the weight-gradient kernel
-  if ((rc = make_map(&m->wg_maps[LW_ACT], m->act, (long long)m->act_slots * m->cap, W, 64)) ||
-      (rc = make_map(&m->wg_maps[LW_FEAT], tc->feat, tc->total_feat_rows, kFeatPad, 64)) ||
-      (rc = make_map(&m->wg_maps[LW_DZ0], m->dz[0], m->cap, W, 64)) || (rc = make_map(&m->wg_maps[LW_DZ1], m->dz[1], m->cap, W, 64)) ||
-      (rc = make_map(&m->wg_maps[LW_BOTT], m->bott, m->cap, 256, 64)) || (rc = make_map(&m->wg_maps[LW_VACT], m->vact, m->cap, 128, 64)) ||
-      (rc = make_map(&m->wg_maps[LW_DZB], m->dz_bott, m->cap, 256, 64)) || (rc = make_map(&m->wg_maps[LW_DZV], m->dz_view, m->cap, 128, 64)) ||
-      (rc = make_map(&m->wg_maps[LW_DH], m->drgb, m->cap, kHeadCols, 64)))
+  if ((rc = make_map(&m->wg_maps[LW_ACT], m->act, (long long)parts * m->act_slots * m->cap, W, 64)) ||
+      (rc = make_map(&m->wg_maps[LW_FEAT], tc->feat, (long long)parts * tc->total_feat_rows, kFeatPad, 64)) ||
+      (rc = make_map(&m->wg_maps[LW_DZ0], m->dz[0], pc, W, 64)) || (rc = make_map(&m->wg_maps[LW_DZ1], m->dz[1], pc, W, 64)) ||
+      (rc = make_map(&m->wg_maps[LW_BOTT], m->bott, pc, 256, 64)) || (rc = make_map(&m->wg_maps[LW_VACT], m->vact, pc, 128, 64)) ||
+      (rc = make_map(&m->wg_maps[LW_DZB], m->dz_bott, pc, 256, 64)) || (rc = make_map(&m->wg_maps[LW_DZV], m->dz_view, pc, 128, 64)) ||
+      (rc = make_map(&m->wg_maps[LW_DH], m->drgb, pc, kHeadCols, 64)))
     return rc;
   HUGS_CUDA(cudaDeviceSynchronize());
   m->train_ready = true;
@@ -240,66 +263,85 @@ namespace {
 void fill_common(DenseParams* p, const LayeredMlp* m, int n_samples) {
   memset(p, 0, sizeof(*p));
   p->b_map = m->map_wt128; p->b_map_64 = m->map_wt64; p->b_map_8 = m->map_wt8;
-  p->a_map[1] = p->a_map[0];
   p->m_rows = n_samples; p->m_tiles = (n_samples + 255) / 256;
+  p->split = m->split ? 1 : 0;
+}
+
+// One source of A columns: `kp` K panels of tensor `map` from (row0, col0), multiplied with weight K columns from wcol0;
+// `lo_rows` = row distance of the tensor's lo half (split-precision mode).
+struct SegSrc { const CUtensorMap* map; int kp, row0, col0, wcol0, lo_rows; };
+
+// A . W as K-concatenated segments; split-precision mode: A_hi W_hi + A_lo W_hi + A_hi W_lo (the lo . lo term is below fp32
+// resolution), `w_lo_rows` = row distance of the lo half of the weight pack.
+void set_segs(DenseParams* p, const LayeredMlp* m, const SegSrc* srcs, int n_src, int w_lo_rows) {
+  int n = 0;
+  const int combos = m->split ? 3 : 1;
+  for (int c = 0; c < combos; ++c) {
+    const bool a_lo = c == 1, w_lo = c == 2;
+    for (int i = 0; i < n_src; ++i) {
+      const SegSrc& s = srcs[i];
+      p->a_map[n] = *s.map; p->a_kp[n] = s.kp; p->a_row0[n] = s.row0 + (a_lo ? s.lo_rows : 0); p->a_col0[n] = s.col0;
+      p->w_col0[n] = s.wcol0; p->w_row_off[n] = w_lo ? w_lo_rows : 0;
+      ++n;
+    }
+  }
+  p->n_seg = n;
 }
 
 }  // namespace
 
 int layered_forward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, bool training, cudaStream_t st) {
   TcState* tc = h->tc;
-  const hugs_model_desc& d = h->d;
-  const MlpViews& mv = h->nerf;
   const int S = h->samples(level), M = n_rays * S, W = m->W, D = m->D, cap = m->cap;
   HUGS_REQUIRE(!training || m->train_ready, "layered path: training buffers missing");
   auto slot = [&](int l) { return training ? l : (l & 1); };
+  const int lo_act = m->act_slots * cap, lo_feat = tc->total_feat_rows;
   int rc;
   bool cat = false;
   for (int l = 0; l < D; ++l) {
     DenseParams p;
     fill_common(&p, m, M);
-    int seg = 0;
-    if (l > 0) {
-      p.a_map[seg] = m->map_act; p.a_kp[seg] = W / 64; p.a_row0[seg] = slot(l - 1) * cap; p.a_col0[seg] = 0; ++seg;
-    }
-    if (l == 0 || cat) {
-      p.a_map[seg] = tc->map_feat; p.a_kp[seg] = kFeatPad / 64; p.a_row0[seg] = tc->feat_row0[level]; p.a_col0[seg] = 0; ++seg;
-    }
-    if (seg == 1) p.a_map[1] = p.a_map[0];
+    SegSrc src[2]; int ns = 0;
+    if (l > 0) src[ns++] = SegSrc{&m->map_act, W / 64, slot(l - 1) * cap, 0, 0, lo_act};
+    if (l == 0 || cat) src[ns++] = SegSrc{&tc->map_feat, kFeatPad / 64, tc->feat_row0[level], 0, l == 0 ? 0 : W, lo_feat};
+    set_segs(&p, m, src, ns, m->rows_f);
     p.b_row0 = m->row_f[l]; p.b_col0 = 0;
     p.n_tiles = W / 256;
     for (int j = 0; j < p.n_tiles; ++j) { p.tile_n0[j] = j * 256; p.tile_bn[j] = 256; p.tile_epi[j] = DE_RELU; }
     p.bias = m->tab + m->bias_off[l];
-    p.out_map = m->map_act; p.out_row0 = slot(l) * cap; p.out_col0 = 0;
+    p.out_map = m->map_act; p.out_row0 = slot(l) * cap; p.out_col0 = 0; p.out_lo_row_off = lo_act;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
     cat = (l % m->skip == 0 && l > 0);
   }
   {  // heads: bottleneck (linear, bf16) + raw density (fp32 column)
     DenseParams p;
     fill_common(&p, m, M);
-    p.a_map[0] = m->map_act; p.a_map[1] = m->map_act; p.a_kp[0] = W / 64; p.a_row0[0] = slot(D - 1) * cap;
+    SegSrc src[1] = {SegSrc{&m->map_act, W / 64, slot(D - 1) * cap, 0, 0, lo_act}};
+    set_segs(&p, m, src, 1, m->rows_f);
     p.b_row0 = m->heads_row_f; p.n_tiles = 2;
     p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_LINEAR;
     p.tile_n0[1] = 256; p.tile_bn[1] = 16; p.tile_epi[1] = DE_HEAD_F32;
     p.bias = m->tab + m->heads_bias_off;
-    p.out_map = m->map_bott; p.out_row0 = 0; p.out_col0 = 0;
+    p.out_map = m->map_bott; p.out_row0 = 0; p.out_col0 = 0; p.out_lo_row_off = cap;
     p.raw_out = h->raw[level]; p.raw_c = 4; p.raw_chan0 = 0; p.raw_nchan = 1;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
   }
   {  // view layer: K = bottleneck; direction encoding / GLO terms arrive as the per-ray bias
     DenseParams p;
     fill_common(&p, m, M);
-    p.a_map[0] = m->map_bott; p.a_map[1] = m->map_bott; p.a_kp[0] = 4;
+    SegSrc src[1] = {SegSrc{&m->map_bott, 4, 0, 0, 0, cap}};
+    set_segs(&p, m, src, 1, m->rows_f);
     p.b_row0 = m->row_f[D + 2]; p.n_tiles = 1;
     p.tile_n0[0] = 0; p.tile_bn[0] = 128; p.tile_epi[0] = DE_VIEW;
     p.viewbias = tc->viewbias; p.view_ld = 128; p.S = S;
-    p.out_map = m->map_vact;
+    p.out_map = m->map_vact; p.out_lo_row_off = cap;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
   }
   {  // rgb head (fp32 columns 1..3 of raw)
     DenseParams p;
     fill_common(&p, m, M);
-    p.a_map[0] = m->map_vact; p.a_map[1] = m->map_vact; p.a_kp[0] = 2;
+    SegSrc src[1] = {SegSrc{&m->map_vact, 2, 0, 0, 0, cap}};
+    set_segs(&p, m, src, 1, m->rows_f);
     p.b_row0 = m->row_f[D + 3]; p.n_tiles = 1;
     p.tile_n0[0] = 0; p.tile_bn[0] = 16; p.tile_epi[0] = DE_HEAD_F32;
     p.bias = m->tab + m->bias_off[D + 3];
@@ -307,7 +349,6 @@ int layered_forward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, bool t
     p.raw_out = h->raw[level]; p.raw_c = 4; p.raw_chan0 = 1; p.raw_nchan = 3;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
   }
-  (void)d; (void)mv;
   return HUGS_OK;
 }
 
@@ -320,11 +361,23 @@ void build_wgrad(hugs_handle* h, LayeredMlp* m, int level, int n_samples) {
   const int W = m->W, D = m->D, cap = m->cap;
   const int T = ((n_samples + 255) / 256) * 4;          // 64-sample stages (rows padded to the 256-row GEMM tiles)
   m->items_host.clear(); m->launches.clear();
+  // row distance of the lo half of every tensor the weight-gradient kernel reads (split-precision mode)
+  const int lo_rows[LW_MAPS] = {m->act_slots * cap, tc->total_feat_rows, cap, cap, cap, cap, cap, cap, cap};
   auto flush = [&](std::vector<WgUnit>& units) {
     std::vector<WgItem> items;
     wgrad_plan(units, T, tc->num_sms, &items);
-    m->launches.push_back({(int)m->items_host.size(), (int)items.size()});
-    m->items_host.insert(m->items_host.end(), items.begin(), items.end());
+    const size_t first = m->items_host.size();
+    // split-precision mode: (A_hi + A_lo)^T (dZ_hi + dZ_lo) as four items; the bias column sums ride on the A_hi items only
+    for (const WgItem& base : items)
+      for (int pa = 0; pa < m->parts; ++pa)
+        for (int pb = 0; pb < m->parts; ++pb) {
+          WgItem w = base;
+          w.a_row0 += pa * lo_rows[w.a_map];
+          w.b_row0 += pb * lo_rows[w.b_map];
+          if (pa > 0) w.bias_mode = 0;
+          m->items_host.push_back(w);
+        }
+    m->launches.push_back({(int)first, (int)(m->items_host.size() - first)});
     units.clear();
   };
   auto unit = [&](int a_map, int a_row0, int a_col0, int b_map, int b_col0, int n, const DenseView& v, int in_base,
@@ -385,7 +438,7 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
   int rc;
   if (m->built_for != M) {
     build_wgrad(h, m, level, M);
-    HUGS_REQUIRE(m->items_host.size() * sizeof(WgItem) <= 4096 * sizeof(WgItem), "layered wgrad: too many work items");
+    HUGS_REQUIRE(m->items_host.size() <= 4096 * 4, "layered wgrad: too many work items");
     HUGS_CUDA(cudaMemcpyAsync(m->items_dev, m->items_host.data(), sizeof(WgItem) * m->items_host.size(),
                               cudaMemcpyHostToDevice, st));
     HUGS_CUDA(cudaStreamSynchronize(st));
@@ -397,24 +450,35 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
     const auto& L = m->launches[launch++];
     return wgrad_launch(h, m->wg_maps, LW_MAPS, m->items_dev + L.first, L.second, grad, st);
   };
+  const int lo_act = m->act_slots * cap;
+  const float* w_rgb = m->tab + m->w_rgb_off;
   {
     ProfScope ps(h, HUGS_K_CHAIN_BWD_NERF, st);
-    if ((rc = launch_bwd_start(h->d_raw[level], m->vact, 128, m->tab + m->w_rgb_off, M, rows_pad, m->dz_view, 128, m->drgb, st)))
+    if ((rc = launch_bwd_start(h->d_raw[level], m->vact, 128, w_rgb, M, rows_pad, m->dz_view, 128, m->drgb,
+                               m->split ? m->dz_view + (size_t)cap * 128 : nullptr,
+                               m->split ? m->drgb + (size_t)cap * kHeadCols : nullptr, st)))
       return rc;
   }
   if ((rc = wgrad())) return rc;
   {
     ProfScope ps(h, HUGS_K_REDUCTIONS, st);
-    if ((rc = wgrad_view_extras(h, m->dz_view, nullptr, 128, n_rays, S, grad, st))) return rc;
+    if ((rc = wgrad_view_extras(h, m->dz_view, m->split ? m->dz_view + (size_t)cap * 128 : nullptr, 128, n_rays, S, grad, st)))
+      return rc;
   }
+  auto bwd_common = [&](DenseParams* p) {
+    fill_common(p, m, M);
+    p->b_map = m->map_wn128;
+    p->exact_rank1 = m->split ? 1 : 0;
+  };
   {  // dZ_bott = dZ_view . W_view[bottleneck rows]^T
     ProfScope ps(h, HUGS_K_CHAIN_BWD_NERF, st);
     DenseParams p;
-    fill_common(&p, m, M);
-    p.a_map[0] = m->map_dzv; p.a_map[1] = m->map_dzv; p.a_kp[0] = 2;
-    p.b_map = m->map_wn128; p.b_row0 = m->row_b[D + 2]; p.n_tiles = 1;
+    bwd_common(&p);
+    SegSrc src[1] = {SegSrc{&m->map_dzv, 2, 0, 0, 0, cap}};
+    set_segs(&p, m, src, 1, m->rows_b);
+    p.b_row0 = m->row_b[D + 2]; p.n_tiles = 1;
     p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_BWD_LINEAR;
-    p.out_map = m->map_dzb;
+    p.out_map = m->map_dzb; p.out_lo_row_off = cap;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
   }
   if ((rc = wgrad())) return rc;
@@ -422,13 +486,14 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
   {  // dZ_{D-1} = (dZ_bott . W_bott^T + d_density (x) w_density) * [act_{D-1} > 0]
     ProfScope ps(h, HUGS_K_CHAIN_BWD_NERF, st);
     DenseParams p;
-    fill_common(&p, m, M);
-    p.a_map[0] = m->map_dzb; p.a_map[1] = m->map_dzb; p.a_kp[0] = 4;
-    p.b_map = m->map_wn128; p.b_row0 = m->row_b[D + 1]; p.n_tiles = W / 256;
+    bwd_common(&p);
+    SegSrc src[1] = {SegSrc{&m->map_dzb, 4, 0, 0, 0, cap}};
+    set_segs(&p, m, src, 1, m->rows_b);
+    p.b_row0 = m->row_b[D + 1]; p.n_tiles = W / 256;
     for (int j = 0; j < p.n_tiles; ++j) { p.tile_n0[j] = j * 256; p.tile_bn[j] = 256; p.tile_epi[j] = DE_BWD_RELU; }
     p.mask_act = m->act; p.mask_ld = W; p.mask_row0 = (D - 1) * cap;
     p.rank1_row = h->d_raw[level]; p.rank1_stride = 4; p.rank1_col = m->tab + m->w_dens_off;
-    p.out_map = m->map_dz[cur];
+    p.out_map = m->map_dz[cur]; p.out_lo_row_off = cap;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
   }
   for (int l = D - 1; l >= 0; --l) {
@@ -436,15 +501,17 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
     if (l == 0) break;
     ProfScope ps(h, HUGS_K_CHAIN_BWD_NERF, st);
     DenseParams p;   // dZ_{l-1} = (dZ_l . W_l[x rows]^T) * [act_{l-1} > 0]
-    fill_common(&p, m, M);
-    p.a_map[0] = m->map_dz[cur]; p.a_map[1] = m->map_dz[cur]; p.a_kp[0] = W / 64;
-    p.b_map = m->map_wn128; p.b_row0 = m->row_b[l]; p.n_tiles = W / 256;
+    bwd_common(&p);
+    SegSrc src[1] = {SegSrc{&m->map_dz[cur], W / 64, 0, 0, 0, cap}};
+    set_segs(&p, m, src, 1, m->rows_b);
+    p.b_row0 = m->row_b[l]; p.n_tiles = W / 256;
     for (int j = 0; j < p.n_tiles; ++j) { p.tile_n0[j] = j * 256; p.tile_bn[j] = 256; p.tile_epi[j] = DE_BWD_RELU; }
     p.mask_act = m->act; p.mask_ld = W; p.mask_row0 = (l - 1) * cap;
-    p.out_map = m->map_dz[cur ^ 1];
+    p.out_map = m->map_dz[cur ^ 1]; p.out_lo_row_off = cap;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
     cur ^= 1;
   }
+  (void)lo_act;
   return HUGS_OK;
 }
 

@@ -336,11 +336,11 @@ int tc_create(hugs_handle* h) {
     set_error("point positional encoding is supported with net_width 256 on the tensor-core path (got %d)", d.nerf_width);
     return HUGS_ERR_UNSUPPORTED;
   }
-  if ((nerf_layered && (d.nerf_width % 256 != 0 || d.nerf_width > 2048 || d.precision == HUGS_PRECISION_TC_SPLIT)) ||
+  if ((nerf_layered && (d.nerf_width % 256 != 0 || d.nerf_width > 2048)) ||
       (d.num_levels > 1 && d.prop_width != kW) || d.bottleneck_width != kW ||
       d.view_width != 128 || h->feat_dim > kFeatPad || (!pe && ((ndeg % 4) != 0 || ndeg > 16))) {
-    set_error("tensor-core path supports NerfMLP.net_width 256 (chain kernel, both precision modes) or 512 / 768 / 1024 "
-              "(layer-at-a-time kernels, bf16 mode), PropMLP.net_width 256, bottleneck 256, view width 128 and <= 512 IPE "
+    set_error("tensor-core path supports NerfMLP.net_width 256 (chain kernel) or 512 / 768 / 1024 "
+              "(layer-at-a-time kernels), PropMLP.net_width 256, bottleneck 256, view width 128 and <= 512 IPE "
               "features with a degree count divisible by 4 (got widths %d/%d/%d/%d, %d features); use HUGS_PRECISION_FP32",
               d.nerf_width, d.prop_width, d.bottleneck_width, d.view_width, h->feat_dim);
     return HUGS_ERR_UNSUPPORTED;

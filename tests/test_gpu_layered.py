@@ -158,3 +158,45 @@ def test_shipped_gins_train_through_train_pstep(tmp_path, name, gin):
                                   verbose=False)
   assert rendering['rgb'].shape == (H_, W_, 3) and torch.isfinite(rendering['rgb']).all()
   model.engine.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# HUGS_PRECISION_TC_SPLIT on the layer-at-a-time path: the SAME dense_tc_kernel / wgrad_kernel with hi + lo operands
+# (A_hi W_hi + A_lo W_hi + A_hi W_lo as K-concatenated segments, fp32 epilogues, hi + lo outputs)
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('width,n,levels', [(512, 70, 2), (1024, 37, 2), (1024, 48, 1)])
+def test_forward_wide_split_vs_fp32_oracle(width, n, levels):
+  """North-star tolerance (1e-4 of the fp32 oracle) for the shipped NerfMLP.net_width = 1024 through the tcgen05 GEMMs."""
+  ocfg, params, rays, gt, eng, flat = _pair(width, n, levels=levels, precision='tc_split')
+  with torch.no_grad():
+    rend, hist = O.model_apply(ocfg, params, rays, 0.6, True, torch.tensor(H.basis_np()))
+  res, eh = eng.forward(flat, rays, 0.6, None, compute_extras=True)
+  torch.cuda.synchronize()
+  stats = {k: _relerr(res[-1][k].cpu(), rend[-1][k]) for k in ('rgb', 'acc', 'distance_mean', 'distance_median')}
+  _report(f'forward_layered_split_w{width}_n{n}_L{levels}', stats)
+  # distances: rays that end on far samples carry the float32 conditioning of the contracted covariance (DESIGN.md (c))
+  assert stats['rgb'] < 1e-4 and stats['acc'] < 1e-4 and stats['distance_mean'] < 3e-4, stats
+  if levels == 1:
+    np.testing.assert_allclose(eh[-1]['density'].cpu().numpy(), hist[-1]['density'].numpy(), rtol=2e-3, atol=2e-4)
+  eng.close()
+
+
+@pytest.mark.parametrize('width,glo', [(512, 0), (1024, 4)])
+def test_training_wide_split_vs_float64_oracle(width, glo):
+  """Gradients of the wide NerfMLP in the split mode against the FLOAT64 oracle: the bound of tests/test_gpu_split.py
+  (1e-3 + 2 x dist(float32 oracle, float64 oracle) + 0.025 / sqrt(n_rays): ReLU gate flips, IPE conditioning)."""
+  from tests.test_gpu_split import _oracle_grads, _cond_compare, _run_engine
+  n = 64
+  from nerf_hugs_b200.engine import Engine
+  ocfg, ecfg = H.config_pair(num_levels=2, n_nerf=128, nerf_width=width, precision='tc_split', max_rays=128, glo=glo)
+  lcfg = O.LossConfig(distortion_loss_mult=0.01, interlevel_loss_mult=1.0)
+  params = O.init_params(ocfg, seed=0, bias_scale=0.1)
+  rays, gt = H.make_rays(n, seed=1)
+  g = torch.Generator().manual_seed(11)
+  jit = [torch.rand(n, 1, generator=g) for _ in range(2)]
+  eng = Engine(ecfg, H.basis_np())
+  ref64, stats = _oracle_grads(ocfg, lcfg, params, rays, gt, jit, torch.float64)
+  grad, st = _run_engine(eng, params, rays, gt, jit, lcfg)
+  rep = _cond_compare(eng, grad, st, ocfg, lcfg, params, rays, gt, jit, stats, ref64, f'split_grads_layered_w{width}_glo{glo}')
+  assert rep['flat_cosine'] > 0.9999, rep
+  eng.close()
