@@ -335,7 +335,9 @@ typedef struct {
   int32_t contract;            /* ... or, with scene contraction, (spatial_distortion_norm2(x) + 2) / 4 */
   int32_t max_samples;         /* n_rays * n_samples the workspace is sized for */
   int32_t max_rays;
-  int32_t reserved_[2];
+  int32_t precision;           /* NerfactoField only: 0 or HUGS_PRECISION_BF16_TC = throughput, HUGS_PRECISION_TC_SPLIT = the same
+                                  tcgen05 GEMMs with bf16 hi + lo operands (fp32-level parity, forward and backward) */
+  int32_t reserved_;
 } hugs_hashfield_desc;
 typedef struct hugs_hashfield hugs_hashfield;
 

@@ -84,7 +84,7 @@ class HashFieldDesc(C.Structure):
               ('base_res', C.c_int32), ('per_level_scale', C.c_float), ('hidden_dim', C.c_int32),
               ('geo_feat_dim', C.c_int32), ('hidden_dim_color', C.c_int32), ('appearance_dim', C.c_int32),
               ('num_embeddings', C.c_int32), ('bound', C.c_float), ('contract', C.c_int32), ('max_samples', C.c_int32),
-              ('max_rays', C.c_int32), ('reserved_', C.c_int32 * 2)]
+              ('max_rays', C.c_int32), ('precision', C.c_int32), ('reserved_', C.c_int32)]
 
 
 class RayBatch(C.Structure):

@@ -172,6 +172,7 @@ struct EncodeArgs {
   __nv_bfloat16* feats;   // [rows_pad, 64] (columns >= L * F zero)
   float* feats_f32;       // optional [n_samples, L * F] (operator-level test hook)
   int rows_pad;
+  __nv_bfloat16* feats_lo;// split-precision mode: residual half (same shape), or nullptr
 };
 
 __global__ void __launch_bounds__(128) hash_encode_kernel(EncodeArgs a) {
@@ -195,6 +196,17 @@ __global__ void __launch_bounds__(128) hash_encode_kernel(EncodeArgs a) {
                           ptx::pack_bf16x2(f[q * 8 + 4], f[q * 8 + 5]), ptx::pack_bf16x2(f[q * 8 + 6], f[q * 8 + 7]));
 #pragma unroll
     for (int q = 4; q < 8; ++q) dst[q] = make_uint4(0u, 0u, 0u, 0u);
+    if (a.feats_lo) {
+      uint4* dl = reinterpret_cast<uint4*>(a.feats_lo + (size_t)s * 64);
+      auto lo2 = [&](int i) {
+        const uint32_t hw = ptx::pack_bf16x2(f[i], f[i + 1]);
+        return ptx::pack_bf16x2(f[i] - __uint_as_float(hw << 16), f[i + 1] - __uint_as_float(hw & 0xFFFF0000u));
+      };
+#pragma unroll
+      for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo2(q * 8), lo2(q * 8 + 2), lo2(q * 8 + 4), lo2(q * 8 + 6));
+#pragma unroll
+      for (int q = 4; q < 8; ++q) dl[q] = make_uint4(0u, 0u, 0u, 0u);
+    }
   }
 }
 
@@ -202,6 +214,7 @@ struct ScatterArgs {
   FieldRays r; HashGridCfg g;
   const __nv_bfloat16* d_feats; int ld;   // [rows, ld] bf16
   float2* grid_grad;
+  const __nv_bfloat16* d_feats_lo;        // split-precision mode: residual half, or nullptr
 };
 
 __global__ void __launch_bounds__(128) hash_scatter_kernel(ScatterArgs a) {
@@ -220,6 +233,16 @@ __global__ void __launch_bounds__(128) hash_scatter_kernel(ScatterArgs a) {
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) { df[q * 8 + 2 * j] = __uint_as_float(w[j] << 16); df[q * 8 + 2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u); }
+    }
+    if (a.d_feats_lo) {
+      const uint4* sl = reinterpret_cast<const uint4*>(a.d_feats_lo + (size_t)s * a.ld);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 v = __ldg(sl + q);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { df[q * 8 + 2 * j] += __uint_as_float(w[j] << 16); df[q * 8 + 2 * j + 1] += __uint_as_float(w[j] & 0xFFFF0000u); }
+      }
     }
   }
   scatter_sample<16>(a.g, a.grid_grad, x, df, live);
@@ -399,14 +422,16 @@ __global__ void sh_inputs_kernel(const float* viewdirs, const int32_t* embed_idx
 
 // raybias[ray][c] = sum_j bf16(inp[ray][j]) * bf16(W[(row0 + j) * out + c]) + b[c]
 __global__ void ray_bias_kernel(const float* inp, int in_dim, const float* W, int row0, const float* bias, int out, int n_rays,
-                                float* rb) {
+                                int exact, float* rb) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_rays * out) return;
   const int ray = idx / out, c = idx % out;
   float acc = 0.f;
-  for (int j = 0; j < in_dim; ++j)
-    acc = fmaf(__bfloat162float(__float2bfloat16(inp[(size_t)ray * in_dim + j])),
-               __bfloat162float(__float2bfloat16(W[(size_t)(row0 + j) * out + c])), acc);
+  for (int j = 0; j < in_dim; ++j) {
+    float x = inp[(size_t)ray * in_dim + j], w = W[(size_t)(row0 + j) * out + c];
+    if (!exact) { x = __bfloat162float(__float2bfloat16(x)); w = __bfloat162float(__float2bfloat16(w)); }
+    acc = fmaf(x, w, acc);
+  }
   rb[idx] = acc + bias[c];
 }
 
@@ -414,7 +439,8 @@ __global__ void ray_bias_kernel(const float* inp, int in_dim, const float* W, in
 // Block = 8 samples x 32 lanes, a lane owns 8 consecutive columns (one 16-byte load / store).
 __global__ void __launch_bounds__(256) field_bwd_start_kernel(const float* d_raw, const __nv_bfloat16* hact, const float* w_rgb,
                                                               const uint8_t* inside, int n_samples, int n_rows_pad,
-                                                              __nv_bfloat16* dz, __nv_bfloat16* dh, float* d_dens) {
+                                                              __nv_bfloat16* dz, __nv_bfloat16* dh, float* d_dens,
+                                                              __nv_bfloat16* dz_lo, __nv_bfloat16* dh_lo) {
   __shared__ float wsm[kH * 3];
   for (int i = threadIdx.x; i < kH * 3; i += blockDim.x) wsm[i] = w_rgb[i];
   __syncthreads();
@@ -423,26 +449,37 @@ __global__ void __launch_bounds__(256) field_bwd_start_kernel(const float* d_raw
   float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
   if (s < n_samples) dr = __ldg(reinterpret_cast<const float4*>(d_raw) + s);
   if (s < n_samples && !inside[s]) dr.x = 0.f;            // density * selector: no density gradient out of range
+  const bool split = dz_lo != nullptr;
   if (lane == 0) {
-    reinterpret_cast<uint4*>(dh + (size_t)s * kHeadCols)[0] =
-        make_uint4(ptx::pack_bf16x2(dr.y, dr.z), ptx::pack_bf16x2(dr.w, dr.x), 0u, 0u);
+    const uint32_t h01 = ptx::pack_bf16x2(dr.y, dr.z), h23 = ptx::pack_bf16x2(dr.w, dr.x);
+    reinterpret_cast<uint4*>(dh + (size_t)s * kHeadCols)[0] = make_uint4(h01, h23, 0u, 0u);
+    if (split)
+      reinterpret_cast<uint4*>(dh_lo + (size_t)s * kHeadCols)[0] =
+          make_uint4(ptx::pack_bf16x2(dr.y - __uint_as_float(h01 << 16), dr.z - __uint_as_float(h01 & 0xFFFF0000u)),
+                     ptx::pack_bf16x2(dr.w - __uint_as_float(h23 << 16), dr.x - __uint_as_float(h23 & 0xFFFF0000u)), 0u, 0u);
     d_dens[s] = dr.x;
   }
-  const float d0 = __bfloat162float(__float2bfloat16(dr.y)), d1 = __bfloat162float(__float2bfloat16(dr.z)),
-              d2 = __bfloat162float(__float2bfloat16(dr.w));
+  float d0 = dr.y, d1 = dr.z, d2 = dr.w;
+  if (!split) {
+    d0 = __bfloat162float(__float2bfloat16(d0)); d1 = __bfloat162float(__float2bfloat16(d1)); d2 = __bfloat162float(__float2bfloat16(d2));
+  }
   uint4 hv = make_uint4(0u, 0u, 0u, 0u);
   if (s < n_samples) hv = __ldg(reinterpret_cast<const uint4*>(hact + (size_t)s * kH) + lane);
   const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-  uint32_t o[4];
+  uint32_t o[4], ol[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
     const int c0 = lane * 8 + 2 * j;
-    const float g0 = d0 * wsm[c0 * 3] + d1 * wsm[c0 * 3 + 1] + d2 * wsm[c0 * 3 + 2];
-    const float g1 = d0 * wsm[c0 * 3 + 3] + d1 * wsm[c0 * 3 + 4] + d2 * wsm[c0 * 3 + 5];
-    // the saved activation is post-ReLU (>= 0): a non-zero bf16 pattern means the gate is open
-    o[j] = ptx::pack_bf16x2((hw[j] & 0xFFFFu) ? g0 : 0.f, (hw[j] >> 16) ? g1 : 0.f);
+    float g0 = d0 * wsm[c0 * 3] + d1 * wsm[c0 * 3 + 1] + d2 * wsm[c0 * 3 + 2];
+    float g1 = d0 * wsm[c0 * 3 + 3] + d1 * wsm[c0 * 3 + 4] + d2 * wsm[c0 * 3 + 5];
+    // the saved activation is post-ReLU (>= 0): a non-zero bf16 pattern (of the hi half) means the gate is open
+    if (!(hw[j] & 0xFFFFu)) g0 = 0.f;
+    if (!(hw[j] >> 16)) g1 = 0.f;
+    o[j] = ptx::pack_bf16x2(g0, g1);
+    ol[j] = ptx::pack_bf16x2(g0 - __uint_as_float(o[j] << 16), g1 - __uint_as_float(o[j] & 0xFFFF0000u));
   }
   reinterpret_cast<uint4*>(dz + (size_t)s * kH)[lane] = make_uint4(o[0], o[1], o[2], o[3]);
+  if (split) reinterpret_cast<uint4*>(dz_lo + (size_t)s * kH)[lane] = make_uint4(ol[0], ol[1], ol[2], ol[3]);
 }
 
 __global__ void inside_mask_kernel(FieldRays r, HashGridCfg g, uint8_t* inside, float* raw, int C) {
@@ -455,30 +492,38 @@ __global__ void inside_mask_kernel(FieldRays r, HashGridCfg g, uint8_t* inside, 
 }
 
 // dzsum[ray][c] = sum over the ray's samples of dZ[s][c]
-__global__ void __launch_bounds__(kH) ray_colsum_kernel(const __nv_bfloat16* dz, int S, int n_rays, float* out) {
+__global__ void __launch_bounds__(kH) ray_colsum_kernel(const __nv_bfloat16* dz, const __nv_bfloat16* dz_lo, int S, int n_rays,
+                                                        float* out) {
   const int ray = blockIdx.x, c = threadIdx.x;
   if (ray >= n_rays) return;
   float acc = 0.f;
   const __nv_bfloat16* src = dz + (size_t)ray * S * kH + c;
   for (int s = 0; s < S; ++s) acc += __bfloat162float(src[(size_t)s * kH]);
+  if (dz_lo) {
+    const __nv_bfloat16* sl = dz_lo + (size_t)ray * S * kH + c;
+    for (int s = 0; s < S; ++s) acc += __bfloat162float(sl[(size_t)s * kH]);
+  }
   out[(size_t)ray * kH + c] = acc;
 }
 
 // dW[row0 + j][c] += sum_ray bf16(inp[ray][j]) * dzsum[ray][c]; block.x = j, block.y = ray chunk, thread = c
 __global__ void __launch_bounds__(kH) ray_input_wgrad_kernel(const float* inp, int in_dim, const float* dzsum, int n_rays,
-                                                             int row0, float* dW) {
+                                                             int row0, int exact, float* dW) {
   const int j = blockIdx.x, c = threadIdx.x;
   const int chunk = (n_rays + gridDim.y - 1) / gridDim.y;
   const int r0 = blockIdx.y * chunk, r1 = min(r0 + chunk, n_rays);
   float acc = 0.f;
-  for (int r = r0; r < r1; ++r)
-    acc = fmaf(__bfloat162float(__float2bfloat16(inp[(size_t)r * in_dim + j])), dzsum[(size_t)r * kH + c], acc);
+  for (int r = r0; r < r1; ++r) {
+    float x = inp[(size_t)r * in_dim + j];
+    if (!exact) x = __bfloat162float(__float2bfloat16(x));
+    acc = fmaf(x, dzsum[(size_t)r * kH + c], acc);
+  }
   if (r1 > r0) atomicAdd(dW + (size_t)(row0 + j) * kH + c, acc);
 }
 
 // d embedding[row][g] += sum_c bf16(W[(row0 + g) * 256 + c]) * dzsum[ray][c]: one warp per ray, lanes over c (coalesced)
 __global__ void __launch_bounds__(256) app_embed_grad_kernel(const float* dzsum, const int32_t* embed_idx, const float* W,
-                                                             int row0, int app, int n_rays, int num_emb, float* d_emb) {
+                                                             int row0, int app, int n_rays, int num_emb, int exact, float* d_emb) {
   const int ray = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (ray >= n_rays) return;
   float z[8];
@@ -490,7 +535,11 @@ __global__ void __launch_bounds__(256) app_embed_grad_kernel(const float* dzsum,
     const float* wrow = W + (size_t)(row0 + g) * kH;
     float acc = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) acc = fmaf(z[q], __bfloat162float(__float2bfloat16(__ldg(wrow + q * 32 + lane))), acc);
+    for (int q = 0; q < 8; ++q) {
+      float w = __ldg(wrow + q * 32 + lane);
+      if (!exact) w = __bfloat162float(__float2bfloat16(w));
+      acc = fmaf(z[q], w, acc);
+    }
     acc = warp_sum(acc);
     if (lane == 0 && ok) atomicAdd(d_emb + (size_t)row * app + g, acc);
   }
@@ -503,6 +552,7 @@ struct PackBlock { int dst, row0, rows, fwd, in0, n_in, out0, n_out, out_stride;
 struct FieldPackArgs {
   PackBlock b[12]; int n;
   const float* params; __nv_bfloat16* wt; __nv_bfloat16* wn; int ldk;
+  int part; long long lo_wt, lo_wn;      // part 1: bf16(w - bf16(w)) into the lo halves (split-precision mode)
 };
 __global__ void field_pack_kernel(FieldPackArgs a) {
   const PackBlock B = a.b[blockIdx.y];
@@ -513,13 +563,15 @@ __global__ void field_pack_kernel(FieldPackArgs a) {
     float v = 0.f;
     if (B.fwd) { if (r < B.n_out && k < B.n_in) v = a.params[B.koff + (long long)(B.in0 + k) * B.out_stride + B.out0 + r]; }
     else       { if (r < B.n_in && k < B.n_out) v = a.params[B.koff + (long long)(B.in0 + r) * B.out_stride + B.out0 + k]; }
-    dst[(size_t)(B.row0 + r) * a.ldk + k] = __float2bfloat16(v);
+    const __nv_bfloat16 hi = __float2bfloat16(v);
+    const long long lo_off = a.part == 0 ? 0 : (B.dst == 0 ? a.lo_wt : a.lo_wn);
+    dst[lo_off + (size_t)(B.row0 + r) * a.ldk + k] = a.part == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
   }
 }
 
 // fp32 tables: biases per launch and the bf16-rounded head kernels of the CUDA-core backward start
 __global__ void field_table_kernel(const float* params, float* tab, long long b_base0, long long b_dens, long long b_geo,
-                                   long long b_head1, long long b_rgb, long long k_dens, long long k_rgb) {
+                                   long long b_head1, long long b_rgb, long long k_dens, long long k_rgb, int exact) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   // [0,256) base0 bias | [256,400) heads: geo bias (64) + zeros, density bias at 256 + 128 | [400,656) head1 bias |
   // [656,672) rgb bias | [672,928) w_dens (bf16-rounded) | [928, 928 + 768) w_rgb [256][3] (bf16-rounded)
@@ -529,8 +581,8 @@ __global__ void field_table_kernel(const float* params, float* tab, long long b_
   else if (i < 400) { const int j = i - 256; if (j < kG) v = params[b_geo + j]; else if (j == 128) v = params[b_dens]; }
   else if (i < 656) v = params[b_head1 + (i - 400)];
   else if (i < 672) { const int j = i - 656; if (j < 3) v = params[b_rgb + j]; }
-  else if (i < 928) v = __bfloat162float(__float2bfloat16(params[k_dens + (i - 672)]));
-  else v = __bfloat162float(__float2bfloat16(params[k_rgb + (i - 928)]));
+  else if (i < 928) { v = params[k_dens + (i - 672)]; if (!exact) v = __bfloat162float(__float2bfloat16(v)); }
+  else { v = params[k_rgb + (i - 928)]; if (!exact) v = __bfloat162float(__float2bfloat16(v)); }
   tab[i] = v;
 }
 
@@ -540,6 +592,7 @@ __global__ void field_table_kernel(const float* params, float* tab, long long b_
 // ====================================================================================================== host side
 using namespace hugs;
 
+constexpr int kMaxWgItems = 4096;
 enum { HF_FEAT = 0, HF_ACT0, HF_GEO, HF_H0, HF_H1, HF_DZH1, HF_DZH0, HF_DGEO, HF_DZA0, HF_DFEAT, HF_DH, HF_MAPS };
 
 struct hugs_hashfield {
@@ -547,6 +600,7 @@ struct hugs_hashfield {
   HashGridCfg g{};
   int device = 0, num_sms = 148;
   bool is_prop = false;
+  bool split = false; int parts = 1;   // HUGS_PRECISION_TC_SPLIT: every bf16 tensor has a lo half `cap` (weights: rows_f / rows_b) rows further down
   int64_t grid_floats = 0, mlp_floats = 0;
   std::vector<hugs_tensor_desc> tensors;
   std::vector<void*> allocs;
@@ -611,19 +665,31 @@ void dense_common(DenseParams* p, const hugs_hashfield* h, int M) {
   memset(p, 0, sizeof(*p));
   p->b_map = h->map_wt128; p->b_map_64 = h->map_wt64; p->b_map_8 = h->map_wt8;
   p->m_rows = M; p->m_tiles = (M + 255) / 256;
+  p->split = h->split ? 1 : 0; p->out_lo_row_off = h->cap; p->exact_rank1 = h->split ? 1 : 0;
+}
+
+// A = `kp` K panels of workspace tensor `buf`; split-precision mode: A_hi W_hi + A_lo W_hi + A_hi W_lo as one accumulation chain
+// (`w_lo_rows` = row distance of the lo half of the weight pack: rows_f forward, rows_b backward)
+void dense_a(DenseParams* p, const hugs_hashfield* h, int buf, int kp, int w_lo_rows) {
+  const int combos = h->split ? 3 : 1;
+  for (int c = 0; c < combos; ++c) {
+    p->a_map[c] = h->map128[buf]; p->a_kp[c] = kp; p->a_row0[c] = c == 1 ? h->cap : 0; p->a_col0[c] = 0;
+    p->w_col0[c] = 0; p->w_row_off[c] = c == 2 ? w_lo_rows : 0;
+  }
+  p->n_seg = combos;
 }
 
 int hf_ensure_training(hugs_hashfield* h) {
   if (h->train_ready || h->is_prop) return HUGS_OK;
   int rc;
   for (int i = HF_DZH1; i < HF_MAPS; ++i) {
-    if ((rc = hf_alloc(h, &h->buf[i], (size_t)h->cap * h->buf_cols[i]))) return rc;
-    if ((rc = make_map(&h->map128[i], h->buf[i], h->cap, h->buf_cols[i], 128)) ||
-        (rc = make_map(&h->map64[i], h->buf[i], h->cap, h->buf_cols[i], 64)))
+    if ((rc = hf_alloc(h, &h->buf[i], (size_t)h->cap * h->parts * h->buf_cols[i]))) return rc;
+    if ((rc = make_map(&h->map128[i], h->buf[i], h->cap * h->parts, h->buf_cols[i], 128)) ||
+        (rc = make_map(&h->map64[i], h->buf[i], h->cap * h->parts, h->buf_cols[i], 64)))
       return rc;
   }
   if ((rc = hf_alloc(h, &h->dzsum, (size_t)h->max_rays * kH)) || (rc = hf_alloc(h, &h->d_dens, (size_t)h->cap)) ||
-      (rc = hf_alloc(h, &h->items_dev, 1024)))
+      (rc = hf_alloc(h, &h->items_dev, kMaxWgItems)))
     return rc;
   if ((rc = wgrad_kernel_init())) return rc;
   HUGS_CUDA(cudaDeviceSynchronize());
@@ -638,8 +704,17 @@ void hf_build_wgrad(hugs_hashfield* h, int M) {
   auto flush = [&]() {
     std::vector<WgItem> items;
     wgrad_plan(units, T, h->num_sms, &items);
-    h->launches.push_back({(int)h->items_host.size(), (int)items.size()});
-    h->items_host.insert(h->items_host.end(), items.begin(), items.end());
+    const size_t first = h->items_host.size();
+    // split-precision mode: (A_hi + A_lo)^T (dZ_hi + dZ_lo) as four items; the bias column sums ride on the A_hi items only
+    for (const WgItem& base : items)
+      for (int pa = 0; pa < h->parts; ++pa)
+        for (int pb = 0; pb < h->parts; ++pb) {
+          WgItem w = base;
+          w.a_row0 += pa * h->cap; w.b_row0 += pb * h->cap;
+          if (pa > 0) w.bias_mode = 0;
+          h->items_host.push_back(w);
+        }
+    h->launches.push_back({(int)first, (int)(h->items_host.size() - first)});
     units.clear();
   };
   int grp = 10;
@@ -696,6 +771,9 @@ HUGS_API int hugs_hashfield_create(const hugs_hashfield_desc* desc, hugs_hashfie
   if (!h) { set_error("out of host memory"); return HUGS_ERR_NOMEM; }
   auto fail = [&](int code) { hugs_hashfield_destroy(h); return code; };
   h->d = d; h->is_prop = is_prop;
+  HUGS_REQUIRE(d.precision == 0 || d.precision == HUGS_PRECISION_BF16_TC || d.precision == HUGS_PRECISION_TC_SPLIT,
+               "hash field: precision must be HUGS_PRECISION_BF16_TC or HUGS_PRECISION_TC_SPLIT, got %d", d.precision);
+  h->split = !is_prop && d.precision == HUGS_PRECISION_TC_SPLIT; h->parts = h->split ? 2 : 1;
   if (cudaGetDevice(&h->device) != cudaSuccess) return fail(HUGS_ERR_CUDA);
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) return fail(HUGS_ERR_CUDA);
@@ -754,17 +832,18 @@ HUGS_API int hugs_hashfield_create(const hugs_hashfield_desc* desc, hugs_hashfie
     int rb = 0;
     h->rb_base0 = rb; rb += 128; h->rb_geo = rb; rb += 256; h->rb_head0 = rb; rb += 128; h->rb_head1 = rb; rb += 256;
     h->rows_b = rb;
-    if ((rc = hf_alloc(h, &h->wt, (size_t)h->rows_f * 256)) || (rc = hf_alloc(h, &h->wn, (size_t)h->rows_b * 256)) ||
+    const int P = h->parts;
+    if ((rc = hf_alloc(h, &h->wt, (size_t)h->rows_f * P * 256)) || (rc = hf_alloc(h, &h->wn, (size_t)h->rows_b * P * 256)) ||
         (rc = hf_alloc(h, &h->tab, 2048)))
       return fail(rc);
-    if ((rc = make_map(&h->map_wt128, h->wt, h->rows_f, 256, 128)) || (rc = make_map(&h->map_wt64, h->wt, h->rows_f, 256, 64)) ||
-        (rc = make_map(&h->map_wt8, h->wt, h->rows_f, 256, 8)) || (rc = make_map(&h->map_wn128, h->wn, h->rows_b, 256, 128)) ||
-        (rc = make_map(&h->map_wn64, h->wn, h->rows_b, 256, 64)))
+    if ((rc = make_map(&h->map_wt128, h->wt, h->rows_f * P, 256, 128)) || (rc = make_map(&h->map_wt64, h->wt, h->rows_f * P, 256, 64)) ||
+        (rc = make_map(&h->map_wt8, h->wt, h->rows_f * P, 256, 8)) || (rc = make_map(&h->map_wn128, h->wn, h->rows_b * P, 256, 128)) ||
+        (rc = make_map(&h->map_wn64, h->wn, h->rows_b * P, 256, 64)))
       return fail(rc);
     for (int i = HF_FEAT; i <= HF_H1; ++i) {
-      if ((rc = hf_alloc(h, &h->buf[i], (size_t)h->cap * h->buf_cols[i]))) return fail(rc);
-      if ((rc = make_map(&h->map128[i], h->buf[i], h->cap, h->buf_cols[i], 128)) ||
-          (rc = make_map(&h->map64[i], h->buf[i], h->cap, h->buf_cols[i], 64)))
+      if ((rc = hf_alloc(h, &h->buf[i], (size_t)h->cap * P * h->buf_cols[i]))) return fail(rc);
+      if ((rc = make_map(&h->map128[i], h->buf[i], h->cap * P, h->buf_cols[i], 128)) ||
+          (rc = make_map(&h->map64[i], h->buf[i], h->cap * P, h->buf_cols[i], 64)))
         return fail(rc);
     }
     h->max_rays = d.max_rays > 0 ? d.max_rays : std::max(1, d.max_samples / 16);
@@ -835,10 +914,14 @@ HUGS_API int hugs_hashfield_params_changed(hugs_hashfield* h, const float* mlp, 
   blk(1, h->rb_geo, 256, 0, 0, kH, 0, kG, kG, h->o_geo_k);
   blk(1, h->rb_head0, 128, 0, 0, kG, 0, kH, kH, h->o_head0_k);
   blk(1, h->rb_head1, 256, 0, 0, kH, 0, kH, kH, h->o_head1_k);
-  field_pack_kernel<<<dim3(64, a.n), 256, 0, st>>>(a);
-  HUGS_LAUNCH_CHECK();
+  a.lo_wt = (long long)h->rows_f * a.ldk; a.lo_wn = (long long)h->rows_b * a.ldk;
+  for (int part = 0; part < h->parts; ++part) {
+    a.part = part;
+    field_pack_kernel<<<dim3(64, a.n), 256, 0, st>>>(a);
+    HUGS_LAUNCH_CHECK();
+  }
   field_table_kernel<<<(928 + 768 + 255) / 256, 256, 0, st>>>(mlp, h->tab, h->o_base0_b, h->o_dens_b, h->o_geo_b, h->o_head1_b,
-                                                             h->o_rgb_b, h->o_dens_k, h->o_rgb_k);
+                                                             h->o_rgb_b, h->o_dens_k, h->o_rgb_k, h->split ? 1 : 0);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
 }
@@ -851,7 +934,7 @@ HUGS_API int hugs_hashfield_encode(hugs_hashfield* h, const float* grid, const h
   HUGS_REQUIRE(h->g.L <= 16, "hugs_hashfield_encode: at most 16 levels");
   const int M = n_rays * n_samples;
   if (M == 0) return HUGS_OK;
-  EncodeArgs a{field_rays(rays, tdist, n_rays, n_samples), h->g, reinterpret_cast<const float2*>(grid), nullptr, features, M};
+  EncodeArgs a{field_rays(rays, tdist, n_rays, n_samples), h->g, reinterpret_cast<const float2*>(grid), nullptr, features, M, nullptr};
   hash_encode_kernel<<<(M + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;
@@ -877,7 +960,8 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
   const int app = h->d.appearance_dim;
   // 1. hash features (bf16 [rows, 64]) and the in-range mask
   {
-    EncodeArgs a{fr, h->g, reinterpret_cast<const float2*>(grid), h->buf[HF_FEAT], nullptr, rows_pad};
+    EncodeArgs a{fr, h->g, reinterpret_cast<const float2*>(grid), h->buf[HF_FEAT], nullptr, rows_pad,
+                 h->split ? h->buf[HF_FEAT] + (size_t)h->cap * 64 : nullptr};
     hash_encode_kernel<<<(rows_pad + 127) / 128, 128, 0, st>>>(a);
     HUGS_LAUNCH_CHECK();
   }
@@ -886,18 +970,18 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
                                                          n_rays, app, h->d.num_embeddings, zero_app, h->ray_in);
   HUGS_LAUNCH_CHECK();
   ray_bias_kernel<<<(n_rays * kH + 255) / 256, 256, 0, st>>>(h->ray_in, kSH + app, mlp + h->o_head0_k, kG, mlp + h->o_head0_b, kH,
-                                                             n_rays, h->ray_bias);
+                                                             n_rays, h->split ? 1 : 0, h->ray_bias);
   HUGS_LAUNCH_CHECK();
   DenseParams p;
   // 3. base MLP layer 0: features -> 256 (ReLU)
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_FEAT]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 1;
+  dense_a(&p, h, HF_FEAT, 1, h->rows_f);
   p.b_row0 = h->rf_base0; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_RELU;
   p.bias = h->tab; p.out_map = h->map128[HF_ACT0];
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   // 4. heads of the base MLP: geometry features (linear, bf16) + raw density (fp32 column 0 of raw)
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_ACT0]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 4;
+  dense_a(&p, h, HF_ACT0, 4, h->rows_f);
   p.b_row0 = h->rf_heads; p.n_tiles = 2;
   p.tile_n0[0] = 0; p.tile_bn[0] = 128; p.tile_epi[0] = DE_LINEAR;
   p.tile_n0[1] = 128; p.tile_bn[1] = 16; p.tile_epi[1] = DE_HEAD_F32;
@@ -906,19 +990,19 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   // 5. colour MLP layer 0: geometry features (K = 64) + per-ray bias -> 256 (ReLU)
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_GEO]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 1;
+  dense_a(&p, h, HF_GEO, 1, h->rows_f);
   p.b_row0 = h->rf_head0; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_VIEW;
   p.viewbias = h->ray_bias; p.view_ld = kH; p.S = n_samples; p.out_map = h->map128[HF_H0];
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   // 6. colour MLP layer 1
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_H0]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 4;
+  dense_a(&p, h, HF_H0, 4, h->rows_f);
   p.b_row0 = h->rf_head1; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_RELU;
   p.bias = h->tab + 400; p.out_map = h->map128[HF_H1];
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   // 7. rgb head (fp32 columns 1..3 of raw)
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_H1]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 4;
+  dense_a(&p, h, HF_H1, 4, h->rows_f);
   p.b_row0 = h->rf_rgb; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 16; p.tile_epi[0] = DE_HEAD_F32;
   p.bias = h->tab + 656; p.out_map = h->map128[HF_H1];
   p.raw_out = raw_out; p.raw_c = 4; p.raw_chan0 = 1; p.raw_nchan = 3;
@@ -949,7 +1033,7 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   const int app = h->d.appearance_dim;
   if (h->built_for != M) {
     hf_build_wgrad(h, M);
-    HUGS_REQUIRE(h->items_host.size() <= 1024, "nerfacto field: too many weight-gradient items");
+    HUGS_REQUIRE(h->items_host.size() <= (size_t)kMaxWgItems, "nerfacto field: too many weight-gradient items");
     HUGS_CUDA(cudaMemcpyAsync(h->items_dev, h->items_host.data(), sizeof(WgItem) * h->items_host.size(), cudaMemcpyHostToDevice, st));
     HUGS_CUDA(cudaStreamSynchronize(st));
     h->built_for = M;
@@ -961,37 +1045,42 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   };
   // start: dZ_head1 from d_rgb, head-gradient rows, masked density gradient
   field_bwd_start_kernel<<<(rows_pad + 7) / 8, 256, 0, st>>>(d_raw, h->buf[HF_H1], h->tab + 928, h->inside, M, rows_pad, h->buf[HF_DZH1],
-                                                  h->buf[HF_DH], h->d_dens);
+                                                  h->buf[HF_DH], h->d_dens,
+                                                  h->split ? h->buf[HF_DZH1] + (size_t)h->cap * kH : nullptr,
+                                                  h->split ? h->buf[HF_DH] + (size_t)h->cap * kHeadCols : nullptr);
   HUGS_LAUNCH_CHECK();
   if ((rc = wgrad())) return rc;
   DenseParams p;
   // dZ_head0 = (dZ_head1 . W_head1^T) * [hact0 > 0]
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_DZH1]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 4;
+  dense_a(&p, h, HF_DZH1, 4, h->rows_b);
   p.b_map = h->map_wn128; p.b_row0 = h->rb_head1; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_BWD_RELU;
   p.mask_act = h->buf[HF_H0]; p.mask_ld = kH; p.mask_row0 = 0; p.out_map = h->map128[HF_DZH0];
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   if ((rc = wgrad())) return rc;
   // per-ray inputs of head0: SH / appearance rows of its kernel and the appearance embedding rows
-  ray_colsum_kernel<<<n_rays, kH, 0, st>>>(h->buf[HF_DZH0], n_samples, n_rays, h->dzsum);
+  ray_colsum_kernel<<<n_rays, kH, 0, st>>>(h->buf[HF_DZH0], h->split ? h->buf[HF_DZH0] + (size_t)h->cap * kH : nullptr, n_samples,
+                                           n_rays, h->dzsum);
   HUGS_LAUNCH_CHECK();
-  ray_input_wgrad_kernel<<<dim3(kSH + app, 32), kH, 0, st>>>(h->ray_in, kSH + app, h->dzsum, n_rays, kG, mlp_grad + h->o_head0_k);
+  ray_input_wgrad_kernel<<<dim3(kSH + app, 32), kH, 0, st>>>(h->ray_in, kSH + app, h->dzsum, n_rays, kG, h->split ? 1 : 0,
+                                                             mlp_grad + h->o_head0_k);
   HUGS_LAUNCH_CHECK();
   if (app > 0) {
     app_embed_grad_kernel<<<(n_rays + 7) / 8, 256, 0, st>>>(h->dzsum, rays->embed_idx, mlp + h->o_head0_k, kG + kSH, app,
-                                                                      n_rays, h->d.num_embeddings, mlp_grad + h->o_emb);
+                                                                      n_rays, h->d.num_embeddings, h->split ? 1 : 0,
+                                                                      mlp_grad + h->o_emb);
     HUGS_LAUNCH_CHECK();
   }
   // d_geo = dZ_head0 . W_head0[geometry rows]^T  (64 columns, linear)
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_DZH0]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 4;
+  dense_a(&p, h, HF_DZH0, 4, h->rows_b);
   p.b_map_64 = h->map_wn64; p.b_row0 = h->rb_head0; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 128; p.tile_epi[0] = DE_BWD_LINEAR;
   p.out_map = h->map128[HF_DGEO];
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   if ((rc = wgrad())) return rc;
   // dZ_act0 = (d_geo . W_geo^T + d_density (x) w_density) * [act0 > 0]
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_DGEO]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 1;
+  dense_a(&p, h, HF_DGEO, 1, h->rows_b);
   p.b_map = h->map_wn128; p.b_row0 = h->rb_geo; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_BWD_RELU;
   p.mask_act = h->buf[HF_ACT0]; p.mask_ld = kH; p.mask_row0 = 0;
   p.rank1_row = h->d_dens; p.rank1_stride = 1; p.rank1_col = h->tab + 672; p.out_map = h->map128[HF_DZA0];
@@ -999,11 +1088,12 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   if ((rc = wgrad())) return rc;
   // d_features = dZ_act0 . W_base0^T (32 columns), then the trilinear scatter into the grid gradient
   dense_common(&p, h, M);
-  p.a_map[0] = h->map128[HF_DZA0]; p.a_map[1] = p.a_map[0]; p.a_kp[0] = 4;
+  dense_a(&p, h, HF_DZA0, 4, h->rows_b);
   p.b_map_64 = h->map_wn64; p.b_row0 = h->rb_base0; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 128; p.tile_epi[0] = DE_BWD_LINEAR;
   p.out_map = h->map128[HF_DFEAT];
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
-  ScatterArgs sa{fr, h->g, h->buf[HF_DFEAT], 128, reinterpret_cast<float2*>(grid_grad)};
+  ScatterArgs sa{fr, h->g, h->buf[HF_DFEAT], 128, reinterpret_cast<float2*>(grid_grad),
+                 h->split ? h->buf[HF_DFEAT] + (size_t)h->cap * 128 : nullptr};
   hash_scatter_kernel<<<(M + 127) / 128, 128, 0, st>>>(sa);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;

@@ -18,6 +18,8 @@ from __future__ import annotations
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Tuple
 
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -280,6 +282,10 @@ class Model(nn.Module):
                                                         contract=enable_scene_contraction, **args))
     bias = -1. if c.density_activation == 'softplus' else 0.      # trunc_exp takes the raw density as is (nerfacto.py:702-710)
     self._render_cfg = ops.render_cfg(c.opaque_background, c.density_activation, bias, 1., 0., 0.)
+    # 'bf16_tc' (throughput) | 'tc_split' (fp32-level parity: bf16 hi + lo operands through the same tcgen05 GEMMs)
+    self.precision = os.environ.get('HUGS_NERFACTO_PRECISION', 'bf16_tc')
+    if self.precision not in ('bf16_tc', 'tc_split'):
+      raise NotImplementedError(f"nerfacto twin: precision {self.precision!r} (use 'bf16_tc' or 'tc_split')")
     self._engines: Dict[str, ops.HashFieldEngine] = {}
     self.jitter_override = None     # test hook: list of draws per level, used in place of torch.rand (ray_utils.py:151-152)
 
@@ -293,7 +299,10 @@ class Model(nn.Module):
   def _engine(self, key: str, module, n_rays: int, n_samples: int, device) -> ops.HashFieldEngine:
     fe = self._engines.get(key)
     need = n_rays * n_samples
-    if fe is not None and fe.device == torch.device(device) and fe.desc.max_samples >= need and fe.desc.max_rays >= n_rays:
+    # 'bf16_tc' (throughput) | 'tc_split' (fp32-level parity through the same tcgen05 GEMMs, forward and backward)
+    precision = {'bf16_tc': 1, 'tc_split': 2}[self.precision]
+    if (fe is not None and fe.device == torch.device(device) and fe.desc.max_samples >= need and fe.desc.max_rays >= n_rays
+        and fe.desc.precision == precision):
       return fe
     g = module.grid()
     d = _lib.HashFieldDesc()
@@ -308,6 +317,7 @@ class Model(nn.Module):
     d.bound, d.contract = float(self.bound), int(self.enable_scene_contraction)
     d.max_samples = max(need, fe.desc.max_samples if fe is not None else 0)
     d.max_rays = max(n_rays, fe.desc.max_rays if fe is not None else 0)
+    d.precision = precision
     if fe is not None:
       fe.close()
     fe = ops.HashFieldEngine(d, device, g.params, module.entries(self.embedding_appearance))

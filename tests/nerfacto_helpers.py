@@ -125,12 +125,14 @@ HASH_CASES = {
 }
 
 
-def build_hash(name, device=None):
+def build_hash(name, device=None, precision=None):
   from nerf_hugs_b200.nerfacto.models import criterion_dict, model_config_dict, model_dict
   case = HASH_CASES[name]
   torch.manual_seed(4321 + case['seed'])
   cfg = model_config_dict['nerfacto'](**case['model'])
   model = model_dict['nerfacto'](cfg, case['bound'], False, case['contraction'])
+  if precision is not None:
+    model.precision = precision
   crit = criterion_dict['nerfacto'](model)
   with torch.no_grad():
     for pname, p in model.named_parameters():
