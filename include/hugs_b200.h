@@ -400,6 +400,28 @@ typedef struct {
 int hugs_make_ray_batch(const hugs_camera_set* cams, const int32_t* cam_idx, const int32_t* pix_x,
                         const int32_t* pix_y, int32_t n_rays, const hugs_ray_batch* out, void* stream);
 
+/* ---- full-frame render pipeline ---- */
+
+/* Frame-sized outputs of one pixel stripe, row-major [rows, width, C]; NULL = skip. */
+typedef struct {
+  float*   rgb;               /* [rows, W, 3] rendering['rgb'] of the final level */
+  float*   acc;               /* [rows, W] */
+  float*   distance_mean;     /* [rows, W] (needs compute_extras, like render_image) */
+  float*   distance_median;   /* [rows, W] */
+  uint8_t* rgb_u8;            /* [rows, W, 3] utils.save_img_u8's quantisation: (clip(nan_to_num(rgb), 0, 1) * 255) truncated */
+  double*  sse;               /* [2], ACCUMULATED (the caller zeroes it): sum over the stripe's pixels and channels of
+                                 (rgb - gt)^2 and of (round(rgb * 255) / 255 - gt)^2 (eval.py:139-143 eval_quantize_metrics)
+                                 against the camera set's image: psnr = -10 log10(sse / (3 H W)) (image.mse_to_psnr) */
+} hugs_frame_out;
+
+/* models.render_image (models.py:568-649) driven by eval.py:104-160 / render.py:164-187 for camera `cam` of a device-resident
+ * dataset, pixel rows [row0, row1) of a width x height image: rays are generated on the device (hugs_make_ray_batch's
+ * arithmetic) and rendered chunk by chunk (max_rays of the handle per chunk) with the deterministic path (rng = None); every
+ * chunk writes straight into the frame-sized outputs.  One call per frame and rank: no host loop, no per-chunk gather. */
+int hugs_render_frame(hugs_handle* h, const float* params, const hugs_camera_set* cams, int32_t cam, int32_t width,
+                      int32_t height, int32_t row0, int32_t row1, float train_frac, int32_t zero_glo,
+                      const hugs_frame_out* out, void* stream);
+
 /* ---- measurement hooks (bench.py): no reference counterpart beyond train.py:162-168 wall-clock ---- */
 
 /* Number of kernels this library has launched in this process (every launch site counts itself). */

@@ -87,6 +87,10 @@ class HashFieldDesc(C.Structure):
               ('max_rays', C.c_int32), ('precision', C.c_int32), ('reserved_', C.c_int32)]
 
 
+class FrameOut(C.Structure):
+  _fields_ = [(n, C.c_void_p) for n in ('rgb', 'acc', 'distance_mean', 'distance_median', 'rgb_u8', 'sse')]
+
+
 class RayBatch(C.Structure):
   _fields_ = [(n, C.c_void_p) for n in ('origins', 'directions', 'viewdirs', 'radii', 'near', 'far', 'lossmult',
                                         'static_mask', 'embed_idx', 'cam_idx', 'pix_coords', 'rgb')]
@@ -115,6 +119,7 @@ SYMBOLS = {
     'hugs_adam_step': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P]),
     'hugs_adam_step_stats': (C.c_int, [_P, _P, _P, _P, _P, C.POINTER(AdamCfg), _P, _P, _P]),
     'hugs_make_ray_batch': (C.c_int, [C.POINTER(CameraSet), _P, _P, _P, _I, C.POINTER(RayBatch), _P]),
+    'hugs_render_frame': (C.c_int, [_P, _P, C.POINTER(CameraSet), _I, _I, _I, _I, _I, _F, _I, C.POINTER(FrameOut), _P]),
     'hugs_field_forward': (C.c_int, [_P, _P, C.POINTER(Rays), _P, _I, _I, _I, _I, _P, _P]),
     'hugs_field_backward': (C.c_int, [_P, _P, C.POINTER(Rays), _I, _I, _P, _P, _P]),
     'hugs_nf_sample_intervals': (C.c_int, [_P, _P, _P, _P, _I, _F, _F, _F, _I, _I, _I, _F, _F, _I, _P, _P, _P, _P, _P]),

@@ -505,6 +505,47 @@ HUGS_API int hugs_forward(hugs_handle* h, const float* params, const hugs_rays* 
                         (cudaStream_t)stream);
 }
 
+HUGS_API int hugs_render_frame(hugs_handle* h, const float* params, const hugs_camera_set* cams, int32_t cam, int32_t width,
+                               int32_t height, int32_t row0, int32_t row1, float train_frac, int32_t zero_glo,
+                               const hugs_frame_out* out, void* stream) {
+  HUGS_REQUIRE(h && params && cams && out && out->rgb, "hugs_render_frame: null argument (rgb is required)");
+  HUGS_REQUIRE(cams->pixtocams && cams->camtoworlds && cams->heights && cams->widths && cams->pixel_offset,
+               "camera set needs pixtocams, camtoworlds, heights, widths and pixel_offset");
+  HUGS_REQUIRE(cams->camtype == 0 || cams->camtype == 1, "camtype must be 0 (perspective) or 1 (fisheye), got %d", cams->camtype);
+  HUGS_REQUIRE(cam >= 0 && width >= 1 && height >= 1 && row0 >= 0 && row0 <= row1 && row1 <= height,
+               "hugs_render_frame: bad stripe rows [%d, %d) of a %d x %d image", row0, row1, width, height);
+  HUGS_REQUIRE(!out->sse || cams->images || cams->images_u8, "hugs_render_frame: sse requested but the camera set holds no images");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int L = h->d.num_levels, chunk = h->d.max_rays;
+  const long long n = (long long)(row1 - row0) * width;
+  if (n == 0) return HUGS_OK;
+  int rc;
+  if (!h->frame_ws && (rc = dev_alloc(h, &h->frame_ws, (size_t)chunk * 15))) return rc;
+  float* w = h->frame_ws;
+  hugs_ray_batch rb{};
+  rb.origins = w; rb.directions = w + (size_t)chunk * 3; rb.viewdirs = w + (size_t)chunk * 6;
+  rb.radii = w + (size_t)chunk * 9; rb.near = w + (size_t)chunk * 10; rb.far = w + (size_t)chunk * 11;
+  rb.lossmult = w + (size_t)chunk * 12; rb.static_mask = w + (size_t)chunk * 13;
+  rb.embed_idx = reinterpret_cast<int32_t*>(w + (size_t)chunk * 14);
+  hugs_rays rays{};
+  rays.origins = rb.origins; rays.directions = rb.directions; rays.viewdirs = rb.viewdirs; rays.radii = rb.radii;
+  rays.near = rb.near; rays.far = rb.far; rays.lossmult = rb.lossmult; rays.embed_idx = rb.embed_idx;
+  const int extras = (out->distance_mean || out->distance_median) ? 1 : 0;
+  std::vector<hugs_level_out> outs((size_t)L);
+  for (long long p0 = 0; p0 < n; p0 += chunk) {
+    const int m = (int)std::min<long long>(chunk, n - p0);
+    if ((rc = launch_frame_rays(*cams, cam, width, (long long)row0 * width + p0, m, rb, st))) return rc;
+    hugs_level_out& o = outs[(size_t)L - 1];
+    o = hugs_level_out{};
+    o.rgb = out->rgb + p0 * 3;
+    if (out->acc) o.acc = out->acc + p0;
+    if (out->distance_mean) o.distance_mean = out->distance_mean + p0;
+    if (out->distance_median) o.distance_median = out->distance_median + p0;
+    if ((rc = forward_levels(h, params, &rays, m, train_frac, nullptr, extras, zero_glo, outs.data(), false, st))) return rc;
+  }
+  return launch_frame_finish(out->rgb, n * 3, *cams, cam, (long long)row0 * width * 3, out->rgb_u8, out->sse, st);
+}
+
 HUGS_API int hugs_loss_and_grad(hugs_handle* h, const float* params, const hugs_rays* rays, const float* rgb_gt,
                                 int32_t n_rays, float train_frac, const float* jitter, const hugs_loss_cfg* loss,
                                 float* grad_out, float* stats_out, void* stream) {

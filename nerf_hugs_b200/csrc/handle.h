@@ -52,6 +52,7 @@ struct hugs_handle {
   float* ray_stats = nullptr;                 // [n, 4 + L]
   float* scalars = nullptr;                   // [64] device scalars (denominators, norms, ...)
   int64_t* tensor_ends = nullptr;             // [tensors.size()] end offset of every parameter tensor (per-tensor statistics)
+  float* frame_ws = nullptr;                  // hugs_render_frame: ray workspace [max_rays, 15] (allocated by its first call)
   std::vector<void*> allocs;
   hugs::TcState* tc = nullptr;
   // ---- optional CUDA-event profiling of kernel classes (hugs_profile_enable / hugs_profile_read) ----

@@ -53,6 +53,12 @@ struct CompositeArgs {
 };
 int launch_composite(const CompositeArgs& a, cudaStream_t stream);
 
+// raygen.cu: rays of pixels [pix0, pix0 + n) (row-major) of one camera; uint8 quantisation + squared error of a rendered stripe
+int launch_frame_rays(const hugs_camera_set& cams, int cam, int width, long long pix0, int n, const hugs_ray_batch& out,
+                      cudaStream_t st);
+int launch_frame_finish(const float* rgb, long long n_values, const hugs_camera_set& cams, int cam, long long value0,
+                        uint8_t* rgb_u8, double* sse, cudaStream_t st);
+
 struct LossBwdArgs {
   // final (NeRF) level
   const float* raw = nullptr;          // [n, S, 4] (raw_density, raw_r, raw_g, raw_b)

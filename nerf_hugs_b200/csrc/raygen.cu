@@ -24,12 +24,15 @@ struct RayGenArgs {
   const int32_t* cam_idx; const int32_t* pix_x; const int32_t* pix_y;
   int n;
   hugs_ray_batch out;
+  int frame_cam, frame_width; long long frame_pix0;   // cam_idx == nullptr: ray i is pixel frame_pix0 + i (row-major) of frame_cam
 };
 
 __global__ void __launch_bounds__(128) make_ray_batch_kernel(RayGenArgs a) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.n) return;
-  const int c = a.cam_idx[i], x = a.pix_x[i], y = a.pix_y[i];
+  int c, x, y;
+  if (a.cam_idx) { c = a.cam_idx[i]; x = a.pix_x[i]; y = a.pix_y[i]; }
+  else { const long long q = a.frame_pix0 + i; c = a.frame_cam; x = (int)(q % a.frame_width); y = (int)(q / a.frame_width); }
   const float* P = a.cams.pixtocams + (size_t)c * 9;
   const float* M = a.cams.camtoworlds + (size_t)c * 12;
   double p[9], m[12];
@@ -121,7 +124,58 @@ __global__ void __launch_bounds__(128) make_ray_batch_kernel(RayGenArgs a) {
   }
 }
 
+// utils.save_img_u8's quantisation and the squared error against the dataset image (eval.py:139-160)
+__global__ void __launch_bounds__(256) frame_finish_kernel(const float* rgb, long long n_values, hugs_camera_set cams, int cam,
+                                                           long long value0, uint8_t* rgb_u8, double* sse) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  float e0 = 0.f, e1 = 0.f;
+  if (i < n_values) {
+    float v = rgb[i];
+    if (rgb_u8) {
+      float q = v != v ? 0.f : v;                       // np.nan_to_num: nan -> 0, +-inf -> +-max float (then clipped)
+      q = fminf(fmaxf(q, 0.f), 1.f);
+      rgb_u8[i] = (uint8_t)(q * 255.f);
+    }
+    if (sse) {
+      const size_t g = (size_t)cams.pixel_offset[cam] * 3 + (size_t)(value0 + i);
+      const float gt = cams.images_u8 ? (float)cams.images_u8[g] / 255.f : __ldg(cams.images + g);
+      e0 = (v - gt) * (v - gt);
+      const float r = rintf(v * 255.f) / 255.f;         // np.round: half to even
+      e1 = (r - gt) * (r - gt);
+    }
+  }
+  if (sse) {
+    __shared__ float s0[8], s1[8];
+    e0 = warp_sum(e0); e1 = warp_sum(e1);
+    if ((threadIdx.x & 31) == 0) { s0[threadIdx.x >> 5] = e0; s1[threadIdx.x >> 5] = e1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double a0 = 0.0, a1 = 0.0;
+      for (int w = 0; w < 8; ++w) { a0 += (double)s0[w]; a1 += (double)s1[w]; }
+      atomicAdd(sse, a0); atomicAdd(sse + 1, a1);
+    }
+  }
+}
+
 }  // namespace
+
+int launch_frame_rays(const hugs_camera_set& cams, int cam, int width, long long pix0, int n, const hugs_ray_batch& out,
+                      cudaStream_t st) {
+  if (n <= 0) return HUGS_OK;
+  RayGenArgs a{cams, nullptr, nullptr, nullptr, n, out, cam, width, pix0};
+  make_ray_batch_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
+int launch_frame_finish(const float* rgb, long long n_values, const hugs_camera_set& cams, int cam, long long value0,
+                        uint8_t* rgb_u8, double* sse, cudaStream_t st) {
+  if (n_values <= 0 || (!rgb_u8 && !sse)) return HUGS_OK;
+  frame_finish_kernel<<<(unsigned)((n_values + 255) / 256), 256, 0, st>>>(rgb, n_values, cams, cam, value0, rgb_u8, sse);
+  HUGS_LAUNCH_CHECK();
+  return HUGS_OK;
+}
+
 }  // namespace hugs
 
 using namespace hugs;
@@ -137,7 +191,7 @@ HUGS_API int hugs_make_ray_batch(const hugs_camera_set* cams, const int32_t* cam
   HUGS_REQUIRE(!out->rgb || cams->images || cams->images_u8, "rgb requested but the camera set holds no images");
   HUGS_REQUIRE(cams->camtype == 0 || cams->camtype == 1, "camtype must be 0 (perspective) or 1 (fisheye), got %d", cams->camtype);
   if (n_rays == 0) return HUGS_OK;
-  RayGenArgs a{*cams, cam_idx, pix_x, pix_y, n_rays, *out};
+  RayGenArgs a{*cams, cam_idx, pix_x, pix_y, n_rays, *out, 0, 0, 0};
   make_ray_batch_kernel<<<(n_rays + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a);
   HUGS_LAUNCH_CHECK();
   return HUGS_OK;

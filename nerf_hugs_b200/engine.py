@@ -218,6 +218,30 @@ class Engine:
     self._keep = keep + [jit]
     return res, hist
 
+  def render_frame(self, params: torch.Tensor, camera_set: '_lib.CameraSet', cam: int, width: int, height: int,
+                   row0: int, row1: int, train_frac: float, zero_glo: bool = True, compute_extras: bool = True,
+                   want_u8: bool = False, want_sse: bool = False) -> Dict[str, torch.Tensor]:
+    """models.render_image for rows [row0, row1) of one camera of a device-resident dataset: ONE library call generates
+    the rays and renders every chunk into frame-sized tensors (hugs_render_frame)."""
+    dev, rows = self.device, row1 - row0
+    out = {'rgb': torch.empty(rows, width, 3, device=dev), 'acc': torch.empty(rows, width, device=dev)}
+    if compute_extras:
+      out['distance_mean'] = torch.empty(rows, width, device=dev)
+      out['distance_median'] = torch.empty(rows, width, device=dev)
+    if want_u8:
+      out['rgb_u8'] = torch.empty(rows, width, 3, device=dev, dtype=torch.uint8)
+    if want_sse:
+      out['sse'] = torch.zeros(2, device=dev, dtype=torch.float64)
+    if rows == 0:
+      return out
+    fo = _lib.FrameOut()
+    for k, v in out.items():
+      setattr(fo, k, v.data_ptr())
+    with torch.cuda.device(dev):
+      check(lib.hugs_render_frame(self._h, _ptr(params), C.byref(camera_set), int(cam), int(width), int(height), int(row0),
+                                  int(row1), float(train_frac), int(zero_glo), C.byref(fo), self._stream()))
+    return out
+
   def loss_and_grad(self, params, rays, rgb_gt, train_frac, jitter, loss_cfg: '_lib.LossCfg',
                     grad_out: Optional[torch.Tensor] = None, stats_out: Optional[torch.Tensor] = None):
     r, keep, n = self._rays(rays)

@@ -189,3 +189,45 @@ def render_image(render_fn: Callable, rays: utils.Rays, rng, config, verbose: bo
     for k in keys:
       rendering[k] = [r[ray_idx.to(r.device)] for r in rendering[k]]
   return rendering
+
+
+def render_frame(model: 'Model', variables, dataset, cam_idx: int, train_frac: float, config,
+                 compute_extras: bool = True, want_u8: bool = False, want_psnr: bool = False) -> Dict[str, Any]:
+  """The full-frame pipeline of eval.py:104-160 / render.py:164-187 for one camera of a device-resident dataset
+  (`datasets.DeviceDataset` or a `datasets.Dataset` over it): `generate_ray_batch` + `models.render_image`
+  (models.py:568-649) + the metric / quantisation steps, without the host loop.
+
+  Every rank renders its stripe of pixel rows with ONE library call (`hugs_render_frame`: on-device ray generation,
+  chunking, frame-sized outputs) and the stripes are all-gathered once per frame (the reference gathers per chunk,
+  train_utils.py:559).  Returns rgb [H, W, 3], acc [H, W], distance_mean / distance_median [H, W] (compute_extras) as
+  device tensors like `render_image`, plus `rgb_u8` (utils.save_img_u8's bytes) and `psnr` / `psnr_quantized`
+  (image.mse_to_psnr of the mean squared error against the dataset image; eval_quantize_metrics) on request.
+  """
+  import torch.distributed as dist
+  dd = getattr(dataset, 'device_dataset', dataset)
+  h, w = int(dd.heights_np[cam_idx]), int(dd.widths_np[cam_idx])
+  world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+  rank = dist.get_rank() if world > 1 else 0
+  rows = -(-h // world)
+  row0, row1 = min(rank * rows, h), min((rank + 1) * rows, h)
+  flat = variables if torch.is_tensor(variables) else model.flat_params(variables)
+  model._ensure_packed(flat)
+  out = model.engine.render_frame(flat, dd._cs, cam_idx, w, h, row0, row1, float(train_frac),
+                                  zero_glo=config.enable_render_zero_glo, compute_extras=compute_extras, want_u8=want_u8,
+                                  want_sse=want_psnr)
+  sse = out.pop('sse', None)
+  if world > 1:
+    for k in list(out.keys()):
+      v = out[k]
+      pad = torch.zeros((rows,) + tuple(v.shape[1:]), device=v.device, dtype=v.dtype)
+      pad[:v.shape[0]] = v
+      parts = [torch.empty_like(pad) for _ in range(world)]
+      dist.all_gather(parts, pad)
+      out[k] = torch.cat(parts)[:h]
+    if sse is not None:
+      dist.all_reduce(sse)
+  if sse is not None:
+    mse = (sse / float(3 * h * w)).cpu()
+    out['psnr'] = float(-10.0 / math.log(10.0) * math.log(max(float(mse[0]), 1e-300)))
+    out['psnr_quantized'] = float(-10.0 / math.log(10.0) * math.log(max(float(mse[1]), 1e-300)))
+  return out

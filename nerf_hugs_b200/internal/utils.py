@@ -61,3 +61,77 @@ def rank_slice(x, rank, world):
   assert n % world == 0, f'global batch {n} is not divisible by the number of ranks {world}'
   per = n // world
   return x[rank * per:(rank + 1) * per]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# image writers of eval.py:156-179 / render.py:175-187 (utils.py:152-163)
+# ------------------------------------------------------------------------------------------------------------------
+def _to_numpy(img):
+  import numpy as np
+  if torch.is_tensor(img):
+    img = img.detach().cpu().numpy()
+  return np.asarray(img)
+
+
+def save_img_u8(img, pth):
+  """utils.save_img_u8 (utils.py:152-157): an image in [0, 1] (or already-quantised uint8 bytes) as a uint8 PNG."""
+  import numpy as np
+  from PIL import Image
+  a = _to_numpy(img)
+  if a.dtype != np.uint8:
+    a = (np.clip(np.nan_to_num(a), 0., 1.) * 255.).astype(np.uint8)
+  with open(pth, 'wb') as f:
+    Image.fromarray(a).save(f, 'PNG')
+
+
+def save_img_f32(depthmap, pth):
+  """utils.save_img_f32 (utils.py:160-163): a float32 TIFF."""
+  import numpy as np
+  from PIL import Image
+  with open(pth, 'wb') as f:
+    Image.fromarray(np.nan_to_num(_to_numpy(depthmap)).astype(np.float32)).save(f, 'TIFF')
+
+
+class AsyncImageWriter:
+  """Writes rendered frames off the render loop: `submit_u8 / submit_f32` copy the device tensor into a pinned host buffer
+  on a side stream (the next frame renders meanwhile) and a worker thread encodes the PNG / TIFF.  `close()` drains."""
+
+  def __init__(self, num_workers: int = 2):
+    from concurrent.futures import ThreadPoolExecutor
+    self._pool = ThreadPoolExecutor(max_workers=num_workers)
+    self._futures = []
+    self._stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+
+  def _stage(self, img):
+    if not (torch.is_tensor(img) and img.is_cuda):
+      return img, None
+    host = torch.empty(img.shape, dtype=img.dtype, pin_memory=True)
+    self._stream.wait_stream(torch.cuda.current_stream(img.device))
+    with torch.cuda.stream(self._stream):
+      host.copy_(img, non_blocking=True)
+      ev = torch.cuda.Event()
+      ev.record(self._stream)
+    img.record_stream(self._stream)
+    return host, ev
+
+  def _submit(self, fn, img, pth):
+    host, ev = self._stage(img)
+
+    def job():
+      if ev is not None:
+        ev.synchronize()
+      fn(host, pth)
+      return pth
+    self._futures.append(self._pool.submit(job))
+
+  def submit_u8(self, img, pth):
+    self._submit(save_img_u8, img, pth)
+
+  def submit_f32(self, img, pth):
+    self._submit(save_img_f32, img, pth)
+
+  def close(self):
+    done = [f.result() for f in self._futures]
+    self._futures = []
+    self._pool.shutdown(wait=True)
+    return done

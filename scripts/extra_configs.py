@@ -159,6 +159,30 @@ def run_render(resolutions=((800, 800), (720, 1280), (1080, 1920), (1440, 2560),
           'outputs': sorted(k for k in out if not k.startswith('ray_'))})
 
 
+def run_render_frame(resolutions=((800, 800), (720, 1280), (1080, 1920), (1440, 2560), (2160, 3840))):
+  """Config 5 through the frame pipeline (models.render_frame -> hugs_render_frame): ray generation on the device INSIDE the timed
+  region, one library call per frame and rank, uint8 quantisation + squared error on the device, one all-gather per frame."""
+  import bench
+  config = configs.load_config([], bench.gin_bindings(4096), save_config=False)
+  dev = device()
+  model, state, _, _, _ = train_utils.setup_model(config, rng=0, max_rays=65536, device=dev)
+  rng = np.random.default_rng(0)
+  for h, w in resolutions:
+    p2c, c2w = sphere_cameras(rng, 1, np.array([[h, w]]))
+    img = rng.integers(0, 256, size=(h, w, 3), dtype=np.uint8)
+    dd = DeviceDataset(p2c, c2w, [h], [w], images=[img], near=0.2, far=1e6)
+    render = lambda: models.render_frame(model, state.params, dd, 0, 1.0, config, compute_extras=True, want_u8=True,
+                                         want_psnr=True)
+    render()                                                                # warm-up
+    ms, out = timed(render, 2, dev)
+    dt = ms * 1e-3
+    assert tuple(out['rgb'].shape) == (h, w, 3) and torch.isfinite(out['rgb']).all() and np.isfinite(out['psnr'])
+    emit({'config': f'BASELINE config 5: full-frame render {w}x{h} through hugs_render_frame (config A weights, compute_extras, '
+                    f'on-device ray generation, uint8 quantisation and PSNR; rows striped over the GPUs, one all-gather per frame)',
+          'metric': 'render rays/s', 'value': h * w / dt, 'frame_s': dt, 'n_gpus': WORLD, 'psnr': out['psnr'],
+          'outputs': sorted(out.keys())})
+
+
 if __name__ == '__main__':
   ap = argparse.ArgumentParser()
   ap.add_argument('what', nargs='*', default=['hugs', 'render'])
@@ -168,6 +192,8 @@ if __name__ == '__main__':
     run_hugs(a.steps)
   if 'render' in a.what:
     run_render()
+  if 'frame' in a.what:
+    run_render_frame()
   if 'b' in a.what:
     run_config_b(a.steps)
   if WORLD > 1:

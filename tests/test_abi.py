@@ -37,6 +37,8 @@ def test_struct_sizes_match_header():
   assert ctypes.sizeof(_lib.RayBatch) == 96
   assert ctypes.sizeof(_lib.NfRenderCfg) == 32
   assert ctypes.sizeof(_lib.TensorCopy) == 32
+  assert ctypes.sizeof(_lib.FrameOut) == 48
+  assert ctypes.sizeof(_lib.HashFieldDesc) == 64
 
 
 def test_create_validates_and_fails_loudly_without_gpu():

@@ -135,3 +135,21 @@ def test_load_dataset_dispatch_is_loud_for_disk_loaders():
   config = configs.load_config([], ["Config.dataset_loader = 'nope'"], save_config=False)
   with pytest.raises(KeyError):
     datasets.load_dataset('train', True, False, 4096, 16, 1, 16, '/tmp/x', config)
+
+
+def test_image_writers_round_trip(tmp_path):
+  # utils.save_img_u8 / save_img_f32 (utils.py:152-163) and the asynchronous writer on host arrays
+  import numpy as np
+  from PIL import Image
+  from nerf_hugs_b200.internal import utils
+  rng = np.random.default_rng(0)
+  img = rng.uniform(-0.2, 1.2, size=(7, 5, 3)).astype(np.float32)
+  img[0, 0, 0] = np.nan
+  depth = rng.uniform(0, 9, size=(7, 5)).astype(np.float32)
+  wr = utils.AsyncImageWriter(num_workers=1)
+  wr.submit_u8(img, str(tmp_path / 'a.png'))
+  wr.submit_f32(depth, str(tmp_path / 'd.tiff'))
+  assert sorted(os.path.basename(p) for p in wr.close()) == ['a.png', 'd.tiff']
+  want = (np.clip(np.nan_to_num(img), 0., 1.) * 255.).astype(np.uint8)
+  assert np.array_equal(np.array(Image.open(tmp_path / 'a.png')), want)
+  assert np.array_equal(np.array(Image.open(tmp_path / 'd.tiff')), depth)
