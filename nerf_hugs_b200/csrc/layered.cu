@@ -6,6 +6,7 @@
 // interleaves one dgrad GEMM and one weight-gradient launch (wgrad_kernel, wgrad_tc.cu) per layer, so only two dZ
 // buffers exist.  The PropMLP (width 256 in every gin) stays on the chain kernel.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "dense_tc.h"
@@ -35,6 +36,8 @@ struct LayeredMlp {
   WgItem* items_dev = nullptr;
   std::vector<WgItem> items_host;
   std::vector<std::pair<int, int>> launches;      // (first item, count) in backward order
+  std::vector<bool> launch_pairs;                 // the launch runs on CTA pairs (wgrad2_kernel)
+  bool wg_pairs = getenv("HUGS_WGRAD_PAIRS") ? atoi(getenv("HUGS_WGRAD_PAIRS")) != 0 : true;   // development switch
   int built_for = -1;
   float* dzv_ray = nullptr;
 };
@@ -360,12 +363,16 @@ void build_wgrad(hugs_handle* h, LayeredMlp* m, int level, int n_samples) {
   const MlpViews& mv = h->nerf;
   const int W = m->W, D = m->D, cap = m->cap;
   const int T = ((n_samples + 255) / 256) * 4;          // 64-sample stages (rows padded to the 256-row GEMM tiles)
-  m->items_host.clear(); m->launches.clear();
+  m->items_host.clear(); m->launches.clear(); m->launch_pairs.clear();
   // row distance of the lo half of every tensor the weight-gradient kernel reads (split-precision mode)
   const int lo_rows[LW_MAPS] = {m->act_slots * cap, tc->total_feat_rows, cap, cap, cap, cap, cap, cap, cap};
   auto flush = [&](std::vector<WgUnit>& units) {
+    // launches made of 256 x 256 kernel blocks only run on CTA pairs (wgrad2_kernel: half the L2 -> SM bytes per FLOP)
+    bool pairs = m->wg_pairs;
+    for (const WgUnit& u : units) pairs = pairs && u.w.n == 256 && u.w.flush_mode == 0;
+    m->launch_pairs.push_back(pairs);
     std::vector<WgItem> items;
-    wgrad_plan(units, T, tc->num_sms, &items);
+    wgrad_plan(units, T, pairs ? tc->num_sms / 2 : tc->num_sms, &items);
     const size_t first = m->items_host.size();
     // split-precision mode: (A_hi + A_lo)^T (dZ_hi + dZ_lo) as four items; the bias column sums ride on the A_hi items only
     for (const WgItem& base : items)
@@ -447,7 +454,11 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
   int launch = 0;
   auto wgrad = [&]() {
     ProfScope ps(h, HUGS_K_WGRAD_NERF, st);
+    const bool pairs = m->launch_pairs[launch];
     const auto& L = m->launches[launch++];
+    if (pairs)
+      return wgrad2_launch_raw(tc->num_sms, h->perm_nb, h->d.max_deg_point - h->d.min_deg_point, h->feat_dim, m->wg_maps, LW_MAPS,
+                               m->items_dev + L.first, L.second, grad, st);
     return wgrad_launch(h, m->wg_maps, LW_MAPS, m->items_dev + L.first, L.second, grad, st);
   };
   const int lo_act = m->act_slots * cap;

@@ -169,6 +169,9 @@ int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgIt
 // the same launch without a model handle (hash-grid fields): feature-permutation parameters passed explicitly
 int wgrad_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
                      const WgItem* dev_items, int n_items, float* grad, cudaStream_t st);
+// CTA-pair variant for launches whose items are all 256 x 256 kernel blocks (n == 256, flush_mode == 0): layered path
+int wgrad2_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
+                      const WgItem* dev_items, int n_items, float* grad, cudaStream_t st);
 int wgrad_kernel_init();
 // view-layer extras shared by the chain and the layered path: dW rows of the direction / GLO inputs, GLO embedding rows
 int wgrad_view_extras(hugs_handle* h, const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int dz_ld, int n_rays, int S,

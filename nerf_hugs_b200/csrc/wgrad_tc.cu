@@ -228,6 +228,197 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
   if (warp == 5) ptx::tmem_dealloc(tmem_base, 512);
 }
 
+// ---------------------------------------------------------------- CTA-pair weight-gradient kernel (wide layers)
+// The layer-at-a-time path (NerfMLP width 512 / 1024) cuts dW[W, W] into 256 x 256 blocks; with one CTA per item every
+// 64-sample stage moves 64 KB (A block + dZ block) from L2 for 1024 tensor-core cycles, and each operand block is read
+// W / 256 times: the kernel above is bound by L2 -> SM bandwidth there, not by HBM.  This variant runs an item on a CTA
+// *pair* (cluster of 2, tcgen05 cta_group::2, M = 256 over the pair): CTA r stages only A columns [128 r, 128 r + 128)
+// and dZ columns [128 r, 128 r + 128) of the item (32 KB per stage and CTA), so the L2 -> SM bytes per FLOP halve.
+// Two 256-column accumulators alternate between items: the flush of item i runs under the MMAs of item i + 1.
+// Items: n == 256, flush_mode == 0 only (the head items keep the one-CTA kernel).
+constexpr int kW2Stages = 6;
+constexpr int kW2StageBytes = 32768;      // A: 2 atoms of 64 samples x 64 columns (16 KB) | dZ: 2 atoms (16 KB)
+constexpr int kW2Threads = 192;
+constexpr int kW2Smem = 1024 + kW2Stages * kW2StageBytes + 512 + kWgScratchFloats * 4;
+
+__global__ void __launch_bounds__(kW2Threads, 1) wgrad2_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + kW2Stages * kW2StageBytes);
+  uint64_t* full = bars;                       // leader: both CTAs' TMA bytes of a stage have landed
+  uint64_t* empty = bars + kW2Stages;          // per CTA: the MMAs that read the stage have completed (multicast commit)
+  uint64_t* full2 = bars + 2 * kW2Stages;      // per CTA: `full` relayed by the issuer to the epilogue warps (bias items)
+  uint64_t* bias_done = bars + 3 * kW2Stages;  // per CTA: the epilogue warps have read the stage's dZ half (bias items)
+  uint64_t* acc_full = bars + 4 * kW2Stages;   // [2] per CTA (multicast commit)
+  uint64_t* acc_empty = acc_full + 2;          // [2] leader: both CTAs' epilogue threads have drained accumulator s
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* scratch = reinterpret_cast<float*>(base + kW2Stages * kW2StageBytes + 512);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  const uint32_t ring_u32 = ptx::smem_u32(base);
+  const uint32_t full_u32 = ptx::smem_u32(full), empty_u32 = ptx::smem_u32(empty), full2_u32 = ptx::smem_u32(full2);
+  const uint32_t biasdone_u32 = ptx::smem_u32(bias_done);
+  const uint32_t accfull_u32 = ptx::smem_u32(acc_full), accempty_u32 = ptx::smem_u32(acc_empty);
+  if (warp == 4 && lane == 0) {
+    for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.maps[i]);
+    for (int i = 0; i < kW2Stages; ++i) {
+      ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); ptx::mbar_init(&full2[i], 1); ptx::mbar_init(&bias_done[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 5) ptx::tmem_alloc_cg2(tmem_ptr, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 4) {
+    // =============================== TMA producer (both CTAs) ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t prev_bias = 0, bd_par = 0;    // bit s: the previous use of stage s was read by the epilogue warps / its parity
+      for (int it = pair; it < p.n_items; it += n_pairs) {
+        const WgItem w = p.items[it];
+        const CUtensorMap* amap = &p.maps[w.a_map];
+        const CUtensorMap* bmap = &p.maps[w.b_map];
+        for (int st = w.st0; st < w.st1; ++st) {
+          ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+          if ((prev_bias >> stage) & 1u) {
+            ptx::mbar_wait_u32(biasdone_u32 + stage * 8, (bd_par >> stage) & 1u);
+            bd_par ^= 1u << stage;
+          }
+          if (w.bias_mode != 0) prev_bias |= 1u << stage; else prev_bias &= ~(1u << stage);
+          if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * kW2StageBytes);
+          const uint32_t bar = ptx::mapa_u32(full_u32 + stage * 8, 0);
+          const uint32_t s = ring_u32 + stage * kW2StageBytes;
+          for (int a = 0; a < 2; ++a)
+            ptx::tma_load_2d_cg2(s + a * 8192, amap, bar, w.a_col0 + rank * 128 + a * 64, w.a_row0 + st * 64);
+          for (int a = 0; a < 2; ++a)
+            ptx::tma_load_2d_cg2(s + 16384 + a * 8192, bmap, bar, w.b_col0 + rank * 128 + a * 64, w.b_row0 + st * 64);
+          if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 5) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (lane == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0, ae_phase = 0;
+      const uint32_t idesc = ptx::make_idesc_bf16(256, 256, 1, 1);
+      int i = 0;
+      for (int it = pair; it < p.n_items; it += n_pairs, ++i) {
+        const WgItem w = p.items[it];
+        const int as = i & 1;
+        if (i >= 2) {
+          ptx::mbar_wait_u32(accempty_u32 + as * 8, (ae_phase >> as) & 1u);
+          ae_phase ^= 1u << as;
+          ptx::tc_fence_after();
+        }
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+        for (int st = w.st0; st < w.st1; ++st) {
+          ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+          ptx::tc_fence_after();
+          if (w.bias_mode != 0) {       // relay to the epilogue warps of both CTAs, which sum the dZ columns of the stage
+            ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(full2_u32 + stage * 8, 0));
+            ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(full2_u32 + stage * 8, 1));
+          }
+          const uint32_t s = ring_u32 + stage * kW2StageBytes;
+#pragma unroll
+          for (int k16 = 0; k16 < 4; ++k16) {
+            const uint64_t da = ptx::make_desc_sw128(s + k16 * 2048, 8192, 1024);
+            const uint64_t db = ptx::make_desc_sw128(s + 16384 + k16 * 2048, 8192, 1024);
+            ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, (st > w.st0 || k16 > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit_mc2_u32(empty_u32 + stage * 8);
+          if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit_mc2_u32(accfull_u32 + as * 8);
+      }
+    }
+  } else {
+    // =============================== epilogue warps (both CTAs) ===============================
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;           // TMEM lane = accumulator row of this CTA's half of M
+    const int t = warp * 32 + lane;                // 0..127
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    uint32_t af_phase = 0, f2_par = 0;
+    int stage = 0;
+    int i = 0;
+    for (int it = pair; it < p.n_items; it += n_pairs, ++i) {
+      const WgItem w = p.items[it];
+      const int as = i & 1;
+      const int nst = w.st1 - w.st0;
+      if (w.bias_mode != 0) {
+        // bias gradients = column sums of this CTA's 128 dZ columns: thread t owns the column pair 2 (t & 63), 2 (t & 63) + 1
+        // over the k half t >> 6 of every stage
+        float s0 = 0.f, s1 = 0.f;
+        const int cp = 2 * (t & 63), cc = cp & 63, atom = cp >> 6, k0 = (t >> 6) * 32;
+        for (int st = 0; st < nst; ++st) {
+          if (lane == 0) ptx::mbar_wait_u32(full2_u32 + stage * 8, (f2_par >> stage) & 1u);
+          f2_par ^= 1u << stage;
+          __syncwarp();
+          const uint8_t* bs = base + stage * kW2StageBytes + 16384 + atom * 8192 + (cc & 7) * 2;
+#pragma unroll 8
+          for (int k = k0; k < k0 + 32; ++k) {
+            const uint32_t pr = *reinterpret_cast<const uint32_t*>(bs + k * 128 + (((cc >> 3) ^ (k & 7)) << 4));
+            s0 += __uint_as_float(pr << 16);
+            s1 += __uint_as_float(pr & 0xFFFF0000u);
+          }
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&bias_done[stage]);
+          if (++stage == kW2Stages) stage = 0;
+        }
+        if (nst > 0) {
+          const int c = w.b_col0 + rank * 128 + cp;
+          atomicAdd(p.grad + w.boff + c, s0); atomicAdd(p.grad + w.boff + c + 1, s1);
+        }
+      } else {
+        stage = (stage + nst) % kW2Stages;
+      }
+      // ---- flush this CTA's 128 accumulator rows ----
+      ptx::mbar_wait_u32(accfull_u32 + as * 8, (af_phase >> as) & 1u);
+      af_phase ^= 1u << as;
+      ptx::tc_fence_after();
+      if (nst > 0) {
+        const int m = rank * 128 + row;
+        int krow;
+        if (w.feat_mode) {
+          const int fp = w.a_col0 + m;
+          krow = fp < p.feat_dim ? w.in_base + ref_feature_col(fp, p.nb, p.ndeg) : -1;
+        } else {
+          krow = (w.in_rows > 0 && m >= w.in_rows) ? -1 : w.in_base + m;
+        }
+        float* sc = scratch + warp * (32 * 33);
+#pragma unroll 1
+        for (int c = 0; c < 256; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld32(lane_addr + (uint32_t)(as * 256 + c), r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) sc[lane * 33 + j] = __uint_as_float(r[j]);
+          __syncwarp();
+          const bool col_ok = w.b_col0 + c + lane < w.out;
+#pragma unroll 4
+          for (int rr = 0; rr < 32; ++rr) {
+            const int kr = __shfl_sync(0xffffffffu, krow, rr);
+            if (kr >= 0 && col_ok)
+              atomicAdd(p.grad + w.koff + (long long)kr * w.out + w.b_col0 + c + lane, sc[rr * 33 + lane]);
+          }
+          __syncwarp();
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(accempty_u32 + as * 8, 0));
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 5) ptx::tmem_dealloc_cg2(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------- CUDA-core reductions (view layer extras)
 // dzv_ray[ray][c] = sum over the ray's samples of dZ_view[s][c]
 __global__ void __launch_bounds__(128) ray_sum_kernel(const __nv_bfloat16* dzv, const __nv_bfloat16* dzv_lo, int ld,
@@ -304,6 +495,7 @@ int wgrad_create(hugs_handle* h) {
   h->allocs.push_back(q);
   w->dzv_ray = static_cast<float*>(q);
   HUGS_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+  HUGS_CUDA(cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2Smem));
   return HUGS_OK;
 }
 
@@ -434,6 +626,32 @@ int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgIt
 
 int wgrad_kernel_init() {
   HUGS_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+  HUGS_CUDA(cudaFuncSetAttribute(wgrad2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kW2Smem));
+  return HUGS_OK;
+}
+
+// The CTA-pair kernel: every item must be a 256 x 256 kernel block (n == 256, flush_mode == 0).
+int wgrad2_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
+                      const WgItem* dev_items, int n_items, float* grad, cudaStream_t st) {
+  if (n_items <= 0) return HUGS_OK;
+  HUGS_REQUIRE(n_maps <= kWgMaxMaps, "wgrad: too many tensor maps");
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  for (int i = 0; i < n_maps; ++i) p.maps[i] = maps[i];
+  for (int i = n_maps; i < kWgMaxMaps; ++i) p.maps[i] = maps[0];
+  p.items = dev_items; p.n_items = n_items;
+  p.nb = perm_nb; p.ndeg = ndeg; p.feat_dim = feat_dim; p.grad = grad;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * std::min(n_items, num_sms / 2));
+  cfg.blockDim = dim3(kW2Threads);
+  cfg.dynamicSmemBytes = kW2Smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  HUGS_CUDA(cudaLaunchKernelEx(&cfg, wgrad2_kernel, p));
+  ++g_launch_count;
   return HUGS_OK;
 }
 
