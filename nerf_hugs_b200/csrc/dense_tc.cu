@@ -148,12 +148,47 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
     uint32_t af_phase = 0;
     int it = 0;
     float v[32];
+    // column sums (p.colsum): tile t = pair + it * n_pairs has N index t % n_tiles, which repeats with this period
+    int cs_period = 1;
+    { const int step = n_pairs % p.n_tiles; for (int x = step; x % p.n_tiles != 0; x += step) ++cs_period; }
+    float cs0[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cs1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int t = pair; t < n_tiles; t += n_pairs, ++it) {
       const int mt = t / p.n_tiles, nt = t % p.n_tiles;
       const int bn = p.tile_bn[nt], n0 = p.tile_n0[nt], epi = p.tile_epi[nt];
       const int as = it & 1;
       const int grow = mt * 256 + rank * 128 + row;     // row of the GEMM (sample index relative to the level)
       const bool valid = grow < p.m_rows;
+      // ReLU gates of a backward tile: the saved activation comes from HBM (microseconds under load) and does not depend on
+      // the accumulator, so all of this thread's gate words are fetched BEFORE the accumulator wait and kept as bit masks
+      // (bit j / 16 + j = low / high half of packed word j is non-zero); padding rows carry no gradient
+      uint32_t gate[4] = {0u, 0u, 0u, 0u};
+      if (epi == DE_BWD_RELU && valid && p.gate_in) {
+        // bit masks written by the forward pass: four words = this thread's 128 columns (bn == 256)
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(p.gate_in + ((size_t)p.gate_row0 + grow) * p.gate_ld +
+                                                             ((n0 + half * (bn / 2)) >> 5)));
+        gate[0] = q.x; gate[1] = q.y; gate[2] = q.z; gate[3] = q.w;
+      } else if (epi == DE_BWD_RELU && valid) {
+        const int cph = bn / 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i * 32 < cph) {
+            const uint4* src = reinterpret_cast<const uint4*>(p.mask_act + ((size_t)p.mask_row0 + grow) * p.mask_ld + n0 +
+                                                              half * cph + i * 32);
+            uint32_t pk[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              const uint4 q = __ldg(src + c);
+              pk[c * 4] = q.x; pk[c * 4 + 1] = q.y; pk[c * 4 + 2] = q.z; pk[c * 4 + 3] = q.w;
+            }
+            // to the column order of the bit-mask format: bit 2 j = low half of word j, bit 2 j + 1 = high half
+            const uint32_t gb = gate_bits16(pk);
+            uint32_t g = 0u;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g |= (((gb >> j) & 1u) << (2 * j)) | (((gb >> (16 + j)) & 1u) << (2 * j + 1));
+            gate[i] = g;
+          }
+        }
+      }
       ptx::mbar_wait_u32(accfull_u32 + as * 8, (af_phase >> as) & 1u);
       af_phase ^= 1u << as;
       ptx::tc_fence_after();
@@ -177,6 +212,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
       if (store_leader) ptx::tma_wait_group_read<0>();
       asm volatile("bar.sync 1, %0;" ::"n"(kDEpiWarps * 32) : "memory");
       const int cols_per_half = bn / 2;                 // 128 | 64
+      uint32_t gw[4] = {0u, 0u, 0u, 0u};                // ReLU gate words of this thread's columns (gate_out)
       for (int c0 = 0; c0 < cols_per_half; c0 += 32) {
         const int col = half * cols_per_half + c0;      // column inside the tile
         load_acc32(acc_addr + (uint32_t)col, v);
@@ -209,22 +245,21 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
               v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
             }
           }
-          // ReLU gate from the saved (post-ReLU, hence >= 0) bf16 activation; padding rows carry no gradient
-          uint4 mk[4];
-          if (valid) {
-            const uint4* src = reinterpret_cast<const uint4*>(p.mask_act + ((size_t)p.mask_row0 + grow) * p.mask_ld + n);
+          const uint32_t g = c0 == 0 ? gate[0] : (c0 == 32 ? gate[1] : (c0 == 64 ? gate[2] : gate[3]));
 #pragma unroll
-            for (int c = 0; c < 4; ++c) mk[c] = __ldg(src + c);
-          } else {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) mk[c] = make_uint4(0u, 0u, 0u, 0u);
-          }
-          apply_mask32(mk, v);
+          for (int k = 0; k < 32; ++k)
+            if (((g >> k) & 1u) == 0u) v[k] = 0.f;
         } else if (epi == DE_BWD_LINEAR) {
           if (!valid) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) v[c] = 0.f;
           }
+        }
+        if (p.gate_out && epi == DE_RELU) {
+          uint32_t g = 0u;
+#pragma unroll
+          for (int k = 0; k < 32; ++k) g |= (v[k] > 0.f ? 1u : 0u) << k;
+          if (c0 == 0) gw[0] = g; else if (c0 == 32) gw[1] = g; else if (c0 == 64) gw[2] = g; else gw[3] = g;
         }
         uint8_t* panel = stage_out + (col >> 6) * kPanelBytes;
         const int chunk0 = (col & 63) >> 3;
@@ -237,6 +272,9 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
         } else if (epi == DE_RELU || epi == DE_VIEW) store_half32<true>(panel, row, chunk0, v);
         else store_half32<false>(panel, row, chunk0, v);
       }
+      if (p.gate_out && epi == DE_RELU && valid && bn == 256)
+        *reinterpret_cast<uint4*>(p.gate_out + ((size_t)p.gate_row0 + grow) * p.gate_ld + ((n0 + half * 128) >> 5)) =
+            make_uint4(gw[0], gw[1], gw[2], gw[3]);
       // accumulator drained: the MMA issuer may reuse it (tile it + 2)
       ptx::tc_fence_before();
       __syncwarp();
@@ -253,8 +291,54 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
         }
         ptx::tma_commit_group();
       }
+      if (p.colsum) {
+        // (after the TMA store has been issued: both only read the panels)
+        // column sums of the staged tile: warp g reads rows g, g + 8, ... (16 x 16 bytes per thread: lane = 16-byte chunk of
+        // the 256-column row, conflict-free), 8 partial sums per thread stay in registers across the tiles of this pair
+        const int n_chunks = bn >> 3;                 // 16-byte chunks per row
+        if (lane < n_chunks) {
+          const uint8_t* pan = stage_out + (lane >> 3) * kPanelBytes;
+          const uint32_t chunk = (uint32_t)lane & 7u;
+          float a[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] = 0.f;
+          for (int part = 0; part < (p.split ? 2 : 1); ++part) {
+            const uint8_t* q = pan + part * kDOutPanels * kPanelBytes;
+#pragma unroll 4
+            for (int r = ew; r < 128; r += kDEpiWarps) {
+              const uint4 w = *reinterpret_cast<const uint4*>(q + r * 128 + (swz_chunk(r, chunk) << 4));
+              a[0] += __uint_as_float(w.x << 16); a[1] += __uint_as_float(w.x & 0xFFFF0000u);
+              a[2] += __uint_as_float(w.y << 16); a[3] += __uint_as_float(w.y & 0xFFFF0000u);
+              a[4] += __uint_as_float(w.z << 16); a[5] += __uint_as_float(w.z & 0xFFFF0000u);
+              a[6] += __uint_as_float(w.w << 16); a[7] += __uint_as_float(w.w & 0xFFFF0000u);
+            }
+          }
+          // a pair revisits the same N tile every cs_period tiles: one atomic per thread and column at the end of the kernel
+          if (cs_period == 1 || (cs_period == 2 && (it & 1) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs0[j] += a[j];
+          } else if (cs_period == 2) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cs1[j] += a[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) atomicAdd(p.colsum + n0 + lane * 8 + j, a[j]);
+          }
+        }
+      }
     }
     if (store_leader) ptx::tma_wait_group<0>();
+    if (p.colsum && cs_period <= 2) {
+      const int nt0 = pair % p.n_tiles, nt1 = (pair + n_pairs) % p.n_tiles;
+      if (pair < n_tiles && lane * 8 < p.tile_bn[nt0]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(p.colsum + p.tile_n0[nt0] + lane * 8 + j, cs0[j]);
+      }
+      if (cs_period == 2 && pair + n_pairs < n_tiles && lane * 8 < p.tile_bn[nt1]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(p.colsum + p.tile_n0[nt1] + lane * 8 + j, cs1[j]);
+      }
+    }
   }
   ptx::tc_fence_before();
   __syncthreads();

@@ -29,6 +29,7 @@ struct LayeredMlp {
   __nv_bfloat16 *act = nullptr, *bott = nullptr, *vact = nullptr;
   int act_slots = 0;
   __nv_bfloat16 *dz[2] = {nullptr, nullptr}, *dz_bott = nullptr, *dz_view = nullptr, *drgb = nullptr;
+  uint32_t* gate = nullptr;       // ReLU gate bit masks of the trunk activations, [D][cap][W / 32] (training)
   CUtensorMap map_act, map_bott, map_vact, map_dz[2], map_dzb, map_dzv;
   CUtensorMap wg_maps[LW_MAPS];
   bool train_ready = false;
@@ -243,6 +244,7 @@ int layered_ensure_training(hugs_handle* h, LayeredMlp* m) {
     if ((rc = lalloc(h, &m->dz[i], parts * m->cap * W))) return rc;
     if ((rc = make_map(&m->map_dz[i], m->dz[i], pc, W, 128))) return rc;
   }
+  if ((rc = lalloc(h, &m->gate, (size_t)D * m->cap * (W / 32)))) return rc;
   if ((rc = lalloc(h, &m->dz_bott, parts * m->cap * 256)) || (rc = lalloc(h, &m->dz_view, parts * m->cap * 128)) ||
       (rc = lalloc(h, &m->drgb, parts * m->cap * kHeadCols)) || (rc = lalloc(h, &m->items_dev, 4096 * 4)))
     return rc;
@@ -313,6 +315,7 @@ int layered_forward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, bool t
     for (int j = 0; j < p.n_tiles; ++j) { p.tile_n0[j] = j * 256; p.tile_bn[j] = 256; p.tile_epi[j] = DE_RELU; }
     p.bias = m->tab + m->bias_off[l];
     p.out_map = m->map_act; p.out_row0 = slot(l) * cap; p.out_col0 = 0; p.out_lo_row_off = lo_act;
+    if (training) { p.gate_out = m->gate; p.gate_ld = W / 32; p.gate_row0 = l * cap; }
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
     cat = (l % m->skip == 0 && l > 0);
   }
@@ -371,8 +374,10 @@ void build_wgrad(hugs_handle* h, LayeredMlp* m, int level, int n_samples) {
     bool pairs = m->wg_pairs;
     for (const WgUnit& u : units) pairs = pairs && u.w.n == 256 && u.w.flush_mode == 0;
     m->launch_pairs.push_back(pairs);
+    // ... whose bias gradients come from the dgrad GEMM that produces dZ (DenseParams::colsum); items count 128-sample stages
+    if (pairs) for (WgUnit& u : units) u.w.bias_mode = 0;
     std::vector<WgItem> items;
-    wgrad_plan(units, T, pairs ? tc->num_sms / 2 : tc->num_sms, &items);
+    wgrad_plan(units, pairs ? T / 2 : T, pairs ? tc->num_sms / 2 : tc->num_sms, &items);
     const size_t first = m->items_host.size();
     // split-precision mode: (A_hi + A_lo)^T (dZ_hi + dZ_lo) as four items; the bias column sums ride on the A_hi items only
     for (const WgItem& base : items)
@@ -456,9 +461,12 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
     ProfScope ps(h, HUGS_K_WGRAD_NERF, st);
     const bool pairs = m->launch_pairs[launch];
     const auto& L = m->launches[launch++];
-    if (pairs)
-      return wgrad2_launch_raw(tc->num_sms, h->perm_nb, h->d.max_deg_point - h->d.min_deg_point, h->feat_dim, m->wg_maps, LW_MAPS,
+    if (pairs) {
+      const CUtensorMap maps128[LW_MAPS] = {m->map_act, tc->map_feat, m->map_dz[0], m->map_dz[1], m->map_bott, m->map_vact,
+                                            m->map_dzb, m->map_dzv, m->wg_maps[LW_DH]};
+      return wgrad2_launch_raw(tc->num_sms, h->perm_nb, h->d.max_deg_point - h->d.min_deg_point, h->feat_dim, maps128, LW_MAPS,
                                m->items_dev + L.first, L.second, grad, st);
+    }
     return wgrad_launch(h, m->wg_maps, LW_MAPS, m->items_dev + L.first, L.second, grad, st);
   };
   const int lo_act = m->act_slots * cap;
@@ -490,6 +498,7 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
     p.b_row0 = m->row_b[D + 2]; p.n_tiles = 1;
     p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_BWD_LINEAR;
     p.out_map = m->map_dzb; p.out_lo_row_off = cap;
+    if (m->wg_pairs) p.colsum = grad + h->nerf.dense[D + 1].bias_off;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
   }
   if ((rc = wgrad())) return rc;
@@ -503,8 +512,10 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
     p.b_row0 = m->row_b[D + 1]; p.n_tiles = W / 256;
     for (int j = 0; j < p.n_tiles; ++j) { p.tile_n0[j] = j * 256; p.tile_bn[j] = 256; p.tile_epi[j] = DE_BWD_RELU; }
     p.mask_act = m->act; p.mask_ld = W; p.mask_row0 = (D - 1) * cap;
+    p.gate_in = m->gate; p.gate_ld = W / 32; p.gate_row0 = (D - 1) * cap;
     p.rank1_row = h->d_raw[level]; p.rank1_stride = 4; p.rank1_col = m->tab + m->w_dens_off;
     p.out_map = m->map_dz[cur]; p.out_lo_row_off = cap;
+    if (m->wg_pairs) p.colsum = grad + h->nerf.dense[D - 1].bias_off;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
   }
   for (int l = D - 1; l >= 0; --l) {
@@ -518,7 +529,9 @@ int layered_backward(hugs_handle* h, LayeredMlp* m, int level, int n_rays, float
     p.b_row0 = m->row_b[l]; p.n_tiles = W / 256;
     for (int j = 0; j < p.n_tiles; ++j) { p.tile_n0[j] = j * 256; p.tile_bn[j] = 256; p.tile_epi[j] = DE_BWD_RELU; }
     p.mask_act = m->act; p.mask_ld = W; p.mask_row0 = (l - 1) * cap;
+    p.gate_in = m->gate; p.gate_ld = W / 32; p.gate_row0 = (l - 1) * cap;
     p.out_map = m->map_dz[cur ^ 1]; p.out_lo_row_off = cap;
+    if (m->wg_pairs) p.colsum = grad + h->nerf.dense[l - 1].bias_off;
     if ((rc = dense_tc_launch(p, tc->num_sms, st))) return rc;
     cur ^= 1;
   }

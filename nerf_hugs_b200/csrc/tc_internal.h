@@ -169,7 +169,8 @@ int wgrad_launch(hugs_handle* h, const CUtensorMap* maps, int n_maps, const WgIt
 // the same launch without a model handle (hash-grid fields): feature-permutation parameters passed explicitly
 int wgrad_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
                      const WgItem* dev_items, int n_items, float* grad, cudaStream_t st);
-// CTA-pair variant for launches whose items are all 256 x 256 kernel blocks (n == 256, flush_mode == 0): layered path
+// CTA-pair variant for launches whose items are all 256 x 256 kernel blocks (n == 256, flush_mode == 0, no bias sums;
+// tensor maps with 128-row boxes, st0 / st1 in 128-sample stages): layered path
 int wgrad2_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
                       const WgItem* dev_items, int n_items, float* grad, cudaStream_t st);
 int wgrad_kernel_init();

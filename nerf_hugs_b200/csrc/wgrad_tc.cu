@@ -19,6 +19,7 @@
 // Reference semantics: jax.value_and_grad of train_utils.py:407-455 restricted to the Dense layers of
 // models.py:449-519.
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include "ptx.cuh"
@@ -229,17 +230,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
 }
 
 // ---------------------------------------------------------------- CTA-pair weight-gradient kernel (wide layers)
-// The layer-at-a-time path (NerfMLP width 512 / 1024) cuts dW[W, W] into 256 x 256 blocks; with one CTA per item every
-// 64-sample stage moves 64 KB (A block + dZ block) from L2 for 1024 tensor-core cycles, and each operand block is read
-// W / 256 times: the kernel above is bound by L2 -> SM bandwidth there, not by HBM.  This variant runs an item on a CTA
-// *pair* (cluster of 2, tcgen05 cta_group::2, M = 256 over the pair): CTA r stages only A columns [128 r, 128 r + 128)
-// and dZ columns [128 r, 128 r + 128) of the item (32 KB per stage and CTA), so the L2 -> SM bytes per FLOP halve.
-// Two 256-column accumulators alternate between items: the flush of item i runs under the MMAs of item i + 1.
-// Items: n == 256, flush_mode == 0 only (the head items keep the one-CTA kernel).
-constexpr int kW2Stages = 6;
-constexpr int kW2StageBytes = 32768;      // A: 2 atoms of 64 samples x 64 columns (16 KB) | dZ: 2 atoms (16 KB)
-constexpr int kW2Threads = 192;
+// The layer-at-a-time path (NerfMLP width 512 / 1024) cuts dW[W, W] into 256 x 256 blocks.  This variant runs an item on a
+// CTA *pair* (cluster of 2, tcgen05 cta_group::2, M = 256 over the pair): CTA r stages A columns [128 r, 128 r + 128) and dZ
+// columns [128 r, 128 r + 128) of the item.  Measured on B200 (profiles/r02_wgrad_pairs.md): at 64-sample stages the two
+// single threads that drive the ring (one barrier wait per stage each, ~400 cycles under load) cannot keep up with 512
+// tensor-core cycles per stage, so a stage is 128 samples (four 16 KB TMA boxes per CTA issued by four lanes, eight MMAs =
+// 1024 cycles per barrier round trip), and the flush of item i runs under the MMAs of item i + 1 (two 256-column
+// accumulators).  Bias gradients (column sums of dZ) are NOT computed here - any reader of the dZ stages next to the ring
+// slowed the kernel down by 1.5 - 2 x - but in the epilogue of the dgrad GEMM that produces dZ (DenseParams::colsum).
+// Items: n == 256, flush_mode == 0, bias_mode == 0; st0 / st1 count 128-sample stages.
+constexpr int kW2Stages = 3;
+constexpr int kW2StageBytes = 65536;      // A: 2 atoms of 128 samples x 64 columns (32 KB) | dZ: 2 atoms (32 KB)
+constexpr int kW2Threads = 192;           // warps 0-3 accumulator flush, 4 TMA producer, 5 MMA issuer
 constexpr int kW2Smem = 1024 + kW2Stages * kW2StageBytes + 512 + kWgScratchFloats * 4;
+static_assert(kW2Smem <= 232448, "shared memory budget");
 
 __global__ void __launch_bounds__(kW2Threads, 1) wgrad2_kernel(const __grid_constant__ WgParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -247,24 +251,19 @@ __global__ void __launch_bounds__(kW2Threads, 1) wgrad2_kernel(const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + kW2Stages * kW2StageBytes);
   uint64_t* full = bars;                       // leader: both CTAs' TMA bytes of a stage have landed
   uint64_t* empty = bars + kW2Stages;          // per CTA: the MMAs that read the stage have completed (multicast commit)
-  uint64_t* full2 = bars + 2 * kW2Stages;      // per CTA: `full` relayed by the issuer to the epilogue warps (bias items)
-  uint64_t* bias_done = bars + 3 * kW2Stages;  // per CTA: the epilogue warps have read the stage's dZ half (bias items)
-  uint64_t* acc_full = bars + 4 * kW2Stages;   // [2] per CTA (multicast commit)
-  uint64_t* acc_empty = acc_full + 2;          // [2] leader: both CTAs' epilogue threads have drained accumulator s
+  uint64_t* acc_full = bars + 2 * kW2Stages;   // [2] per CTA (multicast commit)
+  uint64_t* acc_empty = acc_full + 2;          // [2] leader: both CTAs' flush threads have drained accumulator s
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_empty + 2);
   float* scratch = reinterpret_cast<float*>(base + kW2Stages * kW2StageBytes + 512);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
   const uint32_t ring_u32 = ptx::smem_u32(base);
-  const uint32_t full_u32 = ptx::smem_u32(full), empty_u32 = ptx::smem_u32(empty), full2_u32 = ptx::smem_u32(full2);
-  const uint32_t biasdone_u32 = ptx::smem_u32(bias_done);
+  const uint32_t full_u32 = ptx::smem_u32(full), empty_u32 = ptx::smem_u32(empty);
   const uint32_t accfull_u32 = ptx::smem_u32(acc_full), accempty_u32 = ptx::smem_u32(acc_empty);
   if (warp == 4 && lane == 0) {
     for (int i = 0; i < 4; ++i) ptx::prefetch_tmap(&p.maps[i]);
-    for (int i = 0; i < kW2Stages; ++i) {
-      ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); ptx::mbar_init(&full2[i], 1); ptx::mbar_init(&bias_done[i], 4);
-    }
+    for (int i = 0; i < kW2Stages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 256); }
     ptx::fence_mbar_init();
   }
@@ -276,30 +275,24 @@ __global__ void __launch_bounds__(kW2Threads, 1) wgrad2_kernel(const __grid_cons
   const uint32_t tmem_base = *tmem_ptr;
 
   if (warp == 4) {
-    // =============================== TMA producer (both CTAs) ===============================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      uint32_t prev_bias = 0, bd_par = 0;    // bit s: the previous use of stage s was read by the epilogue warps / its parity
-      for (int it = pair; it < p.n_items; it += n_pairs) {
-        const WgItem w = p.items[it];
-        const CUtensorMap* amap = &p.maps[w.a_map];
-        const CUtensorMap* bmap = &p.maps[w.b_map];
-        for (int st = w.st0; st < w.st1; ++st) {
+    // =============================== TMA producer (both CTAs): lane 0 waits, lanes 0..3 issue one box each ==============
+    int stage = 0; uint32_t phase = 0;
+    const uint32_t bar0 = ptx::mapa_u32(full_u32, 0);
+    for (int it = pair; it < p.n_items; it += n_pairs) {
+      const WgItem w = p.items[it];
+      // lane 0, 1: A atoms; lane 2, 3: dZ atoms
+      const CUtensorMap* map = &p.maps[lane < 2 ? w.a_map : w.b_map];
+      const int col = (lane < 2 ? w.a_col0 : w.b_col0) + rank * 128 + (lane & 1) * 64;
+      const int row0 = lane < 2 ? w.a_row0 : w.b_row0;
+      for (int st = w.st0; st < w.st1; ++st) {
+        if (lane == 0) {
           ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-          if ((prev_bias >> stage) & 1u) {
-            ptx::mbar_wait_u32(biasdone_u32 + stage * 8, (bd_par >> stage) & 1u);
-            bd_par ^= 1u << stage;
-          }
-          if (w.bias_mode != 0) prev_bias |= 1u << stage; else prev_bias &= ~(1u << stage);
           if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * kW2StageBytes);
-          const uint32_t bar = ptx::mapa_u32(full_u32 + stage * 8, 0);
-          const uint32_t s = ring_u32 + stage * kW2StageBytes;
-          for (int a = 0; a < 2; ++a)
-            ptx::tma_load_2d_cg2(s + a * 8192, amap, bar, w.a_col0 + rank * 128 + a * 64, w.a_row0 + st * 64);
-          for (int a = 0; a < 2; ++a)
-            ptx::tma_load_2d_cg2(s + 16384 + a * 8192, bmap, bar, w.b_col0 + rank * 128 + a * 64, w.b_row0 + st * 64);
-          if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (lane < 4)
+          ptx::tma_load_2d_cg2(ring_u32 + stage * kW2StageBytes + lane * 16384, map, bar0 + stage * 8, col, row0 + st * 128);
+        if (++stage == kW2Stages) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 5) {
@@ -320,15 +313,12 @@ __global__ void __launch_bounds__(kW2Threads, 1) wgrad2_kernel(const __grid_cons
         for (int st = w.st0; st < w.st1; ++st) {
           ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
           ptx::tc_fence_after();
-          if (w.bias_mode != 0) {       // relay to the epilogue warps of both CTAs, which sum the dZ columns of the stage
-            ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(full2_u32 + stage * 8, 0));
-            ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(full2_u32 + stage * 8, 1));
-          }
           const uint32_t s = ring_u32 + stage * kW2StageBytes;
 #pragma unroll
-          for (int k16 = 0; k16 < 4; ++k16) {
-            const uint64_t da = ptx::make_desc_sw128(s + k16 * 2048, 8192, 1024);
-            const uint64_t db = ptx::make_desc_sw128(s + 16384 + k16 * 2048, 8192, 1024);
+          for (int k16 = 0; k16 < 8; ++k16) {
+            // MN-major operands: 16 samples = 2048 bytes along K, 64-column atoms 16 KB apart, 8-row groups 1 KB apart
+            const uint64_t da = ptx::make_desc_sw128(s + k16 * 2048, 16384, 1024);
+            const uint64_t db = ptx::make_desc_sw128(s + 32768 + k16 * 2048, 16384, 1024);
             ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, (st > w.st0 || k16 > 0) ? 1u : 0u);
           }
           ptx::mma_commit_mc2_u32(empty_u32 + stage * 8);
@@ -338,46 +328,16 @@ __global__ void __launch_bounds__(kW2Threads, 1) wgrad2_kernel(const __grid_cons
       }
     }
   } else {
-    // =============================== epilogue warps (both CTAs) ===============================
+    // =============================== flush warps 0..3 (both CTAs) ===============================
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;           // TMEM lane = accumulator row of this CTA's half of M
-    const int t = warp * 32 + lane;                // 0..127
     const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    uint32_t af_phase = 0, f2_par = 0;
-    int stage = 0;
+    uint32_t af_phase = 0;
     int i = 0;
     for (int it = pair; it < p.n_items; it += n_pairs, ++i) {
       const WgItem w = p.items[it];
       const int as = i & 1;
       const int nst = w.st1 - w.st0;
-      if (w.bias_mode != 0) {
-        // bias gradients = column sums of this CTA's 128 dZ columns: thread t owns the column pair 2 (t & 63), 2 (t & 63) + 1
-        // over the k half t >> 6 of every stage
-        float s0 = 0.f, s1 = 0.f;
-        const int cp = 2 * (t & 63), cc = cp & 63, atom = cp >> 6, k0 = (t >> 6) * 32;
-        for (int st = 0; st < nst; ++st) {
-          if (lane == 0) ptx::mbar_wait_u32(full2_u32 + stage * 8, (f2_par >> stage) & 1u);
-          f2_par ^= 1u << stage;
-          __syncwarp();
-          const uint8_t* bs = base + stage * kW2StageBytes + 16384 + atom * 8192 + (cc & 7) * 2;
-#pragma unroll 8
-          for (int k = k0; k < k0 + 32; ++k) {
-            const uint32_t pr = *reinterpret_cast<const uint32_t*>(bs + k * 128 + (((cc >> 3) ^ (k & 7)) << 4));
-            s0 += __uint_as_float(pr << 16);
-            s1 += __uint_as_float(pr & 0xFFFF0000u);
-          }
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(&bias_done[stage]);
-          if (++stage == kW2Stages) stage = 0;
-        }
-        if (nst > 0) {
-          const int c = w.b_col0 + rank * 128 + cp;
-          atomicAdd(p.grad + w.boff + c, s0); atomicAdd(p.grad + w.boff + c + 1, s1);
-        }
-      } else {
-        stage = (stage + nst) % kW2Stages;
-      }
-      // ---- flush this CTA's 128 accumulator rows ----
       ptx::mbar_wait_u32(accfull_u32 + as * 8, (af_phase >> as) & 1u);
       af_phase ^= 1u << as;
       ptx::tc_fence_after();
@@ -390,6 +350,8 @@ __global__ void __launch_bounds__(kW2Threads, 1) wgrad2_kernel(const __grid_cons
         } else {
           krow = (w.in_rows > 0 && m >= w.in_rows) ? -1 : w.in_base + m;
         }
+        // thread = accumulator row, but the gradient rows are `out` floats apart: transpose each 32 x 32 block through
+        // shared memory so that one warp instruction adds 32 consecutive floats of one row
         float* sc = scratch + warp * (32 * 33);
 #pragma unroll 1
         for (int c = 0; c < 256; c += 32) {
@@ -630,7 +592,8 @@ int wgrad_kernel_init() {
   return HUGS_OK;
 }
 
-// The CTA-pair kernel: every item must be a 256 x 256 kernel block (n == 256, flush_mode == 0).
+// The CTA-pair kernel: every item must be a 256 x 256 kernel block (n == 256, flush_mode == 0, bias_mode == 0); `maps` have
+// boxes of 128 rows and the items count 128-sample stages.
 int wgrad2_launch_raw(int num_sms, int perm_nb, int ndeg, int feat_dim, const CUtensorMap* maps, int n_maps,
                       const WgItem* dev_items, int n_items, float* grad, cudaStream_t st) {
   if (n_items <= 0) return HUGS_OK;
