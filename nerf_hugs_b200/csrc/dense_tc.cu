@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
             for (int c = 0; c < 32; ++c) v[c] = 0.f;
           }
         }
-        if (p.gate_out && epi == DE_RELU) {
+        if (p.gate_out && (epi == DE_RELU || epi == DE_VIEW)) {
           uint32_t g = 0u;
 #pragma unroll
           for (int k = 0; k < 32; ++k) g |= (v[k] > 0.f ? 1u : 0u) << k;
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
         } else if (epi == DE_RELU || epi == DE_VIEW) store_half32<true>(panel, row, chunk0, v);
         else store_half32<false>(panel, row, chunk0, v);
       }
-      if (p.gate_out && epi == DE_RELU && valid && bn == 256)
+      if (p.gate_out && (epi == DE_RELU || epi == DE_VIEW) && valid && bn == 256)
         *reinterpret_cast<uint4*>(p.gate_out + ((size_t)p.gate_row0 + grow) * p.gate_ld + ((n0 + half * 128) >> 5)) =
             make_uint4(gw[0], gw[1], gw[2], gw[3]);
       // accumulator drained: the MMA issuer may reuse it (tile it + 2)

@@ -44,7 +44,7 @@ struct alignas(64) DenseParams {
   // whose dZ this GEMM produces (column sums of dZ), taken from the staged panels before they are stored; nullptr: off
   float* colsum;
   // ReLU gate bit masks, [rows][gate_ld] 32-bit words, bit k of word j = column 32 j + k is open (output > 0):
-  // gate_out != nullptr: a DE_RELU launch with 256-column tiles also writes them (training forward);
+  // gate_out != nullptr: a DE_RELU / DE_VIEW launch with 256-column tiles also writes them (training forward);
   // gate_in  != nullptr: a DE_BWD_RELU launch reads them instead of the saved activation (16 instead of 256 bytes per thread and
   //                      tile half: the kernel is bound by the shared-memory / L1 data pipe)
   uint32_t* gate_out; const uint32_t* gate_in; int gate_ld, gate_row0;

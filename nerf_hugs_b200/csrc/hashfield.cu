@@ -18,6 +18,7 @@
 // weights in shared memory, nothing but the raw density leaves the SM.  The 256-wide main field runs its five Dense layers
 // on the tcgen05 GEMM kernel of dense_tc.cu (bf16 x bf16 -> fp32 in TMEM) and its weight gradients on wgrad_kernel.
 #include <algorithm>
+#include <cstdlib>
 #include <new>
 #include <string>
 #include <vector>
@@ -440,7 +441,8 @@ __global__ void ray_bias_kernel(const float* inp, int in_dim, const float* W, in
 __global__ void __launch_bounds__(256) field_bwd_start_kernel(const float* d_raw, const __nv_bfloat16* hact, const float* w_rgb,
                                                               const uint8_t* inside, int n_samples, int n_rows_pad,
                                                               __nv_bfloat16* dz, __nv_bfloat16* dh, float* d_dens,
-                                                              __nv_bfloat16* dz_lo, __nv_bfloat16* dh_lo) {
+                                                              __nv_bfloat16* dz_lo, __nv_bfloat16* dh_lo,
+                                                              const uint32_t* gate /* [rows][8] bit masks of hact, or nullptr */) {
   __shared__ float wsm[kH * 3];
   for (int i = threadIdx.x; i < kH * 3; i += blockDim.x) wsm[i] = w_rgb[i];
   __syncthreads();
@@ -463,9 +465,19 @@ __global__ void __launch_bounds__(256) field_bwd_start_kernel(const float* d_raw
   if (!split) {
     d0 = __bfloat162float(__float2bfloat16(d0)); d1 = __bfloat162float(__float2bfloat16(d1)); d2 = __bfloat162float(__float2bfloat16(d2));
   }
-  uint4 hv = make_uint4(0u, 0u, 0u, 0u);
-  if (s < n_samples) hv = __ldg(reinterpret_cast<const uint4*>(hact + (size_t)s * kH) + lane);
-  const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+  // ReLU gates of this lane's 8 columns: bit masks written by the forward GEMM (32 bytes per sample), else the saved
+  // activation itself (512 bytes per sample); gb bit 2 j / 2 j + 1 = column lane * 8 + 2 j / + 1 is open
+  uint32_t gb = 0u;
+  if (s < n_samples) {
+    if (gate) {
+      gb = (__ldg(gate + (size_t)s * (kH / 32) + (lane >> 2)) >> ((lane & 3) * 8)) & 0xFFu;
+    } else {
+      const uint4 hv = __ldg(reinterpret_cast<const uint4*>(hact + (size_t)s * kH) + lane);
+      const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) gb |= ((hw[j] & 0xFFFFu) ? 1u : 0u) << (2 * j) | ((hw[j] >> 16) ? 1u : 0u) << (2 * j + 1);
+    }
+  }
   uint32_t o[4], ol[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -473,8 +485,8 @@ __global__ void __launch_bounds__(256) field_bwd_start_kernel(const float* d_raw
     float g0 = d0 * wsm[c0 * 3] + d1 * wsm[c0 * 3 + 1] + d2 * wsm[c0 * 3 + 2];
     float g1 = d0 * wsm[c0 * 3 + 3] + d1 * wsm[c0 * 3 + 4] + d2 * wsm[c0 * 3 + 5];
     // the saved activation is post-ReLU (>= 0): a non-zero bf16 pattern (of the hi half) means the gate is open
-    if (!(hw[j] & 0xFFFFu)) g0 = 0.f;
-    if (!(hw[j] >> 16)) g1 = 0.f;
+    if (!((gb >> (2 * j)) & 1u)) g0 = 0.f;
+    if (!((gb >> (2 * j + 1)) & 1u)) g1 = 0.f;
     o[j] = ptx::pack_bf16x2(g0, g1);
     ol[j] = ptx::pack_bf16x2(g0 - __uint_as_float(o[j] << 16), g1 - __uint_as_float(o[j] & 0xFFFF0000u));
   }
@@ -618,6 +630,8 @@ struct hugs_hashfield {
   CUtensorMap map128[HF_MAPS], map64[HF_MAPS];
   float *ray_in = nullptr, *ray_bias = nullptr, *dzsum = nullptr, *d_dens = nullptr;
   uint8_t* inside = nullptr;
+  uint32_t* gate = nullptr;          // ReLU gate bit masks of ACT0 | H0, [2][cap][8] 32-bit words (training)
+  bool use_gate = getenv("HUGS_NF_GATE") ? atoi(getenv("HUGS_NF_GATE")) != 0 : true;   // development switch
   bool train_ready = false;
   WgItem* items_dev = nullptr; std::vector<WgItem> items_host; std::vector<std::pair<int, int>> launches; int built_for = -1;
   int max_rays = 0;
@@ -688,6 +702,7 @@ int hf_ensure_training(hugs_hashfield* h) {
         (rc = make_map(&h->map64[i], h->buf[i], h->cap * h->parts, h->buf_cols[i], 64)))
       return rc;
   }
+  if ((rc = hf_alloc(h, &h->gate, (size_t)2 * h->cap * (kH / 32)))) return rc;
   if ((rc = hf_alloc(h, &h->dzsum, (size_t)h->max_rays * kH)) || (rc = hf_alloc(h, &h->d_dens, (size_t)h->cap)) ||
       (rc = hf_alloc(h, &h->items_dev, kMaxWgItems)))
     return rc;
@@ -978,6 +993,7 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
   dense_a(&p, h, HF_FEAT, 1, h->rows_f);
   p.b_row0 = h->rf_base0; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_RELU;
   p.bias = h->tab; p.out_map = h->map128[HF_ACT0];
+  if (training && h->use_gate) { p.gate_out = h->gate; p.gate_ld = kH / 32; p.gate_row0 = 0; }
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   // 4. heads of the base MLP: geometry features (linear, bf16) + raw density (fp32 column 0 of raw)
   dense_common(&p, h, M);
@@ -993,6 +1009,7 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
   dense_a(&p, h, HF_GEO, 1, h->rows_f);
   p.b_row0 = h->rf_head0; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_VIEW;
   p.viewbias = h->ray_bias; p.view_ld = kH; p.S = n_samples; p.out_map = h->map128[HF_H0];
+  if (training && h->use_gate) { p.gate_out = h->gate; p.gate_ld = kH / 32; p.gate_row0 = h->cap; }
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   // 6. colour MLP layer 1
   dense_common(&p, h, M);
@@ -1047,7 +1064,8 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   field_bwd_start_kernel<<<(rows_pad + 7) / 8, 256, 0, st>>>(d_raw, h->buf[HF_H1], h->tab + 928, h->inside, M, rows_pad, h->buf[HF_DZH1],
                                                   h->buf[HF_DH], h->d_dens,
                                                   h->split ? h->buf[HF_DZH1] + (size_t)h->cap * kH : nullptr,
-                                                  h->split ? h->buf[HF_DH] + (size_t)h->cap * kHeadCols : nullptr);
+                                                  h->split ? h->buf[HF_DH] + (size_t)h->cap * kHeadCols : nullptr,
+                                                  nullptr);   // gate bits of H1 measured no faster here (the write in the forward GEMM costs 0.1 ms)
   HUGS_LAUNCH_CHECK();
   if ((rc = wgrad())) return rc;
   DenseParams p;
@@ -1056,6 +1074,7 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   dense_a(&p, h, HF_DZH1, 4, h->rows_b);
   p.b_map = h->map_wn128; p.b_row0 = h->rb_head1; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_BWD_RELU;
   p.mask_act = h->buf[HF_H0]; p.mask_ld = kH; p.mask_row0 = 0; p.out_map = h->map128[HF_DZH0];
+  if (h->use_gate) { p.gate_in = h->gate; p.gate_ld = kH / 32; p.gate_row0 = h->cap; }
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   if ((rc = wgrad())) return rc;
   // per-ray inputs of head0: SH / appearance rows of its kernel and the appearance embedding rows
@@ -1083,6 +1102,7 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
   dense_a(&p, h, HF_DGEO, 1, h->rows_b);
   p.b_map = h->map_wn128; p.b_row0 = h->rb_geo; p.n_tiles = 1; p.tile_n0[0] = 0; p.tile_bn[0] = 256; p.tile_epi[0] = DE_BWD_RELU;
   p.mask_act = h->buf[HF_ACT0]; p.mask_ld = kH; p.mask_row0 = 0;
+  if (h->use_gate) { p.gate_in = h->gate; p.gate_ld = kH / 32; p.gate_row0 = 0; }
   p.rank1_row = h->d_dens; p.rank1_stride = 1; p.rank1_col = h->tab + 672; p.out_map = h->map128[HF_DZA0];
   if ((rc = dense_tc_launch(p, h->num_sms, st))) return rc;
   if ((rc = wgrad())) return rc;
