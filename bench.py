@@ -332,14 +332,17 @@ def run_ours(args):
     # the weight-gradient GEMMs stream every saved activation / dZ / feature row exactly once (unique bytes).
     wg_bytes_nerf = n_nerf * ((8 + 2) * 512 * 2 + 1024 + 128)
     wg_bytes_prop = n_prop * (4 * 512 * 2 + 1024 + 128)
+    wide = wn != 256    # layer-at-a-time path (dense_tc.cu / layered.cu) instead of the chain kernel
     lines = [
-        tensor_line('chain_fwd_nerf', 'mlp_pp_kernel<train, cta_pair> NerfMLP forward chain (tcgen05 cta_group::2)',
+        tensor_line('chain_fwd_nerf', 'dense_tc_kernel NerfMLP forward GEMMs, one launch per layer (tcgen05 cta_group::2)' if wide
+                    else 'mlp_pp_kernel<train, cta_pair> NerfMLP forward chain (tcgen05 cta_group::2)',
                     n_nerf * FLOPS_NERF_SAMPLE),
-        tensor_line('chain_bwd_nerf', 'mlp_pp_kernel<train, cta_pair> NerfMLP dgrad chain',
+        tensor_line('chain_bwd_nerf', 'dense_tc_kernel NerfMLP dgrad GEMMs (+ bias column sums)' if wide
+                    else 'mlp_pp_kernel<train, cta_pair> NerfMLP dgrad chain',
                     n_nerf * 2 * (7 * wn * wn + wn * 256 + 256 * 128)),
         (hbm_line('wgrad_nerf', 'wgrad_kernel NerfMLP weight gradients (tcgen05, MN-major operands)', wg_bytes_nerf)
-         if wn == 256 else tensor_line('wgrad_nerf', 'wgrad_kernel NerfMLP weight gradients, one launch per layer',
-                                       n_nerf * FLOPS_NERF_SAMPLE)),
+         if not wide else tensor_line('wgrad_nerf', 'wgrad2_kernel NerfMLP weight gradients on CTA pairs, one launch per layer '
+                                      '(wgrad_kernel with HUGS_WGRAD_PAIRS=0)', n_nerf * FLOPS_NERF_SAMPLE)),
         tensor_line('chain_fwd_prop', 'mlp_pp_kernel<train, cta_pair> PropMLP forward chain', n_prop * FLOPS_PROP_SAMPLE),
         hbm_line('wgrad_prop', 'wgrad_kernel PropMLP weight gradients', wg_bytes_prop),
     ]
@@ -356,7 +359,8 @@ def run_ours(args):
     dom = max(lines, key=lambda l: l['ms_per_launch'])
     dram, dram_src = ncu_dram_bytes()
     for l in lines:
-      l['traffic'] = dram.get(l['class']) if per_gpu == 4096 else None
+      # the ncu capture is of config A (chain kernels, 4096 rays): other configs carry no measured traffic
+      l['traffic'] = dram.get(l['class']) if (per_gpu == 4096 and not wide and LEVELS == 2) else None
     roofline = dict(dom)
     roofline['traffic_source'] = dram_src
     roofline['dominant_by'] = 'largest CUDA-event time per step among the kernel classes'

@@ -191,6 +191,13 @@ def render_image(render_fn: Callable, rays: utils.Rays, rng, config, verbose: bo
   return rendering
 
 
+def frame_stripe(height: int, rank: int, world: int):
+  """Pixel rows [row0, row1) of rank `rank`: equal stripes of ceil(height / world) rows (the last ranks may get fewer or none),
+  so that the all-gathered, zero-padded stripes concatenate to the frame.  Returns (rows per stripe, row0, row1)."""
+  rows = -(-height // world)
+  return rows, min(rank * rows, height), min((rank + 1) * rows, height)
+
+
 def render_frame(model: 'Model', variables, dataset, cam_idx: int, train_frac: float, config,
                  compute_extras: bool = True, want_u8: bool = False, want_psnr: bool = False) -> Dict[str, Any]:
   """The full-frame pipeline of eval.py:104-160 / render.py:164-187 for one camera of a device-resident dataset
@@ -208,8 +215,7 @@ def render_frame(model: 'Model', variables, dataset, cam_idx: int, train_frac: f
   h, w = int(dd.heights_np[cam_idx]), int(dd.widths_np[cam_idx])
   world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
   rank = dist.get_rank() if world > 1 else 0
-  rows = -(-h // world)
-  row0, row1 = min(rank * rows, h), min((rank + 1) * rows, h)
+  rows, row0, row1 = frame_stripe(h, rank, world)
   flat = variables if torch.is_tensor(variables) else model.flat_params(variables)
   model._ensure_packed(flat)
   out = model.engine.render_frame(flat, dd._cs, cam_idx, w, h, row0, row1, float(train_frac),

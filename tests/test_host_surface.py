@@ -153,3 +153,17 @@ def test_image_writers_round_trip(tmp_path):
   want = (np.clip(np.nan_to_num(img), 0., 1.) * 255.).astype(np.uint8)
   assert np.array_equal(np.array(Image.open(tmp_path / 'a.png')), want)
   assert np.array_equal(np.array(Image.open(tmp_path / 'd.tiff')), depth)
+
+
+def test_frame_stripes_cover_the_frame_once():
+  # models.render_frame: every rank renders one stripe of rows; the gathered, padded stripes concatenate to the frame
+  from nerf_hugs_b200.internal import models
+  for h in (1, 7, 8, 9, 800, 1080, 2160):
+    for world in (1, 2, 3, 8):
+      covered = []
+      for rank in range(world):
+        rows, r0, r1 = models.frame_stripe(h, rank, world)
+        assert 0 <= r0 <= r1 <= h and r1 - r0 <= rows and r0 == min(rank * rows, h)
+        covered += list(range(r0, r1))
+      assert covered == list(range(h))
+      assert rows * world >= h
