@@ -212,6 +212,10 @@ def render_frame(model: 'Model', variables, dataset, cam_idx: int, train_frac: f
   """
   import torch.distributed as dist
   dd = getattr(dataset, 'device_dataset', dataset)
+  if not 0 <= int(cam_idx) < dd.n_cams:
+    raise IndexError(f'render_frame: camera {cam_idx} outside [0, {dd.n_cams})')
+  if want_psnr and dd.images is None and dd.images_u8 is None:
+    raise ValueError('render_frame: want_psnr needs a dataset with images')
   h, w = int(dd.heights_np[cam_idx]), int(dd.widths_np[cam_idx])
   world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
   rank = dist.get_rank() if world > 1 else 0
