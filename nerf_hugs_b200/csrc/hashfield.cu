@@ -262,6 +262,19 @@ struct PropArgs {
   float* mlp_grad;
 };
 
+// two independent fp32 FMAs in one instruction (sm_100 FFMA2): the fused proposal-network kernels are bound by instruction
+// issue, and every lane is an exact fp32 fma, so results do not change
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
+}
+
 constexpr int kPropAcc = (kMaxIn * kPropHidden + 127) / 128;
 __host__ __device__ inline int prop_ldf(int in) { return in | 1; }     // odd row stride: conflict-free staging
 inline size_t prop_smem_bytes(int in, bool backward) {
@@ -308,55 +321,77 @@ __global__ void __launch_bounds__(128) prop_field_kernel(PropArgs a) {
       inside = sample_unit_pos(a.r, a.g, s, x);
       encode_sample<kCap / 2>(a.g, a.grid, x, f);
     }
-    float h[kPropHidden];
+    float2 h2[kPropHidden / 2];         // hidden pre-activations, columns (2 jj, 2 jj + 1)
 #pragma unroll
-    for (int j = 0; j < kPropHidden; ++j) h[j] = b1[j];
+    for (int jj = 0; jj < kPropHidden / 2; ++jj) h2[jj] = *reinterpret_cast<const float2*>(b1 + 2 * jj);
 #pragma unroll
     for (int i = 0; i < kCap; ++i) {
       if (kIn == 0 && i >= in) break;
-      const float fi = f[i];
+      const float2 fi = make_float2(f[i], f[i]);
 #pragma unroll
-      for (int j = 0; j < kPropHidden; ++j) h[j] = fmaf(fi, W1[i * kPropHidden + j], h[j]);
+      for (int jj = 0; jj < kPropHidden / 2; ++jj)
+        h2[jj] = ffma2(fi, *reinterpret_cast<const float2*>(W1 + i * kPropHidden + 2 * jj), h2[jj]);
     }
+#define HUGS_H(j) (((j) & 1) ? h2[(j) >> 1].y : h2[(j) >> 1].x)
     if (!kBackward) {
       float o = b2[0];
 #pragma unroll
-      for (int j = 0; j < kPropHidden; ++j) o = fmaf(fmaxf(h[j], 0.f), w2[j], o);
+      for (int j = 0; j < kPropHidden; ++j) o = fmaf(fmaxf(HUGS_H(j), 0.f), w2[j], o);
       if (live) a.raw[s] = inside ? o : -INFINITY;      // density * selector (nerfacto.py:985-989)
       continue;
     }
     // ---- backward: dZ = d_raw * w2 * [h > 0]; the selector zeroes the density gradient of out-of-range samples ----
     const float dr = (live && inside) ? a.d_raw[s] : 0.f;
-    float df[kCap];
+    float2 df2[kCap];                   // feature gradients: partial sums over the even / odd hidden columns
 #pragma unroll
-    for (int i = 0; i < kCap; ++i) df[i] = 0.f;
+    for (int i = 0; i < kCap; ++i) df2[i] = make_float2(0.f, 0.f);
     __syncthreads();                    // the previous chunk's staging has been consumed
 #pragma unroll
     for (int i = 0; i < kCap; ++i) { if (kIn == 0 && i >= in) break; stF[threadIdx.x * ldf + i] = f[i]; }
 #pragma unroll
-    for (int j = 0; j < kPropHidden; ++j) {
-      const float hj = h[j];
-      const float dz = hj > 0.f ? dr * w2[j] : 0.f;
-      stZ[threadIdx.x * 65 + j] = dz;
-      // dw2[j] += sum over the warp's samples of d_raw * relu(h_j): butterfly sum, kept by lane j % 32
-      const float hs = warp_sum(dr * fmaxf(hj, 0.f));
-      if (lane_id == (j & 31)) { if (j < 32) acc_w2a += hs; else acc_w2b += hs; }
+    for (int jj = 0; jj < kPropHidden / 2; ++jj) {
+      float2 dz2;
 #pragma unroll
-      for (int i = 0; i < kCap; ++i) { if (kIn == 0 && i >= in) break; df[i] = fmaf(W1[i * kPropHidden + j], dz, df[i]); }
+      for (int e = 0; e < 2; ++e) {
+        const int j = 2 * jj + e;
+        const float hj = HUGS_H(j);
+        const float dz = hj > 0.f ? dr * w2[j] : 0.f;
+        stZ[threadIdx.x * 65 + j] = dz;
+        if (e == 0) dz2.x = dz; else dz2.y = dz;
+        // dw2[j] += sum over the warp's samples of d_raw * relu(h_j): butterfly sum, kept by lane j % 32
+        const float hs = warp_sum(dr * fmaxf(hj, 0.f));
+        if (lane_id == (j & 31)) { if (j < 32) acc_w2a += hs; else acc_w2b += hs; }
+      }
+#pragma unroll
+      for (int i = 0; i < kCap; ++i) {
+        if (kIn == 0 && i >= in) break;
+        df2[i] = ffma2(*reinterpret_cast<const float2*>(W1 + i * kPropHidden + 2 * jj), dz2, df2[i]);
+      }
     }
+    float df[kCap];
+#pragma unroll
+    for (int i = 0; i < kCap; ++i) df[i] = df2[i].x + df2[i].y;
+#undef HUGS_H
     __syncthreads();
     scatter_sample<kCap / 2>(a.g, a.grid_grad, x, df, dr != 0.f);
     // dW1[i][j] += sum_t f[t][i] * dZ[t][j]: output o = i * 64 + j (a warp: one i, 32 consecutive j)
+    // o = threadIdx.x + 128 q  =>  j = threadIdx.x % 64 for every q and i = threadIdx.x / 64 + 2 q: one dZ value per sample
+    // serves all of this thread's outputs (the feature values are warp-wide broadcasts)
+    {
+      static_assert(kPropHidden == 64, "output mapping of the weight-gradient loop");
+      const int j = threadIdx.x & 63, i0 = threadIdx.x >> 6;
+      float sacc[kAcc];
 #pragma unroll
-    for (int q = 0; q < kAcc; ++q) {
-      const int o = threadIdx.x + 128 * q;
-      if (o < n_out) {
-        const int i = o / kPropHidden, j = o % kPropHidden;
-        float sacc = 0.f;
-#pragma unroll 8
-        for (int t = 0; t < 128; ++t) sacc = fmaf(stF[t * ldf + i], stZ[t * 65 + j], sacc);
-        acc_w[q] += sacc;
+      for (int q = 0; q < kAcc; ++q) sacc[q] = 0.f;
+#pragma unroll 4
+      for (int t = 0; t < 128; ++t) {
+        const float z = stZ[t * 65 + j];
+#pragma unroll
+        for (int q = 0; q < kAcc; ++q)
+          if (i0 + 2 * q < in) sacc[q] = fmaf(stF[t * ldf + i0 + 2 * q], z, sacc[q]);
       }
+#pragma unroll
+      for (int q = 0; q < kAcc; ++q) acc_w[q] += sacc[q];
     }
     if (threadIdx.x < kPropHidden) {   // db1[j] = sum_t dZ[t][j]
       float sacc = 0.f;
