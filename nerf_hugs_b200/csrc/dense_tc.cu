@@ -304,13 +304,23 @@ __global__ void __launch_bounds__(kDThreads, 1) dense_tc_kernel(const __grid_con
           for (int j = 0; j < 8; ++j) a[j] = 0.f;
           for (int part = 0; part < (p.split ? 2 : 1); ++part) {
             const uint8_t* q = pan + part * kDOutPanels * kPanelBytes;
-#pragma unroll 4
-            for (int r = ew; r < 128; r += kDEpiWarps) {
-              const uint4 w = *reinterpret_cast<const uint4*>(q + r * 128 + (swz_chunk(r, chunk) << 4));
-              a[0] += __uint_as_float(w.x << 16); a[1] += __uint_as_float(w.x & 0xFFFF0000u);
-              a[2] += __uint_as_float(w.y << 16); a[3] += __uint_as_float(w.y & 0xFFFF0000u);
-              a[4] += __uint_as_float(w.z << 16); a[5] += __uint_as_float(w.z & 0xFFFF0000u);
-              a[6] += __uint_as_float(w.w << 16); a[7] += __uint_as_float(w.w & 0xFFFF0000u);
+            // the loads of a batch are issued back to back: a shared-memory load waits hundreds of cycles behind the tensor
+            // core's operand reads, so the latency is paid once per batch, not once per row
+#pragma unroll
+            for (int batch = 0; batch < 2; ++batch) {
+              uint4 w[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const int r = ew + (batch * 8 + k) * kDEpiWarps;
+                w[k] = *reinterpret_cast<const uint4*>(q + r * 128 + (swz_chunk(r, chunk) << 4));
+              }
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                a[0] += __uint_as_float(w[k].x << 16); a[1] += __uint_as_float(w[k].x & 0xFFFF0000u);
+                a[2] += __uint_as_float(w[k].y << 16); a[3] += __uint_as_float(w[k].y & 0xFFFF0000u);
+                a[4] += __uint_as_float(w[k].z << 16); a[5] += __uint_as_float(w[k].z & 0xFFFF0000u);
+                a[6] += __uint_as_float(w[k].w << 16); a[7] += __uint_as_float(w[k].w & 0xFFFF0000u);
+              }
             }
           }
           // a pair revisits the same N tile every cs_period tiles: one atomic per thread and column at the end of the kernel
