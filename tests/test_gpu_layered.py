@@ -52,7 +52,7 @@ def test_forward_wide_one_level_per_sample_outputs():
   eng.close()
 
 
-@pytest.mark.parametrize('width,glo', [(512, 0), (1024, 4)])
+@pytest.mark.parametrize('width,glo', [(512, 0), (768, 0), (1024, 4)])   # 768: three N tiles, the per-tile atomics path of the column sums
 def test_training_wide_nerf_mlp(width, glo):
   """loss + gradients of the wide NerfMLP (and of the 256-wide PropMLP on the chain kernel next to it) against the
   bf16-training oracle; the same tolerances as the chain path's two-level test."""
