@@ -82,29 +82,52 @@ __device__ __forceinline__ __nv_bfloat16 lpack_part(float v, int part) {
   return part == 0 ? hi : __float2bfloat16(v - __bfloat162float(hi));
 }
 
+// Forward pack Wt[r][k] = W[in(k)][n(r)]: a transpose of the flax kernels.  32 x 32 tiles through shared memory: the reads run
+// along the output unit n (contiguous in the [in, out] kernel), the writes along k.
+__global__ void __launch_bounds__(256) layered_pack_wt_kernel(LPackArgs a) {
+  __shared__ float tile[32][33];
+  const int kt = blockIdx.x * 32, rt = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const long long nf = (long long)a.rows_f * a.kmax;
+  {
+    const int r = rt + tx;
+    int li = -1;
+    for (int l = 0; l < a.n; ++l)
+      if (r >= a.e[l].row0 && r < a.e[l].row0 + a.e[l].rows) { li = l; break; }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = kt + ty + 8 * j;
+      float v = 0.f;
+      if (li >= 0 && k < a.kmax) {
+        const LPackEntry& L = a.e[li];
+        const int n = r - L.row0;
+        if (n < L.out) {
+          int in = -1;
+          if (k < L.x_in) in = k;
+          else if (L.feat_in > 0 && k < L.x_in + kFeatPad) {
+            const int fp = k - L.x_in;
+            if (fp < a.feat_dim) in = L.x_in + ref_feature_col(fp, a.nb, a.ndeg);
+          }
+          if (in >= 0) v = a.params[L.koff + (long long)in * L.out_stride + n];
+        }
+      }
+      tile[ty + 8 * j][tx] = v;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int r = rt + ty + 8 * j, k = kt + tx;
+    if (r < a.rows_f && k < a.kmax) a.wt[(long long)r * a.kmax + k + a.part * nf] = lpack_part(tile[tx][ty + 8 * j], a.part);
+  }
+}
+
+// backward pack Wn (the kernels' own [in, out] layout) and the fp32 tables
 __global__ void layered_pack_kernel(LPackArgs a) {
   const long long nf = (long long)a.rows_f * a.kmax, nbk = (long long)a.rows_b * a.W;
   const long long total = a.part == 0 ? nf + nbk + a.tab_floats : nf + nbk;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    if (i < nf) {
-      const int r = (int)(i / a.kmax), k = (int)(i % a.kmax);
-      float v = 0.f;
-      for (int l = 0; l < a.n; ++l) {
-        const LPackEntry& L = a.e[l];
-        if (r < L.row0 || r >= L.row0 + L.rows) continue;
-        const int n = r - L.row0;
-        if (n >= L.out) break;
-        int in = -1;
-        if (k < L.x_in) in = k;
-        else if (L.feat_in > 0 && k < L.x_in + kFeatPad) {
-          const int fp = k - L.x_in;
-          if (fp < a.feat_dim) in = L.x_in + ref_feature_col(fp, a.nb, a.ndeg);
-        }
-        if (in >= 0) v = a.params[L.koff + (long long)in * L.out_stride + n];
-        break;
-      }
-      a.wt[i + a.part * nf] = lpack_part(v, a.part);
-    } else if (i < nf + nbk) {
+  for (long long i = nf + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    if (i < nf + nbk) {
       const long long q = i - nf;
       const int r = (int)(q / a.W), c = (int)(q % a.W);
       float v = 0.f;
@@ -223,6 +246,8 @@ int layered_pack(hugs_handle* h, LayeredMlp* m, const float* params, cudaStream_
   a.exact_heads = m->split ? 1 : 0;
   for (int part = 0; part < m->parts; ++part) {
     a.part = part;
+    layered_pack_wt_kernel<<<dim3((m->kmax + 31) / 32, (m->rows_f + 31) / 32), 256, 0, st>>>(a);
+    HUGS_LAUNCH_CHECK();
     layered_pack_kernel<<<1024, 256, 0, st>>>(a);
     HUGS_LAUNCH_CHECK();
   }
