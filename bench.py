@@ -356,6 +356,13 @@ def run_ours(args):
                 hbm_line('composite_loss', 'composite_kernel + final_loss_bwd_kernel + prop_loss_bwd_kernel + reductions',
                          comp_bytes)]
     lines = [l for l in lines if l['ms_per_launch']]
+    # the weight gradients of the 256-wide path are HBM-bound by construction; the same launch on the tensor lens
+    # (SURVEY §8d FLOPs of the layers it differentiates) is reported next to it
+    for l in lines:
+      if l['class'] in ('wgrad_nerf', 'wgrad_prop') and l['bound'] == 'hbm':
+        fl = (n_nerf * FLOPS_NERF_SAMPLE) if l['class'] == 'wgrad_nerf' else (n_prop * FLOPS_PROP_SAMPLE)
+        l['tensor_lens'] = {'achieved': fl / (l['ms_per_launch'] * 1e-3) / 1e12, 'unit': 'TFLOP/s',
+                            'frac': fl / (l['ms_per_launch'] * 1e-3) / 1e12 / peaks['bf16_sustained']}
     dom = max(lines, key=lambda l: l['ms_per_launch'])
     dram, dram_src = ncu_dram_bytes()
     for l in lines:
