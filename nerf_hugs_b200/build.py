@@ -24,6 +24,7 @@ SOURCES = [
     ('wgrad_tc.cu', []),
     ('dense_tc.cu', []),
     ('layered.cu', []),
+    ('field_chain.cu', []),
     ('hashfield.cu', []),
     ('optim.cu', []),
     ('raygen.cu', []),

@@ -1,0 +1,291 @@
+// Forward chain kernel of the nerfacto field (nerfacto.py:838-875): all five Dense layers of a 256-sample tile on one CTA pair
+// without the activations leaving the SMs between layers.
+//
+//   features [M, 64] --W_base0--> act0 (256, ReLU) --W_geo | w_density--> geo (64, linear) , raw density
+//                    geo --W_head0 + per-ray bias--> h0 (256, ReLU) --W_head1--> h1 (256, ReLU) --W_rgb--> raw rgb
+//
+// The layer-at-a-time path (five dense_tc_kernel launches) is bound by HBM: every layer writes its output and the next launch
+// reads it back (3.7 KB per sample).  Here a link's epilogue leaves the bf16 output in shared memory as the swizzled K-major
+// panels the next link's MMAs read (the layout a TMA load would have produced), so only the hash features are read (128 B per
+// sample) and - in training - the activations the backward pass needs are written once by TMA store (1.8 KB per sample, with 32 B
+// of ReLU gate bits per gated layer).  Structure per CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256 = 128 rows per CTA):
+//
+//   shared memory  X[2][4 panels]  activation ping-pong: link l reads X[l & 1], writes X[(l + 1) & 1]      128 KB
+//                  F[2]            hash-feature panel of the current / next tile (TMA)                        32 KB
+//                  ring[3]         weight stages, <= 128 rows x 64 K per CTA (TMA, half of the N rows each)   48 KB
+//   tensor memory  two 256-column accumulators, alternating per (link, N tile)
+//   warps          0 TMA producer, 1 MMA issuer (leader CTA), 2..9 epilogue
+//
+// One tile is in flight per pair and its links run back to back (the tensor core idles during a link's epilogue): the field is
+// 248 kFLOP per sample against 1.9 KB of mandatory HBM traffic, so the chain only has to keep the HBM queue full.
+// bf16 mode only (the split-precision mode keeps the layer-at-a-time path: its hi + lo panels do not fit).
+#include <algorithm>
+
+#include "tc_device.cuh"
+#include "field_chain.h"
+
+namespace hugs {
+namespace {
+
+constexpr int kFcStages = 3;
+constexpr int kFcStageBytes = 16384;
+constexpr int kFcEpiWarps = 8;
+constexpr int kFcThreads = (2 + kFcEpiWarps) * 32;
+constexpr int kFcSmem = 1024 + 8 * kPanelBytes + 2 * kPanelBytes + kFcStages * kFcStageBytes + 512;
+static_assert(kFcSmem <= 232448, "shared memory budget");
+
+__global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid_constant__ FieldChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* xbuf = base;                                   // X[2][4 panels]
+  uint8_t* fbuf = base + 8 * kPanelBytes;                 // F[2]
+  uint8_t* ring = fbuf + 2 * kPanelBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kFcStages * kFcStageBytes);
+  uint64_t* full = bars;                    // [3] leader: both CTAs' weight bytes of a stage have landed
+  uint64_t* empty = bars + 3;               // [3] per CTA: the MMAs that read the stage have completed
+  uint64_t* f_full = bars + 6;              // [2] leader: both CTAs' feature panels of tile parity q have landed
+  uint64_t* f_free = bars + 8;              // [2] per CTA: link 0's MMAs have read F[q]
+  uint64_t* a_ready = bars + 10;            // [1] leader: both CTAs' epilogues have staged the link's output panels
+  uint64_t* acc_full = bars + 11;           // [2] per CTA
+  uint64_t* acc_empty = bars + 13;          // [2] leader
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)ptx::cluster_ctarank();
+  const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  const uint32_t x_u32 = ptx::smem_u32(xbuf), f_u32 = ptx::smem_u32(fbuf), ring_u32 = ptx::smem_u32(ring);
+  const uint32_t full_u32 = ptx::smem_u32(full), empty_u32 = ptx::smem_u32(empty);
+  const uint32_t ffull_u32 = ptx::smem_u32(f_full), ffree_u32 = ptx::smem_u32(f_free);
+  const uint32_t aready_u32 = ptx::smem_u32(a_ready);
+  const uint32_t accfull_u32 = ptx::smem_u32(acc_full), accempty_u32 = ptx::smem_u32(acc_empty);
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&p.a_map); ptx::prefetch_tmap(&p.b_map); ptx::prefetch_tmap(&p.b_map_64); ptx::prefetch_tmap(&p.b_map_8);
+    for (int i = 0; i < kFcStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&f_full[i], 1); ptx::mbar_init(&f_free[i], 1);
+      ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * kFcEpiWarps);
+    }
+    ptx::mbar_init(a_ready, 2);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) ptx::tmem_alloc_cg2(tmem_ptr, 512);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      uint32_t ff_phase = 0;     // bit q: parity of the next f_free phase of feature buffer q
+      auto load_features = [&](int t, int it) {
+        const int q = it & 1;
+        if (it >= 2) { ptx::mbar_wait_u32(ffree_u32 + q * 8, (ff_phase >> q) & 1u); ff_phase ^= 1u << q; }
+        if (rank == 0) ptx::mbar_expect_tx_u32(ffull_u32 + q * 8, 2 * kPanelBytes);
+        ptx::tma_load_2d_cg2(f_u32 + q * kPanelBytes, &p.a_map, ptx::mapa_u32(ffull_u32 + q * 8, 0), 0, t * 256 + rank * 128);
+      };
+      int it = 0;
+      if (pair < p.m_tiles) load_features(pair, 0);
+      for (int t = pair; t < p.m_tiles; t += n_pairs, ++it) {
+        for (int l = 0; l < p.n_links; ++l) {
+          const FieldChainLink& L = p.link[l];
+          for (int nt = 0; nt < L.n_tiles; ++nt) {
+            const int bn = L.tile_bn[nt], n0 = L.tile_n0[nt];
+            const CUtensorMap* bmap = bn == 256 ? &p.b_map : (bn == 128 ? &p.b_map_64 : &p.b_map_8);
+            const uint32_t bytes = (uint32_t)(bn / 2) * 128u;
+            for (int kp = 0; kp < L.kp; ++kp) {
+              ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+              if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
+              ptx::tma_load_2d_cg2(ring_u32 + stage * kFcStageBytes, bmap, ptx::mapa_u32(full_u32 + stage * 8, 0), kp * 64,
+                                   L.b_row0 + n0 + rank * (bn / 2));
+              if (++stage == kFcStages) { stage = 0; phase ^= 1; }
+            }
+          }
+          // the next tile's features travel under this tile's remaining links
+          if (l == 0 && t + n_pairs < p.m_tiles) load_features(t + n_pairs, it + 1);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer (leader CTA) ===============================
+    if (lane == 0 && rank == 0) {
+      constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
+      int stage = 0; uint32_t phase = 0;
+      uint32_t ae_phase = 0, ff_par = 0, ar_par = 0;
+      int cnt = 0, it = 0;
+      for (int t = pair; t < p.m_tiles; t += n_pairs, ++it) {
+        for (int l = 0; l < p.n_links; ++l) {
+          const FieldChainLink& L = p.link[l];
+          uint32_t a_base;
+          if (l == 0) {
+            const int q = it & 1;
+            ptx::mbar_wait_u32(ffull_u32 + q * 8, (ff_par >> q) & 1u);
+            ff_par ^= 1u << q;
+            a_base = f_u32 + q * kPanelBytes;
+          } else {
+            ptx::mbar_wait_u32(aready_u32, ar_par);
+            ar_par ^= 1u;
+            a_base = x_u32 + (l & 1) * 4 * kPanelBytes;
+          }
+          ptx::tc_fence_after();
+          for (int nt = 0; nt < L.n_tiles; ++nt, ++cnt) {
+            const int bn = L.tile_bn[nt];
+            const uint32_t idesc = ptx::make_idesc_bf16(256, bn, 0, 0);
+            const int as = cnt & 1;
+            if (cnt >= 2) {
+              ptx::mbar_wait_u32(accempty_u32 + as * 8, (ae_phase >> as) & 1u);
+              ae_phase ^= 1u << as;
+              ptx::tc_fence_after();
+            }
+            const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
+            for (int kp = 0; kp < L.kp; ++kp) {
+              ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+              ptx::tc_fence_after();
+              const uint64_t da = ptx::desc_from(kDescHi, a_base + kp * kPanelBytes);
+              const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kFcStageBytes);
+              ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, kp > 0 ? 1u : 0u);
+              ptx::mma_bf16_ss_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
+              ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
+              ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
+              ptx::mma_commit_mc2_u32(empty_u32 + stage * 8);
+              if (++stage == kFcStages) { stage = 0; phase ^= 1; }
+            }
+            ptx::mma_commit_mc2_u32(accfull_u32 + as * 8);
+          }
+          if (l == 0) ptx::mma_commit_mc2_u32(ffree_u32 + (it & 1) * 8);   // F[q] has been read once these MMAs complete
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue warps ===============================
+    const int ew = warp - 2;
+    const int quarter = warp & 3, half = ew >> 2;       // TMEM lane quarter follows the hardware warp id
+    const int row = quarter * 32 + lane;
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const bool leader = ew == 0 && lane == 0;
+    uint32_t af_phase = 0;
+    int cnt = 0;
+    float v[32];
+    for (int t = pair; t < p.m_tiles; t += n_pairs) {
+      const int grow = t * 256 + rank * 128 + row;
+      const bool valid = grow < p.m_rows;
+      for (int l = 0; l < p.n_links; ++l) {
+        const FieldChainLink& L = p.link[l];
+        uint8_t* xout = xbuf + ((l + 1) & 1) * 4 * kPanelBytes;
+        // the TMA store that read X[(l + 1) & 1] two links ago must have finished reading before it is rewritten
+        if (leader) ptx::tma_wait_group_read<1>();
+        asm volatile("bar.sync 1, %0;" ::"n"(kFcEpiWarps * 32) : "memory");
+        int out_panels = 0;
+        for (int nt = 0; nt < L.n_tiles; ++nt, ++cnt) {
+          const int bn = L.tile_bn[nt], n0 = L.tile_n0[nt], epi = L.tile_epi[nt];
+          const int as = cnt & 1;
+          ptx::mbar_wait_u32(accfull_u32 + as * 8, (af_phase >> as) & 1u);
+          af_phase ^= 1u << as;
+          ptx::tc_fence_after();
+          const uint32_t acc_addr = lane_addr + (uint32_t)(as * 256);
+          if (epi == DE_HEAD_F32) {
+            if (half == 0) {
+              uint32_t r4[4];
+              ptx::tmem_ld4(acc_addr, r4);
+              ptx::tmem_ld_wait();
+              if (valid)
+                for (int c = 0; c < L.raw_nchan; ++c)
+                  p.raw_out[(size_t)grow * p.raw_c + L.raw_chan0 + c] = __uint_as_float(r4[c]) + p.bias[L.bias_off + n0 + c];
+            }
+          } else {
+            out_panels = bn / 64;
+            const int cols_per_half = bn / 2;             // 128 | 64
+            uint32_t gw[4] = {0u, 0u, 0u, 0u};
+            for (int c0 = 0; c0 < cols_per_half; c0 += 32) {
+              const int col = half * cols_per_half + c0;
+              load_acc32(acc_addr + (uint32_t)col, v);
+              const int n = n0 + col;
+              if (epi == DE_VIEW) {
+                if (valid) {
+                  const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(grow / p.S) * p.view_ld + n);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 b = __ldg(b4 + c);
+                    v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                  }
+                }
+              } else {
+                const float4* b4 = reinterpret_cast<const float4*>(p.bias + L.bias_off + n);
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                  const float4 b = __ldg(b4 + c);
+                  v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
+                }
+              }
+              if (p.gate_out && L.gate_row0 >= 0) {
+                uint32_t g = 0u;
+#pragma unroll
+                for (int k = 0; k < 32; ++k) g |= (v[k] > 0.f ? 1u : 0u) << k;
+                if (c0 == 0) gw[0] = g; else if (c0 == 32) gw[1] = g; else if (c0 == 64) gw[2] = g; else gw[3] = g;
+              }
+              uint8_t* panel = xout + (col >> 6) * kPanelBytes;
+              const int chunk0 = (col & 63) >> 3;
+              if (epi == DE_LINEAR) store_half32<false>(panel, row, chunk0, v);
+              else store_half32<true>(panel, row, chunk0, v);
+            }
+            if (p.gate_out && L.gate_row0 >= 0 && valid && bn == 256)
+              *reinterpret_cast<uint4*>(p.gate_out + ((size_t)L.gate_row0 + grow) * p.gate_ld + ((n0 + half * 128) >> 5)) =
+                  make_uint4(gw[0], gw[1], gw[2], gw[3]);
+          }
+          // accumulator drained: the issuer may reuse it
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(accempty_u32 + as * 8, 0));
+        }
+        if (out_panels > 0) {
+          // the staged panels become the next link's A operand (async proxy) and, in training, the saved activation
+          ptx::fence_proxy_async();
+          asm volatile("bar.sync 1, %0;" ::"n"(kFcEpiWarps * 32) : "memory");
+          if (leader) {
+            if (l + 1 < p.n_links) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(aready_u32, 0));
+            if (L.store) {
+              for (int pn = 0; pn < out_panels; ++pn)
+                ptx::tma_store_2d(&p.out_map[l], xout + pn * kPanelBytes, pn * 64, t * 256 + rank * 128);
+            }
+            ptx::tma_commit_group();       // (possibly empty: keeps one group per link for the wait_group.read<1> above)
+          }
+        } else if (leader) {
+          ptx::tma_commit_group();
+        }
+      }
+    }
+    if (leader) ptx::tma_wait_group<0>();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc_cg2(tmem_base, 512);
+}
+
+}  // namespace
+
+int field_chain_init() {
+  HUGS_CUDA(cudaFuncSetAttribute(field_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kFcSmem));
+  return HUGS_OK;
+}
+
+int field_chain_launch(const FieldChainParams& p, int num_sms, cudaStream_t st) {
+  if (p.m_tiles <= 0) return HUGS_OK;
+  HUGS_REQUIRE(p.n_links >= 1 && p.n_links <= kFcMaxLinks, "field chain: bad link count %d", p.n_links);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * std::min(p.m_tiles, num_sms / 2));
+  cfg.blockDim = dim3(kFcThreads);
+  cfg.dynamicSmemBytes = kFcSmem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr{};
+  attr.id = cudaLaunchAttributeClusterDimension;
+  attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+  cfg.attrs = &attr; cfg.numAttrs = 1;
+  HUGS_CUDA(cudaLaunchKernelEx(&cfg, field_chain_kernel, p));
+  ++g_launch_count;
+  return HUGS_OK;
+}
+
+}  // namespace hugs

@@ -1,0 +1,35 @@
+// Forward chain kernel of the nerfacto field (field_chain.cu).
+#pragma once
+#include "dense_tc.h"
+
+namespace hugs {
+
+constexpr int kFcMaxLinks = 6;
+
+struct FieldChainLink {
+  int kp;                       // K panels (64 columns) of the link's A operand (link 0: the TMA-loaded feature panel)
+  int b_row0;                   // first weight row of the link inside the forward pack (K-major rows = output units)
+  int n_tiles;                  // 1 or 2 N tiles
+  int tile_n0[2], tile_bn[2], tile_epi[2];   // DenseEpi: DE_RELU / DE_LINEAR / DE_VIEW / DE_HEAD_F32
+  int bias_off;                 // offset of the link's bias row in the fp32 table (indexed by output column)
+  int store;                    // TMA-store the output panels to out_map[link] (training: the saved activation)
+  int gate_row0;                // >= 0: write ReLU gate bits of the output at this row base of gate_out
+  int raw_chan0, raw_nchan;     // DE_HEAD_F32 tiles: channels of raw_out
+};
+
+struct alignas(64) FieldChainParams {
+  CUtensorMap a_map;            // features, bf16 [rows, 64], box 128 x 64
+  CUtensorMap b_map, b_map_64, b_map_8;   // forward weight pack, boxes of 128 / 64 / 8 rows x 64 K
+  CUtensorMap out_map[kFcMaxLinks];       // per link: bf16 [rows, cols], box 128 x 64 (used when link.store)
+  FieldChainLink link[kFcMaxLinks];
+  int n_links, m_tiles, m_rows, S;
+  const float* bias;
+  const float* viewbias; int view_ld;
+  float* raw_out; int raw_c;
+  uint32_t* gate_out; int gate_ld;
+};
+
+int field_chain_init();
+int field_chain_launch(const FieldChainParams& p, int num_sms, cudaStream_t st);
+
+}  // namespace hugs

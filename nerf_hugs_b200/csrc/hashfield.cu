@@ -25,6 +25,7 @@
 
 #include "tc_device.cuh"
 #include "dense_tc.h"
+#include "field_chain.h"
 
 namespace hugs {
 
@@ -667,6 +668,7 @@ struct hugs_hashfield {
   uint8_t* inside = nullptr;
   uint32_t* gate = nullptr;          // ReLU gate bit masks of ACT0 | H0, [2][cap][8] 32-bit words (training)
   bool use_gate = getenv("HUGS_NF_GATE") ? atoi(getenv("HUGS_NF_GATE")) != 0 : true;   // development switch
+  bool use_chain = getenv("HUGS_NF_CHAIN") ? atoi(getenv("HUGS_NF_CHAIN")) != 0 : false; // forward chain kernel (bf16 mode): parity green, not faster yet
   bool train_ready = false;
   WgItem* items_dev = nullptr; std::vector<WgItem> items_host; std::vector<std::pair<int, int>> launches; int built_for = -1;
   int max_rays = 0;
@@ -900,7 +902,7 @@ HUGS_API int hugs_hashfield_create(const hugs_hashfield_desc* desc, hugs_hashfie
     if ((rc = hf_alloc(h, &h->ray_in, (size_t)h->max_rays * (kSH + 64))) || (rc = hf_alloc(h, &h->ray_bias, (size_t)h->max_rays * kH)) ||
         (rc = hf_alloc(h, &h->inside, (size_t)h->cap)))
       return fail(rc);
-    if ((rc = dense_tc_init())) return fail(rc);
+    if ((rc = dense_tc_init()) || (rc = field_chain_init())) return fail(rc);
   }
   {
     cudaError_t e = cudaSuccess;
@@ -1022,6 +1024,39 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
   ray_bias_kernel<<<(n_rays * kH + 255) / 256, 256, 0, st>>>(h->ray_in, kSH + app, mlp + h->o_head0_k, kG, mlp + h->o_head0_b, kH,
                                                              n_rays, h->split ? 1 : 0, h->ray_bias);
   HUGS_LAUNCH_CHECK();
+  if (h->use_chain && !h->split) {
+    // 3-7. all five Dense layers in one launch: the activations stay in shared memory between the layers (field_chain.cu)
+    FieldChainParams c;
+    memset(&c, 0, sizeof(c));
+    c.a_map = h->map128[HF_FEAT]; c.b_map = h->map_wt128; c.b_map_64 = h->map_wt64; c.b_map_8 = h->map_wt8;
+    c.out_map[0] = h->map128[HF_ACT0]; c.out_map[1] = h->map128[HF_GEO]; c.out_map[2] = h->map128[HF_H0];
+    c.out_map[3] = h->map128[HF_H1];
+    auto link = [&](int l, int kp, int b_row0, int bias_off, int store, int gate_row0) {
+      FieldChainLink& L = c.link[l];
+      L.kp = kp; L.b_row0 = b_row0; L.bias_off = bias_off; L.store = store; L.gate_row0 = gate_row0; L.n_tiles = 1;
+      return &L;
+    };
+    const int gate0 = (training && h->use_gate) ? 0 : -1, gate1 = (training && h->use_gate) ? h->cap : -1;
+    FieldChainLink* L = link(0, 1, h->rf_base0, 0, training ? 1 : 0, gate0);
+    L->tile_n0[0] = 0; L->tile_bn[0] = 256; L->tile_epi[0] = DE_RELU;
+    L = link(1, 4, h->rf_heads, 256, training ? 1 : 0, -1);
+    L->n_tiles = 2; L->tile_n0[0] = 0; L->tile_bn[0] = 128; L->tile_epi[0] = DE_LINEAR;
+    L->tile_n0[1] = 128; L->tile_bn[1] = 16; L->tile_epi[1] = DE_HEAD_F32; L->raw_chan0 = 0; L->raw_nchan = 1;
+    L = link(2, 1, h->rf_head0, 0, training ? 1 : 0, gate1);
+    L->tile_n0[0] = 0; L->tile_bn[0] = 256; L->tile_epi[0] = DE_VIEW;
+    L = link(3, 4, h->rf_head1, 400, training ? 1 : 0, -1);
+    L->tile_n0[0] = 0; L->tile_bn[0] = 256; L->tile_epi[0] = DE_RELU;
+    L = link(4, 4, h->rf_rgb, 656, 0, -1);
+    L->tile_n0[0] = 0; L->tile_bn[0] = 16; L->tile_epi[0] = DE_HEAD_F32; L->raw_chan0 = 1; L->raw_nchan = 3;
+    c.n_links = 5; c.m_rows = M; c.m_tiles = (M + 255) / 256; c.S = n_samples;
+    c.bias = h->tab; c.viewbias = h->ray_bias; c.view_ld = kH;
+    c.raw_out = raw_out; c.raw_c = 4;
+    c.gate_out = (training && h->use_gate) ? h->gate : nullptr; c.gate_ld = kH / 32;
+    if ((rc = field_chain_launch(c, h->num_sms, st))) return rc;
+    inside_mask_kernel<<<(M + 255) / 256, 256, 0, st>>>(fr, h->g, h->inside, raw_out, 4);
+    HUGS_LAUNCH_CHECK();
+    return HUGS_OK;
+  }
   DenseParams p;
   // 3. base MLP layer 0: features -> 256 (ReLU)
   dense_common(&p, h, M);
