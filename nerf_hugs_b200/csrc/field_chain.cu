@@ -10,14 +10,14 @@
 // sample) and - in training - the activations the backward pass needs are written once by TMA store (1.8 KB per sample, with 32 B
 // of ReLU gate bits per gated layer).  Structure per CTA pair (cluster of 2, tcgen05 cta_group::2, M = 256 = 128 rows per CTA):
 //
-//   shared memory  X[2][4 panels]  activation ping-pong: link l reads X[l & 1], writes X[(l + 1) & 1]      128 KB
-//                  F[2]            hash-feature panel of the current / next tile (TMA)                        32 KB
-//                  ring[3]         weight stages, <= 128 rows x 64 K per CTA (TMA, half of the N rows each)   48 KB
-//   tensor memory  two 256-column accumulators, alternating per (link, N tile)
-//   warps          0 TMA producer, 1 MMA issuer (leader CTA), 2..9 epilogue
+//   shared memory  X[2 slots][4 panels]  a slot's activation, updated in place by the link epilogues          128 KB
+//                  F[2 slots]            hash-feature panel of the slot's tile (TMA)                          32 KB
+//                  ring[3]               weight stages, <= 128 rows x 64 K per CTA (TMA, half of the N rows)  48 KB
+//   tensor memory  slot s accumulates in columns [256 s, 256 s + 256)
+//   warps          0 TMA producer, 1 MMA issuer (leader CTA), 2..9 epilogue group of slot 0, 10..17 of slot 1
 //
-// One tile is in flight per pair and its links run back to back (the tensor core idles during a link's epilogue): the field is
-// 248 kFLOP per sample against 1.9 KB of mandatory HBM traffic, so the chain only has to keep the HBM queue full.
+// Two tiles are in flight per pair and the issuer alternates between them link by link: one slot's epilogue runs under the
+// other slot's MMAs (with a single tile in flight the chain is latency-bound: measured no faster than five launches).
 // bf16 mode only (the split-precision mode keeps the layer-at-a-time path: its hi + lo panels do not fit).
 #include <algorithm>
 
@@ -29,43 +29,45 @@ namespace {
 
 constexpr int kFcStages = 3;
 constexpr int kFcStageBytes = 16384;
-constexpr int kFcEpiWarps = 8;
-constexpr int kFcThreads = (2 + kFcEpiWarps) * 32;
+constexpr int kFcGroupWarps = 8;                       // epilogue warps per tile slot
+constexpr int kFcThreads = (2 + 2 * kFcGroupWarps) * 32;
 constexpr int kFcSmem = 1024 + 8 * kPanelBytes + 2 * kPanelBytes + kFcStages * kFcStageBytes + 512;
 static_assert(kFcSmem <= 232448, "shared memory budget");
 
+// Two tiles (slots) are in flight per CTA pair: slot s keeps its activation IN PLACE in X[s] (a link's epilogue starts only after
+// all MMAs of the link have completed, so its output may overwrite its input), accumulates in TMEM columns [256 s, 256 s + 256)
+// and has its own group of epilogue warps; the issuer alternates the slots link by link, so slot 0's epilogue runs under slot
+// 1's MMAs and vice versa.
 __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid_constant__ FieldChainParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* xbuf = base;                                   // X[2][4 panels]
-  uint8_t* fbuf = base + 8 * kPanelBytes;                 // F[2]
+  uint8_t* xbuf = base;                                   // X[2 slots][4 panels]
+  uint8_t* fbuf = base + 8 * kPanelBytes;                 // F[2 slots]
   uint8_t* ring = fbuf + 2 * kPanelBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + kFcStages * kFcStageBytes);
   uint64_t* full = bars;                    // [3] leader: both CTAs' weight bytes of a stage have landed
   uint64_t* empty = bars + 3;               // [3] per CTA: the MMAs that read the stage have completed
-  uint64_t* f_full = bars + 6;              // [2] leader: both CTAs' feature panels of tile parity q have landed
-  uint64_t* f_free = bars + 8;              // [2] per CTA: link 0's MMAs have read F[q]
-  uint64_t* a_ready = bars + 10;            // [1] leader: both CTAs' epilogues have staged the link's output panels
-  uint64_t* acc_full = bars + 11;           // [2] per CTA
-  uint64_t* acc_empty = bars + 13;          // [2] leader
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* f_full = bars + 6;              // [2] leader: both CTAs' feature panels of slot s have landed
+  uint64_t* f_free = bars + 8;              // [2] per CTA: link 0's MMAs have read F[s]
+  uint64_t* a_ready = bars + 10;            // [2] leader: both CTAs' epilogue groups of slot s are done with the link
+  uint64_t* acc_full = bars + 12;           // [2] per CTA: the link's MMAs of slot s have completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
+  const int n_units = (p.m_tiles + 1) / 2;                // unit u = tiles 2 u (slot 0) and 2 u + 1 (slot 1)
   const uint32_t x_u32 = ptx::smem_u32(xbuf), f_u32 = ptx::smem_u32(fbuf), ring_u32 = ptx::smem_u32(ring);
   const uint32_t full_u32 = ptx::smem_u32(full), empty_u32 = ptx::smem_u32(empty);
   const uint32_t ffull_u32 = ptx::smem_u32(f_full), ffree_u32 = ptx::smem_u32(f_free);
-  const uint32_t aready_u32 = ptx::smem_u32(a_ready);
-  const uint32_t accfull_u32 = ptx::smem_u32(acc_full), accempty_u32 = ptx::smem_u32(acc_empty);
+  const uint32_t aready_u32 = ptx::smem_u32(a_ready), accfull_u32 = ptx::smem_u32(acc_full);
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&p.a_map); ptx::prefetch_tmap(&p.b_map); ptx::prefetch_tmap(&p.b_map_64); ptx::prefetch_tmap(&p.b_map_8);
     for (int i = 0; i < kFcStages; ++i) { ptx::mbar_init(&full[i], 1); ptx::mbar_init(&empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&f_full[i], 1); ptx::mbar_init(&f_free[i], 1);
-      ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 2 * kFcEpiWarps);
+      ptx::mbar_init(&a_ready[i], 2); ptx::mbar_init(&acc_full[i], 1);
     }
-    ptx::mbar_init(a_ready, 2);
     ptx::fence_mbar_init();
   }
   if (warp == 1) ptx::tmem_alloc_cg2(tmem_ptr, 512);
@@ -79,33 +81,40 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      uint32_t ff_phase = 0;     // bit q: parity of the next f_free phase of feature buffer q
-      auto load_features = [&](int t, int it) {
-        const int q = it & 1;
-        if (it >= 2) { ptx::mbar_wait_u32(ffree_u32 + q * 8, (ff_phase >> q) & 1u); ff_phase ^= 1u << q; }
-        if (rank == 0) ptx::mbar_expect_tx_u32(ffull_u32 + q * 8, 2 * kPanelBytes);
-        ptx::tma_load_2d_cg2(f_u32 + q * kPanelBytes, &p.a_map, ptx::mapa_u32(ffull_u32 + q * 8, 0), 0, t * 256 + rank * 128);
+      uint32_t ff_phase = 0;     // bit s: parity of the next f_free phase of slot s
+      auto load_features = [&](int u, int k) {     // k-th unit of this pair
+        for (int sl = 0; sl < 2; ++sl) {
+          const int t = 2 * u + sl;
+          if (t >= p.m_tiles) break;
+          if (k >= 1) { ptx::mbar_wait_u32(ffree_u32 + sl * 8, (ff_phase >> sl) & 1u); ff_phase ^= 1u << sl; }
+          if (rank == 0) ptx::mbar_expect_tx_u32(ffull_u32 + sl * 8, 2 * kPanelBytes);
+          ptx::tma_load_2d_cg2(f_u32 + sl * kPanelBytes, &p.a_map, ptx::mapa_u32(ffull_u32 + sl * 8, 0), 0, t * 256 + rank * 128);
+        }
       };
-      int it = 0;
-      if (pair < p.m_tiles) load_features(pair, 0);
-      for (int t = pair; t < p.m_tiles; t += n_pairs, ++it) {
+      int k = 0;
+      if (pair < n_units) load_features(pair, 0);
+      for (int u = pair; u < n_units; u += n_pairs, ++k) {
+        const int n_slots = (2 * u + 1 < p.m_tiles) ? 2 : 1;
         for (int l = 0; l < p.n_links; ++l) {
           const FieldChainLink& L = p.link[l];
-          for (int nt = 0; nt < L.n_tiles; ++nt) {
-            const int bn = L.tile_bn[nt], n0 = L.tile_n0[nt];
-            const CUtensorMap* bmap = bn == 256 ? &p.b_map : (bn == 128 ? &p.b_map_64 : &p.b_map_8);
-            const uint32_t bytes = (uint32_t)(bn / 2) * 128u;
-            for (int kp = 0; kp < L.kp; ++kp) {
-              ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
-              if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
-              ptx::tma_load_2d_cg2(ring_u32 + stage * kFcStageBytes, bmap, ptx::mapa_u32(full_u32 + stage * 8, 0), kp * 64,
-                                   L.b_row0 + n0 + rank * (bn / 2));
-              if (++stage == kFcStages) { stage = 0; phase ^= 1; }
+          for (int sl = 0; sl < n_slots; ++sl) {
+            for (int nt = 0; nt < L.n_tiles; ++nt) {
+              const int bn = L.tile_bn[nt], n0 = L.tile_n0[nt];
+              const CUtensorMap* bmap = bn == 256 ? &p.b_map : (bn == 128 ? &p.b_map_64 : &p.b_map_8);
+              const uint32_t bytes = (uint32_t)(bn / 2) * 128u;
+              for (int kp = 0; kp < L.kp; ++kp) {
+                ptx::mbar_wait_u32(empty_u32 + stage * 8, phase ^ 1);
+                if (rank == 0) ptx::mbar_expect_tx_u32(full_u32 + stage * 8, 2 * bytes);
+                ptx::tma_load_2d_cg2(ring_u32 + stage * kFcStageBytes, bmap, ptx::mapa_u32(full_u32 + stage * 8, 0), kp * 64,
+                                     L.b_row0 + n0 + rank * (bn / 2));
+                if (++stage == kFcStages) { stage = 0; phase ^= 1; }
+              }
             }
           }
-          // the next tile's features travel under this tile's remaining links
-          if (l == 0 && t + n_pairs < p.m_tiles) load_features(t + n_pairs, it + 1);
+          // the next unit's features travel under this unit's remaining links (link 0 has released F by then)
+          if (l == 1 && u + n_pairs < n_units) load_features(u + n_pairs, k + 1);
         }
+        if (p.n_links < 2 && u + n_pairs < n_units) load_features(u + n_pairs, k + 1);
       }
     }
   } else if (warp == 1) {
@@ -113,78 +122,84 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
     if (lane == 0 && rank == 0) {
       constexpr uint32_t kDescHi = ptx::desc_hi_sw128(1024);
       int stage = 0; uint32_t phase = 0;
-      uint32_t ae_phase = 0, ff_par = 0, ar_par = 0;
-      int cnt = 0, it = 0;
-      for (int t = pair; t < p.m_tiles; t += n_pairs, ++it) {
+      uint32_t ff_par = 0, ar_par = 0;
+      bool first = true;
+      for (int u = pair; u < n_units; u += n_pairs) {
+        const int n_slots = (2 * u + 1 < p.m_tiles) ? 2 : 1;
         for (int l = 0; l < p.n_links; ++l) {
           const FieldChainLink& L = p.link[l];
-          uint32_t a_base;
-          if (l == 0) {
-            const int q = it & 1;
-            ptx::mbar_wait_u32(ffull_u32 + q * 8, (ff_par >> q) & 1u);
-            ff_par ^= 1u << q;
-            a_base = f_u32 + q * kPanelBytes;
-          } else {
-            ptx::mbar_wait_u32(aready_u32, ar_par);
-            ar_par ^= 1u;
-            a_base = x_u32 + (l & 1) * 4 * kPanelBytes;
-          }
-          ptx::tc_fence_after();
-          for (int nt = 0; nt < L.n_tiles; ++nt, ++cnt) {
-            const int bn = L.tile_bn[nt];
-            const uint32_t idesc = ptx::make_idesc_bf16(256, bn, 0, 0);
-            const int as = cnt & 1;
-            if (cnt >= 2) {
-              ptx::mbar_wait_u32(accempty_u32 + as * 8, (ae_phase >> as) & 1u);
-              ae_phase ^= 1u << as;
-              ptx::tc_fence_after();
+          for (int sl = 0; sl < n_slots; ++sl) {
+            // the slot's epilogue group is done with the previous link (its accumulator is drained, its panels are staged)
+            if (!(first && l == 0)) {
+              ptx::mbar_wait_u32(aready_u32 + sl * 8, (ar_par >> sl) & 1u);
+              ar_par ^= 1u << sl;
             }
-            const uint32_t d_tmem = tmem_base + (uint32_t)(as * 256);
-            for (int kp = 0; kp < L.kp; ++kp) {
-              ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
-              ptx::tc_fence_after();
-              const uint64_t da = ptx::desc_from(kDescHi, a_base + kp * kPanelBytes);
-              const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kFcStageBytes);
-              ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, kp > 0 ? 1u : 0u);
-              ptx::mma_bf16_ss_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
-              ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
-              ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
-              ptx::mma_commit_mc2_u32(empty_u32 + stage * 8);
-              if (++stage == kFcStages) { stage = 0; phase ^= 1; }
+            uint32_t a_base = x_u32 + sl * 4 * kPanelBytes;
+            if (l == 0) {
+              ptx::mbar_wait_u32(ffull_u32 + sl * 8, (ff_par >> sl) & 1u);
+              ff_par ^= 1u << sl;
+              a_base = f_u32 + sl * kPanelBytes;
             }
-            ptx::mma_commit_mc2_u32(accfull_u32 + as * 8);
+            ptx::tc_fence_after();
+            int tcol = 0;
+            for (int nt = 0; nt < L.n_tiles; ++nt) {
+              const int bn = L.tile_bn[nt];
+              const uint32_t idesc = ptx::make_idesc_bf16(256, bn, 0, 0);
+              const uint32_t d_tmem = tmem_base + (uint32_t)(sl * 256 + tcol);
+              for (int kp = 0; kp < L.kp; ++kp) {
+                ptx::mbar_wait_u32(full_u32 + stage * 8, phase);
+                ptx::tc_fence_after();
+                const uint64_t da = ptx::desc_from(kDescHi, a_base + kp * kPanelBytes);
+                const uint64_t db = ptx::desc_from(kDescHi, ring_u32 + stage * kFcStageBytes);
+                ptx::mma_bf16_ss_cg2(d_tmem, da, db, idesc, kp > 0 ? 1u : 0u);
+                ptx::mma_bf16_ss_cg2(d_tmem, da + 2, db + 2, idesc, 1u);
+                ptx::mma_bf16_ss_cg2(d_tmem, da + 4, db + 4, idesc, 1u);
+                ptx::mma_bf16_ss_cg2(d_tmem, da + 6, db + 6, idesc, 1u);
+                ptx::mma_commit_mc2_u32(empty_u32 + stage * 8);
+                if (++stage == kFcStages) { stage = 0; phase ^= 1; }
+              }
+              tcol += bn;
+            }
+            ptx::mma_commit_mc2_u32(accfull_u32 + sl * 8);
+            if (l == 0) ptx::mma_commit_mc2_u32(ffree_u32 + sl * 8);   // F[slot] has been read once these MMAs complete
           }
-          if (l == 0) ptx::mma_commit_mc2_u32(ffree_u32 + (it & 1) * 8);   // F[q] has been read once these MMAs complete
         }
+        first = false;
       }
     }
   } else {
-    // =============================== epilogue warps ===============================
-    const int ew = warp - 2;
+    // =============================== epilogue groups: group g owns tile slot g ===============================
+    const int sl = (warp - 2) / kFcGroupWarps;
+    const int ew = (warp - 2) % kFcGroupWarps;
     const int quarter = warp & 3, half = ew >> 2;       // TMEM lane quarter follows the hardware warp id
     const int row = quarter * 32 + lane;
-    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(sl * 256);
     const bool leader = ew == 0 && lane == 0;
+    uint8_t* xs = xbuf + sl * 4 * kPanelBytes;
     uint32_t af_phase = 0;
-    int cnt = 0;
     float v[32];
-    for (int t = pair; t < p.m_tiles; t += n_pairs) {
+    auto group_sync = [&]() {
+      if (sl == 0) asm volatile("bar.sync 1, %0;" ::"n"(kFcGroupWarps * 32) : "memory");
+      else asm volatile("bar.sync 2, %0;" ::"n"(kFcGroupWarps * 32) : "memory");
+    };
+    for (int u = pair; u < n_units; u += n_pairs) {
+      const int t = 2 * u + sl;
+      if (t >= p.m_tiles) break;                         // (only the last unit can lack its second tile)
       const int grow = t * 256 + rank * 128 + row;
       const bool valid = grow < p.m_rows;
       for (int l = 0; l < p.n_links; ++l) {
         const FieldChainLink& L = p.link[l];
-        uint8_t* xout = xbuf + ((l + 1) & 1) * 4 * kPanelBytes;
-        // the TMA store that read X[(l + 1) & 1] two links ago must have finished reading before it is rewritten
-        if (leader) ptx::tma_wait_group_read<1>();
-        asm volatile("bar.sync 1, %0;" ::"n"(kFcEpiWarps * 32) : "memory");
-        int out_panels = 0;
-        for (int nt = 0; nt < L.n_tiles; ++nt, ++cnt) {
+        ptx::mbar_wait_u32(accfull_u32 + sl * 8, af_phase);
+        af_phase ^= 1u;
+        ptx::tc_fence_after();
+        // the TMA store of the previous link read the panels this epilogue overwrites in place
+        if (leader) ptx::tma_wait_group_read<0>();
+        group_sync();
+        int out_panels = 0, tcol = 0;
+        for (int nt = 0; nt < L.n_tiles; ++nt) {
           const int bn = L.tile_bn[nt], n0 = L.tile_n0[nt], epi = L.tile_epi[nt];
-          const int as = cnt & 1;
-          ptx::mbar_wait_u32(accfull_u32 + as * 8, (af_phase >> as) & 1u);
-          af_phase ^= 1u << as;
-          ptx::tc_fence_after();
-          const uint32_t acc_addr = lane_addr + (uint32_t)(as * 256);
+          const uint32_t acc_addr = lane_addr + (uint32_t)tcol;
+          tcol += bn;
           if (epi == DE_HEAD_F32) {
             if (half == 0) {
               uint32_t r4[4];
@@ -194,65 +209,59 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
                 for (int c = 0; c < L.raw_nchan; ++c)
                   p.raw_out[(size_t)grow * p.raw_c + L.raw_chan0 + c] = __uint_as_float(r4[c]) + p.bias[L.bias_off + n0 + c];
             }
-          } else {
-            out_panels = bn / 64;
-            const int cols_per_half = bn / 2;             // 128 | 64
-            uint32_t gw[4] = {0u, 0u, 0u, 0u};
-            for (int c0 = 0; c0 < cols_per_half; c0 += 32) {
-              const int col = half * cols_per_half + c0;
-              load_acc32(acc_addr + (uint32_t)col, v);
-              const int n = n0 + col;
-              if (epi == DE_VIEW) {
-                if (valid) {
-                  const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(grow / p.S) * p.view_ld + n);
-#pragma unroll
-                  for (int c = 0; c < 8; ++c) {
-                    const float4 b = __ldg(b4 + c);
-                    v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
-                  }
-                }
-              } else {
-                const float4* b4 = reinterpret_cast<const float4*>(p.bias + L.bias_off + n);
+            continue;
+          }
+          out_panels = bn / 64;
+          const int cols_per_half = bn / 2;             // 128 | 64
+          uint32_t gw[4] = {0u, 0u, 0u, 0u};
+          for (int c0 = 0; c0 < cols_per_half; c0 += 32) {
+            const int col = half * cols_per_half + c0;
+            load_acc32(acc_addr + (uint32_t)col, v);
+            const int n = n0 + col;
+            if (epi == DE_VIEW) {
+              if (valid) {
+                const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(grow / p.S) * p.view_ld + n);
 #pragma unroll
                 for (int c = 0; c < 8; ++c) {
                   const float4 b = __ldg(b4 + c);
                   v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
                 }
               }
-              if (p.gate_out && L.gate_row0 >= 0) {
-                uint32_t g = 0u;
+            } else {
+              const float4* b4 = reinterpret_cast<const float4*>(p.bias + L.bias_off + n);
 #pragma unroll
-                for (int k = 0; k < 32; ++k) g |= (v[k] > 0.f ? 1u : 0u) << k;
-                if (c0 == 0) gw[0] = g; else if (c0 == 32) gw[1] = g; else if (c0 == 64) gw[2] = g; else gw[3] = g;
+              for (int c = 0; c < 8; ++c) {
+                const float4 b = __ldg(b4 + c);
+                v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
               }
-              uint8_t* panel = xout + (col >> 6) * kPanelBytes;
-              const int chunk0 = (col & 63) >> 3;
-              if (epi == DE_LINEAR) store_half32<false>(panel, row, chunk0, v);
-              else store_half32<true>(panel, row, chunk0, v);
             }
-            if (p.gate_out && L.gate_row0 >= 0 && valid && bn == 256)
-              *reinterpret_cast<uint4*>(p.gate_out + ((size_t)L.gate_row0 + grow) * p.gate_ld + ((n0 + half * 128) >> 5)) =
-                  make_uint4(gw[0], gw[1], gw[2], gw[3]);
+            if (p.gate_out && L.gate_row0 >= 0) {
+              uint32_t g = 0u;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) g |= (v[k] > 0.f ? 1u : 0u) << k;
+              if (c0 == 0) gw[0] = g; else if (c0 == 32) gw[1] = g; else if (c0 == 64) gw[2] = g; else gw[3] = g;
+            }
+            uint8_t* panel = xs + (col >> 6) * kPanelBytes;
+            const int chunk0 = (col & 63) >> 3;
+            if (epi == DE_LINEAR) store_half32<false>(panel, row, chunk0, v);
+            else store_half32<true>(panel, row, chunk0, v);
           }
-          // accumulator drained: the issuer may reuse it
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(accempty_u32 + as * 8, 0));
+          if (p.gate_out && L.gate_row0 >= 0 && valid && bn == 256)
+            *reinterpret_cast<uint4*>(p.gate_out + ((size_t)L.gate_row0 + grow) * p.gate_ld + ((n0 + half * 128) >> 5)) =
+                make_uint4(gw[0], gw[1], gw[2], gw[3]);
         }
-        if (out_panels > 0) {
-          // the staged panels become the next link's A operand (async proxy) and, in training, the saved activation
-          ptx::fence_proxy_async();
-          asm volatile("bar.sync 1, %0;" ::"n"(kFcEpiWarps * 32) : "memory");
-          if (leader) {
-            if (l + 1 < p.n_links) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(aready_u32, 0));
-            if (L.store) {
-              for (int pn = 0; pn < out_panels; ++pn)
-                ptx::tma_store_2d(&p.out_map[l], xout + pn * kPanelBytes, pn * 64, t * 256 + rank * 128);
-            }
-            ptx::tma_commit_group();       // (possibly empty: keeps one group per link for the wait_group.read<1> above)
+        // accumulator drained and output panels staged: the next link's MMAs (async proxy) may start; in training the panels
+        // are also the saved activation
+        ptx::tc_fence_before();
+        ptx::fence_proxy_async();
+        group_sync();
+        if (leader) {
+          ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(aready_u32 + sl * 8, 0));
+          if (L.store && out_panels > 0) {
+            for (int pn = 0; pn < out_panels; ++pn)
+              ptx::tma_store_2d(&p.out_map[l], xs + pn * kPanelBytes, pn * 64, t * 256 + rank * 128);
+            ptx::tma_commit_group();
           }
-        } else if (leader) {
-          ptx::tma_commit_group();
         }
       }
     }

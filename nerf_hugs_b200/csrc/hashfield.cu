@@ -668,7 +668,7 @@ struct hugs_hashfield {
   uint8_t* inside = nullptr;
   uint32_t* gate = nullptr;          // ReLU gate bit masks of ACT0 | H0, [2][cap][8] 32-bit words (training)
   bool use_gate = getenv("HUGS_NF_GATE") ? atoi(getenv("HUGS_NF_GATE")) != 0 : true;   // development switch
-  bool use_chain = getenv("HUGS_NF_CHAIN") ? atoi(getenv("HUGS_NF_CHAIN")) != 0 : false; // forward chain kernel (bf16 mode): parity green, not faster yet
+  bool use_chain = getenv("HUGS_NF_CHAIN") ? atoi(getenv("HUGS_NF_CHAIN")) != 0 : true;  // forward chain kernel (bf16 mode); 0: five dense_tc launches
   bool train_ready = false;
   WgItem* items_dev = nullptr; std::vector<WgItem> items_host; std::vector<std::pair<int, int>> launches; int built_for = -1;
   int max_rays = 0;
