@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
         }
       };
       int k = 0;
-      if (pair < n_units) load_features(pair, 0);
+      if (pair < n_units && !p.start_mode) load_features(pair, 0);
       for (int u = pair; u < n_units; u += n_pairs, ++k) {
         const int n_slots = (2 * u + 1 < p.m_tiles) ? 2 : 1;
         for (int l = 0; l < p.n_links; ++l) {
@@ -112,9 +112,9 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
             }
           }
           // the next unit's features travel under this unit's remaining links (link 0 has released F by then)
-          if (l == 1 && u + n_pairs < n_units) load_features(u + n_pairs, k + 1);
+          if (l == 1 && u + n_pairs < n_units && !p.start_mode) load_features(u + n_pairs, k + 1);
         }
-        if (p.n_links < 2 && u + n_pairs < n_units) load_features(u + n_pairs, k + 1);
+        if (p.n_links < 2 && u + n_pairs < n_units && !p.start_mode) load_features(u + n_pairs, k + 1);
       }
     }
   } else if (warp == 1) {
@@ -130,12 +130,12 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
           const FieldChainLink& L = p.link[l];
           for (int sl = 0; sl < n_slots; ++sl) {
             // the slot's epilogue group is done with the previous link (its accumulator is drained, its panels are staged)
-            if (!(first && l == 0)) {
+            if (!(first && l == 0) || p.start_mode) {
               ptx::mbar_wait_u32(aready_u32 + sl * 8, (ar_par >> sl) & 1u);
               ar_par ^= 1u << sl;
             }
             uint32_t a_base = x_u32 + sl * 4 * kPanelBytes;
-            if (l == 0) {
+            if (l == 0 && !p.start_mode) {
               ptx::mbar_wait_u32(ffull_u32 + sl * 8, (ff_par >> sl) & 1u);
               ff_par ^= 1u << sl;
               a_base = f_u32 + sl * kPanelBytes;
@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
               tcol += bn;
             }
             ptx::mma_commit_mc2_u32(accfull_u32 + sl * 8);
-            if (l == 0) ptx::mma_commit_mc2_u32(ffree_u32 + sl * 8);   // F[slot] has been read once these MMAs complete
+            if (l == 0 && !p.start_mode) ptx::mma_commit_mc2_u32(ffree_u32 + sl * 8);   // F[slot] has been read once these MMAs complete
           }
         }
         first = false;
@@ -187,6 +187,41 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
       if (t >= p.m_tiles) break;                         // (only the last unit can lack its second tile)
       const int grow = t * 256 + rank * 128 + row;
       const bool valid = grow < p.m_rows;
+      float d_dens = 0.f;
+      if (p.start_mode) {
+        // ---- backward start: dZ of the last colour layer from the head gradients (CUDA cores: K = 3) ----
+        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (valid) dr = __ldg(reinterpret_cast<const float4*>(p.d_raw) + grow);
+        if (valid && !p.inside[grow]) dr.x = 0.f;         // density * selector: no density gradient out of range
+        d_dens = dr.x;
+        const uint32_t h01 = ptx::pack_bf16x2(dr.y, dr.z), h23 = ptx::pack_bf16x2(dr.w, dr.x);
+        if (half == 0) reinterpret_cast<uint4*>(p.dh_out + (size_t)grow * kHeadCols)[0] = make_uint4(h01, h23, 0u, 0u);   // (zeros on padding rows)
+        // bf16-round the head gradient once so that dgrad (here) and wgrad (tensor cores, from dh_out) agree
+        const float d0 = __uint_as_float(h01 << 16), d1 = __uint_as_float(h01 & 0xFFFF0000u), d2 = __uint_as_float(h23 << 16);
+        uint4 gq = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) gq = __ldg(reinterpret_cast<const uint4*>(p.gate_in + ((size_t)p.start_gate_row0 + grow) * p.gate_ld + half * 4));
+        // the previous unit's last store read the panels this op overwrites
+        if (leader) ptx::tma_wait_group_read<0>();
+        group_sync();
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          const int col = half * 128 + c0;
+          const uint32_t g = c0 == 0 ? gq.x : (c0 == 32 ? gq.y : (c0 == 64 ? gq.z : gq.w));
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float* w = p.w_rgb + (col + k) * 3;
+            const float z = d0 * __ldg(w) + d1 * __ldg(w + 1) + d2 * __ldg(w + 2);
+            v[k] = ((g >> k) & 1u) ? z : 0.f;
+          }
+          store_half32<false>(xs + (col >> 6) * kPanelBytes, row, (col & 63) >> 3, v);
+        }
+        ptx::fence_proxy_async();
+        group_sync();
+        if (leader) {
+          ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(aready_u32 + sl * 8, 0));
+          for (int pn = 0; pn < 4; ++pn) ptx::tma_store_2d(&p.start_map, xs + pn * kPanelBytes, pn * 64, t * 256 + rank * 128);
+          ptx::tma_commit_group();
+        }
+      }
       for (int l = 0; l < p.n_links; ++l) {
         const FieldChainLink& L = p.link[l];
         ptx::mbar_wait_u32(accfull_u32 + sl * 8, af_phase);
@@ -218,7 +253,27 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
             const int col = half * cols_per_half + c0;
             load_acc32(acc_addr + (uint32_t)col, v);
             const int n = n0 + col;
-            if (epi == DE_VIEW) {
+            if (epi == DE_BWD_RELU || epi == DE_BWD_LINEAR) {
+              if (epi == DE_BWD_RELU) {
+                if (L.rank1) {   // density head: d_density (bf16-rounded like the head-gradient rows) x w_density
+                  const float dd = __bfloat162float(__float2bfloat16(d_dens));
+                  const float4* w4 = reinterpret_cast<const float4*>(p.rank1_col + n);
+#pragma unroll
+                  for (int c = 0; c < 8; ++c) {
+                    const float4 w = __ldg(w4 + c);
+                    v[c * 4 + 0] = fmaf(dd, w.x, v[c * 4 + 0]); v[c * 4 + 1] = fmaf(dd, w.y, v[c * 4 + 1]);
+                    v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
+                  }
+                }
+                const uint32_t g = valid ? __ldg(p.gate_in + ((size_t)L.gate_in_row0 + grow) * p.gate_ld + (n >> 5)) : 0u;
+#pragma unroll
+                for (int k = 0; k < 32; ++k)
+                  if (((g >> k) & 1u) == 0u) v[k] = 0.f;
+              } else if (!valid) {
+#pragma unroll
+                for (int k = 0; k < 32; ++k) v[k] = 0.f;
+              }
+            } else if (epi == DE_VIEW) {
               if (valid) {
                 const float4* b4 = reinterpret_cast<const float4*>(p.viewbias + (size_t)(grow / p.S) * p.view_ld + n);
 #pragma unroll
@@ -243,8 +298,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
             }
             uint8_t* panel = xs + (col >> 6) * kPanelBytes;
             const int chunk0 = (col & 63) >> 3;
-            if (epi == DE_LINEAR) store_half32<false>(panel, row, chunk0, v);
-            else store_half32<true>(panel, row, chunk0, v);
+            if (epi == DE_RELU || epi == DE_VIEW) store_half32<true>(panel, row, chunk0, v);
+            else store_half32<false>(panel, row, chunk0, v);
           }
           if (p.gate_out && L.gate_row0 >= 0 && valid && bn == 256)
             *reinterpret_cast<uint4*>(p.gate_out + ((size_t)L.gate_row0 + grow) * p.gate_ld + ((n0 + half * 128) >> 5)) =
@@ -256,7 +311,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
         ptx::fence_proxy_async();
         group_sync();
         if (leader) {
-          ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(aready_u32 + sl * 8, 0));
+          // (backward program: the next unit's start op signals the issuer instead of the last link)
+          if (!p.start_mode || l + 1 < p.n_links) ptx::mbar_arrive_cluster_u32(ptx::mapa_u32(aready_u32 + sl * 8, 0));
           if (L.store && out_panels > 0) {
             for (int pn = 0; pn < out_panels; ++pn)
               ptx::tma_store_2d(&p.out_map[l], xs + pn * kPanelBytes, pn * 64, t * 256 + rank * 128);

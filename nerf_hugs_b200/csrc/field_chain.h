@@ -15,6 +15,8 @@ struct FieldChainLink {
   int store;                    // TMA-store the output panels to out_map[link] (training: the saved activation)
   int gate_row0;                // >= 0: write ReLU gate bits of the output at this row base of gate_out
   int raw_chan0, raw_nchan;     // DE_HEAD_F32 tiles: channels of raw_out
+  int gate_in_row0;             // DE_BWD_RELU tiles: row base of the layer's ReLU gate bits in gate_in
+  int rank1;                    // DE_BWD_RELU tiles: add d_density[row] * rank1_col[n] before the gate (density head dgrad)
 };
 
 struct alignas(64) FieldChainParams {
@@ -27,6 +29,17 @@ struct alignas(64) FieldChainParams {
   const float* viewbias; int view_ld;
   float* raw_out; int raw_c;
   uint32_t* gate_out; int gate_ld;
+  // backward program (start_mode = 1): no feature load; the chain starts from dZ of the last colour layer, computed by the slot's
+  // epilogue group from d_raw = (d_density, d_r, d_g, d_b) per sample: dZ[c] = (d_rgb . w_rgb[c]) * [h1[c] > 0]
+  int start_mode;
+  const float* d_raw;           // [M, 4]
+  const uint8_t* inside;        // [M] density * selector mask (no density gradient out of range)
+  const float* w_rgb;           // [256][3] fp32 (bf16-rounded in the bf16 mode)
+  const float* rank1_col;       // [256] density-head weights
+  const uint32_t* gate_in;      // gate bits written by the forward chain
+  int start_gate_row0;          // row base of the last colour layer's gate bits
+  CUtensorMap start_map;        // dZ of the last colour layer [rows, 256] (saved for the weight gradients)
+  __nv_bfloat16* dh_out;        // [M, 64] head-gradient rows (d_r, d_g, d_b, d_density, 0 ...) for the head weight gradients
 };
 
 int field_chain_init();

@@ -666,7 +666,7 @@ struct hugs_hashfield {
   CUtensorMap map128[HF_MAPS], map64[HF_MAPS];
   float *ray_in = nullptr, *ray_bias = nullptr, *dzsum = nullptr, *d_dens = nullptr;
   uint8_t* inside = nullptr;
-  uint32_t* gate = nullptr;          // ReLU gate bit masks of ACT0 | H0, [2][cap][8] 32-bit words (training)
+  uint32_t* gate = nullptr;          // ReLU gate bit masks of ACT0 | H0 | H1 (H1: chain kernels only), [3][cap][8] 32-bit words (training)
   bool use_gate = getenv("HUGS_NF_GATE") ? atoi(getenv("HUGS_NF_GATE")) != 0 : true;   // development switch
   bool use_chain = getenv("HUGS_NF_CHAIN") ? atoi(getenv("HUGS_NF_CHAIN")) != 0 : true;  // forward chain kernel (bf16 mode); 0: five dense_tc launches
   bool train_ready = false;
@@ -739,7 +739,7 @@ int hf_ensure_training(hugs_hashfield* h) {
         (rc = make_map(&h->map64[i], h->buf[i], h->cap * h->parts, h->buf_cols[i], 64)))
       return rc;
   }
-  if ((rc = hf_alloc(h, &h->gate, (size_t)2 * h->cap * (kH / 32)))) return rc;
+  if ((rc = hf_alloc(h, &h->gate, (size_t)3 * h->cap * (kH / 32)))) return rc;
   if ((rc = hf_alloc(h, &h->dzsum, (size_t)h->max_rays * kH)) || (rc = hf_alloc(h, &h->d_dens, (size_t)h->cap)) ||
       (rc = hf_alloc(h, &h->items_dev, kMaxWgItems)))
     return rc;
@@ -1036,7 +1036,8 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
       L.kp = kp; L.b_row0 = b_row0; L.bias_off = bias_off; L.store = store; L.gate_row0 = gate_row0; L.n_tiles = 1;
       return &L;
     };
-    const int gate0 = (training && h->use_gate) ? 0 : -1, gate1 = (training && h->use_gate) ? h->cap : -1;
+    const int gate0 = (training && h->use_gate) ? 0 : -1, gate1 = (training && h->use_gate) ? h->cap : -1,
+              gate2 = (training && h->use_gate) ? 2 * h->cap : -1;      // (the backward chain starts from the gate bits of h1)
     FieldChainLink* L = link(0, 1, h->rf_base0, 0, training ? 1 : 0, gate0);
     L->tile_n0[0] = 0; L->tile_bn[0] = 256; L->tile_epi[0] = DE_RELU;
     L = link(1, 4, h->rf_heads, 256, training ? 1 : 0, -1);
@@ -1044,7 +1045,7 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
     L->tile_n0[1] = 128; L->tile_bn[1] = 16; L->tile_epi[1] = DE_HEAD_F32; L->raw_chan0 = 0; L->raw_nchan = 1;
     L = link(2, 1, h->rf_head0, 0, training ? 1 : 0, gate1);
     L->tile_n0[0] = 0; L->tile_bn[0] = 256; L->tile_epi[0] = DE_VIEW;
-    L = link(3, 4, h->rf_head1, 400, training ? 1 : 0, -1);
+    L = link(3, 4, h->rf_head1, 400, training ? 1 : 0, gate2);
     L->tile_n0[0] = 0; L->tile_bn[0] = 256; L->tile_epi[0] = DE_RELU;
     L = link(4, 4, h->rf_rgb, 656, 0, -1);
     L->tile_n0[0] = 0; L->tile_bn[0] = 16; L->tile_epi[0] = DE_HEAD_F32; L->raw_chan0 = 1; L->raw_nchan = 3;
@@ -1130,6 +1131,44 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
     const auto& L = h->launches[launch++];
     return wgrad_launch_raw(h->num_sms, 0, 1, 1 << 30, h->map64, HF_MAPS, h->items_dev + L.first, L.second, mlp_grad, st);
   };
+  if (h->use_chain && h->use_gate && !h->split) {
+    // the four dgrad GEMMs and the head-gradient start op as ONE chain launch (field_chain.cu, backward program): dZ stays in
+    // shared memory between the layers; every dZ the weight gradients need is written once by TMA store
+    FieldChainParams c;
+    memset(&c, 0, sizeof(c));
+    c.b_map = h->map_wn128; c.b_map_64 = h->map_wn64; c.b_map_8 = h->map_wn64; c.a_map = h->map128[HF_DZH1];
+    c.out_map[0] = h->map128[HF_DZH0]; c.out_map[1] = h->map128[HF_DGEO]; c.out_map[2] = h->map128[HF_DZA0];
+    c.out_map[3] = h->map128[HF_DFEAT];
+    auto link = [&](int l, int kp, int b_row0, int bn, int epi, int gate_in_row0, int rank1) {
+      FieldChainLink& L = c.link[l];
+      L.kp = kp; L.b_row0 = b_row0; L.n_tiles = 1; L.tile_n0[0] = 0; L.tile_bn[0] = bn; L.tile_epi[0] = epi;
+      L.store = 1; L.gate_row0 = -1; L.gate_in_row0 = gate_in_row0; L.rank1 = rank1;
+    };
+    link(0, 4, h->rb_head1, 256, DE_BWD_RELU, h->cap, 0);      // dZ_head0 = (dZ_head1 . W_head1^T) * [h0 > 0]
+    link(1, 4, h->rb_head0, 128, DE_BWD_LINEAR, 0, 0);         // d_geo = dZ_head0 . W_head0[geometry rows]^T
+    link(2, 1, h->rb_geo, 256, DE_BWD_RELU, 0, 1);             // dZ_act0 = (d_geo . W_geo^T + d_density (x) w_density) * [act0 > 0]
+    link(3, 4, h->rb_base0, 128, DE_BWD_LINEAR, 0, 0);         // d_features = dZ_act0 . W_base0^T
+    c.n_links = 4; c.m_rows = M; c.m_tiles = (M + 255) / 256; c.S = n_samples;
+    c.start_mode = 1; c.d_raw = d_raw; c.inside = h->inside; c.w_rgb = h->tab + 928; c.rank1_col = h->tab + 672;
+    c.gate_in = h->gate; c.gate_ld = kH / 32; c.start_gate_row0 = 2 * h->cap; c.start_map = h->map128[HF_DZH1];
+    c.dh_out = h->buf[HF_DH];
+    if ((rc = field_chain_launch(c, h->num_sms, st))) return rc;
+    for (int i = 0; i < 4; ++i)
+      if ((rc = wgrad())) return rc;
+    ray_colsum_kernel<<<n_rays, kH, 0, st>>>(h->buf[HF_DZH0], nullptr, n_samples, n_rays, h->dzsum);
+    HUGS_LAUNCH_CHECK();
+    ray_input_wgrad_kernel<<<dim3(kSH + app, 32), kH, 0, st>>>(h->ray_in, kSH + app, h->dzsum, n_rays, kG, 0, mlp_grad + h->o_head0_k);
+    HUGS_LAUNCH_CHECK();
+    if (app > 0) {
+      app_embed_grad_kernel<<<(n_rays + 7) / 8, 256, 0, st>>>(h->dzsum, rays->embed_idx, mlp + h->o_head0_k, kG + kSH, app, n_rays,
+                                                              h->d.num_embeddings, 0, mlp_grad + h->o_emb);
+      HUGS_LAUNCH_CHECK();
+    }
+    ScatterArgs sa{fr, h->g, h->buf[HF_DFEAT], 128, reinterpret_cast<float2*>(grid_grad), nullptr};
+    hash_scatter_kernel<<<(M + 127) / 128, 128, 0, st>>>(sa);
+    HUGS_LAUNCH_CHECK();
+    return HUGS_OK;
+  }
   // start: dZ_head1 from d_rgb, head-gradient rows, masked density gradient
   field_bwd_start_kernel<<<(rows_pad + 7) / 8, 256, 0, st>>>(d_raw, h->buf[HF_H1], h->tab + 928, h->inside, M, rows_pad, h->buf[HF_DZH1],
                                                   h->buf[HF_DH], h->d_dens,
