@@ -1,3 +1,2 @@
-timeout 700 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/r2_sanitizer_a.log python -m pytest tests/test_gpu_layered.py -q -x -k "training_wide_nerf_mlp or shipped_gins" 2>&1 | tail -3; echo "rc=$?"; tail -3 gpurun_out/r2_sanitizer_a.log
-timeout 500 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/r2_sanitizer_b.log python -m pytest tests/test_gpu_render_frame.py -q -x 2>&1 | tail -3; tail -3 gpurun_out/r2_sanitizer_b.log
-timeout 600 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/r2_sanitizer_c.log python -m pytest tests/test_gpu_nerfacto_hash.py -q -x -k "split or loss_and_gradients" 2>&1 | tail -3; tail -3 gpurun_out/r2_sanitizer_c.log
+timeout 700 compute-sanitizer --tool memcheck --error-exitcode 9 --log-file gpurun_out/r2_sanitizer_d.log python -m pytest tests/test_gpu_nerfacto_hash.py -q -x -k "forward_vs_reference or loss_and_gradients or training_decreases" 2>&1 | tail -3; tail -3 gpurun_out/r2_sanitizer_d.log
+timeout 300 python -m pytest tests/test_gpu_nerfacto_hash.py -q 2>&1 | tail -2
