@@ -31,7 +31,8 @@ constexpr int kFcStages = 3;
 constexpr int kFcStageBytes = 16384;
 constexpr int kFcGroupWarps = 8;                       // epilogue warps per tile slot
 constexpr int kFcThreads = (2 + 2 * kFcGroupWarps) * 32;
-constexpr int kFcSmem = 1024 + 8 * kPanelBytes + 2 * kPanelBytes + kFcStages * kFcStageBytes + 512;
+constexpr int kFcTabFloats = 1792;                      // bias / head-weight table staged in shared memory
+constexpr int kFcSmem = 1024 + 8 * kPanelBytes + 2 * kPanelBytes + kFcStages * kFcStageBytes + 512 + kFcTabFloats * 4;
 static_assert(kFcSmem <= 232448, "shared memory budget");
 
 // Two tiles (slots) are in flight per CTA pair: slot s keeps its activation IN PLACE in X[s] (a link's epilogue starts only after
@@ -52,6 +53,9 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
   uint64_t* a_ready = bars + 10;            // [2] leader: both CTAs' epilogue groups of slot s are done with the link
   uint64_t* acc_full = bars + 12;           // [2] per CTA: the link's MMAs of slot s have completed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
+  // the table the epilogues read for every 32-column chunk: a shared-memory broadcast instead of an L1 / L2 round trip
+  float* btab = reinterpret_cast<float*>(ring + kFcStages * kFcStageBytes + 512);
+  for (int i = threadIdx.x; i < p.n_bias; i += kFcThreads) btab[i] = p.bias[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = (int)ptx::cluster_ctarank();
   const int pair = (int)(blockIdx.x >> 1), n_pairs = (int)(gridDim.x >> 1);
@@ -208,8 +212,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
           const uint32_t g = c0 == 0 ? gq.x : (c0 == 32 ? gq.y : (c0 == 64 ? gq.z : gq.w));
 #pragma unroll
           for (int k = 0; k < 32; ++k) {
-            const float* w = p.w_rgb + (col + k) * 3;
-            const float z = d0 * __ldg(w) + d1 * __ldg(w + 1) + d2 * __ldg(w + 2);
+            const float* w = btab + p.w_rgb_off + (col + k) * 3;
+            const float z = d0 * w[0] + d1 * w[1] + d2 * w[2];
             v[k] = ((g >> k) & 1u) ? z : 0.f;
           }
           store_half32<false>(xs + (col >> 6) * kPanelBytes, row, (col & 63) >> 3, v);
@@ -242,7 +246,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
               ptx::tmem_ld_wait();
               if (valid)
                 for (int c = 0; c < L.raw_nchan; ++c)
-                  p.raw_out[(size_t)grow * p.raw_c + L.raw_chan0 + c] = __uint_as_float(r4[c]) + p.bias[L.bias_off + n0 + c];
+                  p.raw_out[(size_t)grow * p.raw_c + L.raw_chan0 + c] = __uint_as_float(r4[c]) + btab[L.bias_off + n0 + c];
             }
             continue;
           }
@@ -257,10 +261,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
               if (epi == DE_BWD_RELU) {
                 if (L.rank1) {   // density head: d_density (bf16-rounded like the head-gradient rows) x w_density
                   const float dd = __bfloat162float(__float2bfloat16(d_dens));
-                  const float4* w4 = reinterpret_cast<const float4*>(p.rank1_col + n);
+                  const float4* w4 = reinterpret_cast<const float4*>(btab + p.rank1_off + n);
 #pragma unroll
                   for (int c = 0; c < 8; ++c) {
-                    const float4 w = __ldg(w4 + c);
+                    const float4 w = w4[c];
                     v[c * 4 + 0] = fmaf(dd, w.x, v[c * 4 + 0]); v[c * 4 + 1] = fmaf(dd, w.y, v[c * 4 + 1]);
                     v[c * 4 + 2] = fmaf(dd, w.z, v[c * 4 + 2]); v[c * 4 + 3] = fmaf(dd, w.w, v[c * 4 + 3]);
                   }
@@ -283,10 +287,10 @@ __global__ void __launch_bounds__(kFcThreads, 1) field_chain_kernel(const __grid
                 }
               }
             } else {
-              const float4* b4 = reinterpret_cast<const float4*>(p.bias + L.bias_off + n);
+              const float4* b4 = reinterpret_cast<const float4*>(btab + L.bias_off + n);
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
-                const float4 b = __ldg(b4 + c);
+                const float4 b = b4[c];
                 v[c * 4 + 0] += b.x; v[c * 4 + 1] += b.y; v[c * 4 + 2] += b.z; v[c * 4 + 3] += b.w;
               }
             }
@@ -339,6 +343,7 @@ int field_chain_init() {
 int field_chain_launch(const FieldChainParams& p, int num_sms, cudaStream_t st) {
   if (p.m_tiles <= 0) return HUGS_OK;
   HUGS_REQUIRE(p.n_links >= 1 && p.n_links <= kFcMaxLinks, "field chain: bad link count %d", p.n_links);
+  HUGS_REQUIRE(p.bias && p.n_bias >= 0 && p.n_bias <= kFcTabFloats, "field chain: bad table size %d", p.n_bias);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * std::min(p.m_tiles, num_sms / 2));
   cfg.blockDim = dim3(kFcThreads);

@@ -25,7 +25,7 @@ struct alignas(64) FieldChainParams {
   CUtensorMap out_map[kFcMaxLinks];       // per link: bf16 [rows, cols], box 128 x 64 (used when link.store)
   FieldChainLink link[kFcMaxLinks];
   int n_links, m_tiles, m_rows, S;
-  const float* bias;
+  const float* bias; int n_bias;   // fp32 table (biases, head weights): copied to shared memory by every CTA (<= 1792 floats)
   const float* viewbias; int view_ld;
   float* raw_out; int raw_c;
   uint32_t* gate_out; int gate_ld;
@@ -34,8 +34,8 @@ struct alignas(64) FieldChainParams {
   int start_mode;
   const float* d_raw;           // [M, 4]
   const uint8_t* inside;        // [M] density * selector mask (no density gradient out of range)
-  const float* w_rgb;           // [256][3] fp32 (bf16-rounded in the bf16 mode)
-  const float* rank1_col;       // [256] density-head weights
+  int w_rgb_off;                // offset of the rgb-head weights [256][3] (bf16-rounded fp32) in the table
+  int rank1_off;                // offset of the density-head weights [256] in the table
   const uint32_t* gate_in;      // gate bits written by the forward chain
   int start_gate_row0;          // row base of the last colour layer's gate bits
   CUtensorMap start_map;        // dZ of the last colour layer [rows, 256] (saved for the weight gradients)

@@ -1050,7 +1050,7 @@ HUGS_API int hugs_hashfield_forward(hugs_hashfield* h, const float* grid, const 
     L = link(4, 4, h->rf_rgb, 656, 0, -1);
     L->tile_n0[0] = 0; L->tile_bn[0] = 16; L->tile_epi[0] = DE_HEAD_F32; L->raw_chan0 = 1; L->raw_nchan = 3;
     c.n_links = 5; c.m_rows = M; c.m_tiles = (M + 255) / 256; c.S = n_samples;
-    c.bias = h->tab; c.viewbias = h->ray_bias; c.view_ld = kH;
+    c.bias = h->tab; c.n_bias = 928 + 768; c.viewbias = h->ray_bias; c.view_ld = kH;
     c.raw_out = raw_out; c.raw_c = 4;
     c.gate_out = (training && h->use_gate) ? h->gate : nullptr; c.gate_ld = kH / 32;
     if ((rc = field_chain_launch(c, h->num_sms, st))) return rc;
@@ -1149,7 +1149,8 @@ HUGS_API int hugs_hashfield_backward(hugs_hashfield* h, const float* grid, const
     link(2, 1, h->rb_geo, 256, DE_BWD_RELU, 0, 1);             // dZ_act0 = (d_geo . W_geo^T + d_density (x) w_density) * [act0 > 0]
     link(3, 4, h->rb_base0, 128, DE_BWD_LINEAR, 0, 0);         // d_features = dZ_act0 . W_base0^T
     c.n_links = 4; c.m_rows = M; c.m_tiles = (M + 255) / 256; c.S = n_samples;
-    c.start_mode = 1; c.d_raw = d_raw; c.inside = h->inside; c.w_rgb = h->tab + 928; c.rank1_col = h->tab + 672;
+    c.start_mode = 1; c.d_raw = d_raw; c.inside = h->inside; c.bias = h->tab; c.n_bias = 928 + 768; c.w_rgb_off = 928;
+    c.rank1_off = 672;
     c.gate_in = h->gate; c.gate_ld = kH / 32; c.start_gate_row0 = 2 * h->cap; c.start_map = h->map128[HF_DZH1];
     c.dh_out = h->buf[HF_DH];
     if ((rc = field_chain_launch(c, h->num_sms, st))) return rc;
