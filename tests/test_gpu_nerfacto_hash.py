@@ -272,6 +272,29 @@ SPLIT_GRAD_NORM_TOL = 1e-3
 SPLIT_GRAD_TOL = 1.5e-2
 
 
+@pytest.mark.parametrize('switch', ['HUGS_NF_CHAIN', 'HUGS_NF_GATE'])
+def test_nerfacto_layer_at_a_time_field_vs_reference(gold, monkeypatch, switch):
+  # the field's chain kernel is the default; HUGS_NF_CHAIN=0 keeps the five dense_tc launches per direction (the path the
+  # split-precision mode uses) and HUGS_NF_GATE=0 the saved activations as ReLU masks: both stay covered in the bf16 mode
+  monkeypatch.setenv(switch, '0')
+  name = 'withmask'
+  case, model, crit, batch, outputs = _run(gold, name)
+  for k in ('rgb', 'depth', 'accumulation'):
+    assert rel(outputs[k].detach().cpu().numpy(), gold[f'{name}/out/{k}']) < 2e-2, k
+  n = case['n_rays']
+  loss, info, _ = crit(outputs=outputs, batch=batch, data_shape=(n // 16, 4, 4), is_finetune=False,
+                       extra_infos={'curr_step': case['step']})
+  assert abs(float(loss.detach()) - float(gold[f'{name}/loss'])) < 2e-2 * abs(float(gold[f'{name}/loss']))
+  loss.backward()
+  for pname, p in model.named_parameters():
+    if p.numel() == 0:
+      continue
+    want = gold[f'{name}/gsum/{pname}']
+    g = p.grad.detach().cpu().numpy().reshape(-1).astype(np.float64)
+    tol = 2e-2 if pname.startswith('proposal_networks') else 0.15
+    assert abs(np.linalg.norm(g) - want[0]) < tol * want[0] + 1e-12, (pname, np.linalg.norm(g), want[0])
+
+
 def test_nerfacto_training_decreases_the_loss(gold):
   case, model, crit = H.build_hash('withmask', device=DEV)
   batch = H.load_hash_batch(gold, 'withmask', DEV)
