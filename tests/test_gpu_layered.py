@@ -92,6 +92,13 @@ def test_training_wide_nerf_mlp(width, glo):
   eng.close()
 
 
+def test_training_wide_one_cta_weight_gradients(monkeypatch):
+  # HUGS_WGRAD_PAIRS=0: the one-CTA weight-gradient kernel with its own bias column sums (no column sums in the dgrad
+  # epilogue) stays covered; the CTA-pair kernel is the default
+  monkeypatch.setenv('HUGS_WGRAD_PAIRS', '0')
+  test_training_wide_nerf_mlp(1024, 0)
+
+
 GIN_360 = """
 Config.dataset_loader = 'llff'
 Config.near = 0.2
