@@ -417,7 +417,8 @@ typedef struct {
 /* models.render_image (models.py:568-649) driven by eval.py:104-160 / render.py:164-187 for camera `cam` of a device-resident
  * dataset, pixel rows [row0, row1) of a width x height image: rays are generated on the device (hugs_make_ray_batch's
  * arithmetic) and rendered chunk by chunk (max_rays of the handle per chunk) with the deterministic path (rng = None); every
- * chunk writes straight into the frame-sized outputs.  One call per frame and rank: no host loop, no per-chunk gather. */
+ * chunk writes straight into the frame-sized outputs.  One call per frame and rank: no host loop, no per-chunk gather.
+ * `width` / `height` must be the camera's own (cams->widths[cam], cams->heights[cam]: device arrays the host cannot check). */
 int hugs_render_frame(hugs_handle* h, const float* params, const hugs_camera_set* cams, int32_t cam, int32_t width,
                       int32_t height, int32_t row0, int32_t row1, float train_frac, int32_t zero_glo,
                       const hugs_frame_out* out, void* stream);
